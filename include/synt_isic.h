@@ -1,0 +1,121 @@
+/* synt_isic.h -- C ABI of libsynt_isic_b200.so (sm_100a only, no CPU fallback).
+ *
+ * The reference (fims9000/SYNT_ISIC) has NO native interface: its hot path is two lines of
+ * Python that call third-party PyTorch modules,
+ *
+ *     noise_pred = model(latents, t).sample                         image_generator.py:400
+ *     latents = scheduler.step(noise_pred, t, latents).prev_sample  image_generator.py:403
+ *     logits  = self.model(self.preprocess_for_classifier(x))       xai/XAI.py:433-436
+ *
+ * so the drop-in boundary is the Python object protocol, and this
+ * header is the C boundary underneath it: plain pointers and sizes, no torch types.  Each
+ * entry point cites the reference call it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions: every function returns 0 on success or a negative code (-1 bad argument,
+ * -2 CUDA error, -3 unsupported, -4 driver entry point missing); synt_last_error() returns
+ * the message of the calling thread's last failure.  Functions never throw.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Device pointers must belong
+ * to the current CUDA device.  Handles are thread-compatible, not thread-safe (the reference
+ * drives them from one worker thread, main.py:43-56).  Images are fp32 NCHW [B,3,128,128] in
+ * [-1,1] exactly as the reference's tensors (image_generator.py:379).
+ */
+#ifndef SYNT_ISIC_H
+#define SYNT_ISIC_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SYNT_DTYPE_F32 0   /* fp32 verification mode: fp32 FMA kernels end to end          */
+#define SYNT_DTYPE_BF16 1  /* production mode: bf16 tcgen05 GEMMs, fp32 accumulate/state   */
+
+typedef struct synt_unet synt_unet_t;
+typedef struct synt_resnet18 synt_resnet18_t;
+
+const char* synt_version(void);
+const char* synt_last_error(void);
+
+/* ---------------- UNet2DModel  (core/generator/model_manager.py:173-194) ---------------- */
+/* Parameter manifest in diffusers state_dict naming (load_state_dict(strict=True)
+ * at xai/XAI.py:605).  The host packs the fp32 tensors back to back in manifest order. */
+int synt_unet_num_params(void);
+int synt_unet_param_info(int index, char* name, int name_cap, long long* numel, long long* offset);
+long long synt_unet_total_param_count(void);            /* == 25,304,963 */
+
+/* replaces ModelManager._create_model_architecture + load_state_dict (model_manager.py:138-143) */
+int synt_unet_create(const float* params_host, long long n_params, int dtype, synt_unet_t** out);
+int synt_unet_destroy(synt_unet_t* h);
+
+/* replaces `model(latents, t).sample`  (image_generator.py:400): eps = UNet(x, t) */
+int synt_unet_forward(synt_unet_t* h, const float* x_dev, int B, int t, float* eps_dev, void* stream);
+/* same forward, additionally copies the output of module `tap` (diffusers module path, e.g.
+ * "down_blocks.0.resnets.1") as fp32 NCHW into out_dev; used by the parity tests only */
+int synt_unet_debug_forward(synt_unet_t* h, const float* x_dev, int B, int t, const char* tap, float* out_dev,
+                            long long out_cap, int* C, int* H, int* W, void* stream);
+
+/* replaces scheduler.set_timesteps(n) + the per-step coefficient algebra of DDPMScheduler.step
+ * (model_manager.py:199-209): coef[i] = {sqrt(1-abar_t), sqrt(abar_t), c_x0, c_xt, sigma} */
+int synt_unet_set_schedule(synt_unet_t* h, int n_steps, const int* timesteps_host, const float* coef_host);
+/* replaces the whole loop image_generator.py:395-403 for steps [step_begin, step_end):
+ *   x is updated in place; z_dev (optional) is injected noise [n_steps][B,3,H,W], otherwise
+ *   Philox(seed, image_offset+b, step); traj_dev (optional) receives x after every step
+ *   (image_generator.py:407), eps_tap_dev (optional) the raw eps of every step.
+ *   micro_batch <= 0 selects the library default; use_graph != 0 replays a captured CUDA graph. */
+int synt_unet_sample(synt_unet_t* h, float* x_dev, int B, const float* z_dev, unsigned long long seed,
+                     long long image_offset, float* traj_dev, float* eps_tap_dev, int step_begin, int step_end,
+                     int micro_batch, int use_graph, void* stream);
+/* host-buffer form of the same call (what a non-PyTorch caller binds): H2D of x_T, all steps of
+ * the current schedule, uint8 HWC conversion (image_generator.py:441-447), D2H of the images.
+ * x_final_host (optional) receives the fp32 result. */
+int synt_unet_generate_host(synt_unet_t* h, const float* xT_host, int B, unsigned long long seed,
+                            long long image_offset, int micro_batch, unsigned char* images_u8_host,
+                            float* x_final_host);
+long long synt_unet_workspace_bytes(synt_unet_t* h);
+long long synt_unet_launch_count(synt_unet_t* h);        /* kernels launched since creation */
+
+/* ---------------- DDPMScheduler  (core/generator/model_manager.py:196-226) -------------- */
+/* schedule 0 = "squaredcos_cap_v2", 1 = "linear"(beta_start, beta_end); host-only arithmetic.
+ * timesteps_out[n_steps] (int64, "leading" spacing), coef_out[n_steps][5], alphas_cumprod_out[num_train] */
+int synt_ddpm_tables(int num_train, int schedule, float beta_start, float beta_end, int n_steps,
+                     long long* timesteps_out, float* coef_out, float* alphas_cumprod_out);
+/* replaces `scheduler.step(noise_pred, t, latents).prev_sample` (image_generator.py:403) */
+int synt_ddpm_step(const float* eps_dev, const float* x_dev, const float* z_dev, float* out_dev, long long n,
+                   const float* coef5_host, void* stream);
+/* replaces image_generator.py:441-447 (mode 0) / diffusion_generator.py:147-148 (mode 1) */
+int synt_to_uint8(const float* x_dev, int B, int H, int W, int mode, unsigned char* out_dev, void* stream);
+
+/* ---------------- MelanomaClassifierAdaptive / ResNet18  (xai/XAI.py:357-471) ----------- */
+int synt_resnet18_num_params(void);
+int synt_resnet18_param_info(int num_classes, int index, char* name, int name_cap, long long* numel,
+                             long long* offset);   /* torchvision resnet18 state_dict names */
+int synt_resnet18_create(const float* params_host, long long n_params, int num_classes, int dtype,
+                         synt_resnet18_t** out);
+int synt_resnet18_destroy(synt_resnet18_t* h);
+/* replaces `self.model(self.preprocess_for_classifier(x))` (XAI.py:399-436): x in [-1,1] */
+int synt_resnet18_logits(synt_resnet18_t* h, const float* x_dev, int B, float* logits_dev, void* stream);
+int synt_resnet18_logits_host(synt_resnet18_t* h, const float* x_host, int B, float* logits_host);
+int synt_resnet18_debug(synt_resnet18_t* h, const float* x_dev, int B, const char* tap, float* out_dev,
+                        long long out_cap, int* C, int* H, int* W, void* stream);
+long long synt_resnet18_launch_count(synt_resnet18_t* h);
+
+/* replaces counterfactual_intervention_advanced (XAI.py:1454-1597):
+ *   out = clamp(x*(1-M) + I*M, -1, 1); type 0 zero, 1 per-channel mean, 2 5x5 box blur,
+ *   3 noise (aux = injected N(0,1) tensor, scaled by noise_std), 4 aux is the intervention itself */
+int synt_intervene_blend(const float* x_dev, const float* mask_dev, const float* aux_dev, int type, float noise_std,
+                         int B, int C, int H, int W, float* out_dev, void* stream);
+/* replaces the masking loop of compute_shap_approximation (XAI.py:1143-1161):
+ *   out[i] = x with every patch whose mask byte is 0 set to 0; patch_masks [n][H/p][W/p] */
+int synt_patch_mask_apply(const float* x_dev, const unsigned char* patch_masks_dev, int n_masks, int C, int H, int W,
+                          int patch, float* out_dev, void* stream);
+
+/* ---------------- test hook (kernel-level parity tests; not a reference entry point) ------ */
+/* one convolution on caller-provided NHWC tensors: use_tc=1 tcgen05 (bf16), 0 fp32-FMA carrier.
+ * weight is K-major [Cout][K*K*Cin + sc0_C + sc1_C], bf16 for use_tc else fp32. */
+int synt_debug_conv(int use_tc, int act_dtype, const void* in_dev, int B, int H, int W, int Cin, int K, int stride,
+                    int pad, const void* sc0_dev, int sc0_C, const void* sc1_dev, int sc1_C, int sc_stride,
+                    const void* weight_dev, const float* bias_dev, const float* bias2_dev, const void* residual_dev,
+                    int relu, void* out_dev, int Cout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNT_ISIC_H */

@@ -1,0 +1,138 @@
+"""Drop-in for the reference's ``MelanomaClassifierAdaptive`` (xai/XAI.py:357-471).
+
+Same constructor arguments and methods (``forward``, ``get_probabilities``,
+``get_per_class_score``, ``predict``, ``get_confidence``, ``preprocess_for_classifier``); the
+``.model`` attribute is a torchvision ``resnet18`` module used ONLY as the parameter container
+(so ``state_dict``/``named_parameters`` and the Grad-CAM handle ``.model.layer4[-1].conv2``,
+xai/XAI.py:2946, keep working).  Logits are computed by ``libsynt_isic_b200.so``: fused
+preprocess kernel, BN-folded tcgen05 implicit-GEMM convolutions, fused pool+FC.  The folded
+weights are rebuilt whenever a parameter or BN buffer changes (the reference's sanity check
+mutates weights in place, xai/XAI.py:2055-2059).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torchvision import models
+
+from . import _lib
+
+CLASS_NAMES = ["MEL", "NV", "BCC", "AKIEC", "BKL", "DF", "VASC"]     # xai/XAI.py:196
+NUM_CLASSES = 7
+CLASSIFIER_IMAGE_SIZE = 224
+DTYPE_CODES = {"fp32": 0, "bf16": 1}
+
+
+class MelanomaClassifierAdaptive(nn.Module):
+    def __init__(self, num_classes: int = NUM_CLASSES, architecture: str = "auto", pretrained: bool = True,
+                 precision: str = "bf16"):
+        super().__init__()
+        if num_classes not in (7, 8):
+            raise NotImplementedError("the reference builds 7-way (xai_integration.py:79) or 8-way (XAI.py:490) heads")
+        self.num_classes = num_classes
+        # `pretrained=True` asks torchvision for IMAGENET1K_V1 (XAI.py:389); weights are not
+        # downloadable offline, so the container starts random-init and a checkpoint is loaded on top.
+        self.model = models.resnet18(weights=None)
+        self.model.fc = nn.Linear(self.model.fc.in_features, num_classes)
+        self.architecture = "resnet18"
+        self.precision = precision
+        self._handles = {}
+        self._manifest = _lib.resnet18_manifest(num_classes)
+        self.eval()
+
+    # ------------------------------------------------------------------ handle --------
+    def _version_key(self):
+        sd = self.model.state_dict(keep_vars=True)
+        return tuple((v.data_ptr(), v._version) for k, v in sd.items() if not k.endswith("num_batches_tracked"))
+
+    def _handle(self):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("synt_isic_b200 classifier runs on CUDA (sm_100a) only (no CPU fallback)")
+        if self.training:
+            raise RuntimeError("train-mode BatchNorm is outside the hot path: call .eval() (the reference does)")
+        key = self._version_key()
+        cur = self._handles.get(self.precision)
+        if cur is not None and cur[1] == key:
+            return cur[0]
+        if cur is not None:
+            _lib.lib().synt_resnet18_destroy(cur[0])
+        sd = self.model.state_dict()
+        total = self._manifest[-1][2] + self._manifest[-1][1]
+        blob = np.empty(total, dtype=np.float32)
+        for name, numel, off in self._manifest:
+            blob[off:off + numel] = sd[name].detach().float().cpu().reshape(-1).numpy()
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().synt_resnet18_create(blob.ctypes.data, blob.size, self.num_classes,
+                                                       DTYPE_CODES[self.precision], C.byref(h)), "resnet18_create")
+        self._handles[self.precision] = (h, key)
+        return h
+
+    def __del__(self):
+        try:
+            for h, _ in self._handles.values():
+                _lib.lib().synt_resnet18_destroy(h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ reference API -
+    def preprocess_for_classifier(self, x):
+        """Kept for callers that feed ``.model`` directly (Grad-CAM wrapper, XAI.py:2953-2959);
+        the fused CUDA kernel inside ``forward`` does the same arithmetic."""
+        x = torch.clamp((x + 1.0) / 2.0, 0, 1)
+        if x.shape[-1] != CLASSIFIER_IMAGE_SIZE or x.shape[-2] != CLASSIFIER_IMAGE_SIZE:
+            x = F.interpolate(x, size=(CLASSIFIER_IMAGE_SIZE, CLASSIFIER_IMAGE_SIZE), mode="bilinear",
+                              align_corners=False, antialias=True)
+        mean = torch.tensor([0.485, 0.456, 0.406], device=x.device, dtype=x.dtype).view(1, 3, 1, 1)
+        std = torch.tensor([0.229, 0.224, 0.225], device=x.device, dtype=x.dtype).view(1, 3, 1, 1)
+        return (x - mean) / std
+
+    def forward(self, x):
+        dev = next(self.parameters()).device
+        if x.device != dev:
+            x = x.to(dev)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 128, 128):
+            raise ValueError(f"expected [B,3,128,128] in [-1,1], got {tuple(x.shape)}")
+        h = self._handle()
+        x = x.contiguous().float()
+        logits = torch.empty(x.shape[0], self.num_classes, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().synt_resnet18_logits(h, x.data_ptr(), x.shape[0], logits.data_ptr(),
+                                                       _lib.current_stream_ptr()), "resnet18_logits")
+        return logits
+
+    def get_probabilities(self, x):
+        return F.softmax(self.forward(x), dim=1)
+
+    def get_per_class_score(self, x, target_class):
+        return torch.log(self.get_probabilities(x)[:, target_class] + 1e-8)
+
+    def predict(self, x):
+        with torch.no_grad():
+            return torch.argmax(self.forward(x), dim=1)
+
+    def get_confidence(self, x, target_class):
+        with torch.no_grad():
+            return self.get_probabilities(x)[:, target_class]
+
+    def debug_tap(self, x, tap: str):
+        h = self._handle()
+        x = x.contiguous().float()
+        B = x.shape[0]
+        buf = torch.empty(B * 64 * 112 * 112, dtype=torch.float32, device=x.device)
+        c, hh, ww = C.c_int(), C.c_int(), C.c_int()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().synt_resnet18_debug(h, x.data_ptr(), B, tap.encode(), buf.data_ptr(), buf.numel(),
+                                                      C.byref(c), C.byref(hh), C.byref(ww), _lib.current_stream_ptr()),
+                       "resnet18_debug")
+        n = B * c.value * hh.value * ww.value
+        return buf[:n].view(B, c.value, hh.value, ww.value).clone()
+
+    def launch_count(self) -> int:
+        cur = self._handles.get(self.precision)
+        return int(_lib.lib().synt_resnet18_launch_count(cur[0])) if cur else 0

@@ -1,0 +1,479 @@
+// HBM-bound kernels of the UNet path: GroupNorm (stats / finalize / apply+SiLU with
+// channel concat), nearest 2x upsample, the Cin=3 / Cout=3 edge convolutions (conv_out
+// fused with GroupNorm+SiLU on load and DDPMScheduler.step in the epilogue), the
+// stand-alone scheduler step, time-embedding tables and format helpers.
+//
+// Reference semantics (restated, not copied):
+//   diffusers ResnetBlock2D / GroupNorm / Upsample2D  <- core/generator/image_generator.py:400
+//   diffusers DDPMScheduler.step                      <- core/generator/image_generator.py:403
+//   output conversion                                 <- core/generator/image_generator.py:441-447
+#include "kernels.cuh"
+
+namespace synt {
+
+// =============================================================== GroupNorm ==========
+int gn_num_chunks(int B, int HW) {
+    int want = ceil_div(296, B);
+    int maxc = HW / 64 > 0 ? HW / 64 : 1;
+    int n = want < maxc ? want : maxc;
+    return n < 1 ? 1 : n;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ src0, int C0,
+                                                       const T* __restrict__ src1, int C1, int HW, int G,
+                                                       float2* __restrict__ partials, int nchunk) {
+    __shared__ float sm_s[2048];
+    __shared__ float sm_q[2048];
+    const int C = C0 + C1, nvec = C >> 3, lanes = 256 / nvec;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int ppc = (HW + nchunk - 1) / nchunk;
+    const int p0 = chunk * ppc, p1 = min(HW, p0 + ppc);
+    const int v = threadIdx.x % nvec, lane = threadIdx.x / nvec;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    if (lane < lanes) {
+        const bool first = v * 8 < C0;
+        const T* base = first ? src0 + (size_t)b * HW * C0 + v * 8 : src1 + (size_t)b * HW * C1 + (v * 8 - C0);
+        const int Cs = first ? C0 : C1;
+        for (int p = p0 + lane; p < p1; p += lanes) {
+            float x[8];
+            load8<T>(base + (size_t)p * Cs, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += x[i]; q[i] = fmaf(x[i], x[i], q[i]); }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sm_s[lane * C + v * 8 + i] = s[i]; sm_q[lane * C + v * 8 + i] = q[i]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int cpg = C / G, g = threadIdx.x;
+        float ts = 0.f, tq = 0.f;
+        for (int l = 0; l < lanes; ++l)
+            for (int c = 0; c < cpg; ++c) { ts += sm_s[l * C + g * cpg + c]; tq += sm_q[l * C + g * cpg + c]; }
+        partials[((size_t)b * nchunk + chunk) * G + g] = make_float2(ts, tq);
+    }
+}
+
+void gn_stats(const void* src0, int C0, const void* src1, int C1, int dt, int B, int HW, int G, float2* partials,
+              int nchunk, cudaStream_t s) {
+    const int C = C0 + C1;
+    SYNT_CHECK(C % 8 == 0 && C0 % 8 == 0 && C <= 512 && C % G == 0 && G <= 256, "gn_stats: bad channel counts");
+    dim3 grid(nchunk, B);
+    if (dt == DT_F32)
+        gn_stats_kernel<float><<<grid, 256, 0, s>>>((const float*)src0, C0, (const float*)src1, C1, HW, G, partials, nchunk);
+    else
+        gn_stats_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)src0, C0, (const bf16*)src1, C1, HW, G, partials, nchunk);
+    SYNT_LAUNCH_CHECK();
+}
+
+__global__ void gn_finalize_kernel(const float2* __restrict__ partials, int nchunk, int G, int C, int HW, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float2* __restrict__ scale_shift) {
+    const int b = blockIdx.x, c = threadIdx.x;
+    if (c >= C) return;
+    const int cpg = C / G, g = c / cpg;
+    double ts = 0.0, tq = 0.0;
+    for (int k = 0; k < nchunk; ++k) {
+        float2 p = partials[((size_t)b * nchunk + k) * G + g];
+        ts += (double)p.x; tq += (double)p.y;
+    }
+    const double cnt = (double)HW * cpg;
+    const double mean = ts / cnt;
+    double var = tq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = rstd * gamma[c];
+    scale_shift[(size_t)b * C + c] = make_float2(sc, beta[c] - (float)mean * sc);
+}
+
+void gn_finalize(const float2* partials, int B, int nchunk, int G, int C, int HW, float eps, const float* gamma,
+                 const float* beta, float2* scale_shift, cudaStream_t s) {
+    SYNT_CHECK(C <= 512, "gn_finalize: C too large");
+    gn_finalize_kernel<<<B, C, 0, s>>>(partials, nchunk, G, C, HW, eps, gamma, beta, scale_shift);
+    SYNT_LAUNCH_CHECK();
+}
+
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ src0, int C0, const T* __restrict__ src1,
+                                                       int C1, int HW, long long nvec_total,
+                                                       const float2* __restrict__ scale_shift, T* __restrict__ out) {
+    const int C = C0 + C1, nvec = C >> 3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % nvec);
+        const long long pix = i / nvec;             // b*HW + p
+        const int b = (int)(pix / HW);
+        const int c = v * 8;
+        float x[8];
+        if (c < C0) load8<T>(src0 + pix * C0 + c, x);
+        else        load8<T>(src1 + pix * C1 + (c - C0), x);
+        const float4* ss = reinterpret_cast<const float4*>(scale_shift + (size_t)b * C + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 t = __ldg(ss + j);
+            float y0 = fmaf(x[2 * j], t.x, t.y), y1 = fmaf(x[2 * j + 1], t.z, t.w);
+            if (SILU) {
+                if (sizeof(T) == 4) { y0 = silu_precise(y0); y1 = silu_precise(y1); }
+                else                { y0 = silu_f(y0);       y1 = silu_f(y1); }
+            }
+            x[2 * j] = y0; x[2 * j + 1] = y1;
+        }
+        store8<T>(out + pix * C + c, x);
+    }
+}
+
+void gn_apply(const void* src0, int C0, const void* src1, int C1, int dt, int B, int HW, const float2* scale_shift,
+              int silu, void* out, cudaStream_t s) {
+    const int C = C0 + C1;
+    const long long nv = (long long)B * HW * (C / 8);
+    const int blocks = (int)((nv + 255) / 256 < 148 * 16 ? (nv + 255) / 256 : 148 * 16);
+#define GO(T, S) gn_apply_kernel<T, S><<<blocks, 256, 0, s>>>((const T*)src0, C0, (const T*)src1, C1, HW, nv, scale_shift, (T*)out)
+    if (dt == DT_F32) { if (silu) GO(float, true); else GO(float, false); }
+    else              { if (silu) GO(bf16, true);  else GO(bf16, false); }
+#undef GO
+    SYNT_LAUNCH_CHECK();
+}
+
+// =============================================================== upsample ===========
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ in, int H, int W, int C, long long nvec_total, T* __restrict__ out) {
+    const int nvec = C >> 3, Wo = 2 * W, Ho = 2 * H;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % nvec);
+        long long p = i / nvec;
+        const int ox = (int)(p % Wo); p /= Wo;
+        const int oy = (int)(p % Ho);
+        const long long b = p / Ho;
+        const T* src = in + ((b * H + (oy >> 1)) * W + (ox >> 1)) * C + v * 8;
+        float x[8];
+        load8<T>(src, x);
+        store8<T>(out + ((b * Ho + oy) * Wo + ox) * C + v * 8, x);
+    }
+}
+void upsample_nearest2x(const void* in, int dt, int B, int H, int W, int C, void* out, cudaStream_t s) {
+    SYNT_CHECK(C % 8 == 0, "upsample: C % 8");
+    const long long nv = (long long)B * 4 * H * W * (C / 8);
+    const int blocks = (int)((nv + 255) / 256 < 148 * 16 ? (nv + 255) / 256 : 148 * 16);
+    if (dt == DT_F32) upsample2x_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, H, W, C, nv, (float*)out);
+    else              upsample2x_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)in, H, W, C, nv, (bf16*)out);
+    SYNT_LAUNCH_CHECK();
+}
+
+// =============================================================== conv_in (3 -> 64) ==
+template <typename T>
+__global__ void __launch_bounds__(128) conv_in3_kernel(const float* __restrict__ x, const __grid_constant__ ConvInW w,
+                                                       int B, int H, int W, T* __restrict__ out) {
+    const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pix >= (long long)B * H * W) return;
+    const int ox = (int)(pix % W), oy = (int)((pix / W) % H);
+    const long long b = pix / ((long long)H * W);
+    float in[27];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int iy = oy + dy - 1, ix = ox + dx - 1;
+            const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                in[(dy * 3 + dx) * 3 + c] = ok ? __ldg(x + ((b * 3 + c) * H + iy) * W + ix) : 0.f;
+        }
+    T* o = out + pix * 64;
+#pragma unroll
+    for (int n0 = 0; n0 < 64; n0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = w.b[n0 + j];
+#pragma unroll
+        for (int k = 0; k < 27; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(in[k], w.w[k][n0 + j], acc[j]);
+        store8<T>(o + n0, acc);
+    }
+}
+void conv_in3(const float* x, const ConvInW& w, int B, int H, int W, void* out, int dt, cudaStream_t s) {
+    const long long np = (long long)B * H * W;
+    const int blocks = (int)((np + 127) / 128);
+    if (dt == DT_F32) conv_in3_kernel<float><<<blocks, 128, 0, s>>>(x, w, B, H, W, (float*)out);
+    else              conv_in3_kernel<bf16><<<blocks, 128, 0, s>>>(x, w, B, H, W, (bf16*)out);
+    SYNT_LAUNCH_CHECK();
+}
+
+// =============================================================== Philox =============
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        c[0] = hi1 ^ c[1] ^ k0; c[1] = lo1; c[2] = hi0 ^ c[3] ^ k1; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ void philox_normal3(unsigned long long seed, unsigned long long elem, uint32_t step,
+                                               float (&z)[3]) {
+    uint32_t c[4] = {(uint32_t)elem, (uint32_t)(elem >> 32), step, 0x5eed5eedu};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float u0 = ((float)c[0] + 0.5f) * 2.3283064365386963e-10f;   // (0,1)
+    const float u1 = ((float)c[1] + 0.5f) * 2.3283064365386963e-10f;
+    const float u2 = ((float)c[2] + 0.5f) * 2.3283064365386963e-10f;
+    const float u3 = ((float)c[3] + 0.5f) * 2.3283064365386963e-10f;
+    const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+    float s0, c0, s1, c1;
+    __sincosf(6.283185307179586f * u1, &s0, &c0);
+    __sincosf(6.283185307179586f * u3, &s1, &c1);
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; (void)s1;
+}
+
+// =============================================================== conv_out (64 -> 3) =
+// One block = 16x16 output pixels.  The GroupNorm+SiLU'd halo tile (18x18x64) is staged in
+// shared memory as fp32 with a padded pixel stride of 65 floats (bank-conflict-free),
+// weights come from the constant bank (by-value kernel parameter).
+constexpr int CO_TILE = 16, CO_HALO = CO_TILE + 2, CO_STRIDE = 65;
+constexpr int CO_SMEM_BYTES = CO_HALO * CO_HALO * CO_STRIDE * 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_out3_kernel(const T* __restrict__ h, const float2* __restrict__ scale_shift,
+                                                        const __grid_constant__ ConvOutW w, int B, int H, int W,
+                                                        float* __restrict__ eps_out, const __grid_constant__ SchedArgs sch) {
+    extern __shared__ float tile[];
+    const int b = blockIdx.z, y0 = blockIdx.y * CO_TILE, x0 = blockIdx.x * CO_TILE;
+    // ---- stage: 324 halo pixels x 8 vectors of 8 channels
+    for (int i = threadIdx.x; i < CO_HALO * CO_HALO * 8; i += 256) {
+        const int v = i & 7, hp = i >> 3;
+        const int hy = hp / CO_HALO, hx = hp % CO_HALO;
+        const int iy = y0 + hy - 1, ix = x0 + hx - 1;
+        float x[8];
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            load8<T>(h + (((size_t)b * H + iy) * W + ix) * 64 + v * 8, x);
+            const float4* ss = reinterpret_cast<const float4*>(scale_shift + (size_t)b * 64 + v * 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 t = __ldg(ss + j);
+                float a0 = fmaf(x[2 * j], t.x, t.y), a1 = fmaf(x[2 * j + 1], t.z, t.w);
+                if (sizeof(T) == 4) { a0 = silu_precise(a0); a1 = silu_precise(a1); }
+                else                { a0 = silu_f(a0);       a1 = silu_f(a1); }
+                x[2 * j] = a0; x[2 * j + 1] = a1;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tile[hp * CO_STRIDE + v * 8 + j] = x[j];
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / CO_TILE, tx = threadIdx.x % CO_TILE;
+    const int oy = y0 + ty, ox = x0 + tx;
+    float acc0 = w.b[0], acc1 = w.b[1], acc2 = w.b[2];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const float* src = tile + ((ty + tap / 3) * CO_HALO + tx + tap % 3) * CO_STRIDE;
+#pragma unroll 16
+        for (int c = 0; c < 64; ++c) {
+            const float v = src[c];
+            acc0 = fmaf(v, w.w[tap][c][0], acc0);
+            acc1 = fmaf(v, w.w[tap][c][1], acc1);
+            acc2 = fmaf(v, w.w[tap][c][2], acc2);
+        }
+    }
+    if (oy >= H || ox >= W) return;
+    const size_t plane = (size_t)H * W;
+    const size_t i0 = ((size_t)b * 3) * plane + (size_t)oy * W + ox;
+    const float e[3] = {acc0, acc1, acc2};
+    const long long step = sch.step_ptr ? (long long)*sch.step_ptr : 0;
+    if (eps_out) {
+        float* eo = eps_out + step * sch.eps_step_stride;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) eo[i0 + j * plane] = e[j];
+    }
+    if (sch.x) {
+        const float sqrt_b = sch.coef[0], sqrt_a = sch.coef[1], c_x0 = sch.coef[2], c_xt = sch.coef[3],
+                    sigma = sch.coef[4];
+        float z[3] = {0.f, 0.f, 0.f};
+        if (sigma != 0.f) {
+            if (sch.z) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) z[j] = sch.z[step * sch.z_step_stride + i0 + j * plane];
+            } else {
+                const unsigned long long elem = (unsigned long long)(sch.image_offset + b) * plane + (size_t)oy * W + ox;
+                philox_normal3(sch.seed, elem, (uint32_t)step, z);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float xv = sch.x[i0 + j * plane];
+            float x0v = (xv - sqrt_b * e[j]) / sqrt_a;
+            x0v = fminf(fmaxf(x0v, -1.f), 1.f);
+            float prev = c_x0 * x0v + c_xt * xv;
+            if (sigma != 0.f) prev = prev + sigma * z[j];
+            sch.x[i0 + j * plane] = prev;
+            if (sch.traj) sch.traj[step * sch.traj_step_stride + i0 + j * plane] = prev;
+        }
+    }
+}
+
+void conv_out3(const void* h, int dt, const float2* scale_shift, const ConvOutW& w, int B, int H, int W,
+               float* eps_nchw, const SchedArgs& sch, cudaStream_t s) {
+    dim3 grid(ceil_div(W, CO_TILE), ceil_div(H, CO_TILE), B);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SYNT_CUDA(cudaFuncSetAttribute(conv_out3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, CO_SMEM_BYTES));
+        SYNT_CUDA(cudaFuncSetAttribute(conv_out3_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CO_SMEM_BYTES));
+        attr_set = true;
+    }
+    if (dt == DT_F32)
+        conv_out3_kernel<float><<<grid, 256, CO_SMEM_BYTES, s>>>((const float*)h, scale_shift, w, B, H, W, eps_nchw, sch);
+    else
+        conv_out3_kernel<bf16><<<grid, 256, CO_SMEM_BYTES, s>>>((const bf16*)h, scale_shift, w, B, H, W, eps_nchw, sch);
+    SYNT_LAUNCH_CHECK();
+}
+
+// =============================================================== scheduler step =====
+__global__ void ddpm_step_kernel(const float* __restrict__ eps, const float* __restrict__ x, const float* __restrict__ z,
+                                 float* __restrict__ out, long long n, float sqrt_b, float sqrt_a, float c_x0,
+                                 float c_xt, float sigma) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float xv = x[i];
+        float x0 = (xv - sqrt_b * eps[i]) / sqrt_a;
+        x0 = fminf(fmaxf(x0, -1.f), 1.f);
+        float prev = c_x0 * x0 + c_xt * xv;
+        if (z) prev = prev + sigma * z[i];
+        out[i] = prev;
+    }
+}
+void ddpm_step(const float* eps, const float* x, const float* z, float* out, long long n, float sqrt_b, float sqrt_a,
+               float c_x0, float c_xt, float sigma, cudaStream_t s) {
+    const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    ddpm_step_kernel<<<blocks, 256, 0, s>>>(eps, x, z, out, n, sqrt_b, sqrt_a, c_x0, c_xt, sigma);
+    SYNT_LAUNCH_CHECK();
+}
+
+// =============================================================== time embedding =====
+__global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict__ freqs, const float* __restrict__ w1,
+                                                         const float* __restrict__ b1, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, float* __restrict__ emb_silu) {
+    __shared__ float e64[64];
+    __shared__ float h1[256];
+    const int t = blockIdx.x, j = threadIdx.x;
+    if (j < 64) {
+        const float arg = (float)t * freqs[j & 31];
+        e64[j] = j < 32 ? cosf(arg) : sinf(arg);         // flip_sin_to_cos=True -> [cos | sin]
+    }
+    __syncthreads();
+    float a = b1[j];
+    for (int i = 0; i < 64; ++i) a = fmaf(w1[j * 64 + i], e64[i], a);
+    h1[j] = silu_precise(a);
+    __syncthreads();
+    float o = b2[j];
+    for (int i = 0; i < 256; ++i) o = fmaf(w2[j * 256 + i], h1[i], o);
+    emb_silu[(size_t)t * 256 + j] = silu_precise(o);     // every consumer applies SiLU first
+}
+void time_embed_table(const float* freqs32, const float* w1, const float* b1, const float* w2, const float* b2, int T,
+                      float* emb_silu, cudaStream_t s) {
+    time_embed_kernel<<<T, 256, 0, s>>>(freqs32, w1, b1, w2, b2, emb_silu);
+    SYNT_LAUNCH_CHECK();
+}
+
+constexpr int TP_TT = 8;
+__global__ void __launch_bounds__(256) time_proj_kernel(const float* __restrict__ emb_silu, const float* __restrict__ w,
+                                                        const float* __restrict__ b, int T, int ntot,
+                                                        float* __restrict__ table) {
+    __shared__ float e[TP_TT][256];
+    const int t0 = blockIdx.y * TP_TT;
+    for (int i = threadIdx.x; i < TP_TT * 256; i += 256) {
+        const int tt = i / 256;
+        e[tt][i % 256] = (t0 + tt < T) ? emb_silu[(size_t)(t0 + tt) * 256 + i % 256] : 0.f;
+    }
+    __syncthreads();
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= ntot) return;
+    float acc[TP_TT];
+#pragma unroll
+    for (int tt = 0; tt < TP_TT; ++tt) acc[tt] = b[n];
+    const float4* wr = reinterpret_cast<const float4*>(w + (size_t)n * 256);
+    for (int i4 = 0; i4 < 64; ++i4) {
+        const float4 wv = __ldg(wr + i4);
+#pragma unroll
+        for (int tt = 0; tt < TP_TT; ++tt) {
+            acc[tt] = fmaf(wv.x, e[tt][4 * i4 + 0], acc[tt]);
+            acc[tt] = fmaf(wv.y, e[tt][4 * i4 + 1], acc[tt]);
+            acc[tt] = fmaf(wv.z, e[tt][4 * i4 + 2], acc[tt]);
+            acc[tt] = fmaf(wv.w, e[tt][4 * i4 + 3], acc[tt]);
+        }
+    }
+#pragma unroll
+    for (int tt = 0; tt < TP_TT; ++tt)
+        if (t0 + tt < T) table[(size_t)(t0 + tt) * ntot + n] = acc[tt];
+}
+void time_proj_table(const float* emb_silu, const float* w, const float* b, int T, int ntot, float* table,
+                     cudaStream_t s) {
+    dim3 grid(ceil_div(ntot, 256), ceil_div(T, TP_TT));
+    time_proj_kernel<<<grid, 256, 0, s>>>(emb_silu, w, b, T, ntot, table);
+    SYNT_LAUNCH_CHECK();
+}
+
+__global__ void select_timestep_kernel(const float* __restrict__ table, int ntot, const float* __restrict__ coef_table,
+                                       const int* __restrict__ timesteps, const int* __restrict__ step_ptr, int t_direct,
+                                       float* __restrict__ temb_cur, float* __restrict__ coef_cur) {
+    const int step = step_ptr ? *step_ptr : 0;
+    const int t = step_ptr ? timesteps[step] : t_direct;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntot; i += gridDim.x * blockDim.x)
+        temb_cur[i] = table[(size_t)t * ntot + i];
+    if (coef_table && coef_cur && blockIdx.x == 0 && threadIdx.x < 5)
+        coef_cur[threadIdx.x] = coef_table[(size_t)step * 5 + threadIdx.x];
+}
+void select_timestep(const float* table, int ntot, const float* coef_table, const int* timesteps, const int* step_ptr,
+                     int t_direct, float* temb_cur, float* coef_cur, cudaStream_t s) {
+    select_timestep_kernel<<<ceil_div(ntot, 256), 256, 0, s>>>(table, ntot, coef_table, timesteps, step_ptr, t_direct,
+                                                               temb_cur, coef_cur);
+    SYNT_LAUNCH_CHECK();
+}
+__global__ void advance_step_kernel(int* p) { *p += 1; }
+void advance_step(int* step_ptr, cudaStream_t s) {
+    advance_step_kernel<<<1, 1, 0, s>>>(step_ptr);
+    SYNT_LAUNCH_CHECK();
+}
+
+// =============================================================== format helpers =====
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int HW, int C, long long n, float* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long p = i / C;                 // b*HW + pix
+        const long long b = p / HW, pix = p % HW;
+        out[(b * C + c) * HW + pix] = to_f<T>(in[i]);
+    }
+}
+void nhwc_to_nchw_f32(const void* in, int dt, int B, int HW, int C, float* out, cudaStream_t s) {
+    const long long n = (long long)B * HW * C;
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    if (dt == DT_F32) nhwc_to_nchw_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, HW, C, n, out);
+    else              nhwc_to_nchw_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)in, HW, C, n, out);
+    SYNT_LAUNCH_CHECK();
+}
+
+// mode 0: trunc(clamp((x+1)/2, 0, 1) * 255)      core/generator/image_generator.py:441-447
+// mode 1: trunc(clip((x+1)*127.5, 0, 255))       diffusion/diffusion_generator.py:147-148
+__global__ void to_uint8_kernel(const float* __restrict__ x, int HW, long long n, int mode, unsigned char* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % 3);
+        const long long p = i / 3;
+        const long long b = p / HW, pix = p % HW;
+        const float v = x[(b * 3 + c) * HW + pix];
+        float r;
+        if (mode == 0) { float u = (v + 1.f) / 2.f; u = fminf(fmaxf(u, 0.f), 1.f); r = u * 255.f; }
+        else           { r = fminf(fmaxf((v + 1.f) * 127.5f, 0.f), 255.f); }
+        out[i] = (unsigned char)r;                 // C-style truncation == numpy astype(uint8)
+    }
+}
+void to_uint8_hwc(const float* x_nchw, int B, int H, int W, int mode, unsigned char* out, cudaStream_t s) {
+    const long long n = (long long)B * H * W * 3;
+    const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    to_uint8_kernel<<<blocks, 256, 0, s>>>(x_nchw, H * W, n, mode, out);
+    SYNT_LAUNCH_CHECK();
+}
+
+}  // namespace synt

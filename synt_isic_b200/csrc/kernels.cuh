@@ -1,0 +1,118 @@
+// Launcher declarations for every kernel of the SYNT_ISIC hot path.
+// Activations are NHWC ("pixels x channels"), storage type T = float (fp32 verification
+// mode) or bf16 (production mode).  All launchers are asynchronous on `stream`.
+#pragma once
+#include "common.cuh"
+
+namespace synt {
+
+enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// ---------------------------------------------------------------- convolution -------
+// Implicit-GEMM convolution  out[m, n] = sum_k A[m, k] * Wt[n, k]  with
+//   m = output pixel (b, oy, ox), n = output channel,
+//   k = (tap, cin) over the KHxKW window of `in`, followed by optional 1x1 "shortcut"
+//       segments read at the output pixel (times sc_stride) from sc0 / sc1.
+// Epilogue: + bias[n] + bias2[n] + residual[m, n], optional ReLU.
+struct ConvArgs {
+    const void* in = nullptr;          // NHWC [B, H, W, Cin]
+    int B = 0, H = 0, W = 0, Cin = 0;
+    int KH = 3, KW = 3, stride = 1, pad = 1;
+    int Ho = 0, Wo = 0, Cout = 0;
+    const void* sc0 = nullptr; int sc0_C = 0;    // NHWC [B, Ho*sc_stride, Wo*sc_stride, sc0_C]
+    const void* sc1 = nullptr; int sc1_C = 0;
+    int sc_stride = 1;
+    const void* weight = nullptr;      // [Cout][Ktot] K-major; fp32 (SIMT) or bf16 (tcgen05)
+    const float* bias = nullptr;       // [Cout]
+    const float* bias2 = nullptr;      // [Cout] or null (time-embedding row)
+    const void* residual = nullptr;    // NHWC [B, Ho, Wo, Cout] or null
+    int relu = 0;
+    void* out = nullptr;               // NHWC [B, Ho, Wo, Cout]
+    int ktot() const { return KH * KW * Cin + sc0_C + sc1_C; }
+};
+// fp32-FMA implicit GEMM (verification mode and odd shapes); weights are fp32.
+void conv_simt(const ConvArgs& a, int act_dtype, cudaStream_t s);
+// tcgen05/TMEM/TMA implicit GEMM; activations and weights bf16, fp32 accumulate.
+// Requires Cin, sc0_C, sc1_C multiples of 64 and Cout a multiple of 16.
+bool conv_tc_supported(const ConvArgs& a);
+void conv_tc(const ConvArgs& a, cudaStream_t s);
+
+// UNet conv_in: x fp32 NCHW [B,3,H,W] -> NHWC T [B,H,W,64], 3x3 pad 1.
+struct ConvInW { float w[27][64]; float b[64]; };          // k = tap*3 + c
+void conv_in3(const float* x_nchw, const ConvInW& w, int B, int H, int W, void* out, int dt, cudaStream_t s);
+
+// UNet tail: eps = conv_out(SiLU(GN(h))) fused with DDPMScheduler.step.
+struct ConvOutW { float w[9][64][3]; float b[3]; };
+struct SchedArgs {
+    // when x != null the scheduler update runs in the epilogue:
+    //   x0 = clamp((x - sqrt_b*eps)/sqrt_a, -1, 1); x' = c_x0*x0 + c_xt*x + sigma*z
+    float* x = nullptr;                // fp32 NCHW [B,3,H,W], updated IN PLACE
+    const float* coef = nullptr;       // device [5] = {sqrt_b, sqrt_a, c_x0, c_xt, sigma}
+    const float* z = nullptr;          // injected noise of step 0 for these images, or null -> Philox
+    long long z_step_stride = 0;       // elements between consecutive steps of z
+    unsigned long long seed = 0;       // Philox key (used when z == null)
+    const int* step_ptr = nullptr;     // device step counter (selects z / traj / eps frame, Philox offset)
+    float* traj = nullptr;             // optional copy of x' (trajectory frame of step 0)
+    long long traj_step_stride = 0;
+    long long eps_step_stride = 0;     // stride of the eps tap between steps
+    long long image_offset = 0;        // global image index of image 0 of this call (Philox stream id)
+};
+void conv_out3(const void* h, int dt, const float2* scale_shift, const ConvOutW& w, int B, int H, int W,
+               float* eps_nchw /*nullable*/, const SchedArgs& sch, cudaStream_t s);
+
+// Stand-alone DDPMScheduler.step on fp32 NCHW tensors (the drop-in scheduler object).
+void ddpm_step(const float* eps, const float* x, const float* z, float* out, long long n, float sqrt_b,
+               float sqrt_a, float c_x0, float c_xt, float sigma, cudaStream_t s);
+
+// ---------------------------------------------------------------- GroupNorm ---------
+// x = concat_channels(src0[C0], src1[C1]); statistics per (b, group) over HW x (C/G).
+//   gn_stats    -> partial (sum, sumsq) per (b, chunk, group)
+//   gn_finalize -> per (b, c): scale = rstd*gamma, shift = beta - mean*rstd*gamma
+//   gn_apply    -> out = act(x*scale + shift) (NHWC T, channels concatenated)
+int gn_num_chunks(int B, int HW);
+void gn_stats(const void* src0, int C0, const void* src1, int C1, int dt, int B, int HW, int G, float2* partials,
+              int nchunk, cudaStream_t s);
+void gn_finalize(const float2* partials, int B, int nchunk, int G, int C, int HW, float eps, const float* gamma,
+                 const float* beta, float2* scale_shift, cudaStream_t s);
+void gn_apply(const void* src0, int C0, const void* src1, int C1, int dt, int B, int HW, const float2* scale_shift,
+              int silu, void* out, cudaStream_t s);
+
+// ---------------------------------------------------------------- misc --------------
+void upsample_nearest2x(const void* in, int dt, int B, int H, int W, int C, void* out, cudaStream_t s);
+// softmax(q k^T / sqrt(8)) v over qkv NHWC-token layout [B, N, 3*C] (q | k | v), heads of 8.
+void attention_simt(const void* qkv, int dt, int B, int N, int C, void* out, cudaStream_t s);
+bool attention_tc_supported(int N, int C);
+void attention_tc(const void* qkv, int B, int N, int C, void* out, cudaStream_t s);
+
+// time embedding tables: emb[t] = Linear2(SiLU(Linear1(sincos(t)))) for t in [0,T),
+// temb[t][off_r + c] = Linear_r(SiLU(emb[t]))[c] for every resnet r (sum Cout = ntot).
+void time_embed_table(const float* freqs32, const float* w1, const float* b1, const float* w2, const float* b2,
+                      int T, float* emb_silu /*[T][256]*/, cudaStream_t s);
+void time_proj_table(const float* emb_silu, const float* w /*[ntot][256]*/, const float* b, int T, int ntot,
+                     float* table /*[T][ntot]*/, cudaStream_t s);
+// copy row `t` (or timesteps[*step_ptr]) of the tables into the fixed per-step buffers
+void select_timestep(const float* table, int ntot, const float* coef_table /*[T][5] or null*/,
+                     const int* timesteps, const int* step_ptr, int t_direct, float* temb_cur, float* coef_cur,
+                     cudaStream_t s);
+void advance_step(int* step_ptr, cudaStream_t s);
+
+// debug / format helpers
+void nhwc_to_nchw_f32(const void* in, int dt, int B, int HW, int C, float* out, cudaStream_t s);
+void to_uint8_hwc(const float* x_nchw, int B, int H, int W, int mode, unsigned char* out, cudaStream_t s);
+
+// ---------------------------------------------------------------- classifier --------
+// clamp((x+1)/2) -> bilinear 128->224 (align_corners=False) -> ImageNet normalise; optional
+// fused intervention blend x~ = clamp(x(1-M) + I M, -1, 1) before it.
+void classifier_preprocess(const float* x_nchw, int B, int Hin, int Win, int Hout, int Wout, void* out_nhwc,
+                           int Cpad, int dt, cudaStream_t s);
+void maxpool3x3s2(const void* in, int dt, int B, int H, int W, int C, void* out, cudaStream_t s);
+void avgpool_fc(const void* in, int dt, int B, int HW, int C, const float* w, const float* b, int nout,
+                float* logits, cudaStream_t s);
+// interventions (xai/XAI.py:1495-1575): type 0=zero 1=mean 2=blur5 3=noise(injected) 4=given tensor
+void intervene_blend(const float* x, const float* mask, const float* aux, int type, float noise_std, int B, int C,
+                     int H, int W, float* out, cudaStream_t s);
+void patch_mask_apply(const float* x, const unsigned char* patch_masks, int n_masks, int C, int H, int W,
+                      int patch, float* out, cudaStream_t s);
+
+}  // namespace synt

@@ -1,0 +1,470 @@
+// ResNet18 classifier path behind the C ABI: the logit evaluations that Time-SHAP,
+// patch-SHAP and the CSI interventions issue (reference: MelanomaClassifierAdaptive,
+// xai/XAI.py:357-471; call sites xai/XAI.py:1143-1170, :1201-1211, :1622-1671).
+//
+//   preprocess   clamp((x+1)/2,0,1) -> bilinear 128->224 (align_corners=False; antialias is a
+//                no-op when upsampling) -> ImageNet normalise          xai/XAI.py:399-431
+//   backbone     torchvision resnet18, eval-mode BatchNorm folded into conv weight/bias,
+//                ReLU / residual / 1x1-stride-2 downsample fused into the conv epilogue
+//   head         global average pool + Linear(512, num_classes)
+#include "kernels.cuh"
+#include "pool.h"
+#include "../../include/synt_isic.h"
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace synt {
+
+extern thread_local std::string g_last_error;
+
+// =============================================================== kernels ============
+template <typename T>
+__global__ void preprocess_kernel(const float* __restrict__ x, int Hin, int Win, int Hout, int Wout, long long npix,
+                                  T* __restrict__ out) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    const float sy = (float)Hin / (float)Hout, sx = (float)Win / (float)Wout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wout), oy = (int)((i / Wout) % Hout);
+        const long long b = i / ((long long)Wout * Hout);
+        float fy = ((float)oy + 0.5f) * sy - 0.5f; if (fy < 0.f) fy = 0.f;
+        float fx = ((float)ox + 0.5f) * sx - 0.5f; if (fx < 0.f) fx = 0.f;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* pl = x + (b * 3 + c) * (long long)Hin * Win;
+            auto px = [&](int yy, int xx) {
+                float v = (pl[yy * Win + xx] + 1.0f) / 2.0f;
+                return fminf(fmaxf(v, 0.f), 1.f);
+            };
+            const float top = px(y0, x0) * (1.f - lx) + px(y0, x1) * lx;
+            const float bot = px(y1, x0) * (1.f - lx) + px(y1, x1) * lx;
+            const float v = top * (1.f - ly) + bot * ly;
+            out[i * 3 + c] = from_f<T>((v - mean[c]) / stdv[c]);
+        }
+    }
+}
+void classifier_preprocess(const float* x, int B, int Hin, int Win, int Hout, int Wout, void* out, int Cpad, int dt,
+                           cudaStream_t s) {
+    SYNT_CHECK(Cpad == 3, "classifier_preprocess: only C=3 output");
+    const long long npix = (long long)B * Hout * Wout;
+    const int blocks = (int)((npix + 255) / 256 < 148 * 16 ? (npix + 255) / 256 : 148 * 16);
+    if (dt == DT_F32) preprocess_kernel<float><<<blocks, 256, 0, s>>>(x, Hin, Win, Hout, Wout, npix, (float*)out);
+    else              preprocess_kernel<bf16><<<blocks, 256, 0, s>>>(x, Hin, Win, Hout, Wout, npix, (bf16*)out);
+    SYNT_LAUNCH_CHECK();
+}
+
+template <typename T>
+__global__ void maxpool_kernel(const T* __restrict__ in, int H, int W, int C, int Ho, int Wo, long long nvec_total,
+                               T* __restrict__ out) {
+    const int nvec = C >> 3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % nvec);
+        long long p = i / nvec;
+        const int ox = (int)(p % Wo); p /= Wo;
+        const int oy = (int)(p % Ho);
+        const long long b = p / Ho;
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = oy * 2 - 1 + dy;
+            if (iy < 0 || iy >= H) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = ox * 2 - 1 + dx;
+                if (ix < 0 || ix >= W) continue;
+                float x[8];
+                load8<T>(in + ((b * H + iy) * W + ix) * C + v * 8, x);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], x[j]);
+            }
+        }
+        store8<T>(out + ((b * Ho + oy) * Wo + ox) * C + v * 8, m);
+    }
+}
+void maxpool3x3s2(const void* in, int dt, int B, int H, int W, int C, void* out, cudaStream_t s) {
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long nv = (long long)B * Ho * Wo * (C / 8);
+    const int blocks = (int)((nv + 255) / 256 < 148 * 16 ? (nv + 255) / 256 : 148 * 16);
+    if (dt == DT_F32) maxpool_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, H, W, C, Ho, Wo, nv, (float*)out);
+    else              maxpool_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)in, H, W, C, Ho, Wo, nv, (bf16*)out);
+    SYNT_LAUNCH_CHECK();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) avgpool_fc_kernel(const T* __restrict__ in, int HW, int C, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, int nout, float* __restrict__ logits) {
+    __shared__ float pooled[512];
+    const int b = blockIdx.x, c = threadIdx.x;
+    if (c < C) {
+        float s = 0.f;
+        for (int p = 0; p < HW; ++p) s += to_f<T>(in[((size_t)b * HW + p) * C + c]);
+        pooled[c] = s / (float)HW;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int o = warp; o < nout; o += blockDim.x >> 5) {
+        float s = 0.f;
+        for (int i = lane; i < C; i += 32) s = fmaf(pooled[i], w[(size_t)o * C + i], s);
+        s = warp_sum(s);
+        if (lane == 0) logits[(size_t)b * nout + o] = s + bias[o];
+    }
+}
+void avgpool_fc(const void* in, int dt, int B, int HW, int C, const float* w, const float* b, int nout, float* logits,
+                cudaStream_t s) {
+    SYNT_CHECK(C <= 512, "avgpool_fc: C <= 512");
+    if (dt == DT_F32) avgpool_fc_kernel<float><<<B, 512, 0, s>>>((const float*)in, HW, C, w, b, nout, logits);
+    else              avgpool_fc_kernel<bf16><<<B, 512, 0, s>>>((const bf16*)in, HW, C, w, b, nout, logits);
+    SYNT_LAUNCH_CHECK();
+}
+
+// one block per (b, c) plane
+__global__ void __launch_bounds__(256) intervene_kernel(const float* __restrict__ x, const float* __restrict__ mask,
+                                                        const float* __restrict__ aux, int type, float noise_std, int C,
+                                                        int H, int W, float* __restrict__ out) {
+    __shared__ float red[256];
+    __shared__ float mean_s;
+    const int plane = blockIdx.x, b = plane / C, HW = H * W;
+    const float* xp = x + (size_t)plane * HW;
+    const float* mp = mask + (size_t)b * HW;
+    float* op = out + (size_t)plane * HW;
+    if (type == 1) {
+        float s = 0.f;
+        for (int i = threadIdx.x; i < HW; i += 256) s += xp[i];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+        if (threadIdx.x == 0) mean_s = red[0] / (float)HW;
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < HW; i += 256) {
+        float iv;
+        if (type == 0) iv = 0.f;
+        else if (type == 1) iv = mean_s;
+        else if (type == 2) {
+            const int y = i / W, xx = i % W;
+            float s = 0.f;
+            for (int dy = -2; dy <= 2; ++dy)
+                for (int dx = -2; dx <= 2; ++dx) {
+                    const int yy = y + dy, xc = xx + dx;
+                    if (yy >= 0 && yy < H && xc >= 0 && xc < W) s += xp[yy * W + xc];
+                }
+            iv = s / 25.f;                                 // avg_pool2d count_include_pad=True
+        } else if (type == 3) iv = aux[(size_t)plane * HW + i] * noise_std;
+        else iv = aux[(size_t)plane * HW + i];
+        const float m = mp[i];
+        const float v = xp[i] * (1.f - m) + iv * m;
+        op[i] = fminf(fmaxf(v, -1.f), 1.f);
+    }
+}
+void intervene_blend(const float* x, const float* mask, const float* aux, int type, float noise_std, int B, int C, int H,
+                     int W, float* out, cudaStream_t s) {
+    SYNT_CHECK(type >= 0 && type <= 4, "intervene: unknown type");
+    SYNT_CHECK(type < 3 || aux != nullptr, "intervene: aux tensor required");
+    intervene_kernel<<<B * C, 256, 0, s>>>(x, mask, aux, type, noise_std, C, H, W, out);
+    SYNT_LAUNCH_CHECK();
+}
+
+__global__ void patch_mask_kernel(const float* __restrict__ x, const unsigned char* __restrict__ pm, int C, int H, int W,
+                                  int patch, long long n, float* __restrict__ out) {
+    const int pw = W / patch, ph = H / patch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W), y = (int)((i / W) % H);
+        const int c = (int)((i / ((long long)W * H)) % C);
+        const long long k = i / ((long long)W * H * C);
+        const bool keep = pm[(k * ph + y / patch) * pw + xx / patch] != 0;
+        out[i] = keep ? x[((size_t)c * H + y) * W + xx] : 0.f;
+    }
+}
+void patch_mask_apply(const float* x, const unsigned char* pm, int n_masks, int C, int H, int W, int patch, float* out,
+                      cudaStream_t s) {
+    const long long n = (long long)n_masks * C * H * W;
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    patch_mask_kernel<<<blocks, 256, 0, s>>>(x, pm, C, H, W, patch, n, out);
+    SYNT_LAUNCH_CHECK();
+}
+
+// =============================================================== plan ================
+struct RParam { std::string name; long long numel, offset; };
+struct RManifest {
+    std::vector<RParam> params; long long total = 0;
+    void add(const std::string& n, long long numel) { params.push_back({n, numel, total}); total += numel; }
+    void bn(const std::string& p, int c) { add(p + ".weight", c); add(p + ".bias", c); add(p + ".running_mean", c); add(p + ".running_var", c); }
+    long long find(const std::string& n) const {
+        for (auto& s : params) if (s.name == n) return s.offset;
+        throw Error(-1, "resnet manifest: no parameter named " + n);
+    }
+};
+static const int kStageCh[4] = {64, 128, 256, 512};
+static RManifest build_rmanifest(int num_classes) {
+    RManifest m;
+    m.add("conv1.weight", 64 * 3 * 49); m.bn("bn1", 64);
+    int cin = 64;
+    for (int l = 0; l < 4; ++l) {
+        const int c = kStageCh[l];
+        for (int j = 0; j < 2; ++j) {
+            const std::string p = "layer" + std::to_string(l + 1) + "." + std::to_string(j);
+            const int ci = j == 0 ? cin : c;
+            m.add(p + ".conv1.weight", (long long)c * ci * 9); m.bn(p + ".bn1", c);
+            m.add(p + ".conv2.weight", (long long)c * c * 9); m.bn(p + ".bn2", c);
+            if (j == 0 && l > 0) { m.add(p + ".downsample.0.weight", (long long)c * ci); m.bn(p + ".downsample.1", c); }
+        }
+        cin = c;
+    }
+    m.add("fc.weight", (long long)num_classes * 512); m.add("fc.bias", num_classes);
+    return m;
+}
+static const RManifest& rmanifest(int nc = 7) {
+    static RManifest m7 = build_rmanifest(7);
+    static RManifest m8 = build_rmanifest(8);
+    if (nc == 8) return m8;
+    SYNT_CHECK(nc == 7, "resnet18 head must have 7 (xai_integration.py:79) or 8 (XAI.py:490) outputs");
+    return m7;
+}
+
+struct RDev { void* p = nullptr; ~RDev() { if (p) cudaFree(p); } };
+using RPtr = std::shared_ptr<RDev>;
+static RPtr r_upload(const void* h, size_t bytes) {
+    auto b = std::make_shared<RDev>();
+    SYNT_CUDA(cudaMalloc(&b->p, bytes));
+    SYNT_CUDA(cudaMemcpy(b->p, h, bytes, cudaMemcpyHostToDevice));
+    return b;
+}
+static uint16_t r_f2bf(float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16); }
+
+struct RConv {                     // BN-folded conv: weight K-major [cout][k*k*cin (+ csc)], bias [cout]
+    int cin = 0, cout = 0, k = 3, stride = 1, csc = 0;
+    RPtr w; RPtr b; bool bf = false;
+};
+
+// fold eval-mode BN into (w, b): w' = w * g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps)
+static void fold_bn(const float* P, const RManifest& m, const std::string& bn, int cout, std::vector<float>& scale,
+                    std::vector<float>& shift) {
+    const float* g = P + m.find(bn + ".weight"); const float* be = P + m.find(bn + ".bias");
+    const float* mu = P + m.find(bn + ".running_mean"); const float* var = P + m.find(bn + ".running_var");
+    scale.resize(cout); shift.resize(cout);
+    for (int i = 0; i < cout; ++i) {
+        const float s = g[i] / std::sqrt(var[i] + 1e-5f);
+        scale[i] = s; shift[i] = be[i] - mu[i] * s;
+    }
+}
+static RConv make_rconv(const float* P, const RManifest& m, const std::string& conv, const std::string& bn, int cin, int cout,
+                        int k, int stride, const std::string& ds_conv, const std::string& ds_bn, int ds_cin, bool bf) {
+    RConv c; c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.csc = ds_conv.empty() ? 0 : ds_cin; c.bf = bf;
+    const int taps = k * k, ktot = taps * cin + c.csc;
+    std::vector<float> sc, sh, sc2, sh2;
+    fold_bn(P, m, bn, cout, sc, sh);
+    if (c.csc) fold_bn(P, m, ds_bn, cout, sc2, sh2);
+    const float* w = P + m.find(conv + ".weight");
+    const float* wd = c.csc ? P + m.find(ds_conv + ".weight") : nullptr;
+    std::vector<float> pk((size_t)cout * ktot), bias(cout);
+    for (int n = 0; n < cout; ++n) {
+        float* row = pk.data() + (size_t)n * ktot;
+        for (int t = 0; t < taps; ++t)
+            for (int ci = 0; ci < cin; ++ci) row[t * cin + ci] = w[((size_t)n * cin + ci) * taps + t] * sc[n];
+        for (int ci = 0; ci < c.csc; ++ci) row[taps * cin + ci] = wd[(size_t)n * c.csc + ci] * sc2[n];
+        bias[n] = sh[n] + (c.csc ? sh2[n] : 0.f);
+    }
+    if (bf) {
+        std::vector<uint16_t> h(pk.size());
+        for (size_t i = 0; i < pk.size(); ++i) h[i] = r_f2bf(pk[i]);
+        c.w = r_upload(h.data(), h.size() * 2);
+    } else {
+        c.w = r_upload(pk.data(), pk.size() * 4);
+    }
+    c.b = r_upload(bias.data(), bias.size() * 4);
+    return c;
+}
+
+}  // namespace synt
+
+using namespace synt;
+
+struct synt_resnet18 {
+    int dt = DT_BF16, num_classes = 7; bool use_tc = true;
+    RConv stem;                              // 7x7 s2, always the fp32-FMA kernel (Cin = 3)
+    RConv c1[4][2], c2[4][2];
+    RPtr fc_w, fc_b;
+    Pool pool;
+    long long launches = 0;
+    std::string tap_name; float* tap_out = nullptr; long long tap_cap = 0; int tap_C = 0, tap_H = 0, tap_W = 0; bool tap_hit = false;
+};
+
+namespace synt {
+
+struct RFwd {
+    synt_resnet18* r; cudaStream_t s; int B;
+    size_t esz() const { return dtype_size(r->dt); }
+    void* make(int H, int W, int C) { return r->pool.alloc((size_t)B * H * W * C * esz()); }
+    void tap(const std::string& name, void* p, int H, int W, int C) {
+        if (!r->tap_out || name != r->tap_name) return;
+        SYNT_CHECK((long long)B * H * W * C <= r->tap_cap, "debug tap buffer too small");
+        nhwc_to_nchw_f32(p, r->dt, B, H * W, C, r->tap_out, s);
+        r->tap_C = C; r->tap_H = H; r->tap_W = W; r->tap_hit = true;
+    }
+    void conv(const RConv& c, const void* in, int H, int W, const void* sc, int sc_stride, const void* residual, int relu,
+              void* out, int Ho, int Wo) {
+        ConvArgs a; a.in = in; a.B = B; a.H = H; a.W = W; a.Cin = c.cin; a.KH = a.KW = c.k; a.stride = c.stride;
+        a.pad = c.k / 2; a.Ho = Ho; a.Wo = Wo; a.Cout = c.cout;
+        if (c.csc) { a.sc0 = sc; a.sc0_C = c.csc; a.sc_stride = sc_stride; }
+        a.weight = c.w->p; a.bias = (const float*)c.b->p; a.residual = residual; a.relu = relu; a.out = out;
+        if (c.bf) conv_tc(a, s); else conv_simt(a, r->dt, s);
+        ++r->launches;
+    }
+    void run(const float* x_nchw, float* logits) {
+        void* pre = make(224, 224, 3);
+        classifier_preprocess(x_nchw, B, 128, 128, 224, 224, pre, 3, r->dt, s);
+        tap("preprocess", pre, 224, 224, 3);
+        void* c1 = make(112, 112, 64);
+        conv(r->stem, pre, 224, 224, nullptr, 1, nullptr, 1, c1, 112, 112);
+        r->pool.release(pre);
+        tap("relu", c1, 112, 112, 64);
+        void* cur = make(56, 56, 64);
+        maxpool3x3s2(c1, r->dt, B, 112, 112, 64, cur, s);
+        r->pool.release(c1);
+        tap("maxpool", cur, 56, 56, 64);
+        r->launches += 2;
+        int H = 56;
+        for (int l = 0; l < 4; ++l) {
+            const int c = kStageCh[l];
+            for (int j = 0; j < 2; ++j) {
+                const int stride = (j == 0 && l > 0) ? 2 : 1;
+                const int Ho = H / stride;
+                void* h1 = make(Ho, Ho, c);
+                conv(r->c1[l][j], cur, H, H, nullptr, 1, nullptr, 1, h1, Ho, Ho);
+                void* o = make(Ho, Ho, c);
+                if (r->c2[l][j].csc) conv(r->c2[l][j], h1, Ho, Ho, cur, stride, nullptr, 1, o, Ho, Ho);
+                else                 conv(r->c2[l][j], h1, Ho, Ho, nullptr, 1, cur, 1, o, Ho, Ho);
+                r->pool.release(h1); r->pool.release(cur);
+                cur = o; H = Ho;
+                tap("layer" + std::to_string(l + 1) + "." + std::to_string(j), cur, H, H, c);
+            }
+        }
+        avgpool_fc(cur, r->dt, B, H * H, 512, (const float*)r->fc_w->p, (const float*)r->fc_b->p, r->num_classes, logits, s);
+        ++r->launches;
+        r->pool.release(cur);
+    }
+};
+
+}  // namespace synt
+
+#define SYNT_TRY try {
+#define SYNT_CATCH                                                                    \
+    } catch (const synt::Error& e) { synt::g_last_error = e.what(); return e.code;    \
+    } catch (const std::exception& e) { synt::g_last_error = e.what(); return -1; }   \
+    return 0;
+
+extern "C" {
+
+int synt_resnet18_num_params(void) { return (int)rmanifest(7).params.size(); }
+int synt_resnet18_param_info(int num_classes, int i, char* name, int cap, long long* numel, long long* offset) {
+    SYNT_TRY
+    const RManifest& m = rmanifest(num_classes);
+    SYNT_CHECK(i >= 0 && i < (int)m.params.size(), "param index out of range");
+    if (name && cap > 0) { strncpy(name, m.params[i].name.c_str(), cap - 1); name[cap - 1] = 0; }
+    if (numel) *numel = m.params[i].numel;
+    if (offset) *offset = m.params[i].offset;
+    SYNT_CATCH
+}
+
+int synt_resnet18_create(const float* P, long long n_params, int num_classes, int dtype, synt_resnet18_t** out) {
+    SYNT_TRY
+    SYNT_CHECK(P && out, "null argument");
+    const RManifest& m = rmanifest(num_classes);
+    SYNT_CHECK(n_params == m.total, "resnet18 parameter blob has the wrong length");
+    SYNT_CHECK(dtype == DT_F32 || dtype == DT_BF16, "bad dtype");
+    int ndev = 0;
+    SYNT_CUDA(cudaGetDeviceCount(&ndev));
+    SYNT_CHECK(ndev > 0, "no CUDA device: this library has no CPU fallback");
+    std::unique_ptr<synt_resnet18> r(new synt_resnet18());
+    r->dt = dtype; r->num_classes = num_classes;
+    const char* force = getenv("SYNT_FORCE_SIMT");
+    r->use_tc = dtype == DT_BF16 && !(force && force[0] == '1');
+    const bool bf = r->use_tc;
+    r->stem = make_rconv(P, m, "conv1", "bn1", 3, 64, 7, 2, "", "", 0, false);
+    int cin = 64;
+    for (int l = 0; l < 4; ++l) {
+        const int c = kStageCh[l];
+        for (int j = 0; j < 2; ++j) {
+            const std::string p = "layer" + std::to_string(l + 1) + "." + std::to_string(j);
+            const int ci = j == 0 ? cin : c, stride = (j == 0 && l > 0) ? 2 : 1;
+            r->c1[l][j] = make_rconv(P, m, p + ".conv1", p + ".bn1", ci, c, 3, stride, "", "", 0, bf);
+            if (j == 0 && l > 0)
+                r->c2[l][j] = make_rconv(P, m, p + ".conv2", p + ".bn2", c, c, 3, 1, p + ".downsample.0", p + ".downsample.1", ci, bf);
+            else
+                r->c2[l][j] = make_rconv(P, m, p + ".conv2", p + ".bn2", c, c, 3, 1, "", "", 0, bf);
+        }
+        cin = c;
+    }
+    r->fc_w = r_upload(P + m.find("fc.weight"), (size_t)num_classes * 512 * 4);
+    r->fc_b = r_upload(P + m.find("fc.bias"), (size_t)num_classes * 4);
+    *out = r.release();
+    SYNT_CATCH
+}
+int synt_resnet18_destroy(synt_resnet18_t* h) { delete h; return 0; }
+
+int synt_resnet18_logits(synt_resnet18_t* h, const float* x, int B, float* logits, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(h && x && logits && B > 0, "bad argument");
+    const size_t img = (size_t)3 * 128 * 128;
+    const int mb = 64;                                      // bounds the workspace
+    for (int b0 = 0; b0 < B; b0 += mb) {
+        RFwd f{h, (cudaStream_t)stream, B - b0 < mb ? B - b0 : mb};
+        f.run(x + b0 * img, logits + (size_t)b0 * h->num_classes);
+    }
+    SYNT_CATCH
+}
+int synt_resnet18_logits_host(synt_resnet18_t* h, const float* x_host, int B, float* logits_host) {
+    SYNT_TRY
+    SYNT_CHECK(h && x_host && logits_host && B > 0, "bad argument");
+    const size_t n = (size_t)B * 3 * 128 * 128;
+    float* x = (float*)h->pool.alloc(n * 4);
+    float* lg = (float*)h->pool.alloc((size_t)B * h->num_classes * 4);
+    SYNT_CUDA(cudaMemcpyAsync(x, x_host, n * 4, cudaMemcpyHostToDevice, 0));
+    int rc = synt_resnet18_logits(h, x, B, lg, nullptr);
+    if (rc == 0) {
+        SYNT_CUDA(cudaMemcpyAsync(logits_host, lg, (size_t)B * h->num_classes * 4, cudaMemcpyDeviceToHost, 0));
+        SYNT_CUDA(cudaStreamSynchronize(0));
+    }
+    h->pool.release(x); h->pool.release(lg);
+    if (rc != 0) return rc;
+    SYNT_CATCH
+}
+int synt_resnet18_debug(synt_resnet18_t* h, const float* x, int B, const char* tap, float* out, long long cap, int* C,
+                        int* H, int* W, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(h && x && tap && out && B > 0 && B <= 64, "bad argument");
+    h->tap_name = tap; h->tap_out = out; h->tap_cap = cap; h->tap_hit = false;
+    float* lg = (float*)h->pool.alloc((size_t)B * h->num_classes * 4);
+    RFwd f{h, (cudaStream_t)stream, B};
+    f.run(x, lg);
+    h->pool.release(lg);
+    h->tap_out = nullptr;
+    SYNT_CHECK(h->tap_hit, std::string("unknown debug tap: ") + tap);
+    if (C) *C = h->tap_C;
+    if (H) *H = h->tap_H;
+    if (W) *W = h->tap_W;
+    SYNT_CATCH
+}
+long long synt_resnet18_launch_count(synt_resnet18_t* h) { return h ? h->launches : 0; }
+
+int synt_intervene_blend(const float* x, const float* mask, const float* aux, int type, float noise_std, int B, int C,
+                         int H, int W, float* out, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(x && mask && out && B > 0, "bad argument");
+    intervene_blend(x, mask, aux, type, noise_std, B, C, H, W, out, (cudaStream_t)stream);
+    SYNT_CATCH
+}
+int synt_patch_mask_apply(const float* x, const unsigned char* pm, int n_masks, int C, int H, int W, int patch, float* out,
+                          void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(x && pm && out && n_masks > 0 && patch > 0 && H % patch == 0 && W % patch == 0, "bad argument");
+    patch_mask_apply(x, pm, n_masks, C, H, W, patch, out, (cudaStream_t)stream);
+    SYNT_CATCH
+}
+
+}  // extern "C"

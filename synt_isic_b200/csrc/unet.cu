@@ -1,0 +1,782 @@
+// UNet2D execution plan + DDPM sampling loop behind the C ABI (include/synt_isic.h).
+//
+// What it replaces in the reference (paths under /root/reference):
+//   UNet2DModel(...) construction           core/generator/model_manager.py:173-194
+//   model(latents, t).sample                core/generator/image_generator.py:400
+//   scheduler.step(...).prev_sample         core/generator/image_generator.py:403
+//   the T-step loop                         core/generator/image_generator.py:395-403
+// The network topology is diffusers' UNet2DModel for those constructor arguments
+// (SURVEY.md Appendix A.1); weights arrive in diffusers state_dict naming (A.2).
+#include "kernels.cuh"
+#include "pool.h"
+#include "../../include/synt_isic.h"
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace synt {
+
+thread_local std::string g_last_error;
+
+// ------------------------------------------------------------------ manifest ----------
+struct ParamSpec { std::string name; long long numel; long long offset; };
+
+static const int kBlockCh[4] = {64, 128, 256, 256};
+static const bool kDownAttn[4] = {false, false, true, false};
+static const bool kUpAttn[4] = {false, true, false, false};
+constexpr int kTembDim = 256, kGroups = 32, kImg = 128, kTrainSteps = 1000;
+constexpr float kGnEps = 1e-5f;
+
+struct ResnetCfg { std::string prefix; int cin, cout; };
+struct AttnCfg { std::string prefix; int C; };
+
+struct Manifest {
+    std::vector<ParamSpec> params;
+    long long total = 0;
+    void add(const std::string& n, long long numel) { params.push_back({n, numel, total}); total += numel; }
+    void conv(const std::string& p, int cout, int cin, int k) { add(p + ".weight", (long long)cout * cin * k * k); add(p + ".bias", cout); }
+    void linear(const std::string& p, int out, int in) { add(p + ".weight", (long long)out * in); add(p + ".bias", out); }
+    void norm(const std::string& p, int c) { add(p + ".weight", c); add(p + ".bias", c); }
+    void resnet(const std::string& p, int cin, int cout) {
+        norm(p + ".norm1", cin); conv(p + ".conv1", cout, cin, 3); linear(p + ".time_emb_proj", cout, kTembDim);
+        norm(p + ".norm2", cout); conv(p + ".conv2", cout, cout, 3);
+        if (cin != cout) conv(p + ".conv_shortcut", cout, cin, 1);
+    }
+    void attn(const std::string& p, int c) {
+        norm(p + ".group_norm", c); linear(p + ".to_q", c, c); linear(p + ".to_k", c, c); linear(p + ".to_v", c, c);
+        linear(p + ".to_out.0", c, c);
+    }
+    long long find(const std::string& n) const {
+        for (auto& s : params) if (s.name == n) return s.offset;
+        throw Error(-1, "manifest: no parameter named " + n);
+    }
+};
+
+// up-block resnet input channels (diffusers UpBlock2D): see SURVEY.md A.1
+static void up_resnet_channels(int i, int j, int& c_h, int& c_skip, int& cout) {
+    const int rev[4] = {256, 256, 128, 64};
+    cout = rev[i];
+    const int prev = rev[i == 0 ? 0 : i - 1];
+    const int inp = rev[i + 1 < 4 ? i + 1 : 3];
+    c_skip = (j == 2) ? inp : cout;
+    c_h = (j == 0) ? prev : cout;
+}
+
+static Manifest build_manifest() {
+    Manifest m;
+    m.conv("conv_in", 64, 3, 3);
+    m.linear("time_embedding.linear_1", kTembDim, 64);
+    m.linear("time_embedding.linear_2", kTembDim, kTembDim);
+    int out = 64;
+    for (int i = 0; i < 4; ++i) {
+        const int inp = out; out = kBlockCh[i];
+        const std::string b = "down_blocks." + std::to_string(i);
+        for (int j = 0; j < 2; ++j) m.resnet(b + ".resnets." + std::to_string(j), j == 0 ? inp : out, out);
+        if (kDownAttn[i]) for (int j = 0; j < 2; ++j) m.attn(b + ".attentions." + std::to_string(j), out);
+        if (i != 3) m.conv(b + ".downsamplers.0.conv", out, out, 3);
+    }
+    m.attn("mid_block.attentions.0", 256);
+    m.resnet("mid_block.resnets.0", 256, 256);
+    m.resnet("mid_block.resnets.1", 256, 256);
+    for (int i = 0; i < 4; ++i) {
+        const std::string b = "up_blocks." + std::to_string(i);
+        int cout = 0;
+        for (int j = 0; j < 3; ++j) {
+            int ch, cs; up_resnet_channels(i, j, ch, cs, cout);
+            m.resnet(b + ".resnets." + std::to_string(j), ch + cs, cout);
+        }
+        if (kUpAttn[i]) for (int j = 0; j < 3; ++j) m.attn(b + ".attentions." + std::to_string(j), cout);
+        if (i != 3) m.conv(b + ".upsamplers.0.conv", cout, cout, 3);
+    }
+    m.norm("conv_norm_out", 64);
+    m.conv("conv_out", 3, 64, 3);
+    return m;
+}
+static const Manifest& manifest() { static Manifest m = build_manifest(); return m; }
+
+// ------------------------------------------------------------------ host packing ------
+static uint16_t f2bf(float f) {                  // round-to-nearest-even, NaN-safe enough for weights
+    uint32_t u; memcpy(&u, &f, 4);
+    const uint32_t r = 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)((u + r) >> 16);
+}
+
+struct DevBuf {                                   // owns one cudaMalloc
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+using DevPtr = std::shared_ptr<DevBuf>;
+static DevPtr dev_upload(const void* host, size_t bytes) {
+    auto b = std::make_shared<DevBuf>();
+    SYNT_CUDA(cudaMalloc(&b->p, bytes ? bytes : 4));
+    if (bytes) SYNT_CUDA(cudaMemcpy(b->p, host, bytes, cudaMemcpyHostToDevice));
+    return b;
+}
+static DevPtr dev_alloc(size_t bytes) {
+    auto b = std::make_shared<DevBuf>();
+    SYNT_CUDA(cudaMalloc(&b->p, bytes ? bytes : 4));
+    SYNT_CUDA(cudaMemset(b->p, 0, bytes ? bytes : 4));
+    return b;
+}
+
+// conv weight [Cout][Cin][k][k] (+ optional 1x1 shortcut [Cout][Csc]) -> K-major [Cout][k*k*Cin + Csc]
+static std::vector<float> pack_conv(const float* w, int cout, int cin, int k, const float* wsc, int csc) {
+    const int taps = k * k, ktot = taps * cin + csc;
+    std::vector<float> o((size_t)cout * ktot);
+    for (int n = 0; n < cout; ++n) {
+        float* row = o.data() + (size_t)n * ktot;
+        for (int t = 0; t < taps; ++t)
+            for (int c = 0; c < cin; ++c) row[t * cin + c] = w[((size_t)n * cin + c) * taps + t];
+        for (int c = 0; c < csc; ++c) row[taps * cin + c] = wsc[(size_t)n * csc + c];
+    }
+    return o;
+}
+struct WeightDev {                                // one GEMM operand on the device
+    DevPtr f32, b16;
+    const void* get(bool tc) const { return tc ? b16->p : f32->p; }
+};
+static WeightDev upload_weight(const std::vector<float>& w, bool want_f32, bool want_bf16) {
+    WeightDev d;
+    if (want_f32) d.f32 = dev_upload(w.data(), w.size() * 4);
+    if (want_bf16) {
+        std::vector<uint16_t> h(w.size());
+        for (size_t i = 0; i < w.size(); ++i) h[i] = f2bf(w[i]);
+        d.b16 = dev_upload(h.data(), h.size() * 2);
+    }
+    return d;
+}
+
+// ------------------------------------------------------------------ model -------------
+struct Act {                                      // NHWC activation
+    void* p = nullptr; int B = 0, H = 0, W = 0, C = 0;
+    size_t numel() const { return (size_t)B * H * W * C; }
+};
+
+struct ResnetW {
+    std::string name; int cin, cout; bool shortcut; int temb_off;
+    DevPtr g1, b1n, g2, b2n;                      // GroupNorm affine
+    WeightDev w1, w2; DevPtr bias1, bias2;        // bias2 = conv2.bias (+ conv_shortcut.bias)
+};
+struct AttnW {
+    std::string name; int C;
+    DevPtr g, b; WeightDev wqkv, wo; DevPtr bqkv, bo;
+};
+struct ConvW { std::string name; int cin, cout; WeightDev w; DevPtr b; };
+
+}  // namespace synt
+
+using namespace synt;
+
+struct synt_unet {
+    int dt = DT_BF16;
+    bool use_tc = true;                           // tcgen05 convs (bf16 mode) vs fp32-FMA convs
+    bool want_f32_w = false;
+    ConvInW conv_in_w;
+    ConvOutW conv_out_w;
+    DevPtr norm_out_g, norm_out_b;
+    std::vector<ResnetW> down_res[4], up_res[4];
+    std::vector<AttnW> down_attn[4], up_attn[4];
+    std::vector<ConvW> downsample, upsample;      // index = block (3 each)
+    ResnetW mid_res[2]; AttnW mid_attn;
+    int temb_total = 0;
+    DevPtr temb_table;                            // [1000][temb_total]
+    DevPtr temb_cur, coef_cur, step_ctr;          // fixed per-step buffers (graph friendly)
+    DevPtr timesteps_dev, coef_table_dev; int n_steps = 0;
+    std::vector<int> timesteps_host;
+    Pool pool;
+    long long launches = 0;
+    // CUDA graph cache for one sampling step
+    struct GraphKey {
+        float* x; int B; const float* z; float* traj; float* eps; int mb; unsigned long long seed; long long off;
+        bool operator==(const GraphKey& o) const {
+            return x == o.x && B == o.B && z == o.z && traj == o.traj && eps == o.eps && mb == o.mb && seed == o.seed && off == o.off;
+        }
+    } gkey{};
+    cudaGraphExec_t gexec = nullptr;
+    long long graph_nodes = 0;
+    cudaStream_t own_stream = nullptr;            // capture needs a non-legacy stream
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    // debug tap
+    std::string tap_name; float* tap_out = nullptr; long long tap_cap = 0; int tap_C = 0, tap_H = 0, tap_W = 0; bool tap_hit = false;
+
+    ~synt_unet() {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        if (own_stream) cudaStreamDestroy(own_stream);
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_out) cudaEventDestroy(ev_out);
+    }
+};
+
+namespace synt {
+
+static ResnetW make_resnet(const float* P, const std::string& name, int cin, int cout, int temb_off, bool f32, bool b16) {
+    const Manifest& m = manifest();
+    ResnetW r; r.name = name; r.cin = cin; r.cout = cout; r.shortcut = cin != cout; r.temb_off = temb_off;
+    r.g1 = dev_upload(P + m.find(name + ".norm1.weight"), cin * 4);
+    r.b1n = dev_upload(P + m.find(name + ".norm1.bias"), cin * 4);
+    r.g2 = dev_upload(P + m.find(name + ".norm2.weight"), cout * 4);
+    r.b2n = dev_upload(P + m.find(name + ".norm2.bias"), cout * 4);
+    r.w1 = upload_weight(pack_conv(P + m.find(name + ".conv1.weight"), cout, cin, 3, nullptr, 0), f32, b16);
+    r.bias1 = dev_upload(P + m.find(name + ".conv1.bias"), cout * 4);
+    std::vector<float> b2(P + m.find(name + ".conv2.bias"), P + m.find(name + ".conv2.bias") + cout);
+    if (r.shortcut) {
+        const float* bs = P + m.find(name + ".conv_shortcut.bias");
+        for (int i = 0; i < cout; ++i) b2[i] += bs[i];
+        r.w2 = upload_weight(pack_conv(P + m.find(name + ".conv2.weight"), cout, cout, 3,
+                                       P + m.find(name + ".conv_shortcut.weight"), cin), f32, b16);
+    } else {
+        r.w2 = upload_weight(pack_conv(P + m.find(name + ".conv2.weight"), cout, cout, 3, nullptr, 0), f32, b16);
+    }
+    r.bias2 = dev_upload(b2.data(), cout * 4);
+    return r;
+}
+static AttnW make_attn(const float* P, const std::string& name, int C, bool f32, bool b16) {
+    const Manifest& m = manifest();
+    AttnW a; a.name = name; a.C = C;
+    a.g = dev_upload(P + m.find(name + ".group_norm.weight"), C * 4);
+    a.b = dev_upload(P + m.find(name + ".group_norm.bias"), C * 4);
+    std::vector<float> wqkv((size_t)3 * C * C), bqkv(3 * C);
+    const char* nm[3] = {".to_q", ".to_k", ".to_v"};
+    for (int i = 0; i < 3; ++i) {
+        memcpy(wqkv.data() + (size_t)i * C * C, P + m.find(name + nm[i] + ".weight"), (size_t)C * C * 4);
+        memcpy(bqkv.data() + i * C, P + m.find(name + nm[i] + ".bias"), C * 4);
+    }
+    a.wqkv = upload_weight(wqkv, f32, b16);
+    a.bqkv = dev_upload(bqkv.data(), bqkv.size() * 4);
+    std::vector<float> wo(P + m.find(name + ".to_out.0.weight"), P + m.find(name + ".to_out.0.weight") + (size_t)C * C);
+    a.wo = upload_weight(wo, f32, b16);
+    a.bo = dev_upload(P + m.find(name + ".to_out.0.bias"), C * 4);
+    return a;
+}
+static ConvW make_conv(const float* P, const std::string& name, int cin, int cout, bool f32, bool b16) {
+    const Manifest& m = manifest();
+    ConvW c; c.name = name; c.cin = cin; c.cout = cout;
+    c.w = upload_weight(pack_conv(P + m.find(name + ".weight"), cout, cin, 3, nullptr, 0), f32, b16);
+    c.b = dev_upload(P + m.find(name + ".bias"), cout * 4);
+    return c;
+}
+
+static void build_unet(synt_unet* u, const float* P) {
+    const Manifest& m = manifest();
+    const bool b16 = u->dt == DT_BF16 && u->use_tc;
+    const bool f32 = !b16;
+    // edge convolutions (by-value constant-bank weights)
+    {
+        const float* w = P + m.find("conv_in.weight");      // [64][3][3][3]
+        for (int n = 0; n < 64; ++n)
+            for (int c = 0; c < 3; ++c)
+                for (int t = 0; t < 9; ++t) u->conv_in_w.w[t * 3 + c][n] = w[((size_t)n * 3 + c) * 9 + t];
+        memcpy(u->conv_in_w.b, P + m.find("conv_in.bias"), 64 * 4);
+        const float* wo = P + m.find("conv_out.weight");    // [3][64][3][3]
+        for (int n = 0; n < 3; ++n)
+            for (int c = 0; c < 64; ++c)
+                for (int t = 0; t < 9; ++t) u->conv_out_w.w[t][c][n] = wo[((size_t)n * 64 + c) * 9 + t];
+        memcpy(u->conv_out_w.b, P + m.find("conv_out.bias"), 3 * 4);
+        u->norm_out_g = dev_upload(P + m.find("conv_norm_out.weight"), 64 * 4);
+        u->norm_out_b = dev_upload(P + m.find("conv_norm_out.bias"), 64 * 4);
+    }
+    std::vector<float> proj_w, proj_b;            // concatenated time_emb_proj of every resnet
+    auto add_res = [&](const std::string& name, int cin, int cout) {
+        const int off = (int)proj_b.size();
+        const float* w = P + m.find(name + ".time_emb_proj.weight");
+        const float* b = P + m.find(name + ".time_emb_proj.bias");
+        proj_w.insert(proj_w.end(), w, w + (size_t)cout * kTembDim);
+        proj_b.insert(proj_b.end(), b, b + cout);
+        return make_resnet(P, name, cin, cout, off, f32, b16);
+    };
+    int out = 64;
+    for (int i = 0; i < 4; ++i) {
+        const int inp = out; out = kBlockCh[i];
+        const std::string b = "down_blocks." + std::to_string(i);
+        for (int j = 0; j < 2; ++j) u->down_res[i].push_back(add_res(b + ".resnets." + std::to_string(j), j == 0 ? inp : out, out));
+        if (kDownAttn[i]) for (int j = 0; j < 2; ++j) u->down_attn[i].push_back(make_attn(P, b + ".attentions." + std::to_string(j), out, f32, b16));
+        if (i != 3) u->downsample.push_back(make_conv(P, b + ".downsamplers.0.conv", out, out, f32, b16));
+    }
+    u->mid_res[0] = add_res("mid_block.resnets.0", 256, 256);
+    u->mid_attn = make_attn(P, "mid_block.attentions.0", 256, f32, b16);
+    u->mid_res[1] = add_res("mid_block.resnets.1", 256, 256);
+    for (int i = 0; i < 4; ++i) {
+        const std::string b = "up_blocks." + std::to_string(i);
+        int cout = 0;
+        for (int j = 0; j < 3; ++j) {
+            int ch, cs; up_resnet_channels(i, j, ch, cs, cout);
+            u->up_res[i].push_back(add_res(b + ".resnets." + std::to_string(j), ch + cs, cout));
+        }
+        if (kUpAttn[i]) for (int j = 0; j < 3; ++j) u->up_attn[i].push_back(make_attn(P, b + ".attentions." + std::to_string(j), cout, f32, b16));
+        if (i != 3) u->upsample.push_back(make_conv(P, b + ".upsamplers.0.conv", cout, cout, f32, b16));
+    }
+    u->temb_total = (int)proj_b.size();
+
+    // time-embedding tables for all 1000 train timesteps (batch independent: same t for all b)
+    float freqs[32];
+    for (int k = 0; k < 32; ++k) freqs[k] = (float)std::exp(-std::log(10000.0) * (double)k / 32.0);
+    DevPtr d_freq = dev_upload(freqs, sizeof(freqs));
+    DevPtr w1 = dev_upload(P + m.find("time_embedding.linear_1.weight"), 256 * 64 * 4);
+    DevPtr b1 = dev_upload(P + m.find("time_embedding.linear_1.bias"), 256 * 4);
+    DevPtr w2 = dev_upload(P + m.find("time_embedding.linear_2.weight"), 256 * 256 * 4);
+    DevPtr b2 = dev_upload(P + m.find("time_embedding.linear_2.bias"), 256 * 4);
+    DevPtr emb = dev_alloc((size_t)kTrainSteps * 256 * 4);
+    DevPtr pw = dev_upload(proj_w.data(), proj_w.size() * 4);
+    DevPtr pb = dev_upload(proj_b.data(), proj_b.size() * 4);
+    u->temb_table = dev_alloc((size_t)kTrainSteps * u->temb_total * 4);
+    time_embed_table((const float*)d_freq->p, (const float*)w1->p, (const float*)b1->p, (const float*)w2->p,
+                     (const float*)b2->p, kTrainSteps, (float*)emb->p, 0);
+    time_proj_table((const float*)emb->p, (const float*)pw->p, (const float*)pb->p, kTrainSteps, u->temb_total,
+                    (float*)u->temb_table->p, 0);
+    SYNT_CUDA(cudaDeviceSynchronize());
+    u->temb_cur = dev_alloc((size_t)u->temb_total * 4);
+    u->coef_cur = dev_alloc(8 * 4);
+    u->step_ctr = dev_alloc(4);
+}
+
+// ------------------------------------------------------------------ forward -----------
+struct Fwd {
+    synt_unet* u; cudaStream_t s; int B;
+    size_t esz() const { return dtype_size(u->dt); }
+    Act make(int H, int W, int C) {
+        Act a; a.B = B; a.H = H; a.W = W; a.C = C; a.p = u->pool.alloc(a.numel() * esz()); return a;
+    }
+    void drop(Act& a) { u->pool.release(a.p); a.p = nullptr; }
+    void tap(const std::string& name, const Act& a) {
+        if (!u->tap_out || name != u->tap_name) return;
+        SYNT_CHECK((long long)a.numel() <= u->tap_cap, "debug tap buffer too small");
+        nhwc_to_nchw_f32(a.p, u->dt, a.B, a.H * a.W, a.C, u->tap_out, s);
+        u->tap_C = a.C; u->tap_H = a.H; u->tap_W = a.W; u->tap_hit = true;
+        ++u->launches;
+    }
+    // GroupNorm statistics of concat(x0, x1) -> per-(b, c) scale/shift
+    float2* gn_scale_shift(const Act& x0, const Act* x1, const DevPtr& gamma, const DevPtr& beta) {
+        const int C = x0.C + (x1 ? x1->C : 0), HW = x0.H * x0.W;
+        const int nchunk = gn_num_chunks(B, HW);
+        float2* part = (float2*)u->pool.alloc((size_t)B * nchunk * kGroups * sizeof(float2));
+        float2* ss = (float2*)u->pool.alloc((size_t)B * C * sizeof(float2));
+        gn_stats(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, u->dt, B, HW, kGroups, part, nchunk, s);
+        gn_finalize(part, B, nchunk, kGroups, C, HW, kGnEps, (const float*)gamma->p, (const float*)beta->p, ss, s);
+        u->pool.release(part);
+        u->launches += 2;
+        return ss;
+    }
+    Act gn_act(const Act& x0, const Act* x1, const DevPtr& gamma, const DevPtr& beta, bool silu) {
+        float2* ss = gn_scale_shift(x0, x1, gamma, beta);
+        Act o = make(x0.H, x0.W, x0.C + (x1 ? x1->C : 0));
+        gn_apply(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, u->dt, B, x0.H * x0.W, ss, silu ? 1 : 0, o.p, s);
+        u->pool.release(ss);
+        ++u->launches;
+        return o;
+    }
+    void conv(ConvArgs& a, const WeightDev& w) {
+        const bool tc = u->dt == DT_BF16 && u->use_tc && conv_tc_supported(a);
+        a.weight = w.get(tc);
+        if (tc) conv_tc(a, s); else conv_simt(a, u->dt, s);
+        ++u->launches;
+    }
+    Act resnet(const ResnetW& r, const Act& x0, const Act* x1) {
+        const int H = x0.H, W = x0.W;
+        Act a = gn_act(x0, x1, r.g1, r.b1n, true);
+        Act h1 = make(H, W, r.cout);
+        {
+            ConvArgs c; c.in = a.p; c.B = B; c.H = H; c.W = W; c.Cin = r.cin; c.Ho = H; c.Wo = W; c.Cout = r.cout;
+            c.bias = (const float*)r.bias1->p; c.bias2 = (const float*)u->temb_cur->p + r.temb_off; c.out = h1.p;
+            conv(c, r.w1);
+        }
+        drop(a);
+        Act a2 = gn_act(h1, nullptr, r.g2, r.b2n, true);
+        drop(h1);
+        Act o = make(H, W, r.cout);
+        {
+            ConvArgs c; c.in = a2.p; c.B = B; c.H = H; c.W = W; c.Cin = r.cout; c.Ho = H; c.Wo = W; c.Cout = r.cout;
+            c.bias = (const float*)r.bias2->p; c.out = o.p;
+            if (r.shortcut) {
+                c.sc0 = x0.p; c.sc0_C = x0.C;
+                if (x1) { c.sc1 = x1->p; c.sc1_C = x1->C; }
+            } else {
+                SYNT_CHECK(x1 == nullptr, "identity residual with a concatenated input");
+                c.residual = x0.p;
+            }
+            conv(c, r.w2);
+        }
+        drop(a2);
+        tap(r.name, o);
+        return o;
+    }
+    Act attention(const AttnW& w, const Act& x) {
+        const int H = x.H, W = x.W, C = w.C;
+        Act a = gn_act(x, nullptr, w.g, w.b, false);
+        Act qkv = make(H, W, 3 * C);
+        {
+            ConvArgs c; c.in = a.p; c.B = B; c.H = H; c.W = W; c.Cin = C; c.KH = c.KW = 1; c.pad = 0; c.Ho = H; c.Wo = W;
+            c.Cout = 3 * C; c.bias = (const float*)w.bqkv->p; c.out = qkv.p;
+            conv(c, w.wqkv);
+        }
+        drop(a);
+        Act o = make(H, W, C);
+        if (u->dt == DT_BF16 && u->use_tc && attention_tc_supported(H * W, C)) attention_tc(qkv.p, B, H * W, C, o.p, s);
+        else attention_simt(qkv.p, u->dt, B, H * W, C, o.p, s);
+        ++u->launches;
+        drop(qkv);
+        Act out = make(H, W, C);
+        {
+            ConvArgs c; c.in = o.p; c.B = B; c.H = H; c.W = W; c.Cin = C; c.KH = c.KW = 1; c.pad = 0; c.Ho = H; c.Wo = W;
+            c.Cout = C; c.bias = (const float*)w.bo->p; c.residual = x.p; c.out = out.p;
+            conv(c, w.wo);
+        }
+        drop(o);
+        tap(w.name, out);
+        return out;
+    }
+    Act down(const ConvW& w, const Act& x) {
+        Act o = make(x.H / 2, x.W / 2, w.cout);
+        ConvArgs c; c.in = x.p; c.B = B; c.H = x.H; c.W = x.W; c.Cin = w.cin; c.stride = 2; c.Ho = o.H; c.Wo = o.W;
+        c.Cout = w.cout; c.bias = (const float*)w.b->p; c.out = o.p;
+        conv(c, w.w);
+        tap(w.name.substr(0, w.name.size() - 5), o);           // strip ".conv"
+        return o;
+    }
+    Act up(const ConvW& w, const Act& x) {
+        Act up2 = make(x.H * 2, x.W * 2, x.C);
+        upsample_nearest2x(x.p, u->dt, B, x.H, x.W, x.C, up2.p, s);
+        ++u->launches;
+        Act o = make(up2.H, up2.W, w.cout);
+        ConvArgs c; c.in = up2.p; c.B = B; c.H = up2.H; c.W = up2.W; c.Cin = w.cin; c.Ho = o.H; c.Wo = o.W;
+        c.Cout = w.cout; c.bias = (const float*)w.b->p; c.out = o.p;
+        conv(c, w.w);
+        drop(up2);
+        tap(w.name.substr(0, w.name.size() - 5), o);
+        return o;
+    }
+
+    // eps = UNet(x, t) for one micro-batch; temb_cur must already hold the row of t.
+    void run(const float* x_nchw, float* eps_nchw, const SchedArgs& sch) {
+        Act h = make(kImg, kImg, 64);
+        conv_in3(x_nchw, u->conv_in_w, B, kImg, kImg, h.p, u->dt, s);
+        ++u->launches;
+        tap("conv_in", h);
+        std::vector<Act> skips; skips.push_back(h);
+        Act cur = h;                                            // `cur` aliases the top skip
+        for (int i = 0; i < 4; ++i) {
+            for (int j = 0; j < 2; ++j) {
+                Act r = resnet(u->down_res[i][j], cur, nullptr);
+                if (kDownAttn[i]) { Act a = attention(u->down_attn[i][j], r); drop(r); r = a; }
+                skips.push_back(r); cur = r;
+            }
+            if (i != 3) { Act d = down(u->downsample[i], cur); skips.push_back(d); cur = d; }
+        }
+        // mid block (cur is still owned by the skip stack)
+        Act m0 = resnet(u->mid_res[0], cur, nullptr);
+        Act m1 = attention(u->mid_attn, m0); drop(m0);
+        Act hcur = resnet(u->mid_res[1], m1, nullptr); drop(m1);
+        for (int i = 0; i < 4; ++i) {
+            for (int j = 0; j < 3; ++j) {
+                Act skip = skips.back(); skips.pop_back();
+                Act r = resnet(u->up_res[i][j], hcur, &skip);
+                drop(hcur); drop(skip);
+                if (kUpAttn[i]) { Act a = attention(u->up_attn[i][j], r); drop(r); r = a; }
+                hcur = r;
+            }
+            if (i != 3) { Act o = up(u->upsample[i], hcur); drop(hcur); hcur = o; }
+        }
+        float2* ss = gn_scale_shift(hcur, nullptr, u->norm_out_g, u->norm_out_b);
+        conv_out3(hcur.p, u->dt, ss, u->conv_out_w, B, kImg, kImg, eps_nchw, sch, s);
+        ++u->launches;
+        u->pool.release(ss);
+        drop(hcur);
+    }
+};
+
+static int default_micro_batch(int B) { return B <= 16 ? B : 16; }
+
+// one sampling step for all micro-batches (captured into the CUDA graph)
+static void sample_step(synt_unet* u, float* x, int B, const float* z, unsigned long long seed, long long image_offset,
+                        float* traj, float* eps_tap, int mb, cudaStream_t s) {
+    const size_t img = (size_t)3 * kImg * kImg;
+    select_timestep((const float*)u->temb_table->p, u->temb_total, (const float*)u->coef_table_dev->p,
+                    (const int*)u->timesteps_dev->p, (const int*)u->step_ctr->p, 0, (float*)u->temb_cur->p,
+                    (float*)u->coef_cur->p, s);
+    ++u->launches;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+        const int nb = B - b0 < mb ? B - b0 : mb;
+        Fwd f{u, s, nb};
+        SchedArgs sch;
+        sch.x = x + b0 * img; sch.coef = (const float*)u->coef_cur->p;
+        sch.z = z ? z + b0 * img : nullptr; sch.z_step_stride = (long long)B * img;
+        sch.seed = seed; sch.step_ptr = (const int*)u->step_ctr->p;
+        sch.traj = traj ? traj + b0 * img : nullptr; sch.traj_step_stride = (long long)B * img;
+        sch.eps_step_stride = (long long)B * img;
+        sch.image_offset = image_offset + b0;
+        f.run(x + b0 * img, eps_tap ? eps_tap + b0 * img : nullptr, sch);
+    }
+    advance_step((int*)u->step_ctr->p, s);
+    ++u->launches;
+}
+
+}  // namespace synt
+
+// ======================================================================= C ABI ========
+#define SYNT_TRY try {
+#define SYNT_CATCH                                                                    \
+    } catch (const synt::Error& e) { synt::g_last_error = e.what(); return e.code;    \
+    } catch (const std::exception& e) { synt::g_last_error = e.what(); return -1; }   \
+    return 0;
+
+extern "C" {
+
+const char* synt_version(void) { return "synt_isic_b200 0.1 (sm_100a)"; }
+const char* synt_last_error(void) { return synt::g_last_error.c_str(); }
+
+int synt_unet_num_params(void) { return (int)manifest().params.size(); }
+long long synt_unet_total_param_count(void) { return manifest().total; }
+int synt_unet_param_info(int i, char* name, int cap, long long* numel, long long* offset) {
+    SYNT_TRY
+    SYNT_CHECK(i >= 0 && i < (int)manifest().params.size(), "param index out of range");
+    const ParamSpec& p = manifest().params[i];
+    if (name && cap > 0) { strncpy(name, p.name.c_str(), cap - 1); name[cap - 1] = 0; }
+    if (numel) *numel = p.numel;
+    if (offset) *offset = p.offset;
+    SYNT_CATCH
+}
+
+int synt_unet_create(const float* params_host, long long n_params, int dtype, synt_unet_t** out) {
+    SYNT_TRY
+    SYNT_CHECK(params_host && out, "null argument");
+    SYNT_CHECK(n_params == manifest().total, "parameter blob has the wrong length (expected 25,304,963 floats)");
+    SYNT_CHECK(dtype == DT_F32 || dtype == DT_BF16, "dtype must be SYNT_DTYPE_F32 or SYNT_DTYPE_BF16");
+    int ndev = 0;
+    SYNT_CUDA(cudaGetDeviceCount(&ndev));
+    SYNT_CHECK(ndev > 0, "no CUDA device: this library has no CPU fallback");
+    cudaDeviceProp prop; int dev = 0;
+    SYNT_CUDA(cudaGetDevice(&dev));
+    SYNT_CUDA(cudaGetDeviceProperties(&prop, dev));
+    SYNT_CHECK(prop.major == 10, "synt_isic_b200 is built for sm_100a (Blackwell B200) only");
+    std::unique_ptr<synt_unet> u(new synt_unet());
+    u->dt = dtype;
+    const char* force = getenv("SYNT_FORCE_SIMT");
+    u->use_tc = dtype == DT_BF16 && !(force && force[0] == '1');
+    SYNT_CUDA(cudaStreamCreateWithFlags(&u->own_stream, cudaStreamNonBlocking));
+    SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_in, cudaEventDisableTiming));
+    SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_out, cudaEventDisableTiming));
+    build_unet(u.get(), params_host);
+    *out = u.release();
+    SYNT_CATCH
+}
+int synt_unet_destroy(synt_unet_t* h) { delete h; return 0; }
+
+int synt_unet_forward(synt_unet_t* h, const float* x, int B, int t, float* eps, void* stream) {
+    return synt_unet_debug_forward(h, x, B, t, nullptr, eps, 0, nullptr, nullptr, nullptr, stream);
+}
+
+int synt_unet_debug_forward(synt_unet_t* h, const float* x, int B, int t, const char* tap, float* out, long long cap,
+                            int* C, int* H, int* W, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(h && x && B > 0, "bad argument");
+    SYNT_CHECK(t >= 0 && t < kTrainSteps, "timestep out of range [0, 1000)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t img = (size_t)3 * kImg * kImg;
+    const bool dbg = tap != nullptr;
+    float* eps = dbg ? nullptr : out;
+    if (dbg) { h->tap_name = tap; h->tap_out = out; h->tap_cap = cap; h->tap_hit = false; }
+    select_timestep((const float*)h->temb_table->p, h->temb_total, nullptr, nullptr, nullptr, t,
+                    (float*)h->temb_cur->p, nullptr, s);
+    ++h->launches;
+    const int mb = default_micro_batch(B);
+    float* dbg_eps = nullptr;
+    if (dbg && std::string(tap) == "conv_out") { dbg_eps = out; }
+    for (int b0 = 0; b0 < B; b0 += mb) {
+        const int nb = B - b0 < mb ? B - b0 : mb;
+        SYNT_CHECK(!dbg || nb == B, "debug taps need B <= 16");
+        Fwd f{h, s, nb};
+        SchedArgs sch;
+        f.run(x + b0 * img, dbg ? dbg_eps : eps + b0 * img, sch);
+    }
+    if (dbg) {
+        h->tap_out = nullptr;
+        if (dbg_eps) { h->tap_C = 3; h->tap_H = kImg; h->tap_W = kImg; h->tap_hit = true; }
+        SYNT_CHECK(h->tap_hit, std::string("unknown debug tap: ") + tap);
+        if (C) *C = h->tap_C; if (H) *H = h->tap_H; if (W) *W = h->tap_W;
+    }
+    SYNT_CATCH
+}
+
+int synt_unet_set_schedule(synt_unet_t* h, int n_steps, const int* timesteps, const float* coef) {
+    SYNT_TRY
+    SYNT_CHECK(h && timesteps && coef && n_steps > 0 && n_steps <= kTrainSteps, "bad schedule");
+    for (int i = 0; i < n_steps; ++i) SYNT_CHECK(timesteps[i] >= 0 && timesteps[i] < kTrainSteps, "timestep out of range");
+    h->timesteps_dev = dev_upload(timesteps, (size_t)n_steps * 4);
+    h->coef_table_dev = dev_upload(coef, (size_t)n_steps * 5 * 4);
+    h->timesteps_host.assign(timesteps, timesteps + n_steps);
+    h->n_steps = n_steps;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    SYNT_CATCH
+}
+
+int synt_unet_sample(synt_unet_t* h, float* x, int B, const float* z, unsigned long long seed, long long image_offset,
+                     float* traj, float* eps_tap, int step_begin, int step_end, int micro_batch, int use_graph,
+                     void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(h && x && B > 0, "bad argument");
+    SYNT_CHECK(h->n_steps > 0, "synt_unet_set_schedule must be called first");
+    SYNT_CHECK(step_begin >= 0 && step_begin <= step_end && step_end <= h->n_steps, "bad step range");
+    cudaStream_t caller = (cudaStream_t)stream;
+    // the legacy default stream cannot be captured: hop onto the handle's own stream
+    const bool hop = use_graph && (caller == nullptr || caller == cudaStreamLegacy || caller == cudaStreamPerThread);
+    cudaStream_t s = hop ? h->own_stream : caller;
+    struct Rejoin {                                         // make the caller's stream wait for us on every exit
+        synt_unet* h; cudaStream_t from, to; bool on;
+        ~Rejoin() { if (on) { cudaEventRecord(h->ev_out, from); cudaStreamWaitEvent(to, h->ev_out, 0); } }
+    } rejoin{h, s, caller, hop};
+    if (hop) {
+        SYNT_CUDA(cudaEventRecord(h->ev_in, caller));
+        SYNT_CUDA(cudaStreamWaitEvent(s, h->ev_in, 0));
+    }
+    const int mb = micro_batch > 0 ? (micro_batch < B ? micro_batch : B) : default_micro_batch(B);
+    SYNT_CUDA(cudaMemcpyAsync(h->step_ctr->p, &step_begin, 4, cudaMemcpyHostToDevice, s));
+    SYNT_CUDA(cudaStreamSynchronize(s));                    // &step_begin is a stack temporary
+    const int n = step_end - step_begin;
+    if (n == 0) return 0;
+    if (!use_graph) {
+        for (int i = 0; i < n; ++i) sample_step(h, x, B, z, seed, image_offset, traj, eps_tap, mb, s);
+        return 0;
+    }
+    synt_unet::GraphKey key{x, B, z, traj, eps_tap, mb, seed, image_offset};
+    int done = 0;
+    if (!h->gexec || !(key == h->gkey)) {
+        if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+        // one eager step first: sizes the pool (no cudaMalloc may happen during capture)
+        sample_step(h, x, B, z, seed, image_offset, traj, eps_tap, mb, s);
+        done = 1;
+        if (n > 1) {
+            cudaGraph_t g = nullptr;
+            SYNT_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            try {
+                sample_step(h, x, B, z, seed, image_offset, traj, eps_tap, mb, s);
+            } catch (...) {
+                cudaStreamEndCapture(s, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            SYNT_CUDA(cudaStreamEndCapture(s, &g));
+            size_t nn = 0;
+            SYNT_CUDA(cudaGraphGetNodes(g, nullptr, &nn));
+            h->graph_nodes = (long long)nn;
+            SYNT_CUDA(cudaGraphInstantiate(&h->gexec, g, 0));
+            SYNT_CUDA(cudaGraphDestroy(g));
+            h->gkey = key;
+            h->launches -= h->graph_nodes;                  // capture did not execute anything
+        }
+    }
+    for (int i = done; i < n; ++i) {
+        SYNT_CUDA(cudaGraphLaunch(h->gexec, s));
+        h->launches += h->graph_nodes;
+    }
+    SYNT_CATCH
+}
+
+int synt_unet_generate_host(synt_unet_t* h, const float* xT_host, int B, unsigned long long seed, long long image_offset,
+                            int micro_batch, unsigned char* images_u8_host, float* x_final_host) {
+    SYNT_TRY
+    SYNT_CHECK(h && xT_host && B > 0, "bad argument");
+    const size_t n = (size_t)B * 3 * kImg * kImg;
+    float* x = (float*)h->pool.alloc(n * 4);
+    unsigned char* u8 = (unsigned char*)h->pool.alloc(n);
+    cudaStream_t s = h->own_stream;
+    SYNT_CUDA(cudaMemcpyAsync(x, xT_host, n * 4, cudaMemcpyHostToDevice, s));
+    int rc = synt_unet_sample(h, x, B, nullptr, seed, image_offset, nullptr, nullptr, 0, h->n_steps, micro_batch, 1, s);
+    if (rc != 0) { h->pool.release(x); h->pool.release(u8); return rc; }
+    if (images_u8_host) {
+        to_uint8_hwc(x, B, kImg, kImg, 0, u8, s);
+        ++h->launches;
+        SYNT_CUDA(cudaMemcpyAsync(images_u8_host, u8, n, cudaMemcpyDeviceToHost, s));
+    }
+    if (x_final_host) SYNT_CUDA(cudaMemcpyAsync(x_final_host, x, n * 4, cudaMemcpyDeviceToHost, s));
+    SYNT_CUDA(cudaStreamSynchronize(s));
+    h->pool.release(x); h->pool.release(u8);
+    SYNT_CATCH
+}
+
+long long synt_unet_workspace_bytes(synt_unet_t* h) { return h ? (long long)h->pool.total_bytes() : 0; }
+long long synt_unet_launch_count(synt_unet_t* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------- scheduler ----------
+int synt_ddpm_tables(int num_train, int schedule, float beta_start, float beta_end, int n_steps, long long* timesteps_out,
+                     float* coef_out, float* acp_out) {
+    SYNT_TRY
+    SYNT_CHECK(num_train > 0 && n_steps > 0 && n_steps <= num_train, "bad step counts");
+    std::vector<float> betas(num_train), acp(num_train);
+    if (schedule == 0) {                                    // betas_for_alpha_bar: float64 maths, one cast
+        auto abar = [](double t) { double c = std::cos((t + 0.008) / 1.008 * M_PI / 2); return c * c; };
+        for (int i = 0; i < num_train; ++i) {
+            const double t1 = (double)i / num_train, t2 = (double)(i + 1) / num_train;
+            double b = 1.0 - abar(t2) / abar(t1);
+            betas[i] = (float)(b < 0.999 ? b : 0.999);
+        }
+    } else if (schedule == 1) {                             // torch.linspace(beta_start, beta_end, n, float32)
+        const float step = (beta_end - beta_start) / (float)(num_train - 1);
+        for (int i = 0; i < num_train; ++i)
+            betas[i] = i < num_train / 2 ? beta_start + step * (float)i : beta_end - step * (float)(num_train - i - 1);
+    } else {
+        throw Error(-3, "unknown beta schedule");
+    }
+    // torch.cumprod on a CPU float32 tensor accumulates in double (at::acc_type<float,false>)
+    double run = 1.0;
+    for (int i = 0; i < num_train; ++i) { const float a = 1.0f - betas[i]; run *= (double)a; acp[i] = (float)run; }
+    if (acp_out) memcpy(acp_out, acp.data(), (size_t)num_train * 4);
+    const int ratio = num_train / n_steps;                  // "leading" spacing, steps_offset 0
+    for (int i = 0; i < n_steps; ++i) {
+        const long long t = (long long)(n_steps - 1 - i) * ratio;
+        const long long prev = i == n_steps - 1 ? -1 : (long long)(n_steps - 2 - i) * ratio;
+        if (timesteps_out) timesteps_out[i] = t;
+        if (coef_out) {
+            const float a_t = acp[t], a_prev = prev >= 0 ? acp[prev] : 1.0f;
+            const float b_t = 1.0f - a_t, b_prev = 1.0f - a_prev;
+            const float cur_a = a_t / a_prev, cur_b = 1.0f - cur_a;
+            float var = (1.0f - a_prev) / (1.0f - a_t) * cur_b;
+            if (var < 1e-20f) var = 1e-20f;
+            float* c = coef_out + (size_t)i * 5;
+            c[0] = sqrtf(b_t); c[1] = sqrtf(a_t);
+            c[2] = (sqrtf(a_prev) * cur_b) / b_t;
+            c[3] = sqrtf(cur_a) * b_prev / b_t;
+            c[4] = t > 0 ? sqrtf(var) : 0.0f;
+        }
+    }
+    SYNT_CATCH
+}
+
+int synt_ddpm_step(const float* eps, const float* x, const float* z, float* out, long long n, const float* c, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(eps && x && out && c && n > 0, "bad argument");
+    ddpm_step(eps, x, (c[4] != 0.f) ? z : nullptr, out, n, c[0], c[1], c[2], c[3], c[4], (cudaStream_t)stream);
+    SYNT_CATCH
+}
+
+int synt_to_uint8(const float* x, int B, int H, int W, int mode, unsigned char* out, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(x && out && B > 0, "bad argument");
+    to_uint8_hwc(x, B, H, W, mode, out, (cudaStream_t)stream);
+    SYNT_CATCH
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- test hook ----------
+// One convolution through either GEMM carrier, on caller-provided NHWC tensors (kernel-level
+// parity tests: tcgen05 vs fp32-FMA vs torch.nn.functional.conv2d).
+extern "C" int synt_debug_conv(int use_tc, int act_dtype, const void* in, int B, int H, int W, int Cin, int K,
+                               int stride, int pad, const void* sc0, int sc0_C, const void* sc1, int sc1_C,
+                               int sc_stride, const void* weight, const float* bias, const float* bias2,
+                               const void* residual, int relu, void* out, int Cout, void* stream) {
+    SYNT_TRY
+    ConvArgs a;
+    a.in = in; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.KH = a.KW = K; a.stride = stride; a.pad = pad;
+    a.Ho = (H + 2 * pad - K) / stride + 1; a.Wo = (W + 2 * pad - K) / stride + 1; a.Cout = Cout;
+    a.sc0 = sc0; a.sc0_C = sc0_C; a.sc1 = sc1; a.sc1_C = sc1_C; a.sc_stride = sc_stride;
+    a.weight = weight; a.bias = bias; a.bias2 = bias2; a.residual = residual; a.relu = relu; a.out = out;
+    if (use_tc) {
+        SYNT_CHECK(act_dtype == DT_BF16, "tcgen05 conv needs bf16 activations");
+        conv_tc(a, (cudaStream_t)stream);
+    } else {
+        conv_simt(a, act_dtype, (cudaStream_t)stream);
+    }
+    SYNT_CATCH
+}

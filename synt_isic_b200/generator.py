@@ -1,0 +1,338 @@
+"""Generator entry points of the reference with their call signatures kept, driving the
+B200 sampling path instead of the eager ``for t in timesteps`` loop.
+
+  ModelManager      core/generator/model_manager.py:23-353   (model / scheduler factory)
+  ImageGenerator    core/generator/image_generator.py:25-902 (per-class generation, B=1 API)
+  DiffusionGenerator diffusion/diffusion_generator.py:19-275 (batched script-side generator)
+
+Kept verbatim: ``generate_single_image(class_name, output_path, postprocess, seed, ...) ->
+(bool, trajectory|None)``, ``generate_images(class_configs, output_dir, postprocess) -> dict``,
+seed algebra (:586-592, :626-637), x_T from ``torch.Generator(device).manual_seed(seed)``
+(:369-381), noise sha256 (:383-389), uint8 conversion (:441-447), ISIC file naming
+(core/utils/path_manager.py:94-96), colour post-process (:502-545), sidecar JSON (:457-474).
+Out of scope: config/cache/logger plumbing, GUI callbacks beyond the
+progress/stop hooks.
+
+New on B200: ``generate_batch(class_name, seeds)`` samples many images of one class in ONE
+fused loop (the reference's B=1 loop repeated); ``generate_images`` uses it when no
+trajectories are requested.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+from pathlib import Path
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .scheduler import DDPMScheduler
+from .unet import SUPPORTED_CONFIG, UNet2DModel
+
+CLASS_NAMES = ["MEL", "NV", "BCC", "AKIEC", "BKL", "DF", "VASC"]
+
+
+def class_seed_offset(class_name: str) -> int:
+    """core/generator/image_generator.py:586-592"""
+    return int(hashlib.md5(class_name.encode("utf-8")).hexdigest()[:8], 16) & 0x7FFFFFFF
+
+
+def image_seed(base_seed: int, class_name: str, index: int) -> int:
+    """core/generator/image_generator.py:626-630"""
+    return (int(base_seed) + class_seed_offset(class_name) + index) & 0x7FFFFFFF
+
+
+def isic_filename(isic_number: int) -> str:
+    """core/utils/path_manager.py:94-96"""
+    return f"ISIC_{isic_number:07d}.png"
+
+
+def noise_hash(x_T: torch.Tensor) -> str:
+    """core/generator/image_generator.py:383-389"""
+    return hashlib.sha256(x_T.detach().to("cpu").numpy().tobytes()).hexdigest()[:16]
+
+
+def to_uint8_image(latents: torch.Tensor) -> np.ndarray:
+    """core/generator/image_generator.py:441-447 on the GPU: [B,3,H,W] fp32 -> [B,H,W,3] uint8."""
+    from . import _lib
+    x = latents.contiguous().float()
+    B, _, H, W = x.shape
+    out = torch.empty(B, H, W, 3, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().synt_to_uint8(x.data_ptr(), B, H, W, 0, out.data_ptr(), _lib.current_stream_ptr()),
+                   "to_uint8")
+    return out.cpu().numpy()
+
+
+def color_postprocess(img: np.ndarray, stats: Optional[dict]) -> np.ndarray:
+    """core/generator/image_generator.py:502-545 (mean/std match, scale clip [0.6,1.4], alpha 0.35)."""
+    if not stats or "rgb" not in stats or "mean" not in stats["rgb"]:
+        return img
+    target_mean = np.array(stats["rgb"].get("mean", [128, 128, 128]), dtype=np.float32)
+    target_std = np.array(stats["rgb"].get("std", [50, 50, 50]), dtype=np.float32)
+    cur_mean = np.mean(img, axis=(0, 1)).astype(np.float32)
+    cur_std = np.std(img, axis=(0, 1)).astype(np.float32)
+    scale = np.clip(target_std / np.maximum(cur_std, 1e-6), 0.6, 1.4)
+    shifted = (img.astype(np.float32) - cur_mean) * scale + target_mean
+    out = 0.35 * shifted + 0.65 * img.astype(np.float32)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+class ModelManager:
+    """core/generator/model_manager.py: builds the UNet per class, loads ``unet_<CLASS>_best.pth``
+    when present (random-init otherwise -- checkpoints are not shipped), creates the scheduler."""
+
+    def __init__(self, checkpoint_dir: Optional[str] = None, device: str = "cuda", precision: str = "bf16"):
+        self.checkpoint_dir = Path(checkpoint_dir) if checkpoint_dir else None
+        self.device = torch.device(device)
+        self.precision = precision
+        self.loaded_models: Dict[str, UNet2DModel] = {}
+        self.model_metadata: Dict[str, dict] = {}
+        self.inference_steps = 50
+
+    def _create_model_architecture(self) -> UNet2DModel:       # model_manager.py:173-194
+        return UNet2DModel(precision=self.precision, **SUPPORTED_CONFIG)
+
+    def load_model(self, class_name: str, state_dict: Optional[dict] = None) -> bool:   # :89-171
+        model = self._create_model_architecture()
+        meta = {"class": class_name, "source": "random_init"}
+        path = self.checkpoint_dir / f"unet_{class_name}_best.pth" if self.checkpoint_dir else None
+        if state_dict is None and path is not None and path.exists():
+            state_dict = torch.load(str(path), map_location="cpu")
+            meta = {"class": class_name, "source": str(path), "bytes": path.stat().st_size}
+        if state_dict is not None:
+            model.load_state_dict(state_dict)                    # strict (model_manager.py:139)
+        self.loaded_models[class_name] = model.to(self.device).eval()
+        self.model_metadata[class_name] = meta
+        return True
+
+    def create_scheduler(self, class_name: Optional[str] = None) -> DDPMScheduler:       # :196-226
+        s = DDPMScheduler(num_train_timesteps=1000, beta_schedule="squaredcos_cap_v2", prediction_type="epsilon")
+        s.set_timesteps(max(1, min(1000, int(self.inference_steps))))
+        return s
+
+    def change_device(self, device: str):                                                # :319-345
+        self.device = torch.device(device)
+        for k, m in self.loaded_models.items():
+            self.loaded_models[k] = m.to(self.device)
+
+
+class ImageGenerator:
+    def __init__(self, model_manager: Optional[ModelManager] = None, device: str = "cuda",
+                 inference_steps: int = 50, base_seed: Optional[int] = 42, save_trajectory: bool = False,
+                 color_statistics: Optional[dict] = None, precision: str = "bf16",
+                 progress_callback: Optional[Callable[[int, int, str], None]] = None, batch_size: int = 64):
+        self.device = torch.device(device)
+        self.model_manager = model_manager or ModelManager(device=device, precision=precision)
+        self.inference_steps = max(1, min(1000, int(inference_steps)))       # image_generator.py:75-79
+        self.model_manager.inference_steps = self.inference_steps
+        self.base_seed = base_seed
+        self.save_trajectory = save_trajectory
+        self.color_statistics = color_statistics or {}
+        self.progress_callback = progress_callback
+        self.stop_requested = False
+        self.is_generating = False
+        self.batch_size = batch_size
+        self.xai_analyzer = None
+        self.xai_frequency = 0
+        self.progress_every = 5                                               # image_generator.py:435
+
+    def stop_generation(self):                                                # :784-786
+        self.stop_requested = True
+
+    def _update_progress(self, cur, total, msg):
+        if self.progress_callback:
+            self.progress_callback(cur, total, msg)
+
+    def _model(self, class_name: str) -> UNet2DModel:
+        if class_name not in self.model_manager.loaded_models:
+            if not self.model_manager.load_model(class_name):
+                raise RuntimeError(f"could not load a model for class {class_name}")
+        m = self.model_manager.loaded_models[class_name]
+        if str(m.device) != str(self.device):
+            m = m.to(self.device)
+            self.model_manager.loaded_models[class_name] = m
+        return m
+
+    def make_noise(self, seeds: List[Optional[int]]) -> torch.Tensor:
+        """x_T per image exactly as :369-381: a device generator seeded per image."""
+        xs = []
+        for s in seeds:
+            if s is not None:
+                g = torch.Generator(device=self.device)
+                g.manual_seed(int(s))
+                xs.append(torch.randn(1, 3, 128, 128, device=self.device, generator=g))
+            else:
+                xs.append(torch.randn(1, 3, 128, 128, device=self.device))
+        return torch.cat(xs)
+
+    def _denoise(self, model, latents, seed_for_noise: int, want_traj: bool, label: str,
+                 progress_offset_units=0, progress_total_units=0):
+        """The loop of :395-403 as chunked replays of the fused CUDA-graph step: the stop flag
+        (:396) and the progress callback (:435) are honoured between chunks."""
+        scheduler = self.model_manager.create_scheduler()
+        n = len(scheduler.timesteps)
+        traj = torch.empty((n,) + tuple(latents.shape), dtype=torch.float32, device=latents.device) if want_traj else None
+        step = 0
+        while step < n:
+            if self.stop_requested:
+                return None, None
+            end = min(n, step + self.progress_every)
+            model.sample(latents, scheduler, seed=seed_for_noise, trajectory=traj, step_begin=step, step_end=end)
+            step = end
+            total = progress_total_units if progress_total_units > 0 else n
+            self._update_progress(progress_offset_units + step, total, f"Denoising {label}: {step}/{n} ({int(100 * step / n)}%)")
+        return latents, traj
+
+    # ---- reference signature (image_generator.py:308-313) --------------------------------
+    def generate_single_image(self, class_name: str, output_path: str, postprocess: bool = True,
+                              seed: Optional[int] = None, progress_offset_units: int = 0,
+                              progress_total_units: int = 0, overall_index: int = 0,
+                              overall_total: int = 0) -> Tuple[bool, Optional[List[torch.Tensor]]]:
+        try:
+            if self.stop_requested:
+                return False, None
+            model = self._model(class_name)
+            with torch.no_grad():
+                noise = self.make_noise([seed])
+                nhash = noise_hash(noise)
+                latents, traj = self._denoise(model, noise.clone(), seed if seed is not None else 0,
+                                              self.save_trajectory, class_name, progress_offset_units,
+                                              progress_total_units)
+                if latents is None:
+                    return False, None
+            img = to_uint8_image(latents)[0]
+            if postprocess:
+                img = color_postprocess(img, self.color_statistics.get(class_name))
+            self._save(img, output_path, class_name, seed, nhash)
+            trajectory = [traj[i].clone() for i in range(traj.shape[0])] if traj is not None else None
+            return True, trajectory
+        except Exception as e:                                    # reference swallows into (False, None)
+            print(f"generation failed for class {class_name}: {e}")
+            return False, None
+
+    def _save(self, img: np.ndarray, output_path, class_name, seed, nhash):
+        from PIL import Image
+        Image.fromarray(img).save(output_path)
+        meta = {
+            "filename": Path(output_path).name, "class": class_name,
+            "seed": int(seed) if seed is not None else None, "inference_steps": int(self.inference_steps),
+            "scheduler": {"num_train_timesteps": 1000, "beta_schedule": "squaredcos_cap_v2", "prediction_type": "epsilon"},
+            "model": self.model_manager.model_metadata.get(class_name, {}),
+            "device": str(self.device), "noise_hash": nhash,
+        }
+        with open(Path(output_path).with_suffix(".json"), "w", encoding="utf-8") as f:
+            json.dump(meta, f, indent=2, ensure_ascii=False)
+
+    # ---- batched sampling (new) ----------------------------------------------------------
+    def generate_batch(self, class_name: str, seeds: List[int], noise_seed: Optional[int] = None,
+                       image_offset: int = 0) -> Tuple[np.ndarray, torch.Tensor, List[str]]:
+        """Samples len(seeds) images of one class in one fused loop.  Returns (uint8 [B,128,128,3],
+        fp32 finals, x_T hashes)."""
+        model = self._model(class_name)
+        with torch.no_grad():
+            x = self.make_noise(list(seeds))
+            hashes = [noise_hash(x[i:i + 1]) for i in range(x.shape[0])]
+            latents, _ = self._denoise(model, x, noise_seed if noise_seed is not None else int(seeds[0]), False,
+                                       class_name)
+            if latents is None:
+                raise RuntimeError("generation stopped")
+        return to_uint8_image(latents), latents, hashes
+
+    # ---- reference signature (image_generator.py:547-548) ---------------------------------
+    def generate_images(self, class_configs: List[Tuple[str, int]], output_dir: str,
+                        postprocess: bool = True) -> Dict[str, Any]:
+        if self.is_generating:
+            return {"error": "generation already running"}
+        self.is_generating, self.stop_requested = True, False
+        out = Path(output_dir)
+        out.mkdir(parents=True, exist_ok=True)
+        results: Dict[str, Any] = {"generated": {}, "total": 0, "rows": []}
+        try:
+            for class_name, count in class_configs:
+                if self.stop_requested:
+                    break
+                cdir = out / class_name
+                cdir.mkdir(exist_ok=True)
+                seeds = [image_seed(self.base_seed, class_name, i) if self.base_seed is not None
+                         else int.from_bytes(os.urandom(4), "little") & 0x7FFFFFFF for i in range(count)]
+                done = 0
+                if self.save_trajectory or self.xai_analyzer is not None:
+                    for i, s in enumerate(seeds):                # B=1 path keeps per-image trajectories
+                        fp = cdir / isic_filename(i + 1)
+                        ok, traj = self.generate_single_image(class_name, str(fp), postprocess, s)
+                        done += int(ok)
+                        if ok and traj is not None and self.xai_analyzer is not None and self.xai_frequency \
+                                and (i + 1) % self.xai_frequency == 0:
+                            self.xai_analyzer.analyze_trajectory(traj, class_name, s, self.inference_steps,
+                                                                 fp.name, str(fp))
+                        results["rows"].append({"filename": fp.name, "class": class_name, "seed": s})
+                else:
+                    for b0 in range(0, count, self.batch_size):
+                        chunk = seeds[b0:b0 + self.batch_size]
+                        imgs, _, hashes = self.generate_batch(class_name, chunk, image_offset=b0)
+                        for j, img in enumerate(imgs):
+                            fp = cdir / isic_filename(b0 + j + 1)
+                            if postprocess:
+                                img = color_postprocess(img, self.color_statistics.get(class_name))
+                            self._save(img, str(fp), class_name, chunk[j], hashes[j])
+                            results["rows"].append({"filename": fp.name, "class": class_name, "seed": chunk[j]})
+                        done += len(chunk)
+                results["generated"][class_name] = done
+                results["total"] += done
+        finally:
+            self.is_generating = False
+        return results
+
+
+class DiffusionGenerator:
+    """diffusion/diffusion_generator.py:19-275.  NB the reference uses LINEAR betas and never calls
+    set_timesteps here (:123-128) -> 1000 steps; kept."""
+
+    def __init__(self, checkpoint_dir: Optional[str] = None, stats_path: Optional[str] = None, device: str = "cuda",
+                 precision: str = "bf16"):
+        self.device = torch.device(device)
+        self.manager = ModelManager(checkpoint_dir, device, precision)
+        self.color_statistics = {}
+        if stats_path and os.path.exists(stats_path):
+            with open(stats_path, "r", encoding="utf-8") as f:
+                self.color_statistics = json.load(f)
+
+    def _scheduler(self):
+        return DDPMScheduler(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear")
+
+    def _run(self, class_name: str, count: int) -> np.ndarray:
+        if class_name not in self.manager.loaded_models:
+            self.manager.load_model(class_name)
+        model = self.manager.loaded_models[class_name]
+        x = torch.randn(count, 3, 128, 128).to(self.device)      # diffusion_generator.py:131 / :211 (CPU global RNG)
+        model.sample(x, self._scheduler(), seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
+        img = ((x.permute(0, 2, 3, 1).cpu().numpy() + 1) * 127.5).clip(0, 255).astype(np.uint8)   # :147-148
+        return img
+
+    def generate_single_image(self, class_name: str, output_path: str, postprocess: bool = True) -> str:
+        from PIL import Image
+        img = self._run(class_name, 1)[0]
+        if postprocess:
+            img = color_postprocess(img, self.color_statistics.get(class_name))
+        root, ext = os.path.splitext(output_path)
+        save_path = output_path if ext.lower() in (".jpg", ".jpeg") else root + ".jpg"
+        Image.fromarray(img).convert("RGB").save(save_path, format="JPEG", quality=95)
+        return save_path
+
+    def generate_batch_images(self, class_name: str, output_dir: str, count: int, postprocess: bool = True,
+                              batch_size: int = 4) -> List[str]:
+        from PIL import Image
+        os.makedirs(output_dir, exist_ok=True)
+        paths = []
+        for b0 in range(0, count, batch_size):
+            imgs = self._run(class_name, min(batch_size, count - b0))
+            for i, img in enumerate(imgs):
+                if postprocess:
+                    img = color_postprocess(img, self.color_statistics.get(class_name))
+                p = os.path.join(output_dir, f"{class_name}_{b0 + i + 1:04d}.jpg")
+                Image.fromarray(img).convert("RGB").save(p, format="JPEG", quality=95)
+                paths.append(p)
+        return paths

@@ -1,0 +1,285 @@
+"""Classifier-evaluation loops of the reference's XAI pipeline, batched for B200.
+
+Every function keeps the reference's name, arguments and result structure; what changes is how
+the ResNet18 evaluations are issued: the reference calls the classifier at batch 1 once (or
+twice, or 18 times) per frame / coalition / intervention with a ``.item()`` sync each
+(SURVEY.md 3.2); here the distinct inputs are built on the GPU, evaluated in ONE batched call
+of the CUDA classifier and (optionally) sharded across ranks with a single all_gather.
+
+  compute_time_shap                     xai/XAI.py:1179-1234   (2 forwards/frame -> 1 batched)
+  compute_shap_approximation            xai/XAI.py:1111-1177   (513 forwards -> 1 batched)
+  counterfactual_intervention_advanced  xai/XAI.py:1454-1597
+  compute_causal_shift_comprehensive    xai/XAI.py:1600-1700   (18 forwards -> 1 batch of 2)
+  IntegratedXAIAnalyzer                 xai/xai_integration.py:75-132
+
+Out of scope: Integrated Gradients, Grad-CAM (autograd), region
+morphology, statistics and plots.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .classifier import CLASS_NAMES, MelanomaClassifierAdaptive
+from .dist import sharded_eval
+
+SHAP_N_SAMPLES = 512       # xai/XAI.py:240
+NOISE_STD = 0.5            # xai/XAI.py:262
+BLUR_KERNEL_SIZE = 5       # xai/XAI.py:263
+TOP_K_PERCENT = 10         # xai/XAI.py:238
+_TYPE_CODES = {"zero": 0, "mean": 1, "blur": 2, "inpaint": 2, "noise": 3, "gaussian_noise": 3, "shuffle": 4}
+
+
+def _dev(classifier):
+    return next(classifier.parameters()).device
+
+
+def _probs(classifier, images: torch.Tensor, group=None) -> torch.Tensor:
+    """softmax(logits) for a batch of [-1,1] images; the batch is split across ranks when a
+    process group is given (one all_gather of the [n,7] logits)."""
+    with torch.no_grad():
+        logits = sharded_eval(classifier, images, group)
+    return F.softmax(logits, dim=1)
+
+
+# ------------------------------------------------------------------ Time-SHAP -----------
+def compute_time_shap(classifier, trajectory, timesteps, target_class, group=None, verbose=False):
+    """xai/XAI.py:1179-1234.  ``trajectory``: list of [1,3,128,128] tensors or one [T,3,128,128]."""
+    dev = _dev(classifier)
+    frames = trajectory if torch.is_tensor(trajectory) else torch.cat([f.to(dev).reshape(-1, 3, 128, 128) for f in trajectory])
+    frames = frames.to(dev).reshape(-1, 3, 128, 128)
+    p = _probs(classifier, frames, group)[:, target_class]
+    prob_scores = p.double().cpu().numpy()                      # get_confidence(...).item()
+    confidence_scores = torch.log(p + 1e-8).double().cpu().numpy()   # get_per_class_score(...).item()
+    if len(confidence_scores) > 1 and (confidence_scores.max() - confidence_scores.min()) > 1e-6:
+        imp = (confidence_scores - confidence_scores.min()) / (confidence_scores.max() - confidence_scores.min())
+    else:
+        imp = np.ones_like(confidence_scores) / len(confidence_scores)
+    raw = {"confidence_scores": confidence_scores, "probability_scores": prob_scores, "timesteps": timesteps}
+    if verbose:
+        k = int(np.argmax(imp))
+        print(f"Time-SHAP: most important step t={timesteps[k]} (importance {imp[k]:.3f})")
+    return imp, raw
+
+
+# ------------------------------------------------------------------ patch-SHAP ----------
+def draw_patch_masks(n_samples: int, n_h: int = 8, n_w: int = 8) -> torch.Tensor:
+    """The coalition masks exactly as the reference draws them: one ``torch.rand(n_h, n_w) > 0.5``
+    per sample from the global CPU RNG (xai/XAI.py:1145)."""
+    return torch.stack([torch.rand(n_h, n_w) > 0.5 for _ in range(n_samples)])
+
+
+def compute_shap_approximation(classifier, image, target_class, n_samples=SHAP_N_SAMPLES, patch_size=16,
+                               patch_masks: torch.Tensor | None = None, group=None):
+    """xai/XAI.py:1111-1177.  ``patch_masks`` [n,H/p,W/p] bool injects the coalitions."""
+    dev = _dev(classifier)
+    image = image.to(dev).float()
+    _, ch, height, width = image.shape
+    n_h, n_w = height // patch_size, width // patch_size
+    if patch_masks is None:
+        patch_masks = draw_patch_masks(n_samples, n_h, n_w)
+    n_samples = patch_masks.shape[0]
+    pm = patch_masks.to(dev).to(torch.uint8).contiguous()
+    batch = torch.empty(n_samples + 1, ch, height, width, dtype=torch.float32, device=dev)
+    batch[0].zero_()                                            # baseline: black image in [-1,1] space
+    x0 = image[0].contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().synt_patch_mask_apply(x0.data_ptr(), pm.data_ptr(), n_samples, ch, height, width,
+                                                    patch_size, batch[1:].data_ptr(), _lib.current_stream_ptr()),
+                   "patch_mask_apply")
+    scores = torch.log(_probs(classifier, batch, group)[:, target_class] + 1e-8)
+    contrib = scores[1:] - scores[0]                            # masked_score - baseline_score
+    patch_attr = (contrib[:, None, None] * pm.float()).sum(0) / n_samples
+    full = patch_attr.repeat_interleave(patch_size, 0).repeat_interleave(patch_size, 1)
+    return full[None, None].expand(1, ch, height, width).contiguous()
+
+
+# ------------------------------------------------------------------ interventions -------
+def counterfactual_intervention_advanced(image, mask, intervention_type="noise", **kwargs):
+    """xai/XAI.py:1454-1597: x~ = clamp(x (1-M) + I M, -1, 1).  Extra kwargs: ``noise`` injects the
+    N(0,1) tensor, ``generator`` seeds it / the shuffle permutation."""
+    noise_std = kwargs.get("noise_std", NOISE_STD)
+    dev = image.device
+    if not image.is_cuda:
+        raise RuntimeError("interventions run on CUDA tensors (no CPU fallback)")
+    image = image.contiguous().float()
+    B, Cc, H, W = image.shape
+    m = torch.from_numpy(mask) if isinstance(mask, np.ndarray) else mask
+    m = m.float().to(dev)
+    while m.dim() < 3:
+        m = m.unsqueeze(0)
+    if m.dim() == 4:
+        m = m[:, 0]
+    m = m.expand(B, H, W).contiguous()
+    if intervention_type not in _TYPE_CODES:
+        intervention_type = "noise"                             # reference default branch (XAI.py:1563-1565)
+    code = _TYPE_CODES[intervention_type]
+    aux = None
+    gen = kwargs.get("generator")
+    if code == 3:
+        aux = kwargs.get("noise")
+        if aux is None:
+            aux = torch.randn(image.shape, device=dev, generator=gen)
+        if intervention_type == "gaussian_noise":
+            noise_std = max(noise_std, image.std().item() * 0.5)
+    elif code == 4:                                             # shuffle masked pixels per (b, c) plane
+        aux = image.clone()
+        sel = m.bool()
+        for b in range(B):
+            idx = sel[b].reshape(-1).nonzero().squeeze(1)
+            if idx.numel() > 1:
+                for c in range(Cc):
+                    perm = idx[torch.randperm(idx.numel(), device=dev, generator=gen)]
+                    aux[b, c].view(-1)[idx] = image[b, c].reshape(-1)[perm]
+    out = torch.empty_like(image)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().synt_intervene_blend(image.data_ptr(), m.data_ptr(),
+                                                   aux.contiguous().data_ptr() if aux is not None else None, code,
+                                                   float(noise_std), B, Cc, H, W, out.data_ptr(),
+                                                   _lib.current_stream_ptr()), "intervene_blend")
+    mask_tensor = m[:, None].expand(B, Cc, H, W)
+    diff = (image - out).abs()
+    return {
+        "modified_image": out,
+        "mask_tensor": mask_tensor,
+        "difference": diff,
+        "statistics": {
+            "intervention_type": intervention_type,
+            "mask_coverage": float(mask_tensor.float().mean()),
+            "mean_difference": float(diff.mean()),
+            "max_difference": float(diff.max()),
+        },
+        "parameters": {k: v for k, v in kwargs.items() if k not in ("noise", "generator")},
+    }
+
+
+# ------------------------------------------------------------------ CFI -----------------
+def compute_causal_shift_comprehensive(classifier, original_image, modified_image, target_class,
+                                       include_all_classes=True, group=None):
+    """xai/XAI.py:1600-1700 from ONE batched evaluation of the two images."""
+    dev = _dev(classifier)
+    pair = torch.cat([original_image.to(dev).reshape(-1, 3, 128, 128)[:1],
+                      modified_image.to(dev).reshape(-1, 3, 128, 128)[:1]])
+    probs = _probs(classifier, pair, group)
+    po, pm = probs[0:1], probs[1:2]
+    so, sm = torch.log(po[:, target_class] + 1e-8), torch.log(pm[:, target_class] + 1e-8)
+    cfi = so - sm
+    delta = cfi.abs() / (so.abs() + 1e-8)
+    op, mp = int(po.argmax(1)[0]), int(pm.argmax(1)[0])
+    names = CLASS_NAMES
+    res = {
+        "target_class_analysis": {
+            "class_id": target_class, "class_name": names[target_class],
+            "cfi": float(cfi), "delta": float(delta),
+            "original_score": float(so), "modified_score": float(sm),
+            "original_probability": float(po[0, target_class]),
+            "modified_probability": float(pm[0, target_class]),
+            "probability_shift": float(po[0, target_class] - pm[0, target_class]),
+        },
+        "prediction_analysis": {
+            "original_prediction": op, "original_prediction_name": names[op],
+            "modified_prediction": mp, "modified_prediction_name": names[mp],
+            "prediction_changed": bool(op != mp),
+            "original_confidence": float(po.max()), "modified_confidence": float(pm.max()),
+            "confidence_drop": float(po.max() - pm.max()),
+        },
+    }
+    if include_all_classes:
+        allc = []
+        for cid in range(len(names)):
+            a, b = torch.log(po[:, cid] + 1e-8), torch.log(pm[:, cid] + 1e-8)
+            allc.append({
+                "class_id": cid, "class_name": names[cid], "cfi": float(a - b),
+                "delta": float((a - b).abs() / (a.abs() + 1e-8)),
+                "original_probability": float(po[0, cid]), "modified_probability": float(pm[0, cid]),
+                "probability_shift": float(po[0, cid] - pm[0, cid]),
+            })
+        res["all_classes_analysis"] = allc
+    mid = torch.log((po + pm) / 2 + 1e-8)
+    res["distribution_analysis"] = {
+        "kl_divergence": float(F.kl_div(torch.log(pm + 1e-8), po, reduction="sum")),
+        "js_divergence": float(0.5 * (F.kl_div(mid, po, reduction="sum") + F.kl_div(mid, pm, reduction="sum"))),
+        "total_variation": float(0.5 * torch.sum(torch.abs(po - pm))),
+    }
+    return res
+
+
+def csi_batch(classifier, images: torch.Tensor, masks: torch.Tensor, intervention_types, target_classes,
+              noise: torch.Tensor | None = None, group=None):
+    """BASELINE config 5: interventions x ResNet18 inference for a whole batch.  Returns
+    cfi[type][b] = s_c(x_b) - s_c(x~_b) with s_c = log(p_c + 1e-8)."""
+    dev = _dev(classifier)
+    images = images.to(dev).float().contiguous()
+    tc = torch.as_tensor(target_classes, device=dev).long()
+    variants = [images]
+    for it in intervention_types:
+        kw = {"noise": noise} if it in ("noise", "gaussian_noise") and noise is not None else {}
+        variants.append(counterfactual_intervention_advanced(images, masks, it, **kw)["modified_image"])
+    probs = _probs(classifier, torch.cat(variants), group).view(len(variants), images.shape[0], -1)
+    s = torch.log(probs.gather(2, tc.view(1, -1, 1).expand(len(variants), -1, 1)).squeeze(2) + 1e-8)
+    return {it: (s[0] - s[i + 1]) for i, it in enumerate(intervention_types)}
+
+
+# ------------------------------------------------------------------ analyzer ------------
+def select_regions_topk(attribution: torch.Tensor, percent: float = TOP_K_PERCENT):
+    """Top / bottom ``percent`` % masks of an attribution map (threshold part of
+    select_regions_advanced, xai/XAI.py:1340-1451; the scipy morphology clean-up is out of scope)."""
+    a = attribution.float().mean(dim=1)[0] if attribution.dim() == 4 else attribution.float()
+    flat = a.reshape(-1)
+    k = max(1, int(flat.numel() * percent / 100.0))
+    top = torch.zeros_like(flat, dtype=torch.bool)
+    bot = torch.zeros_like(flat, dtype=torch.bool)
+    top[flat.topk(k).indices] = True
+    bot[(-flat).topk(k).indices] = True
+    return top.view_as(a), bot.view_as(a)
+
+
+class IntegratedXAIAnalyzer:
+    """xai/xai_integration.py:75-132, hot-path stages only: Time-SHAP over every frame, patch-SHAP
+    + top/bottom-k interventions + CFI on the key frames [0, T/2, T-4..T-1] (XAI.py:2822-2896)."""
+
+    def __init__(self, device: str = "cuda", verbose: bool = False, precision: str = "bf16", group=None):
+        self.device = torch.device(device)
+        self.verbose = verbose
+        self.group = group
+        # reference: MelanomaClassifierAdaptive(num_classes=7, architecture='auto', pretrained=True)
+        self.classifier = MelanomaClassifierAdaptive(num_classes=7, architecture="auto", pretrained=True,
+                                                     precision=precision).to(self.device).eval()
+
+    def analyze_trajectory(self, trajectory, class_name, seed, inference_steps, filename, file_path, timesteps=None,
+                           shap_samples: int = SHAP_N_SAMPLES, intervention_types=("blur",)):
+        if not trajectory:
+            return None
+        T = len(trajectory)
+        if timesteps is None:
+            timesteps = list(range(T))                           # xai_integration.py:94-95
+        target = CLASS_NAMES.index(class_name) if class_name in CLASS_NAMES else 0
+        imp, raw = compute_time_shap(self.classifier, trajectory, timesteps, target, self.group, self.verbose)
+        key_frames = sorted(set([0, T // 2] + list(range(max(0, T - 4), T))))
+        cfi = {}
+        for k in key_frames:
+            frame = trajectory[k].to(self.device).reshape(1, 3, 128, 128)
+            attr = compute_shap_approximation(self.classifier, frame, target, n_samples=shap_samples, group=self.group)
+            top, bot = select_regions_topk(attr)
+            for rname, mask in (("top_k", top), ("bottom_k", bot)):
+                for it in intervention_types:
+                    mod = counterfactual_intervention_advanced(frame, mask, it)["modified_image"]
+                    r = compute_causal_shift_comprehensive(self.classifier, frame, mod, target, group=self.group)
+                    cfi[f"t_{k}/{rname}/{it}"] = r["target_class_analysis"]
+        return {
+            "filename": filename, "file_path": str(file_path), "class_name": class_name, "seed": seed,
+            "inference_steps": inference_steps, "n_frames": T,
+            "time_shap": {"importance": [float(v) for v in imp],
+                          "confidence_scores": [float(v) for v in raw["confidence_scores"]],
+                          "probability_scores": [float(v) for v in raw["probability_scores"]],
+                          "timesteps": [int(t) for t in timesteps]},
+            "cfi": cfi,
+            "skipped_stages": ["integrated_gradients", "grad_cam", "statistics", "plots"],
+        }
+
+
+def create_integrated_xai_analyzer(device: str = "cuda"):
+    """xai/xai_integration.py:134"""
+    return IntegratedXAIAnalyzer(device=device)

@@ -1,0 +1,98 @@
+"""Kernel-level parity of the two GEMM carriers (tcgen05 implicit GEMM, fp32-FMA implicit GEMM)
+against torch.nn.functional.conv2d on the same (bf16-rounded) operands, through the C ABI."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from synt_isic_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _pack(w, wsc=None):
+    """[Cout,Cin,k,k] (+ [Cout,Csc]) -> K-major [Cout, k*k*Cin + Csc] (tap-major, channel-minor)."""
+    cout = w.shape[0]
+    p = w.permute(0, 2, 3, 1).reshape(cout, -1)
+    if wsc is not None:
+        p = torch.cat([p, wsc.reshape(cout, -1)], dim=1)
+    return p.contiguous()
+
+
+def run_conv(dev, use_tc, B, H, W, Cin, Cout, K, stride, pad, sc=(0, 0), sc_stride=1, residual=False, relu=False,
+             bias2=False, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    dt = torch.bfloat16 if use_tc else torch.float32
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    Ho, Wo = (H + 2 * pad - K) // stride + 1, (W + 2 * pad - K) // stride + 1
+    xs = [torch.randn(B, c, Ho * sc_stride, Wo * sc_stride, generator=g) if c else None for c in sc]
+    ws = [torch.randn(Cout, c, generator=g) / c ** 0.5 if c else None for c in sc]
+    res = torch.randn(B, Cout, Ho, Wo, generator=g) if residual else None
+    b2 = torch.randn(Cout, generator=g) if bias2 else None
+    q = (lambda t: t.to(dt).float()) if use_tc else (lambda t: t)
+    # reference on the same rounded operands, fp32 math on the GPU (TF32 off)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = F.conv2d(q(x).to(dev), q(w).to(dev), b.to(dev), stride=stride, padding=pad)
+    for xi, wi in zip(xs, ws):
+        if xi is not None:
+            ref = ref + F.conv2d(q(xi).to(dev)[:, :, ::sc_stride, ::sc_stride], q(wi).to(dev)[:, :, None, None])
+    if b2 is not None:
+        ref = ref + b2.to(dev)[None, :, None, None]
+    if res is not None:
+        ref = ref + q(res).to(dev)
+    if relu:
+        ref = ref.relu()
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(dt).to(dev) if t is not None else None
+    xin, xs0, xs1, rs = nhwc(x), nhwc(xs[0]), nhwc(xs[1]), nhwc(res)
+    wsc = torch.cat([v for v in ws if v is not None], dim=1) if any(v is not None for v in ws) else None
+    wp = _pack(w, wsc).to(dt).to(dev)
+    bd = b.to(dev)
+    b2d = b2.to(dev) if b2 is not None else None
+    out = torch.empty(B, Ho, Wo, Cout, dtype=dt, device=dev)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    _lib.check(_lib.lib().synt_debug_conv(1 if use_tc else 0, 1 if use_tc else 0, ptr(xin), B, H, W, Cin, K, stride, pad,
+                                          ptr(xs0), sc[0], ptr(xs1), sc[1], sc_stride, ptr(wp), ptr(bd), ptr(b2d),
+                                          ptr(rs), 1 if relu else 0, ptr(out), Cout, _lib.current_stream_ptr()),
+               "debug_conv")
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2)
+    return ((got - ref).norm() / ref.norm()).item(), (got - ref).abs().max().item()
+
+
+CASES = [
+    # B, H, W, Cin, Cout, K, stride, pad, sc, sc_stride, residual, relu, bias2
+    (2, 32, 32, 64, 64, 3, 1, 1, (0, 0), 1, False, False, False),
+    (1, 128, 128, 64, 64, 3, 1, 1, (0, 0), 1, True, False, True),
+    (2, 16, 16, 256, 256, 3, 1, 1, (0, 0), 1, True, False, True),
+    (2, 32, 32, 128, 256, 3, 1, 1, (128, 0), 1, False, False, False),      # fused 1x1 shortcut
+    (1, 32, 32, 256, 256, 3, 1, 1, (256, 128), 1, False, False, True),     # concat shortcut (384 -> 256)
+    (2, 64, 64, 128, 128, 3, 2, 1, (0, 0), 1, False, False, False),        # Downsample2D
+    (2, 32, 32, 256, 768, 1, 1, 0, (0, 0), 1, False, False, False),        # qkv projection
+    (2, 32, 32, 256, 256, 1, 1, 0, (0, 0), 1, True, False, False),         # out projection + residual
+    (3, 56, 56, 64, 64, 3, 1, 1, (0, 0), 1, True, True, False),            # ResNet18 layer1 (ragged 56)
+    (3, 56, 56, 64, 128, 3, 2, 1, (0, 0), 1, False, True, False),          # ResNet18 layer2.0.conv1
+    (3, 28, 28, 128, 128, 3, 1, 1, (64, 0), 2, False, True, False),        # layer2.0.conv2 + 1x1 s2 downsample
+    (3, 14, 14, 256, 256, 3, 1, 1, (0, 0), 1, True, True, False),          # 14x14
+    (3, 7, 7, 512, 512, 3, 1, 1, (0, 0), 1, True, True, False),            # 7x7, two images per tile, odd B
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c[:8])))
+def test_conv_simt_fp32(cuda_dev, case):
+    B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2 = case
+    rel, mx = run_conv(cuda_dev, False, B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2)
+    assert rel < 2e-6, (rel, mx)        # fp32 tolerance: accumulation-order differences only
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c[:8])))
+def test_conv_tcgen05_bf16(cuda_dev, case):
+    B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2 = case
+    rel, mx = run_conv(cuda_dev, True, B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2)
+    assert rel < 4e-3, (rel, mx)        # operands identical; only the bf16 rounding of the OUTPUT differs
+
+
+def test_conv_simt_stem_7x7(cuda_dev):
+    rel, mx = run_conv(cuda_dev, False, 2, 224, 224, 3, 64, 7, 2, 3, relu=True)
+    assert rel < 2e-6, (rel, mx)
