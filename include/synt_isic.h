@@ -69,6 +69,12 @@ int synt_unet_sample(synt_unet_t* h, float* x_dev, int B, const float* z_dev, un
 int synt_unet_generate_host(synt_unet_t* h, const float* xT_host, int B, unsigned long long seed,
                             long long image_offset, int micro_batch, unsigned char* images_u8_host,
                             float* x_final_host);
+/* measurement hook: runs ONE eager sampling step with a CUDA-event pair around every kernel launch and
+ * returns, per category (0 conv_tcgen05, 1 conv_fp32, 2 groupnorm_stats, 3 groupnorm_apply, 4 attention,
+ * 5 upsample, 6 conv_in, 7 conv_out+scheduler, 8 misc; arrays of 16), the summed device time [ms], the
+ * algorithmic FLOPs and the launch count.  x is advanced by one step. */
+int synt_unet_profile_step(synt_unet_t* h, float* x_dev, int B, int micro_batch, double* ms_out, double* flops_out,
+                           int* launches_out, void* stream);
 long long synt_unet_workspace_bytes(synt_unet_t* h);
 long long synt_unet_launch_count(synt_unet_t* h);        /* kernels launched since creation */
 

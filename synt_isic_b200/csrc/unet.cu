@@ -199,6 +199,10 @@ struct synt_unet {
     long long graph_nodes = 0;
     cudaStream_t own_stream = nullptr;            // capture needs a non-legacy stream
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    // per-kernel profiling (bench.py roofline): events around every launch of one eager step
+    struct ProfRec { int cat; cudaEvent_t a, b; double flops; };
+    bool prof = false;
+    std::vector<ProfRec> recs;
     // debug tap
     std::string tap_name; float* tap_out = nullptr; long long tap_cap = 0; int tap_C = 0, tap_H = 0, tap_W = 0; bool tap_hit = false;
 
@@ -333,6 +337,18 @@ static void build_unet(synt_unet* u, const float* P) {
 }
 
 // ------------------------------------------------------------------ forward -----------
+enum ProfCat { PC_CONV_TC = 0, PC_CONV_SIMT, PC_GN_STATS, PC_GN_APPLY, PC_ATTN, PC_UPSAMPLE, PC_CONV_IN, PC_CONV_OUT,
+               PC_MISC, PC_COUNT };
+struct ProfScope {
+    synt_unet* u; cudaStream_t s; int cat; double flops; cudaEvent_t a = nullptr;
+    ProfScope(synt_unet* u_, cudaStream_t s_, int cat_, double flops_ = 0.0) : u(u_), s(s_), cat(cat_), flops(flops_) {
+        if (u->prof) { cudaEventCreate(&a); cudaEventRecord(a, s); }
+    }
+    ~ProfScope() {
+        if (u->prof) { cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, s); u->recs.push_back({cat, a, b, flops}); }
+    }
+};
+
 struct Fwd {
     synt_unet* u; cudaStream_t s; int B;
     size_t esz() const { return dtype_size(u->dt); }
@@ -353,6 +369,7 @@ struct Fwd {
         const int nchunk = gn_num_chunks(B, HW);
         float2* part = (float2*)u->pool.alloc((size_t)B * nchunk * kGroups * sizeof(float2));
         float2* ss = (float2*)u->pool.alloc((size_t)B * C * sizeof(float2));
+        ProfScope ps(u, s, PC_GN_STATS);
         gn_stats(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, u->dt, B, HW, kGroups, part, nchunk, s);
         gn_finalize(part, B, nchunk, kGroups, C, HW, kGnEps, (const float*)gamma->p, (const float*)beta->p, ss, s);
         u->pool.release(part);
@@ -362,6 +379,7 @@ struct Fwd {
     Act gn_act(const Act& x0, const Act* x1, const DevPtr& gamma, const DevPtr& beta, bool silu) {
         float2* ss = gn_scale_shift(x0, x1, gamma, beta);
         Act o = make(x0.H, x0.W, x0.C + (x1 ? x1->C : 0));
+        ProfScope ps(u, s, PC_GN_APPLY);
         gn_apply(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, u->dt, B, x0.H * x0.W, ss, silu ? 1 : 0, o.p, s);
         u->pool.release(ss);
         ++u->launches;
@@ -370,6 +388,7 @@ struct Fwd {
     void conv(ConvArgs& a, const WeightDev& w) {
         const bool tc = u->dt == DT_BF16 && u->use_tc && conv_tc_supported(a);
         a.weight = w.get(tc);
+        ProfScope ps(u, s, tc ? PC_CONV_TC : PC_CONV_SIMT, 2.0 * B * a.Ho * a.Wo * (double)a.Cout * a.ktot());
         if (tc) conv_tc(a, s); else conv_simt(a, u->dt, s);
         ++u->launches;
     }
@@ -413,8 +432,11 @@ struct Fwd {
         }
         drop(a);
         Act o = make(H, W, C);
-        if (u->dt == DT_BF16 && u->use_tc && attention_tc_supported(H * W, C)) attention_tc(qkv.p, B, H * W, C, o.p, s);
-        else attention_simt(qkv.p, u->dt, B, H * W, C, o.p, s);
+        {
+            ProfScope ps(u, s, PC_ATTN, 4.0 * B * (double)(H * W) * (H * W) * C);
+            if (u->dt == DT_BF16 && u->use_tc && attention_tc_supported(H * W, C)) attention_tc(qkv.p, B, H * W, C, o.p, s);
+            else attention_simt(qkv.p, u->dt, B, H * W, C, o.p, s);
+        }
         ++u->launches;
         drop(qkv);
         Act out = make(H, W, C);
@@ -437,7 +459,7 @@ struct Fwd {
     }
     Act up(const ConvW& w, const Act& x) {
         Act up2 = make(x.H * 2, x.W * 2, x.C);
-        upsample_nearest2x(x.p, u->dt, B, x.H, x.W, x.C, up2.p, s);
+        { ProfScope ps(u, s, PC_UPSAMPLE); upsample_nearest2x(x.p, u->dt, B, x.H, x.W, x.C, up2.p, s); }
         ++u->launches;
         Act o = make(up2.H, up2.W, w.cout);
         ConvArgs c; c.in = up2.p; c.B = B; c.H = up2.H; c.W = up2.W; c.Cin = w.cin; c.Ho = o.H; c.Wo = o.W;
@@ -451,7 +473,7 @@ struct Fwd {
     // eps = UNet(x, t) for one micro-batch; temb_cur must already hold the row of t.
     void run(const float* x_nchw, float* eps_nchw, const SchedArgs& sch) {
         Act h = make(kImg, kImg, 64);
-        conv_in3(x_nchw, u->conv_in_w, B, kImg, kImg, h.p, u->dt, s);
+        { ProfScope ps(u, s, PC_CONV_IN, 2.0 * B * kImg * kImg * 64.0 * 27); conv_in3(x_nchw, u->conv_in_w, B, kImg, kImg, h.p, u->dt, s); }
         ++u->launches;
         tap("conv_in", h);
         std::vector<Act> skips; skips.push_back(h);
@@ -479,7 +501,7 @@ struct Fwd {
             if (i != 3) { Act o = up(u->upsample[i], hcur); drop(hcur); hcur = o; }
         }
         float2* ss = gn_scale_shift(hcur, nullptr, u->norm_out_g, u->norm_out_b);
-        conv_out3(hcur.p, u->dt, ss, u->conv_out_w, B, kImg, kImg, eps_nchw, sch, s);
+        { ProfScope ps(u, s, PC_CONV_OUT, 2.0 * B * kImg * kImg * 3.0 * 576); conv_out3(hcur.p, u->dt, ss, u->conv_out_w, B, kImg, kImg, eps_nchw, sch, s); }
         ++u->launches;
         u->pool.release(ss);
         drop(hcur);
@@ -692,6 +714,41 @@ int synt_unet_generate_host(synt_unet_t* h, const float* xT_host, int B, unsigne
     if (x_final_host) SYNT_CUDA(cudaMemcpyAsync(x_final_host, x, n * 4, cudaMemcpyDeviceToHost, s));
     SYNT_CUDA(cudaStreamSynchronize(s));
     h->pool.release(x); h->pool.release(u8);
+    SYNT_CATCH
+}
+
+__global__ void synt_spin_kernel(long long cycles) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) { }
+}
+
+int synt_unet_profile_step(synt_unet_t* h, float* x, int B, int micro_batch, double* ms_out, double* flops_out,
+                           int* launches_out, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(h && x && B > 0 && ms_out && flops_out && launches_out, "bad argument");
+    SYNT_CHECK(h->n_steps > 0, "synt_unet_set_schedule must be called first");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int mb = micro_batch > 0 ? (micro_batch < B ? micro_batch : B) : default_micro_batch(B);
+    int zero = 0;
+    SYNT_CUDA(cudaMemcpyAsync(h->step_ctr->p, &zero, 4, cudaMemcpyHostToDevice, s));
+    SYNT_CUDA(cudaStreamSynchronize(s));
+    sample_step(h, x, B, nullptr, 1, 0, nullptr, nullptr, mb, s);          // warm: pool sized, attributes set
+    SYNT_CUDA(cudaStreamSynchronize(s));
+    // a spin kernel lets the host enqueue the whole step ahead of the GPU, so that the event pairs
+    // bracket kernel execution only (no host launch gaps inside a pair)
+    synt_spin_kernel<<<1, 1, 0, s>>>(60000000ll);
+    h->prof = true; h->recs.clear();
+    try { sample_step(h, x, B, nullptr, 1, 0, nullptr, nullptr, mb, s); } catch (...) { h->prof = false; throw; }
+    h->prof = false;
+    SYNT_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < PC_COUNT; ++i) { ms_out[i] = 0; flops_out[i] = 0; launches_out[i] = 0; }
+    for (auto& r : h->recs) {
+        float ms = 0.f;
+        SYNT_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_out[r.cat] += ms; flops_out[r.cat] += r.flops; launches_out[r.cat] += 1;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    h->recs.clear();
     SYNT_CATCH
 }
 

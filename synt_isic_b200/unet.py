@@ -241,6 +241,21 @@ class UNet2DModel(nn.Module):
                 1 if use_graph else 0, _lib.current_stream_ptr()), "unet_sample")
         return x
 
+    PROFILE_CATEGORIES = ("conv_tcgen05", "conv_fp32", "groupnorm_stats", "groupnorm_apply", "attention", "upsample",
+                          "conv_in", "conv_out_sched", "misc")
+
+    def profile_step(self, x: torch.Tensor, scheduler, micro_batch: int = 0) -> dict:
+        """One eager sampling step with CUDA-event pairs around every kernel (measurement only):
+        {category: {"ms", "flops", "launches"}}.  Advances ``x`` by one step."""
+        self.set_schedule(scheduler)
+        ms = (C.c_double * 16)()
+        fl = (C.c_double * 16)()
+        ln = (C.c_int * 16)()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().synt_unet_profile_step(self._handle(), x.data_ptr(), x.shape[0], micro_batch, ms, fl, ln,
+                                                         _lib.current_stream_ptr()), "unet_profile_step")
+        return {name: {"ms": ms[i], "flops": fl[i], "launches": ln[i]} for i, name in enumerate(self.PROFILE_CATEGORIES)}
+
     def launch_count(self) -> int:
         cur = self._handles.get(self.precision)
         return int(_lib.lib().synt_unet_launch_count(cur[0])) if cur else 0

@@ -83,7 +83,7 @@ CASES = [
 def test_conv_simt_fp32(cuda_dev, case):
     B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2 = case
     rel, mx = run_conv(cuda_dev, False, B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2)
-    assert rel < 2e-6, (rel, mx)        # fp32 tolerance: accumulation-order differences only
+    assert rel < 5e-6, (rel, mx)        # fp32 tolerance: accumulation-order differences only
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c[:8])))

@@ -1,0 +1,209 @@
+"""GPU parity of the UNet2D forward, the scheduler step and the fused sampling loop against the
+oracle (same random-init weights, same injected noise), through the drop-in objects / C ABI.
+
+Tolerances (north_star): per-step eps rel-L2 <= 1e-2 in bf16, <= 1e-5 in the fp32 verification
+mode; final images PSNR >= 40 dB; timestep indexing bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.ddpm import DDPMSchedulerOracle
+from oracle.unet2d import build_unet
+from synt_isic_b200 import DDPMScheduler, SUPPORTED_CONFIG, UNet2DModel
+from synt_isic_b200.generator import to_uint8_image
+
+pytestmark = pytest.mark.gpu
+
+EPS_TOL = {"fp32": 1e-5, "bf16": 1e-2}
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def psnr(a, b, peak=2.0):
+    mse = ((a.double() - b.double()) ** 2).mean().item()
+    return 10 * math.log10(peak * peak / max(mse, 1e-30))
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return build_unet(0)
+
+
+@pytest.fixture(scope="module")
+def models(oracle, cuda_dev):
+    out = {}
+    for prec in ("fp32", "bf16"):
+        m = UNet2DModel(precision=prec, **SUPPORTED_CONFIG)
+        m.load_state_dict(oracle.state_dict(), strict=True)
+        out[prec] = m.to(cuda_dev)
+    return out
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("t", [980, 0])
+def test_unet_forward_eps(oracle, models, cuda_dev, prec, t):
+    g = torch.Generator().manual_seed(t + 1)
+    x = torch.randn(2, 3, 128, 128, generator=g)
+    with torch.no_grad():
+        ref = oracle(x, torch.tensor(t)).sample
+    got = models[prec](x.to(cuda_dev), torch.tensor(t, device=cuda_dev)).sample     # 0-d tensor timestep
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert rel(got.cpu(), ref) <= EPS_TOL[prec]
+
+
+def test_timestep_argument_forms_agree(models, cuda_dev):
+    x = torch.randn(1, 3, 128, 128, device=cuda_dev)
+    m = models["fp32"]
+    a = m(x, 500).sample
+    assert torch.equal(a, m(x, torch.tensor([500], device=cuda_dev)).sample)        # XAI.py:611
+    assert torch.equal(a, m(x, timestep=torch.tensor(500)).sample)                  # diffusion_generator.py:141
+    assert not torch.equal(a, m(x, 499).sample)
+
+
+def test_batch_consistency_and_ragged_batch(models, cuda_dev):
+    """B=19 spans two micro-batches (16 + 3); every image must equal its B=1 result."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(19, 3, 128, 128, generator=g).to(cuda_dev)
+    m = models["bf16"]
+    full = m(x, 321).sample
+    for i in (0, 15, 16, 18):
+        one = m(x[i:i + 1].contiguous(), 321).sample
+        assert rel(full[i:i + 1].cpu(), one.cpu()) < 2e-3          # GroupNorm chunking differs with B -> fp32 sum order
+
+
+@pytest.mark.parametrize("prec", ["fp32"])
+def test_intermediate_modules(oracle, models, cuda_dev, prec):
+    taps = ["conv_in", "down_blocks.1.resnets.0", "down_blocks.2.attentions.1", "down_blocks.2.downsamplers.0",
+            "mid_block.attentions.0", "up_blocks.1.resnets.2", "up_blocks.2.upsamplers.0", "up_blocks.3.resnets.2"]
+    cap = {}
+    mods = dict(oracle.named_modules())
+    hooks = [mods[t].register_forward_hook(lambda m, i, o, t=t: cap.__setitem__(t, o.detach())) for t in taps]
+    x = torch.randn(1, 3, 128, 128, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        oracle(x, 700)
+    for h in hooks:
+        h.remove()
+    for t in taps:
+        got = models[prec].debug_tap(x.to(cuda_dev), 700, t).cpu()
+        assert got.shape == cap[t].shape
+        assert rel(got, cap[t]) < 1e-5, t
+
+
+def test_scheduler_step_matches_oracle(cuda_dev):
+    s, o = DDPMScheduler(beta_schedule="squaredcos_cap_v2"), DDPMSchedulerOracle()
+    s.set_timesteps(50)
+    o.set_timesteps(50)
+    g = torch.Generator().manual_seed(0)
+    x, eps, z = (torch.randn(2, 3, 128, 128, generator=g) for _ in range(3))
+    for t in (980, 500, 20, 0):
+        ref = o.step(eps, t, x, noise=z).prev_sample
+        got = s.step(eps.to(cuda_dev), torch.tensor(t), x.to(cuda_dev), noise=z.to(cuda_dev)).prev_sample.cpu()
+        assert (got - ref).abs().max().item() <= 4e-6 * max(1.0, ref.abs().max().item()), t    # FMA contraction only
+    # no generator -> global device RNG, like the reference (image_generator.py:403)
+    torch.manual_seed(7)
+    a = s.step(eps.to(cuda_dev), 980, x.to(cuda_dev)).prev_sample
+    torch.manual_seed(7)
+    b = s.step(eps.to(cuda_dev), 980, x.to(cuda_dev)).prev_sample
+    assert torch.equal(a, b)
+
+
+def _oracle_loop(oracle, n_steps, x_T, z):
+    o = DDPMSchedulerOracle()
+    o.set_timesteps(n_steps)
+    x, traj, eps_all = x_T.clone(), [], []
+    with torch.no_grad():
+        for i, t in enumerate(o.timesteps):
+            eps = oracle(x, t).sample
+            x = o.step(eps, t, x, noise=z[i]).prev_sample
+            traj.append(x.clone())
+            eps_all.append(eps)
+    return x, torch.stack(traj), torch.stack(eps_all)
+
+
+@pytest.mark.parametrize("prec,n_steps", [("fp32", 6), ("bf16", 50)])
+def test_sampling_loop_config1(oracle, models, cuda_dev, prec, n_steps):
+    """BASELINE configs[0]: 1 MEL image, 50 steps, injected x_T and per-step z; fused loop (CUDA
+    graph, scheduler in the conv_out epilogue) vs the oracle's eager loop."""
+    g = torch.Generator().manual_seed(42)
+    x_T = torch.randn(1, 3, 128, 128, generator=g)
+    z = torch.randn(n_steps, 1, 3, 128, 128, generator=g)
+    ref, ref_traj, ref_eps = _oracle_loop(oracle, n_steps, x_T, z)
+    s = DDPMScheduler(num_train_timesteps=1000, beta_schedule="squaredcos_cap_v2", prediction_type="epsilon")
+    s.set_timesteps(n_steps)
+    m = models[prec]
+    x = x_T.to(cuda_dev).clone()
+    traj = torch.empty(n_steps, 1, 3, 128, 128, device=cuda_dev)
+    eps = torch.empty_like(traj)
+    m.sample(x, s, noise=z.to(cuda_dev).contiguous(), trajectory=traj, eps_tap=eps)
+    torch.cuda.synchronize()
+    assert torch.equal(traj[-1], x)
+    p = psnr(x.cpu(), ref)
+    assert p >= 40.0, p
+    if prec == "fp32":
+        assert rel(x.cpu(), ref) < 1e-4 and rel(eps[0].cpu(), ref_eps[0]) <= 1e-5
+    else:
+        assert rel(eps[0].cpu(), ref_eps[0]) <= 1e-2           # first step: identical input
+    u8 = to_uint8_image(x)
+    want = ((ref.squeeze(0).permute(1, 2, 0) + 1) / 2).clamp(0, 1).numpy() * 255
+    assert np.abs(u8[0].astype(np.int32) - want.astype(np.uint8).astype(np.int32)).max() <= (1 if prec == "fp32" else 12)
+
+
+def test_teacher_forced_eps_bf16(oracle, models, cuda_dev):
+    """Per-step eps of the bf16 path on the ORACLE's x_t (no drift): rel-L2 <= 1e-2 at every probed step."""
+    n = 10
+    g = torch.Generator().manual_seed(11)
+    x_T = torch.randn(1, 3, 128, 128, generator=g)
+    z = torch.randn(n, 1, 3, 128, 128, generator=g)
+    _, traj, eps_all = _oracle_loop(oracle, n, x_T, z)
+    o = DDPMSchedulerOracle()
+    o.set_timesteps(n)
+    xs = [x_T] + [traj[i] for i in range(n - 1)]
+    for i in (0, 3, 6, 9):
+        got = models["bf16"](xs[i].to(cuda_dev), o.timesteps[i]).sample.cpu()
+        assert rel(got, eps_all[i]) <= 1e-2, (i, rel(got, eps_all[i]))
+
+
+def test_graph_replay_equals_eager_and_chunked(models, cuda_dev):
+    s = DDPMScheduler(beta_schedule="squaredcos_cap_v2")
+    s.set_timesteps(8)
+    g = torch.Generator().manual_seed(5)
+    x_T = torch.randn(3, 3, 128, 128, generator=g).to(cuda_dev)
+    z = torch.randn(8, 3, 3, 128, 128, generator=g).to(cuda_dev)
+    m = models["bf16"]
+    a = x_T.clone(); m.sample(a, s, noise=z, use_graph=False)
+    b = x_T.clone(); m.sample(b, s, noise=z, use_graph=True)
+    c = x_T.clone()
+    for lo in range(0, 8, 3):                                   # stop-flag / progress chunks (image_generator.py:396,435)
+        m.sample(c, s, noise=z, step_begin=lo, step_end=min(8, lo + 3))
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    d = x_T.clone(); m.sample(d, s, seed=77)                    # Philox noise: deterministic in (seed, image, step)
+    e = x_T.clone(); m.sample(e, s, seed=77)
+    f = x_T.clone(); m.sample(f, s, seed=78)
+    assert torch.equal(d, e) and not torch.equal(d, f) and torch.isfinite(d).all()
+
+
+def test_philox_noise_is_standard_normal(models, cuda_dev):
+    """One step at t with sigma>0 on eps-independent state: recover z = (x' - mu)/sigma statistics."""
+    s = DDPMScheduler(beta_schedule="squaredcos_cap_v2")
+    s.set_timesteps(1000)
+    m = models["bf16"]
+    x0 = torch.zeros(8, 3, 128, 128, device=cuda_dev)
+    a = x0.clone(); m.sample(a, s, seed=1, step_begin=0, step_end=1)
+    zeros = torch.zeros(1000, 8, 3, 128, 128, device=cuda_dev) if False else None
+    b = x0.clone()
+    s2 = DDPMScheduler(beta_schedule="squaredcos_cap_v2"); s2.set_timesteps(1000)
+    # same step with injected zero noise gives mu
+    zero_noise = torch.zeros(1, 8, 3, 128, 128, device=cuda_dev)
+    s3 = DDPMScheduler(beta_schedule="squaredcos_cap_v2"); s3.set_timesteps(1)
+    sigma = float(s._coef[0][4])
+    # mu via eager pieces: eps from forward at t=999, scheduler step with z=0
+    eps = m(x0, 999).sample
+    mu = s.step(eps, 999, x0, noise=torch.zeros_like(x0)).prev_sample
+    zhat = (a - mu) / sigma
+    assert abs(zhat.mean().item()) < 0.01 and abs(zhat.std().item() - 1.0) < 0.01
+    assert abs((zhat ** 4).mean().item() - 3.0) < 0.1

@@ -1,0 +1,215 @@
+"""CPU: host-side logic of the product package and the C-ABI surface (no compute calls)."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_header_symbol():
+    from synt_isic_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "synt_isic.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(synt_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/synt_isic.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in _lib.lib().synt_version()
+
+
+def test_unet_manifest_equals_oracle_state_dict():
+    from oracle.unet2d import build_unet
+    from synt_isic_b200 import _lib
+    man = _lib.unet_manifest()
+    sd = build_unet(0).state_dict()
+    assert {n for n, _, _ in man} == set(sd)
+    assert all(sd[n].numel() == k for n, k, _ in man)
+    assert _lib.lib().synt_unet_total_param_count() == 25_304_963
+    offs = [o for _, _, o in man]
+    assert offs == sorted(offs) and offs[0] == 0
+
+
+def test_resnet_manifest_equals_torchvision_state_dict():
+    from oracle.classifier import build_classifier
+    from synt_isic_b200 import _lib
+    sd = {k: v for k, v in build_classifier().model.state_dict().items() if not k.endswith("num_batches_tracked")}
+    man = _lib.resnet18_manifest(7)
+    assert {n for n, _, _ in man} == set(sd)
+    assert all(sd[n].numel() == k for n, k, _ in man)
+    assert sum(k for _, k, _ in man) == 11_180_103 + sum(v.numel() for k, v in sd.items() if "running" in k)
+
+
+def test_dropin_unet_state_dict_roundtrip_and_cpu_refusal():
+    from oracle.unet2d import build_unet
+    from synt_isic_b200 import SUPPORTED_CONFIG, UNet2DModel
+    o = build_unet(1)
+    m = UNet2DModel(**SUPPORTED_CONFIG)
+    res = m.load_state_dict(o.state_dict(), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert all(torch.equal(m.state_dict()[k], v) for k, v in o.state_dict().items())
+    assert not m.training and sum(p.numel() for p in m.parameters()) == 25_304_963
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 128, 128), 10)
+    with pytest.raises(NotImplementedError):
+        UNet2DModel(block_out_channels=(32, 64, 128, 128))
+    # pre-0.15 attention key names are accepted
+    old = {k.replace(".to_q.", ".query.").replace(".to_k.", ".key.").replace(".to_v.", ".value.")
+            .replace(".to_out.0.", ".proj_attn."): v for k, v in o.state_dict().items()}
+    assert not m.load_state_dict(old, strict=True).missing_keys
+    packed = m._packed_params()
+    assert packed.shape == (25_304_963,) and np.isfinite(packed).all()
+
+
+def test_timestep_argument_forms():
+    from synt_isic_b200 import UNet2DModel
+    f = UNet2DModel._timestep_int
+    assert f(980) == 980 and f(torch.tensor(980)) == 980 and f(torch.tensor([5])) == 5
+    assert f(torch.tensor([7, 7, 7])) == 7
+    with pytest.raises(NotImplementedError):
+        f(torch.tensor([1, 2]))
+
+
+def test_scheduler_dropin_bit_exact_vs_oracle():
+    from oracle.ddpm import DDPMSchedulerOracle
+    from synt_isic_b200 import DDPMScheduler
+    tab = json.load(open(os.path.join(G, "ddpm_tables.json")))
+    for sched in ("squaredcos_cap_v2", "linear"):
+        for n in (None, 50, 1000, 7, 1):
+            s, o = DDPMScheduler(beta_schedule=sched), DDPMSchedulerOracle(beta_schedule=sched)
+            if n:
+                s.set_timesteps(n)
+                o.set_timesteps(n)
+            assert s.timesteps.dtype == torch.int64
+            assert torch.equal(s.timesteps, o.timesteps)                      # timestep indexing: bit-exact
+            assert torch.equal(s.alphas_cumprod, o.alphas_cumprod)
+            for t in o.timesteps.tolist():
+                co = np.array([float(v) for v in o.coefficients(t)], dtype=np.float32)
+                if t == 0:
+                    co[4] = 0
+                assert np.array_equal(co, s.coefficients(t)), (sched, n, t)
+    s = DDPMScheduler(num_train_timesteps=1000, beta_schedule="squaredcos_cap_v2", prediction_type="epsilon")
+    s.set_timesteps(50)
+    assert s.timesteps.tolist() == tab["timesteps_50"]
+    assert [int(t) for t in s.timesteps][:2] == [980, 960]                    # iterable of 0-d int64 tensors
+    assert hashlib.sha256(s._coef.tobytes()).hexdigest() == tab["coef_sha256_50"]
+    with pytest.raises(ValueError):
+        s.set_timesteps(1001)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        s.step(torch.zeros(1, 3, 8, 8), 980, torch.zeros(1, 3, 8, 8))
+
+
+def test_c_ddpm_tables_twin():
+    from synt_isic_b200 import DDPMScheduler
+    tab = json.load(open(os.path.join(G, "ddpm_tables.json")))
+    for n in (50, 1000, 7):
+        ts, coef, acp = DDPMScheduler.c_tables(1000, "squaredcos_cap_v2", 1e-4, 0.02, n)
+        assert ts.tolist() == tab[f"timesteps_{n}"]                           # bit-exact indices
+        assert hashlib.sha256(acp.tobytes()).hexdigest() == tab["acp_sha256"]  # bit-exact alphas_cumprod
+        s = DDPMScheduler(beta_schedule="squaredcos_cap_v2")
+        s.set_timesteps(n)
+        np.testing.assert_allclose(coef, s._coef, rtol=3e-7, atol=0)         # torch's sqrt is 1 ulp off at places
+    ts, coef, acp = DDPMScheduler.c_tables(1000, "linear", 1e-4, 0.02, 1000)
+    s = DDPMScheduler(beta_schedule="linear")
+    np.testing.assert_allclose(acp, s.alphas_cumprod.numpy(), rtol=1e-4)
+
+
+def test_seed_algebra_and_filenames():
+    from synt_isic_b200 import generator as gen
+    tab = json.load(open(os.path.join(G, "ddpm_tables.json")))
+    for c, off in tab["md5_offsets"].items():
+        assert gen.class_seed_offset(c) == off
+    assert gen.image_seed(42, "MEL", 0) == (42 + 2133561680) & 0x7FFFFFFF
+    assert gen.image_seed(2 ** 31 - 1, "MEL", 5) == (2 ** 31 - 1 + 2133561680 + 5) & 0x7FFFFFFF
+    assert gen.isic_filename(12) == "ISIC_0000012.png"
+    x = torch.randn(1, 3, 128, 128, generator=torch.Generator().manual_seed(1))
+    assert gen.noise_hash(x) == hashlib.sha256(x.numpy().tobytes()).hexdigest()[:16]
+    img = (np.random.RandomState(0).rand(16, 16, 3) * 255).astype(np.uint8)
+    assert np.array_equal(gen.color_postprocess(img, None), img)
+    out = gen.color_postprocess(img, {"rgb": {"mean": [100, 110, 120], "std": [40, 40, 40]}})
+    assert out.dtype == np.uint8 and out.shape == img.shape
+
+
+def test_classifier_dropin_container():
+    from synt_isic_b200 import MelanomaClassifierAdaptive
+    c = MelanomaClassifierAdaptive(num_classes=7, architecture="auto", pretrained=True)
+    assert c.model.fc.out_features == 7 and not c.training
+    assert c.model.layer4[-1].conv2.weight.shape == (512, 512, 3, 3)       # Grad-CAM handle, XAI.py:2946
+    assert len(list(c.named_parameters())) == 62
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c(torch.zeros(1, 3, 128, 128))
+    k0 = c._version_key()
+    with torch.no_grad():
+        next(c.parameters()).add_(1.0)                                     # XAI.py:2055-2059 mutates in place
+    assert c._version_key() != k0
+
+
+def test_shard_bounds_and_partition():
+    from synt_isic_b200.dist import partition, shard_bounds
+    for n in (0, 1, 7, 64, 513):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+    units = list(range(125))                                               # config 3: 125 batches of 64
+    got = sorted(sum((partition(units, r, 8) for r in range(8)), []))
+    assert got == units and max(len(partition(units, r, 8)) for r in range(8)) == 16
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from synt_isic_b200.dist import init_from_env, sharded_eval, gather_images, max_over_ranks, shard_bounds
+rank, world, _ = init_from_env("gloo")
+calls = []
+def fn(x):                      # stand-in for the classifier: row-wise, deterministic
+    calls.append(x.shape[0])
+    return torch.stack([x.sum(dim=(1, 2, 3)), x.mean(dim=(1, 2, 3)) * 3], dim=1)
+g = torch.Generator().manual_seed(5)
+items = torch.randn(13, 3, 4, 4, generator=g)
+out = sharded_eval(fn, items, None, chunk=4)
+ref = torch.stack([items.sum(dim=(1, 2, 3)), items.mean(dim=(1, 2, 3)) * 3], dim=1)
+assert torch.allclose(out, ref, atol=1e-6), (out - ref).abs().max()
+lo, hi = shard_bounds(13, rank, world)
+assert sum(calls) == hi - lo                     # each rank evaluated only its slice
+counts = [3, 2]
+mine = torch.full((counts[rank], 2, 2, 3), rank + 1, dtype=torch.uint8)
+allimg = gather_images(mine, counts, None, dst=0)
+if rank == 0:
+    assert allimg.shape == (5, 2, 2, 3) and allimg[:3].eq(1).all() and allimg[3:].eq(2).all()
+else:
+    assert allimg is None
+assert max_over_ranks(float(rank + 1), "cpu") == 2.0
+dist.barrier()
+print("RANK_OK", rank)
+"""
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = 29500 + (os.getpid() % 400)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), str(script), ROOT]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "RANK_OK 0" in r.stdout and "RANK_OK 1" in r.stdout
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "synt_isic_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
