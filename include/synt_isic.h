@@ -121,6 +121,11 @@ int synt_debug_conv(int use_tc, int act_dtype, const void* in_dev, int B, int H,
                     const void* weight_dev, const float* bias_dev, const float* bias2_dev, const void* residual_dev,
                     int relu, void* out_dev, int Cout, void* stream);
 
+/* softmax(q k^T / sqrt(8)) v on caller-provided tensors: use_tc=0: qkv [B,N,3C] (q|k|v); use_tc=1: the
+ * zero-interleaved bf16 layout [B,N,5C] consumed by the tcgen05 attention kernel. out: [B,N,C]. */
+int synt_debug_attention(int use_tc, int act_dtype, const void* qkv_dev, int B, int N, int C, void* out_dev,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,9 +91,4 @@ void attention_simt(const void* qkv, int dt, int B, int N, int C, void* out, cud
     SYNT_LAUNCH_CHECK();
 }
 
-bool attention_tc_supported(int, int) { return false; }
-void attention_tc(const void*, int, int, int, void*, cudaStream_t) {
-    throw Error(-3, "attention_tc: not built in this revision");
-}
-
 }  // namespace synt

@@ -1,0 +1,325 @@
+// Fused tcgen05 self-attention for the UNet's low-resolution blocks (diffusers Attention +
+// AttnProcessor2_0 reached from core/generator/image_generator.py:400): 32 heads of d = 8,
+// sequence N = 1024 (32x32) or 256 (16x16).
+//
+// Inputs (produced by the qkv projection GEMM with zero-interleaved weights, so no separate
+// padding pass exists):
+//   qkv' [B*N, 1280] bf16 = ( q' 512 | k' 512 | v 256 );  q'/k' hold each head as 16 columns
+//          = 8 real dims + 8 zeros (UMMA_K = 16 for bf16), q' pre-scaled by log2(e)/sqrt(8);
+//   vt   [B*32, 16, N] bf16 = per head V^T padded to 16 rows: rows 0..7 = v dims, row 8 = 1
+//          (so the P.V MMA also produces the softmax denominator), rows 9..15 = 0.
+//
+// One CTA = 128 queries x 4 heads of one image.  Per head and 128-key chunk:
+//   S  = Q_h K_h^T     one tcgen05.mma  M128 x N128 x K16  -> TMEM (fp32, log2 domain)
+//   P  = exp2(S - m)   softmax warps: tcgen05.ld -> ex2 -> bf16 -> swizzled st.shared
+//   O_h += P V_h       eight tcgen05.mma M128 x N16 x K16, P from shared memory
+// Exact two-pass softmax: pass 1 streams K once to get the row maxima m (MMA + TMEM read only),
+// pass 2 recomputes S and accumulates O without any rescaling.  d = 8 makes the kernel
+// exp-bound (N^2 ex2 per head), the MMAs are <10% of its time; two softmax warpgroups work on
+// alternate heads so that the MUFU pipes stay busy while the other group waits for its MMA.
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
+// warps 2..5 softmax warpgroup 0 (heads 0,2), warps 6..9 softmax warpgroup 1 (heads 1,3).
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace synt {
+
+using namespace ptx;
+
+constexpr int ATC_THREADS = 320;
+constexpr int ATC_STAGES = 3;
+constexpr int ATC_Q_BYTES = 128 * 128;                 // 128 queries x (4 heads x 16) bf16
+constexpr int ATC_K_BYTES = 128 * 128;                 // 128 keys    x (4 heads x 16) bf16
+constexpr int ATC_V_BYTES = 2 * 4 * 16 * 128;          // 2 key blocks x 4 heads x 16 rows x 64 keys
+constexpr int ATC_STAGE_BYTES = ATC_K_BYTES + ATC_V_BYTES;
+constexpr int ATC_P_BYTES = 2 * 128 * 128;             // 128 queries x 128 keys bf16 (2 blocks of 64 keys)
+constexpr int ATC_OFF_STAGE = ATC_Q_BYTES;
+constexpr int ATC_OFF_P = ATC_OFF_STAGE + ATC_STAGES * ATC_STAGE_BYTES;
+constexpr int ATC_OFF_BAR = ATC_OFF_P + 2 * ATC_P_BYTES;
+constexpr int ATC_SMEM = ATC_OFF_BAR + 256 + 1024;
+constexpr uint32_t ATC_TMEM_COLS = 512;                // S0 [0,128) S1 [128,256) O_h [256+16h, +16)
+
+struct AttnTcMaps { CUtensorMap qk; CUtensorMap vt; };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, int N,
+                                                                      int C, bf16* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_OFF_BAR);
+    uint64_t* full_bar = bars;                   // [STAGES]
+    uint64_t* empty_bar = bars + ATC_STAGES;     // [STAGES]
+    uint64_t* s_full = bars + 2 * ATC_STAGES;    // [2]
+    uint64_t* s_free = s_full + 2;               // [2]
+    uint64_t* p_full = s_free + 2;               // [2]
+    uint64_t* p_free = p_full + 2;               // [2]
+    uint64_t* q_full = p_free + 2;
+    uint64_t* o_full = q_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, hg = blockIdx.y, b = blockIdx.z;
+    const int n_chunks = N / 128;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.qk);
+        prefetch_tmap(&maps.vt);
+        for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 128);
+            mbar_init(&p_full[g], 128); mbar_init(&p_free[g], 1);
+        }
+        mbar_init(q_full, 1); mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<ATC_TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            mbar_arrive_expect_tx(q_full, ATC_Q_BYTES);
+            tma_load_2d(smem, &maps.qk, q_full, hg * 64, b * N + q0);
+            int stage = 0; uint32_t phase = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t* sk = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], pass == 0 ? ATC_K_BYTES : ATC_STAGE_BYTES);
+                    tma_load_2d(sk, &maps.qk, &full_bar[stage], 512 + hg * 64, b * N + c * 128);
+                    if (pass == 1) {
+                        tma_load_3d(sk + ATC_K_BYTES, &maps.vt, &full_bar[stage], c * 128, 0, b * (C / 8) + hg * 4);
+                        tma_load_3d(sk + ATC_K_BYTES + ATC_V_BYTES / 2, &maps.vt, &full_bar[stage], c * 128 + 64, 0,
+                                    b * (C / 8) + hg * 4);
+                    }
+                    if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, 16);
+            const uint32_t q_addr = smem_u32(smem);
+            const uint32_t p_addr = smem_u32(smem + ATC_OFF_P);
+            uint32_t sfree_ph[2] = {0, 0}, pfull_ph[2] = {0, 0};
+            int stage = 0; uint32_t phase = 0;
+            mbar_wait(q_full, 0);
+            auto issue_s = [&](int j, uint32_t k_addr) {
+                const int g = j & 1;
+                mbar_wait(&s_free[g], sfree_ph[g] ^ 1u); sfree_ph[g] ^= 1u;
+                tc_fence_after();
+                umma_bf16(tmem + g * 128, make_smem_desc_sw128(q_addr) + 2 * j, make_smem_desc_sw128(k_addr) + 2 * j,
+                          idesc_s, 0u);
+                umma_commit(&s_full[g]);
+            };
+            // ---- pass 1: row maxima (S only)
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES);
+                for (int j = 0; j < 4; ++j) issue_s(j, k_addr);
+                umma_commit(&empty_bar[stage]);
+                if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+            }
+            // ---- pass 2: S, then P.V of the previous unit (software pipelined by one unit)
+            int pend_j = -1, pend_c = 0, pend_stage = 0;
+            auto issue_pv = [&]() {
+                const int g = pend_j & 1;
+                mbar_wait(&p_full[g], pfull_ph[g]); pfull_ph[g] ^= 1u;
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(smem + ATC_OFF_STAGE + pend_stage * ATC_STAGE_BYTES + ATC_K_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t dp = make_smem_desc_sw128(p_addr + g * ATC_P_BYTES + kb * 16384);
+                    const uint64_t dv = make_smem_desc_sw128(v_addr + kb * (ATC_V_BYTES / 2) + pend_j * 2048);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem + 256 + pend_j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv,
+                                  (pend_c | kb | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&p_free[g]);
+                if (pend_j == 3) umma_commit(&empty_bar[pend_stage]);
+            };
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES);
+                for (int j = 0; j < 4; ++j) {
+                    issue_s(j, k_addr);
+                    if (pend_j >= 0) issue_pv();
+                    pend_j = j; pend_c = c; pend_stage = stage;
+                }
+                if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+            }
+            issue_pv();
+            umma_commit(o_full);
+        }
+    } else {
+        // ===================== softmax warpgroups =====================
+        const int g = (warp - 2) >> 2;                     // warpgroup 0 / 1
+        const int quarter = warp & 3;                      // TMEM lane quarter of this warp
+        const int r = quarter * 32 + lane;                 // query row
+        const uint32_t s_taddr = tmem + ((uint32_t)(quarter * 32) << 16) + g * 128;
+        uint32_t sfull_ph = 0, pfree_ph = 0;
+        float m[2] = {-INFINITY, -INFINITY};               // row maxima of heads g and g+2
+        // ---- pass 1
+        for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                mbar_wait(&s_full[g], sfull_ph); sfull_ph ^= 1u;
+                tc_fence_after();
+                float mx = m[jj];
+#pragma unroll 1
+                for (int piece = 0; piece < 4; ++piece) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(s_taddr + piece * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
+                m[jj] = mx;
+                tc_fence_before();
+                mbar_arrive(&s_free[g]);
+            }
+        }
+        // ---- pass 2
+        uint8_t* p_row = smem + ATC_OFF_P + g * ATC_P_BYTES + r * 128;
+        const int sw = r & 7;
+        for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                mbar_wait(&s_full[g], sfull_ph); sfull_ph ^= 1u;
+                tc_fence_after();
+                mbar_wait(&p_free[g], pfree_ph ^ 1u); pfree_ph ^= 1u;     // previous P.V finished reading P[g]
+                const float mrow = m[jj];
+#pragma unroll 1
+                for (int piece = 0; piece < 4; ++piece) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(s_taddr + piece * 32, v);
+                    tmem_ld_wait();
+                    if (piece == 3) { tc_fence_before(); mbar_arrive(&s_free[g]); }   // S[g] fully in registers
+                    uint32_t w[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        w[i] = pack_bf16x2(ex2_approx(__uint_as_float(v[2 * i]) - mrow),
+                                           ex2_approx(__uint_as_float(v[2 * i + 1]) - mrow));
+                    uint8_t* blk = p_row + (piece >> 1) * 16384;           // 64-key block
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int chunk16 = ((piece & 1) * 4 + q) ^ sw;   // SWIZZLE_128B: 16-byte chunk ^ (row & 7)
+                        *reinterpret_cast<uint4*>(blk + chunk16 * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                    }
+                }
+                fence_proxy_async();                                       // generic-proxy writes -> async proxy (UMMA)
+                mbar_arrive(&p_full[g]);
+            }
+        }
+        // ---- epilogue: O_h / rowsum -> bf16 NHWC
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int j = g + 2 * jj;
+            uint32_t v[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + 256 + j * 16)
+                : "memory");
+            tmem_ld_wait();
+            const float inv = 1.0f / __uint_as_float(v[8]);
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[i]) * inv;
+            store8<bf16>(out + ((size_t)b * N + q0 + r) * C + (hg * 4 + j) * 8, o);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<ATC_TMEM_COLS>(tmem);
+}
+
+// ---- V^T builder: vt[b*H + h][16][N] from the v part of qkv' -------------------------------
+__global__ void __launch_bounds__(256) build_vt_kernel(const bf16* __restrict__ qkv, int N, int C, int ldq, int voff,
+                                                       bf16* __restrict__ vt) {
+    __shared__ bf16 tile[64][256 + 8];
+    const int b = blockIdx.y, t0 = blockIdx.x * 64;
+    const int H = C / 8;
+    for (int i = threadIdx.x; i < 64 * (C / 8); i += 256) {
+        const int tok = i / (C / 8), v8 = i % (C / 8);
+        *reinterpret_cast<uint4*>(&tile[tok][v8 * 8]) =
+            *reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + t0 + tok) * ldq + voff + v8 * 8);
+    }
+    __syncthreads();
+    // each thread writes 8 consecutive tokens (16 B) of one (head, row)
+    for (int i = threadIdx.x; i < H * 16 * 8; i += 256) {
+        const int seg = i & 7, row = (i >> 3) & 15, h = i >> 7;
+        __align__(16) bf16 vals[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            bf16 x;
+            if (row < 8) x = tile[seg * 8 + k][h * 8 + row];
+            else x = __float2bfloat16_rn(row == 8 ? 1.0f : 0.0f);
+            vals[k] = x;
+        }
+        *reinterpret_cast<uint4*>(vt + (((size_t)b * H + h) * 16 + row) * N + t0 + seg * 8) = *reinterpret_cast<const uint4*>(vals);
+    }
+}
+
+bool attention_tc_supported(int N, int C) { return (N % 128 == 0) && C == 256; }
+
+// qkv: [B, N, 1280] bf16 (q' | k' | v), vt scratch: [B*32, 16, N] bf16, out: [B, N, 256] bf16
+void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* out, cudaStream_t s) {
+    SYNT_CHECK(attention_tc_supported(N, C), "attention_tc: unsupported shape");
+    const int ldq = 5 * C;                                         // 2*2C + C = 1280
+    build_vt_kernel<<<dim3(N / 64, B), 256, 0, s>>>((const bf16*)qkv, N, C, ldq, 4 * C, (bf16*)vt_scratch);
+    SYNT_LAUNCH_CHECK();
+    AttnTcMaps maps;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)ldq, (cuuint64_t)B * N};
+        cuuint64_t strides[1] = {(cuuint64_t)ldq * 2};
+        cuuint32_t box[2] = {64, 128};
+        encode_bf16_sw128(&maps.qk, qkv, 2, dims, strides, box, "attention qk");
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)N, 16, (cuuint64_t)B * (C / 8)};
+        cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)N * 32};
+        cuuint32_t box[3] = {64, 16, 4};
+        encode_bf16_sw128(&maps.vt, vt_scratch, 3, dims, strides, box, "attention vt");
+    }
+    static bool attr = false;
+    if (!attr) {
+        SYNT_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+        attr = true;
+    }
+    attention_tc_kernel<<<dim3(N / 128, C / 32, B), ATC_THREADS, ATC_SMEM, s>>>(maps, N, C, (bf16*)out);
+    SYNT_LAUNCH_CHECK();
+}
+
+}  // namespace synt

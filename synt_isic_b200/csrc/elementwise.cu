@@ -13,8 +13,8 @@ namespace synt {
 
 // =============================================================== GroupNorm ==========
 int gn_num_chunks(int B, int HW) {
-    int want = ceil_div(296, B);
-    int maxc = HW / 64 > 0 ? HW / 64 : 1;
+    int want = ceil_div(148 * 8, B);
+    int maxc = HW / 32 > 0 ? HW / 32 : 1;
     int n = want < maxc ? want : maxc;
     return n < 1 ? 1 : n;
 }
@@ -37,7 +37,17 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ src
         const bool first = v * 8 < C0;
         const T* base = first ? src0 + (size_t)b * HW * C0 + v * 8 : src1 + (size_t)b * HW * C1 + (v * 8 - C0);
         const int Cs = first ? C0 : C1;
-        for (int p = p0 + lane; p < p1; p += lanes) {
+        int p = p0 + lane;
+        for (; p + 3 * lanes < p1; p += 4 * lanes) {          // 4 independent 16/32-byte loads in flight
+            float x[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load8<T>(base + (size_t)(p + u * lanes) * Cs, x[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s[i] += x[u][i]; q[i] = fmaf(x[u][i], x[u][i], q[i]); }
+        }
+        for (; p < p1; p += lanes) {
             float x[8];
             load8<T>(base + (size_t)p * Cs, x);
 #pragma unroll
@@ -100,27 +110,39 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ src
                                                        int C1, int HW, long long nvec_total,
                                                        const float2* __restrict__ scale_shift, T* __restrict__ out) {
     const int C = C0 + C1, nvec = C >> 3;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int v = (int)(i % nvec);
-        const long long pix = i / nvec;             // b*HW + p
-        const int b = (int)(pix / HW);
-        const int c = v * 8;
-        float x[8];
-        if (c < C0) load8<T>(src0 + pix * C0 + c, x);
-        else        load8<T>(src1 + pix * C1 + (c - C0), x);
-        const float4* ss = reinterpret_cast<const float4*>(scale_shift + (size_t)b * C + c);
+    constexpr int U = 4;                                      // independent vectors in flight per thread
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < nvec_total; i0 += U * stride) {
+        float x[U][8];
+        long long pix[U]; int c[U];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 t = __ldg(ss + j);
-            float y0 = fmaf(x[2 * j], t.x, t.y), y1 = fmaf(x[2 * j + 1], t.z, t.w);
-            if (SILU) {
-                if (sizeof(T) == 4) { y0 = silu_precise(y0); y1 = silu_precise(y1); }
-                else                { y0 = silu_f(y0);       y1 = silu_f(y1); }
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < nvec_total) {
+                c[u] = (int)(i % nvec) * 8;
+                pix[u] = i / nvec;                            // b*HW + p
+                if (c[u] < C0) load8<T>(src0 + pix[u] * C0 + c[u], x[u]);
+                else           load8<T>(src1 + pix[u] * C1 + (c[u] - C0), x[u]);
             }
-            x[2 * j] = y0; x[2 * j + 1] = y1;
         }
-        store8<T>(out + pix * C + c, x);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= nvec_total) break;
+            const int b = (int)(pix[u] / HW);
+            const float4* ss = reinterpret_cast<const float4*>(scale_shift + (size_t)b * C + c[u]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 t = __ldg(ss + j);
+                float y0 = fmaf(x[u][2 * j], t.x, t.y), y1 = fmaf(x[u][2 * j + 1], t.z, t.w);
+                if (SILU) {
+                    if (sizeof(T) == 4) { y0 = silu_precise(y0); y1 = silu_precise(y1); }
+                    else                { y0 = silu_f(y0);       y1 = silu_f(y1); }
+                }
+                x[u][2 * j] = y0; x[u][2 * j + 1] = y1;
+            }
+            store8<T>(out + pix[u] * C + c[u], x[u]);
+        }
     }
 }
 
@@ -128,7 +150,8 @@ void gn_apply(const void* src0, int C0, const void* src1, int C1, int dt, int B,
               int silu, void* out, cudaStream_t s) {
     const int C = C0 + C1;
     const long long nv = (long long)B * HW * (C / 8);
-    const int blocks = (int)((nv + 255) / 256 < 148 * 16 ? (nv + 255) / 256 : 148 * 16);
+    const long long want = (nv + 256 * 4 - 1) / (256 * 4);
+    const int blocks = (int)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
 #define GO(T, S) gn_apply_kernel<T, S><<<blocks, 256, 0, s>>>((const T*)src0, C0, (const T*)src1, C1, HW, nv, scale_shift, (T*)out)
     if (dt == DT_F32) { if (silu) GO(float, true); else GO(float, false); }
     else              { if (silu) GO(bf16, true);  else GO(bf16, false); }

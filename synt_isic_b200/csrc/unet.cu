@@ -163,6 +163,7 @@ struct ResnetW {
 struct AttnW {
     std::string name; int C;
     DevPtr g, b; WeightDev wqkv, wo; DevPtr bqkv, bo;
+    WeightDev wqkv_tc; DevPtr bqkv_tc;            // zero-interleaved (q' | k' | v) projection for attention_tc
 };
 struct ConvW { std::string name; int cin, cout; WeightDev w; DevPtr b; };
 
@@ -250,6 +251,26 @@ static AttnW make_attn(const float* P, const std::string& name, int C, bool f32,
     }
     a.wqkv = upload_weight(wqkv, f32, b16);
     a.bqkv = dev_upload(bqkv.data(), bqkv.size() * 4);
+    if (b16) {
+        // q'/k': head h -> 16 rows (8 real + 8 zero) so that one UMMA_K=16 step covers a head; the
+        // softmax scale and the exp->exp2 conversion are folded into q'
+        const float qscale = 1.4426950408889634f / std::sqrt(8.0f);
+        std::vector<float> wp((size_t)5 * C * C, 0.f), bp(5 * C, 0.f);
+        for (int h = 0; h < C / 8; ++h)
+            for (int d = 0; d < 8; ++d) {
+                const int src = h * 8 + d, dq = h * 16 + d, dk = 2 * C + h * 16 + d;
+                for (int i = 0; i < C; ++i) {
+                    wp[(size_t)dq * C + i] = wqkv[(size_t)src * C + i] * qscale;
+                    wp[(size_t)dk * C + i] = wqkv[(size_t)(C + src) * C + i];
+                }
+                bp[dq] = bqkv[src] * qscale;
+                bp[dk] = bqkv[C + src];
+            }
+        memcpy(wp.data() + (size_t)4 * C * C, wqkv.data() + (size_t)2 * C * C, (size_t)C * C * 4);
+        memcpy(bp.data() + 4 * C, bqkv.data() + 2 * C, C * 4);
+        a.wqkv_tc = upload_weight(wp, false, true);
+        a.bqkv_tc = dev_upload(bp.data(), bp.size() * 4);
+    }
     std::vector<float> wo(P + m.find(name + ".to_out.0.weight"), P + m.find(name + ".to_out.0.weight") + (size_t)C * C);
     a.wo = upload_weight(wo, f32, b16);
     a.bo = dev_upload(P + m.find(name + ".to_out.0.bias"), C * 4);
@@ -424,18 +445,25 @@ struct Fwd {
     Act attention(const AttnW& w, const Act& x) {
         const int H = x.H, W = x.W, C = w.C;
         Act a = gn_act(x, nullptr, w.g, w.b, false);
-        Act qkv = make(H, W, 3 * C);
+        const bool tc = u->dt == DT_BF16 && u->use_tc && attention_tc_supported(H * W, C);
+        Act qkv = make(H, W, tc ? 5 * C : 3 * C);
         {
             ConvArgs c; c.in = a.p; c.B = B; c.H = H; c.W = W; c.Cin = C; c.KH = c.KW = 1; c.pad = 0; c.Ho = H; c.Wo = W;
-            c.Cout = 3 * C; c.bias = (const float*)w.bqkv->p; c.out = qkv.p;
-            conv(c, w.wqkv);
+            c.Cout = qkv.C; c.bias = (const float*)(tc ? w.bqkv_tc : w.bqkv)->p; c.out = qkv.p;
+            conv(c, tc ? w.wqkv_tc : w.wqkv);
         }
         drop(a);
         Act o = make(H, W, C);
         {
             ProfScope ps(u, s, PC_ATTN, 4.0 * B * (double)(H * W) * (H * W) * C);
-            if (u->dt == DT_BF16 && u->use_tc && attention_tc_supported(H * W, C)) attention_tc(qkv.p, B, H * W, C, o.p, s);
-            else attention_simt(qkv.p, u->dt, B, H * W, C, o.p, s);
+            if (tc) {
+                void* vt = u->pool.alloc((size_t)B * (C / 8) * 16 * H * W * 2);
+                attention_tc(qkv.p, B, H * W, C, vt, o.p, s);
+                u->pool.release(vt);
+                ++u->launches;
+            } else {
+                attention_simt(qkv.p, u->dt, B, H * W, C, o.p, s);
+            }
         }
         ++u->launches;
         drop(qkv);
@@ -834,6 +862,25 @@ extern "C" int synt_debug_conv(int use_tc, int act_dtype, const void* in, int B,
         conv_tc(a, (cudaStream_t)stream);
     } else {
         conv_simt(a, act_dtype, (cudaStream_t)stream);
+    }
+    SYNT_CATCH
+}
+
+// attention core on caller-provided tensors: use_tc=0 -> qkv [B,N,3C] (q|k|v) of `act_dtype`;
+// use_tc=1 -> qkv' [B,N,5C] bf16 in the zero-interleaved layout of attention_tc (see kernels.cuh)
+extern "C" int synt_debug_attention(int use_tc, int act_dtype, const void* qkv, int B, int N, int C, void* out,
+                                    void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(qkv && out && B > 0, "bad argument");
+    if (use_tc) {
+        SYNT_CHECK(act_dtype == DT_BF16 && attention_tc_supported(N, C), "attention_tc: unsupported");
+        void* vt = nullptr;
+        SYNT_CUDA(cudaMalloc(&vt, (size_t)B * (C / 8) * 16 * N * 2));
+        try { attention_tc(qkv, B, N, C, vt, out, (cudaStream_t)stream); } catch (...) { cudaFree(vt); throw; }
+        SYNT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        cudaFree(vt);
+    } else {
+        attention_simt(qkv, act_dtype, B, N, C, out, (cudaStream_t)stream);
     }
     SYNT_CATCH
 }

@@ -76,6 +76,10 @@ CASES = [
     (3, 28, 28, 128, 128, 3, 1, 1, (64, 0), 2, False, True, False),        # layer2.0.conv2 + 1x1 s2 downsample
     (3, 14, 14, 256, 256, 3, 1, 1, (0, 0), 1, True, True, False),          # 14x14
     (3, 7, 7, 512, 512, 3, 1, 1, (0, 0), 1, True, True, False),            # 7x7, two images per tile, odd B
+    (16, 32, 32, 256, 256, 3, 1, 1, (0, 0), 1, True, False, True),         # 128 pixel tiles x 2 -> N tile 128
+    (40, 32, 32, 128, 256, 3, 1, 1, (128, 0), 1, False, False, False),     # 320 pixel tiles -> N tile 256
+    (10, 64, 64, 128, 128, 3, 1, 1, (0, 0), 1, True, False, False),        # N tile 128, 3 smem stages
+    (20, 32, 32, 256, 1280, 1, 1, 0, (0, 0), 1, False, False, False),      # zero-interleaved qkv projection, N tile 256
 ]
 
 

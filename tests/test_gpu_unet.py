@@ -64,15 +64,25 @@ def test_timestep_argument_forms_agree(models, cuda_dev):
     assert not torch.equal(a, m(x, 499).sample)
 
 
-def test_batch_consistency_and_ragged_batch(models, cuda_dev):
-    """B=19 spans two micro-batches (16 + 3); every image must equal its B=1 result."""
+def test_batch_consistency_and_ragged_batch(oracle, models, cuda_dev):
+    """B=19 spans two micro-batches (16 + 3) and selects other GEMM tile shapes than B=1.  fp32 mode: every
+    image equals its B=1 result up to summation order.  bf16 mode: any two executions that differ in a
+    single fp32 rounding decorrelate to the bf16 noise floor within a few layers (rounding-flip cascade),
+    so the batched result is checked against the ORACLE at the eps tolerance instead."""
     g = torch.Generator().manual_seed(9)
-    x = torch.randn(19, 3, 128, 128, generator=g).to(cuda_dev)
-    m = models["bf16"]
-    full = m(x, 321).sample
+    x = torch.randn(19, 3, 128, 128, generator=g)
+    xd = x.to(cuda_dev)
+    full = models["fp32"](xd, 321).sample
     for i in (0, 15, 16, 18):
-        one = m(x[i:i + 1].contiguous(), 321).sample
-        assert rel(full[i:i + 1].cpu(), one.cpu()) < 2e-3          # GroupNorm chunking differs with B -> fp32 sum order
+        one = models["fp32"](xd[i:i + 1].contiguous(), 321).sample
+        assert rel(full[i:i + 1].cpu(), one.cpu()) < 1e-5
+    with torch.no_grad():
+        ref = oracle(x, 321).sample
+    assert rel(full.cpu(), ref) <= 1e-5
+    got = models["bf16"](xd, 321).sample.cpu()
+    assert rel(got, ref) <= 1e-2
+    for i in (0, 16, 18):
+        assert rel(got[i], ref[i]) <= 1.2e-2
 
 
 @pytest.mark.parametrize("prec", ["fp32"])
