@@ -75,6 +75,8 @@ int synt_unet_generate_host(synt_unet_t* h, const float* xT_host, int B, unsigne
  * algorithmic FLOPs and the launch count.  x is advanced by one step. */
 int synt_unet_profile_step(synt_unet_t* h, float* x_dev, int B, int micro_batch, double* ms_out, double* flops_out,
                            int* launches_out, void* stream);
+/* per-launch rows {category, ms, flops, M, N, K} of the last profiled step; returns the row count */
+int synt_unet_profile_records(synt_unet_t* h, double* rows6, int cap);
 long long synt_unet_workspace_bytes(synt_unet_t* h);
 long long synt_unet_launch_count(synt_unet_t* h);        /* kernels launched since creation */
 

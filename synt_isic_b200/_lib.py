@@ -32,6 +32,7 @@ SIGNATURES = {
     "synt_unet_sample": (C.c_int, [vp, vp, C.c_int, vp, C.c_ulonglong, C.c_longlong, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "synt_unet_generate_host": (C.c_int, [vp, vp, C.c_int, C.c_ulonglong, C.c_longlong, C.c_int, vp, vp]),
     "synt_unet_profile_step": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), c_i32p, vp]),
+    "synt_unet_profile_records": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),
     "synt_unet_workspace_bytes": (C.c_longlong, [vp]),
     "synt_unet_launch_count": (C.c_longlong, [vp]),
     "synt_ddpm_tables": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, c_i64p, c_f32p, c_f32p]),

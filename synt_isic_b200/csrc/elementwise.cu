@@ -13,7 +13,7 @@ namespace synt {
 
 // =============================================================== GroupNorm ==========
 int gn_num_chunks(int B, int HW) {
-    int want = ceil_div(148 * 8, B);
+    int want = ceil_div(148 * 6, B);
     int maxc = HW / 32 > 0 ? HW / 32 : 1;
     int n = want < maxc ? want : maxc;
     return n < 1 ? 1 : n;
@@ -78,81 +78,108 @@ void gn_stats(const void* src0, int C0, const void* src1, int C1, int dt, int B,
     SYNT_LAUNCH_CHECK();
 }
 
-__global__ void gn_finalize_kernel(const float2* __restrict__ partials, int nchunk, int G, int C, int HW, float eps,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float2* __restrict__ scale_shift) {
-    const int b = blockIdx.x, c = threadIdx.x;
-    if (c >= C) return;
-    const int cpg = C / G, g = c / cpg;
-    double ts = 0.0, tq = 0.0;
-    for (int k = 0; k < nchunk; ++k) {
-        float2 p = partials[((size_t)b * nchunk + k) * G + g];
-        ts += (double)p.x; tq += (double)p.y;
+// one block per image: 8 threads per group sum the chunk partials (fixed order -> deterministic),
+// then every channel gets scale = rstd*gamma, shift = beta - mean*scale
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float2* __restrict__ partials, int nchunk, int G, int C,
+                                                          int HW, float eps, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float2* __restrict__ scale_shift) {
+    __shared__ float2 stat[32];                              // (mean, rstd) per group, G <= 32
+    const int b = blockIdx.x, g = threadIdx.x >> 3, part = threadIdx.x & 7;
+    if (g < G) {
+        double ts = 0.0, tq = 0.0;
+        for (int k = part; k < nchunk; k += 8) {
+            const float2 p = partials[((size_t)b * nchunk + k) * G + g];
+            ts += (double)p.x; tq += (double)p.y;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            ts += __shfl_xor_sync(0xffffffffu, ts, o);
+            tq += __shfl_xor_sync(0xffffffffu, tq, o);
+        }
+        if (part == 0) {
+            const double cnt = (double)HW * (C / G);
+            const double mean = ts / cnt;
+            double var = tq / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            stat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+        }
     }
-    const double cnt = (double)HW * cpg;
-    const double mean = ts / cnt;
-    double var = tq / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = rstd * gamma[c];
-    scale_shift[(size_t)b * C + c] = make_float2(sc, beta[c] - (float)mean * sc);
+    __syncthreads();
+    const int cpg = C / G;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const float2 st = stat[c / cpg];
+        const float sc = st.y * gamma[c];
+        scale_shift[(size_t)b * C + c] = make_float2(sc, beta[c] - st.x * sc);
+    }
 }
 
 void gn_finalize(const float2* partials, int B, int nchunk, int G, int C, int HW, float eps, const float* gamma,
                  const float* beta, float2* scale_shift, cudaStream_t s) {
-    SYNT_CHECK(C <= 512, "gn_finalize: C too large");
-    gn_finalize_kernel<<<B, C, 0, s>>>(partials, nchunk, G, C, HW, eps, gamma, beta, scale_shift);
+    SYNT_CHECK(C <= 512 && G <= 32, "gn_finalize: C <= 512, G <= 32");
+    gn_finalize_kernel<<<B, 256, 0, s>>>(partials, nchunk, G, C, HW, eps, gamma, beta, scale_shift);
     SYNT_LAUNCH_CHECK();
 }
 
+// silu(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx) per element
+__device__ __forceinline__ float silu_tanh(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
+// Each thread owns ONE 8-channel vector position (its scale/shift live in registers) and streams the
+// pixels of its block's range with 4 independent 16-byte loads in flight.
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ src0, int C0, const T* __restrict__ src1,
-                                                       int C1, int HW, long long nvec_total,
-                                                       const float2* __restrict__ scale_shift, T* __restrict__ out) {
-    const int C = C0 + C1, nvec = C >> 3;
-    constexpr int U = 4;                                      // independent vectors in flight per thread
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < nvec_total; i0 += U * stride) {
-        float x[U][8];
-        long long pix[U]; int c[U];
+                                                       int C1, int HW, int ppb, const float2* __restrict__ scale_shift,
+                                                       T* __restrict__ out) {
+    const int C = C0 + C1, nvec = C >> 3, rows = 256 / nvec;
+    const int b = blockIdx.y;
+    const int v = threadIdx.x % nvec, prow = threadIdx.x / nvec;
+    if (prow >= rows) return;
+    const int c = v * 8;
+    float sc[8], sh[8];
+    {
+        const float4* ss = reinterpret_cast<const float4*>(scale_shift + (size_t)b * C + c);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            if (i < nvec_total) {
-                c[u] = (int)(i % nvec) * 8;
-                pix[u] = i / nvec;                            // b*HW + p
-                if (c[u] < C0) load8<T>(src0 + pix[u] * C0 + c[u], x[u]);
-                else           load8<T>(src1 + pix[u] * C1 + (c[u] - C0), x[u]);
-            }
+        for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldg(ss + j);
+            sc[2 * j] = t.x; sh[2 * j] = t.y; sc[2 * j + 1] = t.z; sh[2 * j + 1] = t.w;
         }
+    }
+    const bool first = c < C0;
+    const T* src = first ? src0 + (size_t)b * HW * C0 + c : src1 + (size_t)b * HW * C1 + (c - C0);
+    const int Cs = first ? C0 : C1;
+    T* dst = out + (size_t)b * HW * C + c;
+    const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
+    constexpr int U = 4;
+    for (int p = p0 + prow; p < p1; p += U * rows) {
+        float x[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (p + u * rows < p1) load8<T>(src + (size_t)(p + u * rows) * Cs, x[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            if (i >= nvec_total) break;
-            const int b = (int)(pix[u] / HW);
-            const float4* ss = reinterpret_cast<const float4*>(scale_shift + (size_t)b * C + c[u]);
+            if (p + u * rows >= p1) break;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 t = __ldg(ss + j);
-                float y0 = fmaf(x[u][2 * j], t.x, t.y), y1 = fmaf(x[u][2 * j + 1], t.z, t.w);
-                if (SILU) {
-                    if (sizeof(T) == 4) { y0 = silu_precise(y0); y1 = silu_precise(y1); }
-                    else                { y0 = silu_f(y0);       y1 = silu_f(y1); }
-                }
-                x[u][2 * j] = y0; x[u][2 * j + 1] = y1;
+            for (int i = 0; i < 8; ++i) {
+                float y = fmaf(x[u][i], sc[i], sh[i]);
+                if (SILU) y = (sizeof(T) == 4) ? silu_precise(y) : silu_tanh(y);
+                x[u][i] = y;
             }
-            store8<T>(out + pix[u] * C + c[u], x[u]);
+            store8<T>(dst + (size_t)(p + u * rows) * C, x[u]);
         }
     }
 }
 
 void gn_apply(const void* src0, int C0, const void* src1, int C1, int dt, int B, int HW, const float2* scale_shift,
               int silu, void* out, cudaStream_t s) {
-    const int C = C0 + C1;
-    const long long nv = (long long)B * HW * (C / 8);
-    const long long want = (nv + 256 * 4 - 1) / (256 * 4);
-    const int blocks = (int)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
-#define GO(T, S) gn_apply_kernel<T, S><<<blocks, 256, 0, s>>>((const T*)src0, C0, (const T*)src1, C1, HW, nv, scale_shift, (T*)out)
+    const int C = C0 + C1, nvec = C / 8, rows = 256 / nvec;
+    int ppb = rows * 16;                                     // 16 pixels per thread
+    if (ppb > HW) ppb = HW;
+    dim3 grid(ceil_div(HW, ppb), B);
+#define GO(T, S) gn_apply_kernel<T, S><<<grid, 256, 0, s>>>((const T*)src0, C0, (const T*)src1, C1, HW, ppb, scale_shift, (T*)out)
     if (dt == DT_F32) { if (silu) GO(float, true); else GO(float, false); }
     else              { if (silu) GO(bf16, true);  else GO(bf16, false); }
 #undef GO
@@ -277,7 +304,7 @@ __global__ void __launch_bounds__(256) conv_out3_kernel(const T* __restrict__ h,
                 float4 t = __ldg(ss + j);
                 float a0 = fmaf(x[2 * j], t.x, t.y), a1 = fmaf(x[2 * j + 1], t.z, t.w);
                 if (sizeof(T) == 4) { a0 = silu_precise(a0); a1 = silu_precise(a1); }
-                else                { a0 = silu_f(a0);       a1 = silu_f(a1); }
+                else                { a0 = silu_tanh(a0);    a1 = silu_tanh(a1); }
                 x[2 * j] = a0; x[2 * j + 1] = a1;
             }
         } else {

@@ -37,6 +37,8 @@ void conv_simt(const ConvArgs& a, int act_dtype, cudaStream_t s);
 // Requires Cin, sc0_C, sc1_C multiples of 64 and Cout a multiple of 16.
 bool conv_tc_supported(const ConvArgs& a);
 void conv_tc(const ConvArgs& a, cudaStream_t s);
+// experimental: 3x3 stride-1 conv with one halo-tile load per channel chunk (see conv_tc_halo.cu)
+void conv_tc_halo(const ConvArgs& a, int variant, cudaStream_t s);
 
 // UNet conv_in: x fp32 NCHW [B,3,H,W] -> NHWC T [B,H,W,64], 3x3 pad 1.
 struct ConvInW { float w[27][64]; float b[64]; };          // k = tap*3 + c

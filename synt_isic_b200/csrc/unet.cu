@@ -201,7 +201,8 @@ struct synt_unet {
     cudaStream_t own_stream = nullptr;            // capture needs a non-legacy stream
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     // per-kernel profiling (bench.py roofline): events around every launch of one eager step
-    struct ProfRec { int cat; cudaEvent_t a, b; double flops; };
+    struct ProfRec { int cat; cudaEvent_t a, b; double flops; int m, n, k; float ms; };
+    std::vector<ProfRec> last_recs;
     bool prof = false;
     std::vector<ProfRec> recs;
     // debug tap
@@ -361,12 +362,13 @@ static void build_unet(synt_unet* u, const float* P) {
 enum ProfCat { PC_CONV_TC = 0, PC_CONV_SIMT, PC_GN_STATS, PC_GN_APPLY, PC_ATTN, PC_UPSAMPLE, PC_CONV_IN, PC_CONV_OUT,
                PC_MISC, PC_COUNT };
 struct ProfScope {
-    synt_unet* u; cudaStream_t s; int cat; double flops; cudaEvent_t a = nullptr;
-    ProfScope(synt_unet* u_, cudaStream_t s_, int cat_, double flops_ = 0.0) : u(u_), s(s_), cat(cat_), flops(flops_) {
+    synt_unet* u; cudaStream_t s; int cat; double flops; cudaEvent_t a = nullptr; int m = 0, n = 0, k = 0;
+    ProfScope(synt_unet* u_, cudaStream_t s_, int cat_, double flops_ = 0.0, int m_ = 0, int n_ = 0, int k_ = 0)
+        : u(u_), s(s_), cat(cat_), flops(flops_), m(m_), n(n_), k(k_) {
         if (u->prof) { cudaEventCreate(&a); cudaEventRecord(a, s); }
     }
     ~ProfScope() {
-        if (u->prof) { cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, s); u->recs.push_back({cat, a, b, flops}); }
+        if (u->prof) { cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, s); u->recs.push_back({cat, a, b, flops, m, n, k, 0.f}); }
     }
 };
 
@@ -409,7 +411,8 @@ struct Fwd {
     void conv(ConvArgs& a, const WeightDev& w) {
         const bool tc = u->dt == DT_BF16 && u->use_tc && conv_tc_supported(a);
         a.weight = w.get(tc);
-        ProfScope ps(u, s, tc ? PC_CONV_TC : PC_CONV_SIMT, 2.0 * B * a.Ho * a.Wo * (double)a.Cout * a.ktot());
+        ProfScope ps(u, s, tc ? PC_CONV_TC : PC_CONV_SIMT, 2.0 * B * a.Ho * a.Wo * (double)a.Cout * a.ktot(), B * a.Ho * a.Wo,
+                     a.Cout, a.ktot());
         if (tc) conv_tc(a, s); else conv_simt(a, u->dt, s);
         ++u->launches;
     }
@@ -775,9 +778,24 @@ int synt_unet_profile_step(synt_unet_t* h, float* x, int B, int micro_batch, dou
         SYNT_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
         ms_out[r.cat] += ms; flops_out[r.cat] += r.flops; launches_out[r.cat] += 1;
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        r.ms = ms;
     }
+    h->last_recs = h->recs;
     h->recs.clear();
     SYNT_CATCH
+}
+
+// per-launch records of the last synt_unet_profile_step: rows of {category, ms, flops, M, N, K}
+int synt_unet_profile_records(synt_unet_t* h, double* rows6, int cap) {
+    if (!h) return 0;
+    int n = 0;
+    for (auto& r : h->last_recs) {
+        if (n >= cap) break;
+        double* o = rows6 + (size_t)n * 6;
+        o[0] = r.cat; o[1] = r.ms; o[2] = r.flops; o[3] = r.m; o[4] = r.n; o[5] = r.k;
+        ++n;
+    }
+    return n;
 }
 
 long long synt_unet_workspace_bytes(synt_unet_t* h) { return h ? (long long)h->pool.total_bytes() : 0; }
@@ -857,7 +875,10 @@ extern "C" int synt_debug_conv(int use_tc, int act_dtype, const void* in, int B,
     a.Ho = (H + 2 * pad - K) / stride + 1; a.Wo = (W + 2 * pad - K) / stride + 1; a.Cout = Cout;
     a.sc0 = sc0; a.sc0_C = sc0_C; a.sc1 = sc1; a.sc1_C = sc1_C; a.sc_stride = sc_stride;
     a.weight = weight; a.bias = bias; a.bias2 = bias2; a.residual = residual; a.relu = relu; a.out = out;
-    if (use_tc) {
+    if (use_tc >= 2) {
+        SYNT_CHECK(act_dtype == DT_BF16, "tcgen05 conv needs bf16 activations");
+        conv_tc_halo(a, use_tc - 2, (cudaStream_t)stream);
+    } else if (use_tc) {
         SYNT_CHECK(act_dtype == DT_BF16, "tcgen05 conv needs bf16 activations");
         conv_tc(a, (cudaStream_t)stream);
     } else {

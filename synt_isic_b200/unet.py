@@ -256,6 +256,16 @@ class UNet2DModel(nn.Module):
                                                          _lib.current_stream_ptr()), "unet_profile_step")
         return {name: {"ms": ms[i], "flops": fl[i], "launches": ln[i]} for i, name in enumerate(self.PROFILE_CATEGORIES)}
 
+    def profile_records(self):
+        """Per-launch rows (category, ms, flops, M, N, K) of the last ``profile_step``."""
+        cur = self._handles.get(self.precision)
+        if not cur:
+            return []
+        buf = (C.c_double * (6 * 4096))()
+        n = _lib.lib().synt_unet_profile_records(cur[0], buf, 4096)
+        return [(self.PROFILE_CATEGORIES[int(buf[6 * i])], buf[6 * i + 1], buf[6 * i + 2], int(buf[6 * i + 3]),
+                 int(buf[6 * i + 4]), int(buf[6 * i + 5])) for i in range(n)]
+
     def launch_count(self) -> int:
         cur = self._handles.get(self.precision)
         return int(_lib.lib().synt_unet_launch_count(cur[0])) if cur else 0
