@@ -1,0 +1,316 @@
+// Persistent tcgen05 implicit-GEMM kernel for the 3x3 stride-1 convolutions of the UNet
+// (85% of the path's FLOPs; diffusers ResnetBlock2D.conv1/conv2 and Upsample2D.conv reached from
+// core/generator/image_generator.py:400), including the fused 1x1 shortcut segments.
+//
+// Why a second kernel: conv_tc.cu (one CTA per 128-pixel tile, one TMA box per filter tap) moves
+// 16 KB (A) + BN*128 B (B) from L2 per 64-deep K step, i.e. 96 B/clk/SM at full MMA rate for
+// BN = 256 -- the measured ceiling is ~40 B/clk/SM, so it runs at ~40% of the tensor pipe.  Here
+//   * A: ONE halo-tile TMA load per 64-channel chunk serves all nine taps of TWO vertically
+//     adjacent 16x8-pixel tiles: the (34 x 10 pixel) halo is a SWIZZLE_128B smem tile whose nine
+//     tap views are plain address offsets ((dy*10+dx)*128 B, 8-row group stride 1280 B) of the
+//     UMMA descriptor -- measured legal on B200 (the 128B swizzle is a function of absolute
+//     shared-memory address bits; tools/exp_halo.py).  A traffic drops 9 x 32 KB -> 43.5 KB.
+//   * B: each weight tile (one tap x 64 channels x BN) feeds the MMAs of both M tiles.
+//   * persistent CTAs (one per SM) with double-buffered TMEM accumulators: the epilogue of super-
+//     tile i (TMEM -> registers -> bias/temb/residual -> bf16 -> swizzled smem -> TMA store)
+//     overlaps the mainloop of super-tile i+1.
+// L2 -> smem bytes per MMA clock: (43.5 KB + 9*BN*128 B) / (36*BN clk) = 42 B/clk for BN = 128.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5
+// epilogue.  Rings: A halo slots (2), B weight-tile slots (NB), TMEM accumulator buffers (2).
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace synt {
+
+using namespace ptx;
+
+constexpr int V2_THREADS = 192;
+constexpr int V2_MT = 2;                                   // M tiles (16x8 pixels each) per super-tile
+constexpr int V2_A_SLOT = 44032;                           // 34*10*128 = 43,520 rounded up to 1 KB
+constexpr int V2_A_BYTES = 34 * 10 * 128;
+constexpr int V2_A_BYTES_2IMG = 2 * 18 * 10 * 128;         // 16x16 images: two images' halos (46,080 > slot? no: see below)
+constexpr int V2_A_STAGES = 2;
+
+template <int BN>
+struct V2Smem {
+    static constexpr int A_SLOT = 46080;                   // max(34*10, 2*18*10) * 128, already 1 KB aligned
+    static constexpr int B_TILE = BN * 128;
+    static constexpr int STAGING = 128 * BN * 2;           // one M tile of bf16 output
+    static constexpr int NB = (BN == 128) ? 6 : 8;
+    static constexpr int OFF_B = V2_A_STAGES * A_SLOT;
+    static constexpr int OFF_STAGING = OFF_B + NB * B_TILE;
+    static constexpr int OFF_BAR = OFF_STAGING + STAGING;
+    static constexpr int TOTAL = OFF_BAR + 512 + 1024;
+};
+
+struct V2Maps { CUtensorMap a[3]; CUtensorMap b; CUtensorMap out; };   // a[0] main, a[1]/a[2] shortcut sources
+struct V2Params {
+    int n_work;              // super-tiles x N tiles
+    int n_ntiles, tiles_x, supers_per_img, imgs_per_super, row_off;
+    int seg_chunks[3];       // 64-channel chunks of main / sc0 / sc1
+    int B, H, W, Cout;
+    const float* bias; const float* bias2; const bf16* residual; int relu;
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct V2Work { int n0, y0, x0, nt; };
+__device__ __forceinline__ V2Work v2_decode(const V2Params& p, int w) {
+    V2Work o;
+    o.nt = w % p.n_ntiles;
+    const int st = w / p.n_ntiles;
+    const int per_img = p.tiles_x * p.supers_per_img;
+    const int grp = st / per_img, rem = st % per_img;
+    o.n0 = grp * p.imgs_per_super;
+    o.y0 = (rem / p.tiles_x) * (p.imgs_per_super == 1 ? 32 : 0);
+    o.x0 = (rem % p.tiles_x) * 8;
+    return o;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ V2Maps maps,
+                                                                 const __grid_constant__ V2Params p, bf16* __restrict__ out) {
+    using L = V2Smem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* a_full = bars;                        // [2]
+    uint64_t* a_empty = a_full + V2_A_STAGES;       // [2]
+    uint64_t* b_full = a_empty + V2_A_STAGES;       // [NB]
+    uint64_t* b_empty = b_full + L::NB;             // [NB]
+    uint64_t* t_full = b_empty + L::NB;             // [2]
+    uint64_t* t_empty = t_full + 2;                 // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a_bytes = p.imgs_per_super == 1 ? 34 * 10 * 128 : 2 * 18 * 10 * 128;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.b); prefetch_tmap(&maps.out);
+        for (int s = 0; s < V2_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < L::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+                const V2Work wk = v2_decode(p, w);
+                int kchunk = 0;                                       // running 64-wide K block index into the weights
+                for (int seg = 0; seg < 3; ++seg) {
+                    const int taps = seg == 0 ? 9 : 1;
+                    for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
+                        mbar_wait(&a_empty[as], aph ^ 1u);
+                        mbar_arrive_expect_tx(&a_full[as], a_bytes);
+                        tma_load_4d(smem + as * L::A_SLOT, &maps.a[seg], &a_full[as], ch * 64, wk.x0 - 1, wk.y0 - 1, wk.n0);
+                        if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
+                        for (int tap = 0; tap < taps; ++tap) {
+                            // weights are K-major [Cout][tap][cin]: K block of (tap, ch) = tap*chunks + ch
+                            const int kb = seg == 0 ? tap * p.seg_chunks[0] + ch : kchunk + ch;
+                            mbar_wait(&b_empty[bs], bph ^ 1u);
+                            mbar_arrive_expect_tx(&b_full[bs], L::B_TILE);
+                            tma_load_2d(smem + L::OFF_B + bs * L::B_TILE, &maps.b, &b_full[bs], kb * 64, wk.nt * BN);
+                            if (++bs == L::NB) { bs = 0; bph ^= 1u; }
+                        }
+                    }
+                    kchunk += (seg == 0 ? 9 : 1) * p.seg_chunks[seg];
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int tb = 0; uint32_t tph = 0;
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+                mbar_wait(&t_empty[tb], tph ^ 1u);                    // epilogue drained this accumulator pair
+                tc_fence_after();
+                uint32_t first = 1;
+                for (int seg = 0; seg < 3; ++seg) {
+                    const int taps = seg == 0 ? 9 : 1;
+                    for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
+                        mbar_wait(&a_full[as], aph);
+                        tc_fence_after();
+                        const uint32_t a_base = smem_u32(smem + as * L::A_SLOT);
+                        for (int tap = 0; tap < taps; ++tap) {
+                            const int dy = seg == 0 ? tap / 3 : 1, dx = seg == 0 ? tap % 3 : 1;
+                            mbar_wait(&b_full[bs], bph);
+                            tc_fence_after();
+                            const uint64_t db = make_smem_desc_sw128(smem_u32(smem + L::OFF_B + bs * L::B_TILE));
+#pragma unroll
+                            for (int mt = 0; mt < V2_MT; ++mt) {
+                                const uint64_t da = make_smem_desc_sw128(a_base + ((mt * p.row_off + dy) * 10 + dx) * 128, 1280);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16(tmem + (tb * V2_MT + mt) * BN, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+                            }
+                            first = 0;
+                            umma_commit(&b_empty[bs]);
+                            if (++bs == L::NB) { bs = 0; bph ^= 1u; }
+                        }
+                        umma_commit(&a_empty[as]);
+                        if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
+                    }
+                }
+                umma_commit(&t_full[tb]);
+                if (++tb == 2) { tb = 0; tph ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3, r = q * 32 + lane;                  // accumulator row = pixel (r/8, r%8) of the 16x8 tile
+        uint8_t* staging = smem + L::OFF_STAGING;
+        const int sw = r & 7;
+        int tb = 0; uint32_t tph = 0;
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            const V2Work wk = v2_decode(p, w);
+            mbar_wait(&t_full[tb], tph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < V2_MT; ++mt) {
+                const int n_img = wk.n0 + (p.imgs_per_super == 1 ? 0 : mt);
+                const int ty0 = wk.y0 + (p.imgs_per_super == 1 ? 16 * mt : 0);
+                const int oy = ty0 + (r >> 3), ox = wk.x0 + (r & 7);
+                const bool valid = n_img < p.B;                      // H, W are multiples of the tile
+                const size_t pix = ((size_t)n_img * p.H + oy) * p.W + ox;
+                if (threadIdx.x == 64) tma_store_wait_read();        // previous TMA store has read the staging tile
+                epi_bar_sync();
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tb * V2_MT + mt) * BN + c0), v);
+                    tmem_ld_wait();
+                    const int n = wk.nt * BN + c0;
+                    uint8_t* srow = staging + (c0 >> 6) * 16384 + r * 128;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) + __ldg(p.bias + n + g * 8 + j);
+                        if (p.bias2) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] += __ldg(p.bias2 + n + g * 8 + j);
+                        }
+                        if (p.residual && valid) {
+                            float rr[8];
+                            load8<bf16>(p.residual + pix * p.Cout + n + g * 8, rr);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] += rr[j];
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        uint4 pk;
+                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                        const int chunk16 = (((c0 & 63) >> 3) + g) ^ sw;
+                        *reinterpret_cast<uint4*>(srow + chunk16 * 16) = pk;
+                    }
+                }
+                if (mt == V2_MT - 1) { tc_fence_before(); mbar_arrive(&t_empty[tb]); }   // accumulators fully read
+                fence_proxy_async();
+                epi_bar_sync();
+                if (threadIdx.x == 64 && valid) {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_store_4d(&maps.out, staging + j * 16384, wk.nt * BN + j * 64, wk.x0, ty0, n_img);
+                    tma_store_commit();
+                }
+            }
+            if (++tb == 2) { tb = 0; tph ^= 1u; }
+        }
+        if (threadIdx.x == 64) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+    (void)out;
+}
+
+bool conv_tc2_supported(const ConvArgs& a) {
+    if (a.KH != 3 || a.KW != 3 || a.stride != 1 || a.pad != 1 || a.sc_stride != 1) return false;
+    if (a.Cin % 64 || a.sc0_C % 64 || a.sc1_C % 64 || a.Cout % 64) return false;
+    if (a.W % 8 || a.H % 16) return false;
+    if (a.H % 32 != 0 && a.H != 16) return false;
+    return true;
+}
+
+template <int BN>
+static void launch_v2(const V2Maps& maps, const V2Params& p, int grid, bf16* out, cudaStream_t s) {
+    using L = V2Smem<BN>;
+    static bool attr = false;
+    if (!attr) {
+        SYNT_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr = true;
+    }
+    conv_tc2_kernel<BN><<<grid, V2_THREADS, L::TOTAL, s>>>(maps, p, out);
+    SYNT_LAUNCH_CHECK();
+}
+
+static void make_halo_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_h, int box_n) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, 10, (cuuint32_t)box_h, (cuuint32_t)box_n};
+    encode_bf16_sw128(m, base, 4, dims, strides, box, "halo activation");
+}
+
+void conv_tc2(const ConvArgs& a, cudaStream_t s) {
+    SYNT_CHECK(conv_tc2_supported(a), "conv_tc2: unsupported shape");
+    SYNT_CHECK(a.bias != nullptr, "conv_tc2: bias required");
+    const int BN = (a.Cout % 128 == 0) ? 128 : 64;
+    V2Params p{};
+    p.imgs_per_super = a.H == 16 ? 2 : 1;
+    p.row_off = a.H == 16 ? 18 : 16;
+    p.tiles_x = a.W / 8;
+    p.supers_per_img = a.H == 16 ? 1 : a.H / 32;
+    p.n_ntiles = a.Cout / BN;
+    const int n_super = ceil_div(a.B, p.imgs_per_super) * p.tiles_x * p.supers_per_img;
+    p.n_work = n_super * p.n_ntiles;
+    p.seg_chunks[0] = a.Cin / 64; p.seg_chunks[1] = a.sc0_C / 64; p.seg_chunks[2] = a.sc1_C / 64;
+    p.B = a.B; p.H = a.H; p.W = a.W; p.Cout = a.Cout;
+    p.bias = a.bias; p.bias2 = a.bias2; p.residual = (const bf16*)a.residual; p.relu = a.relu;
+    V2Maps maps;
+    const int bh = a.H == 16 ? 18 : 34, bn = a.H == 16 ? 2 : 1;
+    make_halo_map(&maps.a[0], a.in, a.B, a.H, a.W, a.Cin, bh, bn);
+    if (a.sc0_C) make_halo_map(&maps.a[1], a.sc0, a.B, a.H, a.W, a.sc0_C, bh, bn); else maps.a[1] = maps.a[0];
+    if (a.sc1_C) make_halo_map(&maps.a[2], a.sc1, a.B, a.H, a.W, a.sc1_C, bh, bn); else maps.a[2] = maps.a[0];
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)a.ktot(), (cuuint64_t)a.Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)a.ktot() * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)BN};
+        encode_bf16_sw128(&maps.b, a.weight, 2, dims, strides, box, "v2 weight");
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+        cuuint64_t strides[3] = {(cuuint64_t)a.Cout * 2, (cuuint64_t)a.W * a.Cout * 2, (cuuint64_t)a.H * a.W * a.Cout * 2};
+        cuuint32_t box[4] = {64, 8, 16, 1};
+        encode_bf16_sw128(&maps.out, a.out, 4, dims, strides, box, "v2 output");
+    }
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int grid = p.n_work < num_sms ? p.n_work : num_sms;
+    if (BN == 128) launch_v2<128>(maps, p, grid, (bf16*)a.out, s);
+    else           launch_v2<64>(maps, p, grid, (bf16*)a.out, s);
+}
+
+}  // namespace synt

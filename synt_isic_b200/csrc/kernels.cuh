@@ -37,6 +37,9 @@ void conv_simt(const ConvArgs& a, int act_dtype, cudaStream_t s);
 // Requires Cin, sc0_C, sc1_C multiples of 64 and Cout a multiple of 16.
 bool conv_tc_supported(const ConvArgs& a);
 void conv_tc(const ConvArgs& a, cudaStream_t s);
+// persistent halo-tile kernel for 3x3 stride-1 convs (+ fused 1x1 shortcut segments), see conv_tc2.cu
+bool conv_tc2_supported(const ConvArgs& a);
+void conv_tc2(const ConvArgs& a, cudaStream_t s);
 // experimental: 3x3 stride-1 conv with one halo-tile load per channel chunk (see conv_tc_halo.cu)
 void conv_tc_halo(const ConvArgs& a, int variant, cudaStream_t s);
 

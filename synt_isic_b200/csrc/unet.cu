@@ -175,6 +175,7 @@ struct synt_unet {
     int dt = DT_BF16;
     bool use_tc = true;                           // tcgen05 convs (bf16 mode) vs fp32-FMA convs
     bool want_f32_w = false;
+    bool use_v2 = true;                           // persistent halo-tile kernel for 3x3 stride-1 convs
     ConvInW conv_in_w;
     ConvOutW conv_out_w;
     DevPtr norm_out_g, norm_out_b;
@@ -413,7 +414,9 @@ struct Fwd {
         a.weight = w.get(tc);
         ProfScope ps(u, s, tc ? PC_CONV_TC : PC_CONV_SIMT, 2.0 * B * a.Ho * a.Wo * (double)a.Cout * a.ktot(), B * a.Ho * a.Wo,
                      a.Cout, a.ktot());
-        if (tc) conv_tc(a, s); else conv_simt(a, u->dt, s);
+        if (tc && u->use_v2 && conv_tc2_supported(a)) conv_tc2(a, s);
+        else if (tc) conv_tc(a, s);
+        else conv_simt(a, u->dt, s);
         ++u->launches;
     }
     Act resnet(const ResnetW& r, const Act& x0, const Act* x1) {
@@ -539,7 +542,7 @@ struct Fwd {
     }
 };
 
-static int default_micro_batch(int B) { return B <= 16 ? B : 16; }
+static int default_micro_batch(int B) { return B <= 64 ? B : 64; }     // measured: no L2 benefit from smaller slices
 
 // one sampling step for all micro-batches (captured into the CUDA graph)
 static void sample_step(synt_unet* u, float* x, int B, const float* z, unsigned long long seed, long long image_offset,
@@ -607,6 +610,8 @@ int synt_unet_create(const float* params_host, long long n_params, int dtype, sy
     u->dt = dtype;
     const char* force = getenv("SYNT_FORCE_SIMT");
     u->use_tc = dtype == DT_BF16 && !(force && force[0] == '1');
+    const char* v2 = getenv("SYNT_CONV_V2");
+    u->use_v2 = !(v2 && v2[0] == '0');
     SYNT_CUDA(cudaStreamCreateWithFlags(&u->own_stream, cudaStreamNonBlocking));
     SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_in, cudaEventDisableTiming));
     SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_out, cudaEventDisableTiming));
@@ -875,7 +880,10 @@ extern "C" int synt_debug_conv(int use_tc, int act_dtype, const void* in, int B,
     a.Ho = (H + 2 * pad - K) / stride + 1; a.Wo = (W + 2 * pad - K) / stride + 1; a.Cout = Cout;
     a.sc0 = sc0; a.sc0_C = sc0_C; a.sc1 = sc1; a.sc1_C = sc1_C; a.sc_stride = sc_stride;
     a.weight = weight; a.bias = bias; a.bias2 = bias2; a.residual = residual; a.relu = relu; a.out = out;
-    if (use_tc >= 2) {
+    if (use_tc == 6) {
+        SYNT_CHECK(act_dtype == DT_BF16 && conv_tc2_supported(a), "conv_tc2: unsupported");
+        conv_tc2(a, (cudaStream_t)stream);
+    } else if (use_tc >= 2) {
         SYNT_CHECK(act_dtype == DT_BF16, "tcgen05 conv needs bf16 activations");
         conv_tc_halo(a, use_tc - 2, (cudaStream_t)stream);
     } else if (use_tc) {

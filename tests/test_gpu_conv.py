@@ -18,8 +18,9 @@ def _pack(w, wsc=None):
     return p.contiguous()
 
 
-def run_conv(dev, use_tc, B, H, W, Cin, Cout, K, stride, pad, sc=(0, 0), sc_stride=1, residual=False, relu=False,
+def run_conv(dev, mode, B, H, W, Cin, Cout, K, stride, pad, sc=(0, 0), sc_stride=1, residual=False, relu=False,
              bias2=False, seed=0):
+    use_tc = mode != 0
     g = torch.Generator().manual_seed(seed)
     dt = torch.bfloat16 if use_tc else torch.float32
     x = torch.randn(B, Cin, H, W, generator=g)
@@ -52,7 +53,7 @@ def run_conv(dev, use_tc, B, H, W, Cin, Cout, K, stride, pad, sc=(0, 0), sc_stri
     b2d = b2.to(dev) if b2 is not None else None
     out = torch.empty(B, Ho, Wo, Cout, dtype=dt, device=dev)
     ptr = lambda t: t.data_ptr() if t is not None else None
-    _lib.check(_lib.lib().synt_debug_conv(1 if use_tc else 0, 1 if use_tc else 0, ptr(xin), B, H, W, Cin, K, stride, pad,
+    _lib.check(_lib.lib().synt_debug_conv(int(mode), 1 if use_tc else 0, ptr(xin), B, H, W, Cin, K, stride, pad,
                                           ptr(xs0), sc[0], ptr(xs1), sc[1], sc_stride, ptr(wp), ptr(bd), ptr(b2d),
                                           ptr(rs), 1 if relu else 0, ptr(out), Cout, _lib.current_stream_ptr()),
                "debug_conv")
@@ -100,3 +101,18 @@ def test_conv_tcgen05_bf16(cuda_dev, case):
 def test_conv_simt_stem_7x7(cuda_dev):
     rel, mx = run_conv(cuda_dev, False, 2, 224, 224, 3, 64, 7, 2, 3, relu=True)
     assert rel < 2e-6, (rel, mx)
+
+
+V2_CASES = [c for c in CASES if c[5] == 3 and c[6] == 1 and c[1] % 16 == 0 and (c[1] % 32 == 0 or c[1] == 16) and c[9] == 1] + [
+    (3, 16, 16, 512, 256, 3, 1, 1, (256, 256), 1, False, False, True),     # up_blocks.0: concat shortcut, odd B, 2 images/super-tile
+    (5, 64, 64, 192, 128, 3, 1, 1, (128, 64), 1, False, False, True),      # up_blocks.2.resnets.2 conv2-like
+    (2, 128, 128, 128, 64, 3, 1, 1, (0, 0), 1, True, False, False),        # persistent: 256 super-tiles on 148 CTAs
+]
+
+
+@pytest.mark.parametrize("case", V2_CASES, ids=lambda c: "x".join(map(str, c[:8])))
+def test_conv_tcgen05_persistent_halo(cuda_dev, case):
+    """conv_tc2: persistent halo-tile kernel (3x3 stride 1)."""
+    B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2 = case
+    rel, mx = run_conv(cuda_dev, 6, B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2)
+    assert rel < 4e-3, (rel, mx)
