@@ -52,6 +52,7 @@ struct V2Params {
     int seg_chunks[3];       // 64-channel chunks of main / sc0 / sc1
     int B, H, W, Cout;
     const float* bias; const float* bias2; const bf16* residual; int relu;
+    float2* stats; int stats_slots;   // optional fused GroupNorm partials [B][stats_slots][Cout]
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
@@ -236,6 +237,25 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         tma_store_4d(&maps.out, staging + j * 16384, wk.nt * BN + j * 64, wk.x0, ty0, n_img);
                     tma_store_commit();
                 }
+                if (p.stats && valid) {
+                    // fused GroupNorm statistics: per-channel (sum, sumsq) of the bf16 values just staged,
+                    // one partial row per (tile, row-half); thread = one column, fixed summation order
+                    const int et = threadIdx.x - 64;                 // 0..127
+                    const int col = et % BN, half = et / BN;          // BN = 128: half = 0, all 128 rows
+                    constexpr int ROWS = BN;                          // rows per thread: 128 (BN=128) or 64 (BN=64)
+                    const uint8_t* sb = staging + (col >> 6) * 16384 + (col & 7) * 2;
+                    const int ck = (col & 63) >> 3;
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                    for (int i = 0; i < ROWS; ++i) {
+                        const int row = half * ROWS + i;
+                        const float x = __bfloat162float(*reinterpret_cast<const bf16*>(sb + row * 128 + ((ck ^ (row & 7)) << 4)));
+                        s1 += x; s2 = fmaf(x, x, s2);
+                    }
+                    const int tile_in_img = (ty0 >> 4) * p.tiles_x + (wk.x0 >> 3);
+                    const int slot = tile_in_img * (128 / BN) + half;
+                    p.stats[((size_t)n_img * p.stats_slots + slot) * p.Cout + wk.nt * BN + col] = make_float2(s1, s2);
+                }
             }
             if (++tb == 2) { tb = 0; tph ^= 1u; }
         }
@@ -248,11 +268,18 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
 }
 
 bool conv_tc2_supported(const ConvArgs& a) {
-    if (a.KH != 3 || a.KW != 3 || a.stride != 1 || a.pad != 1 || a.sc_stride != 1) return false;
+    const bool k3 = a.KH == 3 && a.KW == 3 && a.pad == 1;
+    const bool k1 = a.KH == 1 && a.KW == 1 && a.pad == 0 && a.sc0_C == 0 && a.sc1_C == 0;   // runs as a "shortcut-only" conv
+    if (!(k3 || k1) || a.stride != 1 || a.sc_stride != 1) return false;
     if (a.Cin % 64 || a.sc0_C % 64 || a.sc1_C % 64 || a.Cout % 64) return false;
     if (a.W % 8 || a.H % 16) return false;
     if (a.H % 32 != 0 && a.H != 16) return false;
     return true;
+}
+
+int conv_tc2_stats_slots(const ConvArgs& a) {
+    const int BN = (a.Cout % 128 == 0) ? 128 : 64;
+    return (a.H / 16) * (a.W / 8) * (128 / BN);
 }
 
 template <int BN>
@@ -286,13 +313,16 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     p.n_ntiles = a.Cout / BN;
     const int n_super = ceil_div(a.B, p.imgs_per_super) * p.tiles_x * p.supers_per_img;
     p.n_work = n_super * p.n_ntiles;
-    p.seg_chunks[0] = a.Cin / 64; p.seg_chunks[1] = a.sc0_C / 64; p.seg_chunks[2] = a.sc1_C / 64;
+    const bool k1 = a.KH == 1;                          // 1x1 conv == centre-tap-only segment of the same machinery
+    p.seg_chunks[0] = k1 ? 0 : a.Cin / 64; p.seg_chunks[1] = k1 ? a.Cin / 64 : a.sc0_C / 64; p.seg_chunks[2] = a.sc1_C / 64;
     p.B = a.B; p.H = a.H; p.W = a.W; p.Cout = a.Cout;
     p.bias = a.bias; p.bias2 = a.bias2; p.residual = (const bf16*)a.residual; p.relu = a.relu;
+    p.stats = a.stats_out; p.stats_slots = conv_tc2_stats_slots(a);
     V2Maps maps;
     const int bh = a.H == 16 ? 18 : 34, bn = a.H == 16 ? 2 : 1;
     make_halo_map(&maps.a[0], a.in, a.B, a.H, a.W, a.Cin, bh, bn);
-    if (a.sc0_C) make_halo_map(&maps.a[1], a.sc0, a.B, a.H, a.W, a.sc0_C, bh, bn); else maps.a[1] = maps.a[0];
+    if (k1) maps.a[1] = maps.a[0];
+    else if (a.sc0_C) make_halo_map(&maps.a[1], a.sc0, a.B, a.H, a.W, a.sc0_C, bh, bn); else maps.a[1] = maps.a[0];
     if (a.sc1_C) make_halo_map(&maps.a[2], a.sc1, a.B, a.H, a.W, a.sc1_C, bh, bn); else maps.a[2] = maps.a[0];
     {
         cuuint64_t dims[2] = {(cuuint64_t)a.ktot(), (cuuint64_t)a.Cout};

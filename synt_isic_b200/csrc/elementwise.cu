@@ -120,6 +120,60 @@ void gn_finalize(const float2* partials, int B, int nchunk, int G, int C, int HW
     SYNT_LAUNCH_CHECK();
 }
 
+// Per-channel partials -> scale/shift.  One block per image; channel sums in double, fixed order.
+__global__ void __launch_bounds__(256) gn_finalize_channels_kernel(const float2* __restrict__ partA, int SA, int C0,
+                                                                   const float2* __restrict__ partB, int SB, int C1, int G,
+                                                                   int HW, float eps, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta,
+                                                                   float2* __restrict__ scale_shift) {
+    __shared__ double cs[4][512];
+    __shared__ double cq[4][512];
+    __shared__ float2 stat[32];
+    const int b = blockIdx.x, C = C0 + C1;
+    const int nslice = C <= 256 ? 256 / C : 1;              // threads cooperating on one channel
+    auto channel_sum = [&](int c, int slice) {
+        const bool first = c < C0;
+        const float2* base = first ? partA + (size_t)b * SA * C0 + c : partB + (size_t)b * SB * C1 + (c - C0);
+        const int S = first ? SA : SB, Cs = first ? C0 : C1;
+        double ts = 0.0, tq = 0.0;
+        for (int k = slice; k < S; k += nslice) {
+            const float2 v = __ldg(base + (size_t)k * Cs);
+            ts += (double)v.x; tq += (double)v.y;
+        }
+        cs[slice][c] = ts; cq[slice][c] = tq;
+    };
+    if (C <= 256) {
+        const int c = threadIdx.x % C, slice = threadIdx.x / C;
+        if (slice < nslice) channel_sum(c, slice);
+    } else {
+        for (int c = threadIdx.x; c < C; c += 256) channel_sum(c, 0);
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    if (threadIdx.x < G) {
+        double ts = 0.0, tq = 0.0;
+        for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c)
+            for (int sl = 0; sl < nslice; ++sl) { ts += cs[sl][c]; tq += cq[sl][c]; }
+        const double cnt = (double)HW * cpg;
+        const double mean = ts / cnt;
+        double var = tq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stat[threadIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const float2 st = stat[c / cpg];
+        const float sc = st.y * gamma[c];
+        scale_shift[(size_t)b * C + c] = make_float2(sc, beta[c] - st.x * sc);
+    }
+}
+void gn_finalize_channels(const float2* partA, int SA, int C0, const float2* partB, int SB, int C1, int B, int G, int HW,
+                          float eps, const float* gamma, const float* beta, float2* scale_shift, cudaStream_t s) {
+    SYNT_CHECK(C0 + C1 <= 512 && G <= 32 && (C0 + C1) % G == 0, "gn_finalize_channels: bad channel counts");
+    gn_finalize_channels_kernel<<<B, 256, 0, s>>>(partA, SA, C0, partB, SB, C1, G, HW, eps, gamma, beta, scale_shift);
+    SYNT_LAUNCH_CHECK();
+}
+
 // silu(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx) per element
 __device__ __forceinline__ float silu_tanh(float x) {
     const float h = 0.5f * x;

@@ -29,6 +29,7 @@ struct ConvArgs {
     const void* residual = nullptr;    // NHWC [B, Ho, Wo, Cout] or null
     int relu = 0;
     void* out = nullptr;               // NHWC [B, Ho, Wo, Cout]
+    float2* stats_out = nullptr;       // conv_tc2 only: per-channel (sum, sumsq) partials [B][slots][Cout] of `out`
     int ktot() const { return KH * KW * Cin + sc0_C + sc1_C; }
 };
 // fp32-FMA implicit GEMM (verification mode and odd shapes); weights are fp32.
@@ -40,6 +41,7 @@ void conv_tc(const ConvArgs& a, cudaStream_t s);
 // persistent halo-tile kernel for 3x3 stride-1 convs (+ fused 1x1 shortcut segments), see conv_tc2.cu
 bool conv_tc2_supported(const ConvArgs& a);
 void conv_tc2(const ConvArgs& a, cudaStream_t s);
+int conv_tc2_stats_slots(const ConvArgs& a);     // partial rows per image written when stats_out != null
 // experimental: 3x3 stride-1 conv with one halo-tile load per channel chunk (see conv_tc_halo.cu)
 void conv_tc_halo(const ConvArgs& a, int variant, cudaStream_t s);
 
@@ -80,6 +82,9 @@ void gn_stats(const void* src0, int C0, const void* src1, int C1, int dt, int B,
               int nchunk, cudaStream_t s);
 void gn_finalize(const float2* partials, int B, int nchunk, int G, int C, int HW, float eps, const float* gamma,
                  const float* beta, float2* scale_shift, cudaStream_t s);
+// finalize from PER-CHANNEL partials of one or two (concatenated) tensors: partA [B][SA][C0], partB [B][SB][C1]
+void gn_finalize_channels(const float2* partA, int SA, int C0, const float2* partB, int SB, int C1, int B, int G, int HW,
+                          float eps, const float* gamma, const float* beta, float2* scale_shift, cudaStream_t s);
 void gn_apply(const void* src0, int C0, const void* src1, int C1, int dt, int B, int HW, const float2* scale_shift,
               int silu, void* out, cudaStream_t s);
 

@@ -152,6 +152,7 @@ static WeightDev upload_weight(const std::vector<float>& w, bool want_f32, bool 
 // ------------------------------------------------------------------ model -------------
 struct Act {                                      // NHWC activation
     void* p = nullptr; int B = 0, H = 0, W = 0, C = 0;
+    float2* stats = nullptr; int stats_slots = 0;  // per-channel (sum, sumsq) partials [B][slots][C] for GroupNorm
     size_t numel() const { return (size_t)B * H * W * C; }
 };
 
@@ -379,7 +380,16 @@ struct Fwd {
     Act make(int H, int W, int C) {
         Act a; a.B = B; a.H = H; a.W = W; a.C = C; a.p = u->pool.alloc(a.numel() * esz()); return a;
     }
-    void drop(Act& a) { u->pool.release(a.p); a.p = nullptr; }
+    void drop(Act& a) { u->pool.release(a.p); u->pool.release(a.stats); a.p = nullptr; a.stats = nullptr; }
+    // per-channel statistics by the stand-alone kernel (tensors whose producer does not fuse them)
+    void standalone_stats(Act& a) {
+        const int HW = a.H * a.W;
+        a.stats_slots = gn_num_chunks(B, HW);
+        a.stats = (float2*)u->pool.alloc((size_t)B * a.stats_slots * a.C * sizeof(float2));
+        ProfScope ps(u, s, PC_GN_STATS);
+        gn_stats(a.p, a.C, nullptr, 0, u->dt, B, HW, a.C, a.stats, a.stats_slots, s);
+        ++u->launches;
+    }
     void tap(const std::string& name, const Act& a) {
         if (!u->tap_out || name != u->tap_name) return;
         SYNT_CHECK((long long)a.numel() <= u->tap_cap, "debug tap buffer too small");
@@ -390,14 +400,12 @@ struct Fwd {
     // GroupNorm statistics of concat(x0, x1) -> per-(b, c) scale/shift
     float2* gn_scale_shift(const Act& x0, const Act* x1, const DevPtr& gamma, const DevPtr& beta) {
         const int C = x0.C + (x1 ? x1->C : 0), HW = x0.H * x0.W;
-        const int nchunk = gn_num_chunks(B, HW);
-        float2* part = (float2*)u->pool.alloc((size_t)B * nchunk * kGroups * sizeof(float2));
+        SYNT_CHECK(x0.stats && (!x1 || x1->stats), "GroupNorm input without statistics");
         float2* ss = (float2*)u->pool.alloc((size_t)B * C * sizeof(float2));
         ProfScope ps(u, s, PC_GN_STATS);
-        gn_stats(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, u->dt, B, HW, kGroups, part, nchunk, s);
-        gn_finalize(part, B, nchunk, kGroups, C, HW, kGnEps, (const float*)gamma->p, (const float*)beta->p, ss, s);
-        u->pool.release(part);
-        u->launches += 2;
+        gn_finalize_channels(x0.stats, x0.stats_slots, x0.C, x1 ? x1->stats : nullptr, x1 ? x1->stats_slots : 0,
+                             x1 ? x1->C : 0, B, kGroups, HW, kGnEps, (const float*)gamma->p, (const float*)beta->p, ss, s);
+        ++u->launches;
         return ss;
     }
     Act gn_act(const Act& x0, const Act* x1, const DevPtr& gamma, const DevPtr& beta, bool silu) {
@@ -409,15 +417,25 @@ struct Fwd {
         ++u->launches;
         return o;
     }
-    void conv(ConvArgs& a, const WeightDev& w) {
+    // `out` receives GroupNorm statistics when want_stats: fused in the conv_tc2 epilogue, else stand-alone
+    void conv(ConvArgs& a, const WeightDev& w, Act* out = nullptr, bool want_stats = false) {
         const bool tc = u->dt == DT_BF16 && u->use_tc && conv_tc_supported(a);
+        const bool v2 = tc && u->use_v2 && conv_tc2_supported(a);
         a.weight = w.get(tc);
-        ProfScope ps(u, s, tc ? PC_CONV_TC : PC_CONV_SIMT, 2.0 * B * a.Ho * a.Wo * (double)a.Cout * a.ktot(), B * a.Ho * a.Wo,
-                     a.Cout, a.ktot());
-        if (tc && u->use_v2 && conv_tc2_supported(a)) conv_tc2(a, s);
-        else if (tc) conv_tc(a, s);
-        else conv_simt(a, u->dt, s);
-        ++u->launches;
+        if (want_stats && v2) {
+            out->stats_slots = conv_tc2_stats_slots(a);
+            out->stats = (float2*)u->pool.alloc((size_t)B * out->stats_slots * a.Cout * sizeof(float2));
+            a.stats_out = out->stats;
+        }
+        {
+            ProfScope ps(u, s, tc ? PC_CONV_TC : PC_CONV_SIMT, 2.0 * B * a.Ho * a.Wo * (double)a.Cout * a.ktot(),
+                         B * a.Ho * a.Wo, a.Cout, a.ktot());
+            if (v2) conv_tc2(a, s);
+            else if (tc) conv_tc(a, s);
+            else conv_simt(a, u->dt, s);
+            ++u->launches;
+        }
+        if (want_stats && !v2) standalone_stats(*out);
     }
     Act resnet(const ResnetW& r, const Act& x0, const Act* x1) {
         const int H = x0.H, W = x0.W;
@@ -426,7 +444,7 @@ struct Fwd {
         {
             ConvArgs c; c.in = a.p; c.B = B; c.H = H; c.W = W; c.Cin = r.cin; c.Ho = H; c.Wo = W; c.Cout = r.cout;
             c.bias = (const float*)r.bias1->p; c.bias2 = (const float*)u->temb_cur->p + r.temb_off; c.out = h1.p;
-            conv(c, r.w1);
+            conv(c, r.w1, &h1, true);
         }
         drop(a);
         Act a2 = gn_act(h1, nullptr, r.g2, r.b2n, true);
@@ -442,7 +460,7 @@ struct Fwd {
                 SYNT_CHECK(x1 == nullptr, "identity residual with a concatenated input");
                 c.residual = x0.p;
             }
-            conv(c, r.w2);
+            conv(c, r.w2, &o, true);
         }
         drop(a2);
         tap(r.name, o);
@@ -477,7 +495,7 @@ struct Fwd {
         {
             ConvArgs c; c.in = o.p; c.B = B; c.H = H; c.W = W; c.Cin = C; c.KH = c.KW = 1; c.pad = 0; c.Ho = H; c.Wo = W;
             c.Cout = C; c.bias = (const float*)w.bo->p; c.residual = x.p; c.out = out.p;
-            conv(c, w.wo);
+            conv(c, w.wo, &out, true);
         }
         drop(o);
         tap(w.name, out);
@@ -487,7 +505,7 @@ struct Fwd {
         Act o = make(x.H / 2, x.W / 2, w.cout);
         ConvArgs c; c.in = x.p; c.B = B; c.H = x.H; c.W = x.W; c.Cin = w.cin; c.stride = 2; c.Ho = o.H; c.Wo = o.W;
         c.Cout = w.cout; c.bias = (const float*)w.b->p; c.out = o.p;
-        conv(c, w.w);
+        conv(c, w.w, &o, true);
         tap(w.name.substr(0, w.name.size() - 5), o);           // strip ".conv"
         return o;
     }
@@ -498,7 +516,7 @@ struct Fwd {
         Act o = make(up2.H, up2.W, w.cout);
         ConvArgs c; c.in = up2.p; c.B = B; c.H = up2.H; c.W = up2.W; c.Cin = w.cin; c.Ho = o.H; c.Wo = o.W;
         c.Cout = w.cout; c.bias = (const float*)w.b->p; c.out = o.p;
-        conv(c, w.w);
+        conv(c, w.w, &o, true);
         drop(up2);
         tap(w.name.substr(0, w.name.size() - 5), o);
         return o;
@@ -509,6 +527,7 @@ struct Fwd {
         Act h = make(kImg, kImg, 64);
         { ProfScope ps(u, s, PC_CONV_IN, 2.0 * B * kImg * kImg * 64.0 * 27); conv_in3(x_nchw, u->conv_in_w, B, kImg, kImg, h.p, u->dt, s); }
         ++u->launches;
+        standalone_stats(h);
         tap("conv_in", h);
         std::vector<Act> skips; skips.push_back(h);
         Act cur = h;                                            // `cur` aliases the top skip

@@ -103,7 +103,7 @@ def test_conv_simt_stem_7x7(cuda_dev):
     assert rel < 2e-6, (rel, mx)
 
 
-V2_CASES = [c for c in CASES if c[5] == 3 and c[6] == 1 and c[1] % 16 == 0 and (c[1] % 32 == 0 or c[1] == 16) and c[9] == 1] + [
+V2_CASES = [c for c in CASES if c[5] in (1, 3) and c[6] == 1 and c[1] % 16 == 0 and (c[1] % 32 == 0 or c[1] == 16) and c[9] == 1] + [
     (3, 16, 16, 512, 256, 3, 1, 1, (256, 256), 1, False, False, True),     # up_blocks.0: concat shortcut, odd B, 2 images/super-tile
     (5, 64, 64, 192, 128, 3, 1, 1, (128, 64), 1, False, False, True),      # up_blocks.2.resnets.2 conv2-like
     (2, 128, 128, 128, 64, 3, 1, 1, (0, 0), 1, True, False, False),        # persistent: 256 super-tiles on 148 CTAs
