@@ -9,17 +9,19 @@
 //   vt   [B*32, 16, N] bf16 = per head V^T padded to 16 rows: rows 0..7 = v dims, row 8 = 1
 //          (so the P.V MMA also produces the softmax denominator), rows 9..15 = 0.
 //
-// One CTA = 128 queries x 4 heads of one image.  Per head and 128-key chunk:
-//   S  = Q_h K_h^T     one tcgen05.mma  M128 x N128 x K16  -> TMEM (fp32, log2 domain)
+// One CTA = 128 queries x 4 heads of one image; one pass over the keys in chunks of 128:
+//   S  = Q_h K_h^T     one tcgen05.mma  M128 x N128 x K16  -> TMEM (fp32, log2 domain), 3 S buffers
 //   P  = exp2(S - m)   softmax warps: tcgen05.ld -> ex2 -> bf16 -> swizzled st.shared
 //   O_h += P V_h       eight tcgen05.mma M128 x N16 x K16, P from shared memory
-// Exact two-pass softmax: pass 1 streams K once to get the row maxima m (MMA + TMEM read only),
-// pass 2 recomputes S and accumulates O without any rescaling.  d = 8 makes the kernel
-// exp-bound (N^2 ex2 per head), the MMAs are <10% of its time; two softmax warpgroups work on
-// alternate heads so that the MUFU pipes stay busy while the other group waits for its MMA.
+// Online softmax with LAZY rescaling: the running reference m of a row only moves when the chunk
+// maximum exceeds it by more than 2^8; then O_h (16 TMEM columns incl. the denominator column)
+// is scaled in place by the softmax warps (tcgen05.ld/st) while no MMA on O_h is in flight.  The
+// result is mathematically the exact softmax.  d = 8 makes the kernel exp/TMEM-read bound
+// (N^2 ex2 per head; the MMAs are <10% of its time).
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
-// warps 2..5 softmax warpgroup 0 (heads 0,2), warps 6..9 softmax warpgroup 1 (heads 1,3).
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 TMEM allocator + S-MMA issuer, warp 2
+// P.V-MMA issuer, warp 3 idle, warps 4..7 softmax warpgroup 0 (heads 0,2), warps 8..11 softmax
+// warpgroup 1 (heads 1,3).
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -28,7 +30,7 @@ namespace synt {
 
 using namespace ptx;
 
-constexpr int ATC_THREADS = 320;
+constexpr int ATC_THREADS = 384;
 constexpr int ATC_STAGES = 3;
 constexpr int ATC_Q_BYTES = 128 * 128;                 // 128 queries x (4 heads x 16) bf16
 constexpr int ATC_K_BYTES = 128 * 128;                 // 128 keys    x (4 heads x 16) bf16
@@ -39,7 +41,10 @@ constexpr int ATC_OFF_STAGE = ATC_Q_BYTES;
 constexpr int ATC_OFF_P = ATC_OFF_STAGE + ATC_STAGES * ATC_STAGE_BYTES;
 constexpr int ATC_OFF_BAR = ATC_OFF_P + 2 * ATC_P_BYTES;
 constexpr int ATC_SMEM = ATC_OFF_BAR + 256 + 1024;
-constexpr uint32_t ATC_TMEM_COLS = 512;                // S0 [0,128) S1 [128,256) O_h [256+16h, +16)
+constexpr uint32_t ATC_TMEM_COLS = 512;                // S buffers [0,384), O_h [384+16h, +16)
+constexpr int ATC_NS = 3;                              // S buffers
+constexpr uint32_t ATC_O_COL = 384;
+constexpr float ATC_LAZY = 8.0f;                       // rescale only when the max grows by more than 2^8
 
 struct AttnTcMaps { CUtensorMap qk; CUtensorMap vt; };
 
@@ -59,6 +64,24 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, int N,
                                                                       int C, bf16* __restrict__ out) {
@@ -68,9 +91,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_OFF_BAR);
     uint64_t* full_bar = bars;                   // [STAGES]
     uint64_t* empty_bar = bars + ATC_STAGES;     // [STAGES]
-    uint64_t* s_full = bars + 2 * ATC_STAGES;    // [2]
-    uint64_t* s_free = s_full + 2;               // [2]
-    uint64_t* p_full = s_free + 2;               // [2]
+    uint64_t* s_full = bars + 2 * ATC_STAGES;    // [NS]
+    uint64_t* s_free = s_full + ATC_NS;          // [NS]
+    uint64_t* p_full = s_free + ATC_NS;          // [2]
     uint64_t* p_free = p_full + 2;               // [2]
     uint64_t* q_full = p_free + 2;
     uint64_t* o_full = q_full + 1;
@@ -79,15 +102,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, hg = blockIdx.y, b = blockIdx.z;
     const int n_chunks = N / 128;
+    const int n_units = n_chunks * 4;            // unit u = chunk*4 + head
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.qk);
         prefetch_tmap(&maps.vt);
         for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int g = 0; g < 2; ++g) {
-            mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 128);
-            mbar_init(&p_full[g], 128); mbar_init(&p_free[g], 1);
-        }
+        for (int s = 0; s < ATC_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 128); }
+        for (int g = 0; g < 2; ++g) { mbar_init(&p_full[g], 128); mbar_init(&p_free[g], 1); }
         mbar_init(q_full, 1); mbar_init(o_full, 1);
         fence_barrier_init();
     }
@@ -103,137 +125,122 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
             mbar_arrive_expect_tx(q_full, ATC_Q_BYTES);
             tma_load_2d(smem, &maps.qk, q_full, hg * 64, b * N + q0);
             int stage = 0; uint32_t phase = 0;
-            for (int pass = 0; pass < 2; ++pass) {
-                for (int c = 0; c < n_chunks; ++c) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    uint8_t* sk = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], pass == 0 ? ATC_K_BYTES : ATC_STAGE_BYTES);
-                    tma_load_2d(sk, &maps.qk, &full_bar[stage], 512 + hg * 64, b * N + c * 128);
-                    if (pass == 1) {
-                        tma_load_3d(sk + ATC_K_BYTES, &maps.vt, &full_bar[stage], c * 128, 0, b * (C / 8) + hg * 4);
-                        tma_load_3d(sk + ATC_K_BYTES + ATC_V_BYTES / 2, &maps.vt, &full_bar[stage], c * 128 + 64, 0,
-                                    b * (C / 8) + hg * 4);
-                    }
-                    if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
-                }
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                uint8_t* sk = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], ATC_STAGE_BYTES);
+                tma_load_2d(sk, &maps.qk, &full_bar[stage], 512 + hg * 64, b * N + c * 128);
+                tma_load_3d(sk + ATC_K_BYTES, &maps.vt, &full_bar[stage], c * 128, 0, b * (C / 8) + hg * 4);
+                tma_load_3d(sk + ATC_K_BYTES + ATC_V_BYTES / 2, &maps.vt, &full_bar[stage], c * 128 + 64, 0,
+                            b * (C / 8) + hg * 4);
+                if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // ===================== MMA issuer =====================
+            // ===================== S = Q K^T issuer =====================
             constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(128, 16);
             const uint32_t q_addr = smem_u32(smem);
-            const uint32_t p_addr = smem_u32(smem + ATC_OFF_P);
-            uint32_t sfree_ph[2] = {0, 0}, pfull_ph[2] = {0, 0};
             int stage = 0; uint32_t phase = 0;
             mbar_wait(q_full, 0);
-            auto issue_s = [&](int j, uint32_t k_addr) {
-                const int g = j & 1;
-                mbar_wait(&s_free[g], sfree_ph[g] ^ 1u); sfree_ph[g] ^= 1u;
-                tc_fence_after();
-                umma_bf16(tmem + g * 128, make_smem_desc_sw128(q_addr) + 2 * j, make_smem_desc_sw128(k_addr) + 2 * j,
-                          idesc_s, 0u);
-                umma_commit(&s_full[g]);
-            };
-            // ---- pass 1: row maxima (S only)
-            for (int c = 0; c < n_chunks; ++c) {
-                mbar_wait(&full_bar[stage], phase);
+            for (int u = 0; u < n_units; ++u) {
+                const int j = u & 3, sb = u % ATC_NS;
+                if (j == 0) { mbar_wait(&full_bar[stage], phase); }
+                mbar_wait(&s_free[sb], (((uint32_t)(u / ATC_NS)) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES);
-                for (int j = 0; j < 4; ++j) issue_s(j, k_addr);
-                umma_commit(&empty_bar[stage]);
-                if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+                umma_bf16(tmem + sb * 128, make_smem_desc_sw128(q_addr) + 2 * j, make_smem_desc_sw128(k_addr) + 2 * j,
+                          idesc_s, 0u);
+                umma_commit(&s_full[sb]);
+                if (j == 3) { if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; } }
             }
-            // ---- pass 2: S, then P.V of the previous unit (software pipelined by one unit)
-            int pend_j = -1, pend_c = 0, pend_stage = 0;
-            auto issue_pv = [&]() {
-                const int g = pend_j & 1;
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // ===================== O += P V issuer =====================
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, 16);
+            const uint32_t p_addr = smem_u32(smem + ATC_OFF_P);
+            int stage = 0; uint32_t phase = 0; uint32_t pfull_ph[2] = {0, 0};
+            for (int u = 0; u < n_units; ++u) {
+                const int j = u & 3, c = u >> 2, g = j & 1;
+                if (j == 0) mbar_wait(&full_bar[stage], phase);          // V of this chunk has landed
                 mbar_wait(&p_full[g], pfull_ph[g]); pfull_ph[g] ^= 1u;
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(smem + ATC_OFF_STAGE + pend_stage * ATC_STAGE_BYTES + ATC_K_BYTES);
+                const uint32_t v_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES + ATC_K_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
                     const uint64_t dp = make_smem_desc_sw128(p_addr + g * ATC_P_BYTES + kb * 16384);
-                    const uint64_t dv = make_smem_desc_sw128(v_addr + kb * (ATC_V_BYTES / 2) + pend_j * 2048);
+                    const uint64_t dv = make_smem_desc_sw128(v_addr + kb * (ATC_V_BYTES / 2) + j * 2048);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(tmem + 256 + pend_j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv,
-                                  (pend_c | kb | kk) != 0 ? 1u : 0u);
+                        umma_bf16(tmem + ATC_O_COL + j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv, (c | kb | kk) != 0 ? 1u : 0u);
                 }
                 umma_commit(&p_free[g]);
-                if (pend_j == 3) umma_commit(&empty_bar[pend_stage]);
-            };
-            for (int c = 0; c < n_chunks; ++c) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t k_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES);
-                for (int j = 0; j < 4; ++j) {
-                    issue_s(j, k_addr);
-                    if (pend_j >= 0) issue_pv();
-                    pend_j = j; pend_c = c; pend_stage = stage;
+                if (j == 3) {
+                    umma_commit(&empty_bar[stage]);                      // all S and P.V reads of this stage are done
+                    if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
             }
-            issue_pv();
             umma_commit(o_full);
         }
-    } else {
+    } else if (warp >= 4) {
         // ===================== softmax warpgroups =====================
-        const int g = (warp - 2) >> 2;                     // warpgroup 0 / 1
+        const int g = (warp - 4) >> 2;                     // warpgroup 0 / 1
         const int quarter = warp & 3;                      // TMEM lane quarter of this warp
         const int r = quarter * 32 + lane;                 // query row
-        const uint32_t s_taddr = tmem + ((uint32_t)(quarter * 32) << 16) + g * 128;
-        uint32_t sfull_ph = 0, pfree_ph = 0;
-        float m[2] = {-INFINITY, -INFINITY};               // row maxima of heads g and g+2
-        // ---- pass 1
-        for (int c = 0; c < n_chunks; ++c) {
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                mbar_wait(&s_full[g], sfull_ph); sfull_ph ^= 1u;
-                tc_fence_after();
-                float mx = m[jj];
-#pragma unroll 1
-                for (int piece = 0; piece < 4; ++piece) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(s_taddr + piece * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                }
-                m[jj] = mx;
-                tc_fence_before();
-                mbar_arrive(&s_free[g]);
-            }
-        }
-        // ---- pass 2
+        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+        uint32_t pfree_ph = 0;
+        float m[2] = {0.f, 0.f};                           // running softmax reference of heads g and g+2
         uint8_t* p_row = smem + ATC_OFF_P + g * ATC_P_BYTES + r * 128;
         const int sw = r & 7;
         for (int c = 0; c < n_chunks; ++c) {
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
-                mbar_wait(&s_full[g], sfull_ph); sfull_ph ^= 1u;
+                const int j = g + 2 * jj, u = c * 4 + j, sb = u % ATC_NS;
+                mbar_wait(&s_full[sb], ((uint32_t)(u / ATC_NS)) & 1u);
                 tc_fence_after();
-                mbar_wait(&p_free[g], pfree_ph ^ 1u); pfree_ph ^= 1u;     // previous P.V finished reading P[g]
-                const float mrow = m[jj];
-#pragma unroll 1
-                for (int piece = 0; piece < 4; ++piece) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(s_taddr + piece * 32, v);
-                    tmem_ld_wait();
-                    if (piece == 3) { tc_fence_before(); mbar_arrive(&s_free[g]); }   // S[g] fully in registers
-                    uint32_t w[16];
+                uint32_t v[128];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        w[i] = pack_bf16x2(ex2_approx(__uint_as_float(v[2 * i]) - mrow),
-                                           ex2_approx(__uint_as_float(v[2 * i + 1]) - mrow));
+                for (int piece = 0; piece < 4; ++piece)
+                    tmem_ld_32x32b_x32(lane_addr + sb * 128 + piece * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[piece * 32]));
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&s_free[sb]);                  // S buffer is in registers
+                float cmax = __uint_as_float(v[0]);
+#pragma unroll
+                for (int i = 1; i < 128; ++i) cmax = fmaxf(cmax, __uint_as_float(v[i]));
+                float alpha = 1.0f;
+                bool moved = false;
+                if (c == 0) { m[jj] = cmax; }
+                else if (cmax > m[jj] + ATC_LAZY) { alpha = ex2_approx(m[jj] - cmax); m[jj] = cmax; moved = true; }
+                mbar_wait(&p_free[g], pfree_ph ^ 1u); pfree_ph ^= 1u;     // P.V of this group's previous unit is complete:
+                                                                          // P[g] is free and O_j has no MMA in flight
+                if (__any_sync(0xffffffffu, moved)) {
+                    tc_fence_after();
+                    uint32_t o[16];
+                    tmem_ld_x16(lane_addr + ATC_O_COL + j * 16, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st_x16(lane_addr + ATC_O_COL + j * 16, o);
+                }
+                const float mrow = m[jj];
+#pragma unroll
+                for (int piece = 0; piece < 4; ++piece) {
                     uint8_t* blk = p_row + (piece >> 1) * 16384;           // 64-key block
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = piece * 32 + q * 8 + i * 2;
+                            w[i] = pack_bf16x2(ex2_approx(__uint_as_float(v[e]) - mrow), ex2_approx(__uint_as_float(v[e + 1]) - mrow));
+                        }
                         const int chunk16 = ((piece & 1) * 4 + q) ^ sw;   // SWIZZLE_128B: 16-byte chunk ^ (row & 7)
-                        *reinterpret_cast<uint4*>(blk + chunk16 * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                        *reinterpret_cast<uint4*>(blk + chunk16 * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
+                tc_fence_before();
                 fence_proxy_async();                                       // generic-proxy writes -> async proxy (UMMA)
                 mbar_arrive(&p_full[g]);
             }
@@ -245,13 +252,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
         for (int jj = 0; jj < 2; ++jj) {
             const int j = g + 2 * jj;
             uint32_t v[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + 256 + j * 16)
-                : "memory");
+            tmem_ld_x16(lane_addr + ATC_O_COL + j * 16, v);
             tmem_ld_wait();
             const float inv = 1.0f / __uint_as_float(v[8]);
             float o[8];
