@@ -28,20 +28,20 @@ using namespace ptx;
 
 constexpr int V2_THREADS = 192;
 constexpr int V2_MT = 2;                                   // M tiles (16x8 pixels each) per super-tile
-constexpr int V2_A_SLOT = 44032;                           // 34*10*128 = 43,520 rounded up to 1 KB
-constexpr int V2_A_BYTES = 34 * 10 * 128;
-constexpr int V2_A_BYTES_2IMG = 2 * 18 * 10 * 128;         // 16x16 images: two images' halos (46,080 > slot? no: see below)
 constexpr int V2_A_STAGES = 2;
 
-template <int BN>
+// RES = true: the whole weight matrix of the layer (<= 12 K blocks of 64 x BN) stays resident in shared
+// memory for the life of the persistent CTA (Cout = 64 layers with Ktot <= 768: L2 traffic is A only).
+template <int BN, bool RES>
 struct V2Smem {
     static constexpr int A_SLOT = 46080;                   // max(34*10, 2*18*10) * 128, already 1 KB aligned
     static constexpr int B_TILE = BN * 128;
     static constexpr int STAGING = 128 * BN * 2;           // one M tile of bf16 output
-    static constexpr int NB = (BN == 128) ? 6 : 8;
+    static constexpr int NB = RES ? 12 : ((BN == 128) ? 6 : 8);
     static constexpr int OFF_B = V2_A_STAGES * A_SLOT;
     static constexpr int OFF_STAGING = OFF_B + NB * B_TILE;
-    static constexpr int OFF_BAR = OFF_STAGING + STAGING;
+    static constexpr int OFF_BIAS = OFF_STAGING + STAGING;
+    static constexpr int OFF_BAR = OFF_BIAS + BN * 4;
     static constexpr int TOTAL = OFF_BAR + 512 + 1024;
 };
 
@@ -78,10 +78,10 @@ __device__ __forceinline__ V2Work v2_decode(const V2Params& p, int w) {
     return o;
 }
 
-template <int BN>
+template <int BN, bool RES>
 __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ V2Maps maps,
                                                                  const __grid_constant__ V2Params p, bf16* __restrict__ out) {
-    using L = V2Smem<BN>;
+    using L = V2Smem<BN, RES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -113,6 +113,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         if (lane == 0) {
             // ===================== TMA producer =====================
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+            if (RES) {                                                // whole weight matrix, once (n_ntiles == 1)
+                const int nkb = 9 * p.seg_chunks[0] + p.seg_chunks[1] + p.seg_chunks[2];
+                mbar_arrive_expect_tx(&b_full[0], nkb * L::B_TILE);
+                for (int kb = 0; kb < nkb; ++kb)
+                    tma_load_2d(smem + L::OFF_B + kb * L::B_TILE, &maps.b, &b_full[0], kb * 64, 0);
+            }
             for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
                 const V2Work wk = v2_decode(p, w);
                 int kchunk = 0;                                       // running 64-wide K block index into the weights
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         mbar_arrive_expect_tx(&a_full[as], a_bytes);
                         tma_load_4d(smem + as * L::A_SLOT, &maps.a[seg], &a_full[as], ch * 64, wk.x0 - 1, wk.y0 - 1, wk.n0);
                         if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
-                        for (int tap = 0; tap < taps; ++tap) {
+                        for (int tap = 0; tap < taps && !RES; ++tap) {
                             // weights are K-major [Cout][tap][cin]: K block of (tap, ch) = tap*chunks + ch
                             const int kb = seg == 0 ? tap * p.seg_chunks[0] + ch : kchunk + ch;
                             mbar_wait(&b_empty[bs], bph ^ 1u);
@@ -141,10 +147,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             // ===================== MMA issuer =====================
             constexpr uint32_t idesc = make_idesc_bf16(128, BN);
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int tb = 0; uint32_t tph = 0;
+            if (RES) mbar_wait(&b_full[0], 0);
             for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
                 mbar_wait(&t_empty[tb], tph ^ 1u);                    // epilogue drained this accumulator pair
                 tc_fence_after();
                 uint32_t first = 1;
+                int kchunk = 0;
                 for (int seg = 0; seg < 3; ++seg) {
                     const int taps = seg == 0 ? 9 : 1;
                     for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
@@ -153,8 +161,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         const uint32_t a_base = smem_u32(smem + as * L::A_SLOT);
                         for (int tap = 0; tap < taps; ++tap) {
                             const int dy = seg == 0 ? tap / 3 : 1, dx = seg == 0 ? tap % 3 : 1;
-                            mbar_wait(&b_full[bs], bph);
-                            tc_fence_after();
+                            if (RES) bs = seg == 0 ? tap * p.seg_chunks[0] + ch : kchunk + ch;
+                            else { mbar_wait(&b_full[bs], bph); tc_fence_after(); }
                             const uint64_t db = make_smem_desc_sw128(smem_u32(smem + L::OFF_B + bs * L::B_TILE));
 #pragma unroll
                             for (int mt = 0; mt < V2_MT; ++mt) {
@@ -164,12 +172,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                                     umma_bf16(tmem + (tb * V2_MT + mt) * BN, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
                             }
                             first = 0;
-                            umma_commit(&b_empty[bs]);
-                            if (++bs == L::NB) { bs = 0; bph ^= 1u; }
+                            if (!RES) {
+                                umma_commit(&b_empty[bs]);
+                                if (++bs == L::NB) { bs = 0; bph ^= 1u; }
+                            }
                         }
                         umma_commit(&a_empty[as]);
                         if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
                     }
+                    kchunk += (seg == 0 ? 9 : 1) * p.seg_chunks[seg];
                 }
                 umma_commit(&t_full[tb]);
                 if (++tb == 2) { tb = 0; tph ^= 1u; }
@@ -179,10 +190,18 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3, r = q * 32 + lane;                  // accumulator row = pixel (r/8, r%8) of the 16x8 tile
         uint8_t* staging = smem + L::OFF_STAGING;
+        float* bias_s = reinterpret_cast<float*>(smem + L::OFF_BIAS);
         const int sw = r & 7;
-        int tb = 0; uint32_t tph = 0;
+        int tb = 0; uint32_t tph = 0; int last_nt = -1;
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
             const V2Work wk = v2_decode(p, w);
+            if (wk.nt != last_nt) {                                  // (bias + time-embedding row) of this N tile -> smem
+                epi_bar_sync();
+                const int et = threadIdx.x - 64;
+                if (et < BN) bias_s[et] = p.bias[wk.nt * BN + et] + (p.bias2 ? p.bias2[wk.nt * BN + et] : 0.f);
+                last_nt = wk.nt;
+                epi_bar_sync();
+            }
             mbar_wait(&t_full[tb], tph);
             tc_fence_after();
 #pragma unroll 1
@@ -192,29 +211,38 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 const int oy = ty0 + (r >> 3), ox = wk.x0 + (r & 7);
                 const bool valid = n_img < p.B;                      // H, W are multiples of the tile
                 const size_t pix = ((size_t)n_img * p.H + oy) * p.W + ox;
+                uint4 rres[BN / 8];                                  // the row's residual, in flight while TMEM drains
+                const bool has_res = p.residual != nullptr && valid;
+                if (has_res) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + wk.nt * BN);
+#pragma unroll
+                    for (int i = 0; i < BN / 8; ++i) rres[i] = __ldg(rp + i);
+                }
                 if (threadIdx.x == 64) tma_store_wait_read();        // previous TMA store has read the staging tile
                 epi_bar_sync();
-#pragma unroll 1
+#pragma unroll
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tb * V2_MT + mt) * BN + c0), v);
                     tmem_ld_wait();
-                    const int n = wk.nt * BN + c0;
                     uint8_t* srow = staging + (c0 >> 6) * 16384 + r * 128;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         float f[8];
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8 + 4);
+                        f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                        f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                        f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                        f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                        if (has_res) {
+                            const uint4 rv = rres[(c0 >> 3) + g];
+                            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) + __ldg(p.bias + n + g * 8 + j);
-                        if (p.bias2) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] += __ldg(p.bias2 + n + g * 8 + j);
-                        }
-                        if (p.residual && valid) {
-                            float rr[8];
-                            load8<bf16>(p.residual + pix * p.Cout + n + g * 8, rr);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] += rr[j];
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 t = __bfloat1622float2(rh[j]);
+                                f[2 * j] += t.x; f[2 * j + 1] += t.y;
+                            }
                         }
                         if (p.relu) {
 #pragma unroll
@@ -282,15 +310,15 @@ int conv_tc2_stats_slots(const ConvArgs& a) {
     return (a.H / 16) * (a.W / 8) * (128 / BN);
 }
 
-template <int BN>
+template <int BN, bool RES>
 static void launch_v2(const V2Maps& maps, const V2Params& p, int grid, bf16* out, cudaStream_t s) {
-    using L = V2Smem<BN>;
+    using L = V2Smem<BN, RES>;
     static bool attr = false;
     if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SYNT_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr = true;
     }
-    conv_tc2_kernel<BN><<<grid, V2_THREADS, L::TOTAL, s>>>(maps, p, out);
+    conv_tc2_kernel<BN, RES><<<grid, V2_THREADS, L::TOTAL, s>>>(maps, p, out);
     SYNT_LAUNCH_CHECK();
 }
 
@@ -339,8 +367,10 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     static int num_sms = 0;
     if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
     const int grid = p.n_work < num_sms ? p.n_work : num_sms;
-    if (BN == 128) launch_v2<128>(maps, p, grid, (bf16*)a.out, s);
-    else           launch_v2<64>(maps, p, grid, (bf16*)a.out, s);
+    const bool resident = BN == 64 && p.n_ntiles == 1 && a.ktot() / 64 <= 12;
+    if (BN == 128)     launch_v2<128, false>(maps, p, grid, (bf16*)a.out, s);
+    else if (resident) launch_v2<64, true>(maps, p, grid, (bf16*)a.out, s);
+    else               launch_v2<64, false>(maps, p, grid, (bf16*)a.out, s);
 }
 
 }  // namespace synt
