@@ -65,17 +65,28 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-struct V2Work { int n0, y0, x0, nt; };
+// Work item w = ((image group) * n_ntiles + nt) * super_tiles_per_group + tile: a CTA owns a CONTIGUOUS range
+// of w, i.e. mostly consecutive tiles of one (image, N tile) -- GroupNorm partial sums are carried in
+// registers across them and flushed once per (image, N tile, CTA).
+struct V2Work { int n0, y0, x0, nt, grp; };
 __device__ __forceinline__ V2Work v2_decode(const V2Params& p, int w) {
     V2Work o;
-    o.nt = w % p.n_ntiles;
-    const int st = w / p.n_ntiles;
     const int per_img = p.tiles_x * p.supers_per_img;
-    const int grp = st / per_img, rem = st % per_img;
-    o.n0 = grp * p.imgs_per_super;
+    const int rem = w % per_img, key = w / per_img;
+    o.nt = key % p.n_ntiles;
+    o.grp = key / p.n_ntiles;
+    o.n0 = o.grp * p.imgs_per_super;
     o.y0 = (rem / p.tiles_x) * (p.imgs_per_super == 1 ? 32 : 0);
     o.x0 = (rem % p.tiles_x) * 8;
     return o;
+}
+__device__ __forceinline__ int v2_range_lo(const V2Params& p, int k) { return (int)(((long long)k * p.n_work) / (int)gridDim.x); }
+// index of the CTA whose contiguous range contains work item w
+__device__ __forceinline__ int v2_owner(const V2Params& p, int w) {
+    int k = (int)(((long long)w * (int)gridDim.x) / p.n_work);
+    while (k + 1 < (int)gridDim.x && v2_range_lo(p, k + 1) <= w) ++k;
+    while (k > 0 && v2_range_lo(p, k) > w) --k;
+    return k;
 }
 
 template <int BN, bool RES>
@@ -95,6 +106,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = p.imgs_per_super == 1 ? 34 * 10 * 128 : 2 * 18 * 10 * 128;
+    const int w_lo = v2_range_lo(p, blockIdx.x), w_hi = v2_range_lo(p, blockIdx.x + 1);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.b); prefetch_tmap(&maps.out);
@@ -119,7 +131,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d(smem + L::OFF_B + kb * L::B_TILE, &maps.b, &b_full[0], kb * 64, 0);
             }
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            for (int w = w_lo; w < w_hi; ++w) {
                 const V2Work wk = v2_decode(p, w);
                 int kchunk = 0;                                       // running 64-wide K block index into the weights
                 for (int seg = 0; seg < 3; ++seg) {
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             constexpr uint32_t idesc = make_idesc_bf16(128, BN);
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int tb = 0; uint32_t tph = 0;
             if (RES) mbar_wait(&b_full[0], 0);
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            for (int w = w_lo; w < w_hi; ++w) {
                 mbar_wait(&t_empty[tb], tph ^ 1u);                    // epilogue drained this accumulator pair
                 tc_fence_after();
                 uint32_t first = 1;
@@ -193,7 +205,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         float* bias_s = reinterpret_cast<float*>(smem + L::OFF_BIAS);
         const int sw = r & 7;
         int tb = 0; uint32_t tph = 0; int last_nt = -1;
-        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+        float acc1 = 0.f, acc2 = 0.f;                               // GroupNorm partials carried across tiles
+        for (int w = w_lo; w < w_hi; ++w) {
             const V2Work wk = v2_decode(p, w);
             if (wk.nt != last_nt) {                                  // (bias + time-embedding row) of this N tile -> smem
                 epi_bar_sync();
@@ -266,8 +279,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                     tma_store_commit();
                 }
                 if (p.stats && valid) {
-                    // fused GroupNorm statistics: per-channel (sum, sumsq) of the bf16 values just staged,
-                    // one partial row per (tile, row-half); thread = one column, fixed summation order
+                    // fused GroupNorm statistics: per-channel (sum, sumsq) of the bf16 values just staged;
+                    // thread = one column (x one row half for BN = 64), fixed summation order
                     const int et = threadIdx.x - 64;                 // 0..127
                     const int col = et % BN, half = et / BN;          // BN = 128: half = 0, all 128 rows
                     constexpr int ROWS = BN;                          // rows per thread: 128 (BN=128) or 64 (BN=64)
@@ -280,9 +293,24 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         const float x = __bfloat162float(*reinterpret_cast<const bf16*>(sb + row * 128 + ((ck ^ (row & 7)) << 4)));
                         s1 += x; s2 = fmaf(x, x, s2);
                     }
-                    const int tile_in_img = (ty0 >> 4) * p.tiles_x + (wk.x0 >> 3);
-                    const int slot = tile_in_img * (128 / BN) + half;
-                    p.stats[((size_t)n_img * p.stats_slots + slot) * p.Cout + wk.nt * BN + col] = make_float2(s1, s2);
+                    if (p.imgs_per_super == 2) {                      // 16x16 images: one partial row per tile
+                        const int slot = (wk.x0 >> 3) * (128 / BN) + half;
+                        p.stats[((size_t)n_img * p.stats_slots + slot) * p.Cout + wk.nt * BN + col] = make_float2(s1, s2);
+                    } else {
+                        acc1 += s1; acc2 += s2;
+                    }
+                }
+            }
+            if (p.stats && p.imgs_per_super == 1) {
+                // flush when the next work item belongs to another (image, N tile) or the range ends
+                const int per_img = p.tiles_x * p.supers_per_img;
+                if (w + 1 == w_hi || (w + 1) / per_img != w / per_img) {
+                    const int et = threadIdx.x - 64, col = et % BN, half = et / BN;
+                    const int first_owner = v2_owner(p, (w / per_img) * per_img);
+                    const int slot = ((int)blockIdx.x - first_owner) * (128 / BN) + half;
+                    if (slot < p.stats_slots)
+                        p.stats[((size_t)wk.n0 * p.stats_slots + slot) * p.Cout + wk.nt * BN + col] = make_float2(acc1, acc2);
+                    acc1 = 0.f; acc2 = 0.f;
                 }
             }
             if (++tb == 2) { tb = 0; tph ^= 1u; }
@@ -305,9 +333,21 @@ bool conv_tc2_supported(const ConvArgs& a) {
     return true;
 }
 
+static int v2_num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+    return n;
+}
+// partial rows per image in stats_out (rows that no CTA writes must be zero: the caller memsets the buffer)
 int conv_tc2_stats_slots(const ConvArgs& a) {
     const int BN = (a.Cout % 128 == 0) ? 128 : 64;
-    return (a.H / 16) * (a.W / 8) * (128 / BN);
+    if (a.H == 16) return (a.W / 8) * (128 / BN);
+    const int per_img = (a.W / 8) * (a.H / 32);                      // super-tiles per image
+    const long long n_work = (long long)a.B * per_img * (a.Cout / BN);
+    const int grid = (int)(n_work < v2_num_sms() ? n_work : v2_num_sms());
+    int ctas = (int)((per_img * (long long)grid + n_work - 1) / n_work) + 1;   // CTAs that can touch one (image, N tile)
+    if (ctas > per_img) ctas = per_img;
+    return ctas * (128 / BN);
 }
 
 template <int BN, bool RES>
@@ -364,9 +404,10 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
         cuuint32_t box[4] = {64, 8, 16, 1};
         encode_bf16_sw128(&maps.out, a.out, 4, dims, strides, box, "v2 output");
     }
-    static int num_sms = 0;
-    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int num_sms = v2_num_sms();
     const int grid = p.n_work < num_sms ? p.n_work : num_sms;
+    if (a.stats_out)
+        SYNT_CUDA(cudaMemsetAsync(a.stats_out, 0, (size_t)a.B * p.stats_slots * a.Cout * sizeof(float2), s));
     const bool resident = BN == 64 && p.n_ntiles == 1 && a.ktot() / 64 <= 12;
     if (BN == 128)     launch_v2<128, false>(maps, p, grid, (bf16*)a.out, s);
     else if (resident) launch_v2<64, true>(maps, p, grid, (bf16*)a.out, s);

@@ -182,28 +182,59 @@ __device__ __forceinline__ float silu_tanh(float x) {
     return fmaf(h, t, h);
 }
 
-// Each thread owns ONE 8-channel vector position (its scale/shift live in registers) and streams the
-// pixels of its block's range with 4 independent 16-byte loads in flight.
+// GroupNorm (+SiLU) apply with the FINALIZE folded in: every block first reduces the per-channel partial
+// sums of its image (a handful of rows per tensor) to scale/shift in shared memory, then each thread
+// owns ONE 8-channel vector position (its scale/shift live in registers) and streams the pixels of the
+// block's range with 4 independent 16-byte loads in flight.
+struct GnSrc { const void* x; const float2* part; int C; int slots; };
+
 template <typename T, bool SILU>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ src0, int C0, const T* __restrict__ src1,
-                                                       int C1, int HW, int ppb, const float2* __restrict__ scale_shift,
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc a, GnSrc b2, int HW, int ppb, int G, float eps,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        T* __restrict__ out) {
-    const int C = C0 + C1, nvec = C >> 3, rows = 256 / nvec;
+    __shared__ double csum[512];
+    __shared__ double csq[512];
+    __shared__ float2 stat[32];
+    __shared__ float2 ss_s[512];
+    const int C0 = a.C, C1 = b2.C, C = C0 + C1, nvec = C >> 3, rows = 256 / nvec;
     const int b = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const bool first = c < C0;
+        const float2* base = first ? a.part + (size_t)b * a.slots * C0 + c : b2.part + (size_t)b * b2.slots * C1 + (c - C0);
+        const int S = first ? a.slots : b2.slots, Cs = first ? C0 : C1;
+        double ts = 0.0, tq = 0.0;
+        for (int k = 0; k < S; ++k) {
+            const float2 v = __ldg(base + (size_t)k * Cs);
+            ts += (double)v.x; tq += (double)v.y;
+        }
+        csum[c] = ts; csq[c] = tq;
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    if (threadIdx.x < G) {
+        double ts = 0.0, tq = 0.0;
+        for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { ts += csum[c]; tq += csq[c]; }
+        const double cnt = (double)HW * cpg;
+        const double mean = ts / cnt;
+        double var = tq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stat[threadIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const float2 st = stat[c / cpg];
+        const float sc = st.y * gamma[c];
+        ss_s[c] = make_float2(sc, beta[c] - st.x * sc);
+    }
+    __syncthreads();
     const int v = threadIdx.x % nvec, prow = threadIdx.x / nvec;
     if (prow >= rows) return;
     const int c = v * 8;
     float sc[8], sh[8];
-    {
-        const float4* ss = reinterpret_cast<const float4*>(scale_shift + (size_t)b * C + c);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 t = __ldg(ss + j);
-            sc[2 * j] = t.x; sh[2 * j] = t.y; sc[2 * j + 1] = t.z; sh[2 * j + 1] = t.w;
-        }
-    }
+    for (int j = 0; j < 8; ++j) { const float2 t = ss_s[c + j]; sc[j] = t.x; sh[j] = t.y; }
     const bool first = c < C0;
-    const T* src = first ? src0 + (size_t)b * HW * C0 + c : src1 + (size_t)b * HW * C1 + (c - C0);
+    const T* src = first ? (const T*)a.x + (size_t)b * HW * C0 + c : (const T*)b2.x + (size_t)b * HW * C1 + (c - C0);
     const int Cs = first ? C0 : C1;
     T* dst = out + (size_t)b * HW * C + c;
     const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
@@ -227,13 +258,16 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ src
     }
 }
 
-void gn_apply(const void* src0, int C0, const void* src1, int C1, int dt, int B, int HW, const float2* scale_shift,
-              int silu, void* out, cudaStream_t s) {
+void gn_apply_fused(const void* src0, const float2* part0, int slots0, int C0, const void* src1, const float2* part1,
+                    int slots1, int C1, int dt, int B, int HW, int G, float eps, const float* gamma, const float* beta,
+                    int silu, void* out, cudaStream_t s) {
     const int C = C0 + C1, nvec = C / 8, rows = 256 / nvec;
-    int ppb = rows * 16;                                     // 16 pixels per thread
+    SYNT_CHECK(C <= 512 && G <= 32 && C % G == 0 && C0 % 8 == 0 && C % 8 == 0, "gn_apply_fused: bad channel counts");
+    int ppb = rows * 32;                                     // 32 pixels per thread: amortises the finalize prologue
     if (ppb > HW) ppb = HW;
     dim3 grid(ceil_div(HW, ppb), B);
-#define GO(T, S) gn_apply_kernel<T, S><<<grid, 256, 0, s>>>((const T*)src0, C0, (const T*)src1, C1, HW, ppb, scale_shift, (T*)out)
+    GnSrc a{src0, part0, C0, slots0}, b{src1, part1, C1, slots1};
+#define GO(T, S) gn_apply_kernel<T, S><<<grid, 256, 0, s>>>(a, b, HW, ppb, G, eps, gamma, beta, (T*)out)
     if (dt == DT_F32) { if (silu) GO(float, true); else GO(float, false); }
     else              { if (silu) GO(bf16, true);  else GO(bf16, false); }
 #undef GO

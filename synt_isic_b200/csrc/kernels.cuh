@@ -85,8 +85,11 @@ void gn_finalize(const float2* partials, int B, int nchunk, int G, int C, int HW
 // finalize from PER-CHANNEL partials of one or two (concatenated) tensors: partA [B][SA][C0], partB [B][SB][C1]
 void gn_finalize_channels(const float2* partA, int SA, int C0, const float2* partB, int SB, int C1, int B, int G, int HW,
                           float eps, const float* gamma, const float* beta, float2* scale_shift, cudaStream_t s);
-void gn_apply(const void* src0, int C0, const void* src1, int C1, int dt, int B, int HW, const float2* scale_shift,
-              int silu, void* out, cudaStream_t s);
+// out = act(GroupNorm(concat(src0, src1))) with the statistics finalize folded into the kernel:
+// part0/part1 are the per-channel (sum, sumsq) partial rows [B][slots][C] of the two tensors
+void gn_apply_fused(const void* src0, const float2* part0, int slots0, int C0, const void* src1, const float2* part1,
+                    int slots1, int C1, int dt, int B, int HW, int G, float eps, const float* gamma, const float* beta,
+                    int silu, void* out, cudaStream_t s);
 
 // ---------------------------------------------------------------- misc --------------
 void upsample_nearest2x(const void* in, int dt, int B, int H, int W, int C, void* out, cudaStream_t s);
