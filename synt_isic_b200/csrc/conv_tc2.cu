@@ -53,6 +53,7 @@ struct V2Params {
     int B, H, W, Cout;
     const float* bias; const float* bias2; const bf16* residual; int relu;
     float2* stats; int stats_slots;   // optional fused GroupNorm partials [B][stats_slots][Cout]
+    int chunk;                         // consecutive work items per CTA turn (divides the super-tiles per image)
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
@@ -65,9 +66,10 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// Work item w = ((image group) * n_ntiles + nt) * super_tiles_per_group + tile: a CTA owns a CONTIGUOUS range
-// of w, i.e. mostly consecutive tiles of one (image, N tile) -- GroupNorm partial sums are carried in
-// registers across them and flushed once per (image, N tile, CTA).
+// Work item w = ((image group) * n_ntiles + nt) * super_tiles_per_group + tile.  CTAs take CHUNKS of R
+// consecutive items round-robin (chunk c -> CTA c % grid): neighbouring CTAs work on neighbouring tiles
+// (L2/DRAM locality) while each chunk stays inside one (image, N tile), so GroupNorm partial sums are
+// carried in registers across the chunk and written once -- slot = chunk index within the image.
 struct V2Work { int n0, y0, x0, nt, grp; };
 __device__ __forceinline__ V2Work v2_decode(const V2Params& p, int w) {
     V2Work o;
@@ -80,13 +82,11 @@ __device__ __forceinline__ V2Work v2_decode(const V2Params& p, int w) {
     o.x0 = (rem % p.tiles_x) * 8;
     return o;
 }
-__device__ __forceinline__ int v2_range_lo(const V2Params& p, int k) { return (int)(((long long)k * p.n_work) / (int)gridDim.x); }
-// index of the CTA whose contiguous range contains work item w
-__device__ __forceinline__ int v2_owner(const V2Params& p, int w) {
-    int k = (int)(((long long)w * (int)gridDim.x) / p.n_work);
-    while (k + 1 < (int)gridDim.x && v2_range_lo(p, k + 1) <= w) ++k;
-    while (k > 0 && v2_range_lo(p, k) > w) --k;
-    return k;
+// iteration i of this CTA -> work item (or -1 when exhausted)
+__device__ __forceinline__ int v2_item(const V2Params& p, int i) {
+    const int chunk = (i / p.chunk) * (int)gridDim.x + (int)blockIdx.x;
+    const int w = chunk * p.chunk + i % p.chunk;
+    return w < p.n_work ? w : -1;
 }
 
 template <int BN, bool RES>
@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = p.imgs_per_super == 1 ? 34 * 10 * 128 : 2 * 18 * 10 * 128;
-    const int w_lo = v2_range_lo(p, blockIdx.x), w_hi = v2_range_lo(p, blockIdx.x + 1);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.b); prefetch_tmap(&maps.out);
@@ -131,7 +130,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d(smem + L::OFF_B + kb * L::B_TILE, &maps.b, &b_full[0], kb * 64, 0);
             }
-            for (int w = w_lo; w < w_hi; ++w) {
+            for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
                 const V2Work wk = v2_decode(p, w);
                 int kchunk = 0;                                       // running 64-wide K block index into the weights
                 for (int seg = 0; seg < 3; ++seg) {
@@ -160,7 +159,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             constexpr uint32_t idesc = make_idesc_bf16(128, BN);
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int tb = 0; uint32_t tph = 0;
             if (RES) mbar_wait(&b_full[0], 0);
-            for (int w = w_lo; w < w_hi; ++w) {
+            for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
                 mbar_wait(&t_empty[tb], tph ^ 1u);                    // epilogue drained this accumulator pair
                 tc_fence_after();
                 uint32_t first = 1;
@@ -206,7 +205,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         const int sw = r & 7;
         int tb = 0; uint32_t tph = 0; int last_nt = -1;
         float acc1 = 0.f, acc2 = 0.f;                               // GroupNorm partials carried across tiles
-        for (int w = w_lo; w < w_hi; ++w) {
+        for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
             const V2Work wk = v2_decode(p, w);
             if (wk.nt != last_nt) {                                  // (bias + time-embedding row) of this N tile -> smem
                 epi_bar_sync();
@@ -301,17 +300,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                     }
                 }
             }
-            if (p.stats && p.imgs_per_super == 1) {
-                // flush when the next work item belongs to another (image, N tile) or the range ends
+            if (p.stats && p.imgs_per_super == 1 && (w + 1) % p.chunk == 0) {
+                // end of this chunk (chunks never straddle an (image, N tile)): one partial row per chunk
                 const int per_img = p.tiles_x * p.supers_per_img;
-                if (w + 1 == w_hi || (w + 1) / per_img != w / per_img) {
-                    const int et = threadIdx.x - 64, col = et % BN, half = et / BN;
-                    const int first_owner = v2_owner(p, (w / per_img) * per_img);
-                    const int slot = ((int)blockIdx.x - first_owner) * (128 / BN) + half;
-                    if (slot < p.stats_slots)
-                        p.stats[((size_t)wk.n0 * p.stats_slots + slot) * p.Cout + wk.nt * BN + col] = make_float2(acc1, acc2);
-                    acc1 = 0.f; acc2 = 0.f;
-                }
+                const int et = threadIdx.x - 64, col = et % BN, half = et / BN;
+                const int slot = ((w % per_img) / p.chunk) * (128 / BN) + half;
+                p.stats[((size_t)wk.n0 * p.stats_slots + slot) * p.Cout + wk.nt * BN + col] = make_float2(acc1, acc2);
+                acc1 = 0.f; acc2 = 0.f;
             }
             if (++tb == 2) { tb = 0; tph ^= 1u; }
         }
@@ -338,16 +333,28 @@ static int v2_num_sms() {
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
     return n;
 }
-// partial rows per image in stats_out (rows that no CTA writes must be zero: the caller memsets the buffer)
+// consecutive work items per CTA turn: the divisor of the super-tiles per image (<= 8) with the smallest
+// makespan ceil(chunks / grid) * R; ties go to the larger R (fewer GroupNorm partial rows)
+static int v2_chunk(const ConvArgs& a, int BN) {
+    if (a.H == 16) return 1;
+    const int per_img = (a.W / 8) * (a.H / 32);
+    const long long n_work = (long long)a.B * per_img * (a.Cout / BN);
+    const long long grid = n_work < v2_num_sms() ? n_work : v2_num_sms();
+    int best = 1; long long best_span = -1;
+    for (int R = 8; R >= 1; R >>= 1) {
+        if (per_img % R) continue;
+        const long long chunks = n_work / R;
+        const long long span = ((chunks + grid - 1) / grid) * R;
+        if (best_span < 0 || span < best_span) { best = R; best_span = span; }
+    }
+    return best;
+}
+// partial rows per image in stats_out (every row is written exactly once by the kernel)
 int conv_tc2_stats_slots(const ConvArgs& a) {
     const int BN = (a.Cout % 128 == 0) ? 128 : 64;
     if (a.H == 16) return (a.W / 8) * (128 / BN);
-    const int per_img = (a.W / 8) * (a.H / 32);                      // super-tiles per image
-    const long long n_work = (long long)a.B * per_img * (a.Cout / BN);
-    const int grid = (int)(n_work < v2_num_sms() ? n_work : v2_num_sms());
-    int ctas = (int)((per_img * (long long)grid + n_work - 1) / n_work) + 1;   // CTAs that can touch one (image, N tile)
-    if (ctas > per_img) ctas = per_img;
-    return ctas * (128 / BN);
+    const int per_img = (a.W / 8) * (a.H / 32);
+    return (per_img / v2_chunk(a, BN)) * (128 / BN);
 }
 
 template <int BN, bool RES>
@@ -386,6 +393,7 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     p.B = a.B; p.H = a.H; p.W = a.W; p.Cout = a.Cout;
     p.bias = a.bias; p.bias2 = a.bias2; p.residual = (const bf16*)a.residual; p.relu = a.relu;
     p.stats = a.stats_out; p.stats_slots = conv_tc2_stats_slots(a);
+    p.chunk = v2_chunk(a, BN);
     V2Maps maps;
     const int bh = a.H == 16 ? 18 : 34, bn = a.H == 16 ? 2 : 1;
     make_halo_map(&maps.a[0], a.in, a.B, a.H, a.W, a.Cin, bh, bn);
@@ -406,8 +414,7 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     }
     const int num_sms = v2_num_sms();
     const int grid = p.n_work < num_sms ? p.n_work : num_sms;
-    if (a.stats_out)
-        SYNT_CUDA(cudaMemsetAsync(a.stats_out, 0, (size_t)a.B * p.stats_slots * a.Cout * sizeof(float2), s));
+
     const bool resident = BN == 64 && p.n_ntiles == 1 && a.ktot() / 64 <= 12;
     if (BN == 128)     launch_v2<128, false>(maps, p, grid, (bf16*)a.out, s);
     else if (resident) launch_v2<64, true>(maps, p, grid, (bf16*)a.out, s);

@@ -191,13 +191,16 @@ struct GnSrc { const void* x; const float2* part; int C; int slots; };
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc a, GnSrc b2, int HW, int ppb, int G, float eps,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       T* __restrict__ out) {
+                                                       const float2* __restrict__ scale_shift, T* __restrict__ out) {
     __shared__ double csum[512];
     __shared__ double csq[512];
     __shared__ float2 stat[32];
     __shared__ float2 ss_s[512];
     const int C0 = a.C, C1 = b2.C, C = C0 + C1, nvec = C >> 3, rows = 256 / nvec;
     const int b = blockIdx.y;
+    if (scale_shift) {                                       // finalize already done by gn_finalize_channels
+        for (int c = threadIdx.x; c < C; c += 256) ss_s[c] = scale_shift[(size_t)b * C + c];
+    } else {
     for (int c = threadIdx.x; c < C; c += 256) {
         const bool first = c < C0;
         const float2* base = first ? a.part + (size_t)b * a.slots * C0 + c : b2.part + (size_t)b * b2.slots * C1 + (c - C0);
@@ -225,6 +228,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc a, GnSrc b2, int HW
         const float2 st = stat[c / cpg];
         const float sc = st.y * gamma[c];
         ss_s[c] = make_float2(sc, beta[c] - st.x * sc);
+    }
     }
     __syncthreads();
     const int v = threadIdx.x % nvec, prow = threadIdx.x / nvec;
@@ -260,14 +264,14 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc a, GnSrc b2, int HW
 
 void gn_apply_fused(const void* src0, const float2* part0, int slots0, int C0, const void* src1, const float2* part1,
                     int slots1, int C1, int dt, int B, int HW, int G, float eps, const float* gamma, const float* beta,
-                    int silu, void* out, cudaStream_t s) {
+                    const float2* scale_shift, int silu, void* out, cudaStream_t s) {
     const int C = C0 + C1, nvec = C / 8, rows = 256 / nvec;
     SYNT_CHECK(C <= 512 && G <= 32 && C % G == 0 && C0 % 8 == 0 && C % 8 == 0, "gn_apply_fused: bad channel counts");
-    int ppb = rows * 32;                                     // 32 pixels per thread: amortises the finalize prologue
+    int ppb = rows * (scale_shift ? 16 : 32);                // pixels per thread (more when the finalize prologue runs)
     if (ppb > HW) ppb = HW;
     dim3 grid(ceil_div(HW, ppb), B);
     GnSrc a{src0, part0, C0, slots0}, b{src1, part1, C1, slots1};
-#define GO(T, S) gn_apply_kernel<T, S><<<grid, 256, 0, s>>>(a, b, HW, ppb, G, eps, gamma, beta, (T*)out)
+#define GO(T, S) gn_apply_kernel<T, S><<<grid, 256, 0, s>>>(a, b, HW, ppb, G, eps, gamma, beta, scale_shift, (T*)out)
     if (dt == DT_F32) { if (silu) GO(float, true); else GO(float, false); }
     else              { if (silu) GO(bf16, true);  else GO(bf16, false); }
 #undef GO

@@ -89,6 +89,7 @@ void gn_finalize_channels(const float2* partA, int SA, int C0, const float2* par
 // part0/part1 are the per-channel (sum, sumsq) partial rows [B][slots][C] of the two tensors
 void gn_apply_fused(const void* src0, const float2* part0, int slots0, int C0, const void* src1, const float2* part1,
                     int slots1, int C1, int dt, int B, int HW, int G, float eps, const float* gamma, const float* beta,
+                    const float2* scale_shift /* precomputed by gn_finalize_channels, or null = finalize in-kernel */,
                     int silu, void* out, cudaStream_t s);
 
 // ---------------------------------------------------------------- misc --------------

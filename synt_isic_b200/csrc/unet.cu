@@ -410,11 +410,13 @@ struct Fwd {
     }
     Act gn_act(const Act& x0, const Act* x1, const DevPtr& gamma, const DevPtr& beta, bool silu) {
         SYNT_CHECK(x0.stats && (!x1 || x1->stats), "GroupNorm input without statistics");
+        float2* ss = gn_scale_shift(x0, x1, gamma, beta);
         Act o = make(x0.H, x0.W, x0.C + (x1 ? x1->C : 0));
         ProfScope ps(u, s, PC_GN_APPLY);
         gn_apply_fused(x0.p, x0.stats, x0.stats_slots, x0.C, x1 ? x1->p : nullptr, x1 ? x1->stats : nullptr,
                        x1 ? x1->stats_slots : 0, x1 ? x1->C : 0, u->dt, B, x0.H * x0.W, kGroups, kGnEps,
-                       (const float*)gamma->p, (const float*)beta->p, silu ? 1 : 0, o.p, s);
+                       (const float*)gamma->p, (const float*)beta->p, ss, silu ? 1 : 0, o.p, s);
+        u->pool.release(ss);
         ++u->launches;
         return o;
     }
