@@ -188,19 +188,17 @@ __device__ __forceinline__ float silu_tanh(float x) {
 // block's range with 4 independent 16-byte loads in flight.
 struct GnSrc { const void* x; const float2* part; int C; int slots; };
 
-template <typename T, bool SILU>
-__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc a, GnSrc b2, int HW, int ppb, int G, float eps,
+template <typename T, bool SILU, bool FUSED>
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(GnSrc a, GnSrc b2, int HW, int ppb, int G, float eps,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float2* __restrict__ scale_shift, T* __restrict__ out) {
-    __shared__ double csum[512];
-    __shared__ double csq[512];
+    __shared__ double csum[FUSED ? 512 : 1];
+    __shared__ double csq[FUSED ? 512 : 1];
     __shared__ float2 stat[32];
-    __shared__ float2 ss_s[512];
+    __shared__ float2 ss_s[FUSED ? 512 : 1];
     const int C0 = a.C, C1 = b2.C, C = C0 + C1, nvec = C >> 3, rows = 256 / nvec;
     const int b = blockIdx.y;
-    if (scale_shift) {                                       // finalize already done by gn_finalize_channels
-        for (int c = threadIdx.x; c < C; c += 256) ss_s[c] = scale_shift[(size_t)b * C + c];
-    } else {
+    if (FUSED) {                                             // finalize in-kernel from the partial rows
     for (int c = threadIdx.x; c < C; c += 256) {
         const bool first = c < C0;
         const float2* base = first ? a.part + (size_t)b * a.slots * C0 + c : b2.part + (size_t)b * b2.slots * C1 + (c - C0);
@@ -229,14 +227,23 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc a, GnSrc b2, int HW
         const float sc = st.y * gamma[c];
         ss_s[c] = make_float2(sc, beta[c] - st.x * sc);
     }
-    }
     __syncthreads();
+    }
     const int v = threadIdx.x % nvec, prow = threadIdx.x / nvec;
     if (prow >= rows) return;
     const int c = v * 8;
     float sc[8], sh[8];
+    if (!FUSED) {                                            // finalize already done by gn_finalize_channels
+        const float4* ss = reinterpret_cast<const float4*>(scale_shift + (size_t)b * C + c);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const float2 t = ss_s[c + j]; sc[j] = t.x; sh[j] = t.y; }
+        for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldg(ss + j);
+            sc[2 * j] = t.x; sh[2 * j] = t.y; sc[2 * j + 1] = t.z; sh[2 * j + 1] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float2 t = ss_s[c + j]; sc[j] = t.x; sh[j] = t.y; }
+    }
     const bool first = c < C0;
     const T* src = first ? (const T*)a.x + (size_t)b * HW * C0 + c : (const T*)b2.x + (size_t)b * HW * C1 + (c - C0);
     const int Cs = first ? C0 : C1;
@@ -271,9 +278,11 @@ void gn_apply_fused(const void* src0, const float2* part0, int slots0, int C0, c
     if (ppb > HW) ppb = HW;
     dim3 grid(ceil_div(HW, ppb), B);
     GnSrc a{src0, part0, C0, slots0}, b{src1, part1, C1, slots1};
-#define GO(T, S) gn_apply_kernel<T, S><<<grid, 256, 0, s>>>(a, b, HW, ppb, G, eps, gamma, beta, scale_shift, (T*)out)
-    if (dt == DT_F32) { if (silu) GO(float, true); else GO(float, false); }
-    else              { if (silu) GO(bf16, true);  else GO(bf16, false); }
+#define GO(T, S, F) gn_apply_kernel<T, S, F><<<grid, 256, 0, s>>>(a, b, HW, ppb, G, eps, gamma, beta, scale_shift, (T*)out)
+#define GO2(T, S) do { if (scale_shift) GO(T, S, false); else GO(T, S, true); } while (0)
+    if (dt == DT_F32) { if (silu) GO2(float, true); else GO2(float, false); }
+    else              { if (silu) GO2(bf16, true);  else GO2(bf16, false); }
+#undef GO2
 #undef GO
     SYNT_LAUNCH_CHECK();
 }

@@ -412,7 +412,7 @@ struct Fwd {
         SYNT_CHECK(x0.stats && (!x1 || x1->stats), "GroupNorm input without statistics");
         float2* ss = gn_scale_shift(x0, x1, gamma, beta);
         Act o = make(x0.H, x0.W, x0.C + (x1 ? x1->C : 0));
-        ProfScope ps(u, s, PC_GN_APPLY);
+        ProfScope ps(u, s, PC_GN_APPLY, 0.0, B * x0.H * x0.W, o.C, x1 ? x1->C : 0);
         gn_apply_fused(x0.p, x0.stats, x0.stats_slots, x0.C, x1 ? x1->p : nullptr, x1 ? x1->stats : nullptr,
                        x1 ? x1->stats_slots : 0, x1 ? x1->C : 0, u->dt, B, x0.H * x0.W, kGroups, kGnEps,
                        (const float*)gamma->p, (const float*)beta->p, ss, silu ? 1 : 0, o.p, s);
