@@ -123,6 +123,13 @@ int synt_debug_conv(int use_tc, int act_dtype, const void* in_dev, int B, int H,
                     const void* weight_dev, const float* bias_dev, const float* bias2_dev, const void* residual_dev,
                     int relu, void* out_dev, int Cout, void* stream);
 
+/* the persistent conv kernel with its fused-input features: main input = channel concat (in | in1),
+ * GroupNorm scale/shift gn_ss [B][Cin+Cin1] (float2) applied in-kernel (gn_mode 1 affine, 2 affine+SiLU);
+ * stats_out (optional) receives per-channel (sum, sumsq) partial rows [B][*stats_slots][Cout] of the output */
+int synt_debug_conv_gn(const void* in_dev, int Cin, const void* in1_dev, int Cin1, const void* gn_ss_dev, int gn_mode,
+                       int B, int H, int W, int K, const void* sc0_dev, int sc0_C, const void* weight_dev,
+                       const float* bias_dev, const void* residual_dev, void* out_dev, int Cout, void* stats_out_dev,
+                       int* stats_slots, void* stream);
 /* softmax(q k^T / sqrt(8)) v on caller-provided tensors: use_tc=0: qkv [B,N,3C] (q|k|v); use_tc=1: the
  * zero-interleaved bf16 layout [B,N,5C] consumed by the tcgen05 attention kernel. out: [B,N,C]. */
 int synt_debug_attention(int use_tc, int act_dtype, const void* qkv_dev, int B, int N, int C, void* out_dev,

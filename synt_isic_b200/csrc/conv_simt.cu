@@ -123,6 +123,7 @@ void conv_simt(const ConvArgs& a, int dt, cudaStream_t s) {
     g.Ho = a.Ho; g.Wo = a.Wo; g.Cout = a.Cout; g.sc0_C = a.sc0_C; g.sc1_C = a.sc1_C; g.sc_stride = a.sc_stride;
     g.Kmain = a.KH * a.KW * a.Cin; g.Ktot = a.ktot(); g.M = (long long)a.B * a.Ho * a.Wo;
     SYNT_CHECK(a.bias != nullptr, "conv_simt: bias required");
+    SYNT_CHECK(a.Cin1 == 0 && a.gn_mode == 0, "conv_simt: concat / fused-GroupNorm inputs are conv_tc2 features");
     const bool vec = (a.Cin % 16 == 0) && (a.sc0_C % 16 == 0) && (a.sc1_C % 16 == 0);
     dim3 grid((unsigned)((g.M + SB_M - 1) / SB_M), ceil_div(a.Cout, SB_N));
 #define GO(T, V)                                                                                                 \

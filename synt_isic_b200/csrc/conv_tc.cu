@@ -233,6 +233,7 @@ static void make_weight_map(CUtensorMap* m, const bf16* w, int Cout, int Ktot, i
 }
 
 bool conv_tc_supported(const ConvArgs& a) {
+    if (a.Cin1 || a.gn_mode) return false;                 // channel-concat / fused-GroupNorm inputs: conv_tc2 only
     if (a.Cin % 64 || a.sc0_C % 64 || a.sc1_C % 64 || a.Cout % 64) return false;
     if (a.stride != 1 && a.stride != 2) return false;
     if (a.stride == 2 && ((a.H & 1) || (a.W & 1))) return false;

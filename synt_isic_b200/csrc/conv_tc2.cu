@@ -14,10 +14,15 @@
 //   * persistent CTAs (one per SM) with double-buffered TMEM accumulators: the epilogue of super-
 //     tile i (TMEM -> registers -> bias/temb/residual -> bf16 -> swizzled smem -> TMA store)
 //     overlaps the mainloop of super-tile i+1.
+//   * GroupNorm(+SiLU) of the INPUT is applied in shared memory: four transform warps rewrite each
+//     halo tile in place (y = act(x*scale[n,c] + shift[n,c]); out-of-image pixels stay 0 = the conv
+//     padding of the activated tensor) between the TMA landing and the MMAs, once per input element
+//     -- the normalised activation tensor is never materialised in HBM.
 // L2 -> smem bytes per MMA clock: (43.5 KB + 9*BN*128 B) / (36*BN clk) = 42 B/clk for BN = 128.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5
-// epilogue.  Rings: A halo slots (2), B weight-tile slots (NB), TMEM accumulator buffers (2).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5
+// epilogue, warps 6..9 input transform.  Rings: A halo slots (2), B weight-tile slots (NB), TMEM
+// accumulator buffers (2).
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -26,7 +31,8 @@ namespace synt {
 
 using namespace ptx;
 
-constexpr int V2_THREADS = 192;
+constexpr int V2_THREADS = 320;
+constexpr int V2_XF_THREADS = 128;                         // transform warps 6..9
 constexpr int V2_MT = 2;                                   // M tiles (16x8 pixels each) per super-tile
 constexpr int V2_A_STAGES = 2;
 
@@ -45,11 +51,16 @@ struct V2Smem {
     static constexpr int TOTAL = OFF_BAR + 512 + 1024;
 };
 
-struct V2Maps { CUtensorMap a[3]; CUtensorMap b; CUtensorMap out; };   // a[0] main, a[1]/a[2] shortcut sources
+struct V2Maps { CUtensorMap a[4]; CUtensorMap b; CUtensorMap out; };   // a[i]: activation source of segment i
+// A K segment = one source tensor: `chunks` 64-channel blocks x `taps` (9 = 3x3 window, 1 = centre tap);
+// weight K block of (tap, chunk) = kb_base + tap*kb_stride + chunk; xform: 0 raw, 1 GroupNorm affine,
+// 2 affine + SiLU with scale/shift rows gn_ss[n][ss_off + channel].
+struct V2Seg { int chunks, taps, kb_base, kb_stride, xform, ss_off; };
 struct V2Params {
     int n_work;              // super-tiles x N tiles
     int n_ntiles, tiles_x, supers_per_img, imgs_per_super, row_off;
-    int seg_chunks[3];       // 64-channel chunks of main / sc0 / sc1
+    int n_seg; V2Seg seg[4];
+    const float2* gn_ss; int gn_C;     // GroupNorm scale/shift [B][gn_C] of the (concatenated) main input
     int B, H, W, Cout;
     const float* bias; const float* bias2; const bf16* residual; int relu;
     float2* stats; int stats_slots;   // optional fused GroupNorm partials [B][stats_slots][Cout]
@@ -64,6 +75,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float silu_tanh_v2(float x) {      // x*sigmoid(x) = h + h*tanh(h), h = x/2 (one MUFU op)
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // Work item w = ((image group) * n_ntiles + nt) * super_tiles_per_group + tile.  CTAs take CHUNKS of R
@@ -99,7 +116,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* a_full = bars;                        // [2]
     uint64_t* a_empty = a_full + V2_A_STAGES;       // [2]
-    uint64_t* b_full = a_empty + V2_A_STAGES;       // [NB]
+    uint64_t* a_ready = a_empty + V2_A_STAGES;      // [2] halo tile transformed (or passed through)
+    uint64_t* b_full = a_ready + V2_A_STAGES;       // [NB]
     uint64_t* b_empty = b_full + L::NB;             // [NB]
     uint64_t* t_full = b_empty + L::NB;             // [2]
     uint64_t* t_empty = t_full + 2;                 // [2]
@@ -109,7 +127,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.b); prefetch_tmap(&maps.out);
-        for (int s = 0; s < V2_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < V2_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_ready[s], V2_XF_THREADS); }
         for (int s = 0; s < L::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 128); }
         fence_barrier_init();
@@ -125,31 +143,29 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             // ===================== TMA producer =====================
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
             if (RES) {                                                // whole weight matrix, once (n_ntiles == 1)
-                const int nkb = 9 * p.seg_chunks[0] + p.seg_chunks[1] + p.seg_chunks[2];
+                int nkb = 0;
+                for (int sg = 0; sg < p.n_seg; ++sg) nkb += p.seg[sg].chunks * p.seg[sg].taps;
                 mbar_arrive_expect_tx(&b_full[0], nkb * L::B_TILE);
                 for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d(smem + L::OFF_B + kb * L::B_TILE, &maps.b, &b_full[0], kb * 64, 0);
             }
             for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
                 const V2Work wk = v2_decode(p, w);
-                int kchunk = 0;                                       // running 64-wide K block index into the weights
-                for (int seg = 0; seg < 3; ++seg) {
-                    const int taps = seg == 0 ? 9 : 1;
-                    for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
+                for (int sg = 0; sg < p.n_seg; ++sg) {
+                    const V2Seg sp = p.seg[sg];
+                    for (int ch = 0; ch < sp.chunks; ++ch) {
                         mbar_wait(&a_empty[as], aph ^ 1u);
                         mbar_arrive_expect_tx(&a_full[as], a_bytes);
-                        tma_load_4d(smem + as * L::A_SLOT, &maps.a[seg], &a_full[as], ch * 64, wk.x0 - 1, wk.y0 - 1, wk.n0);
+                        tma_load_4d(smem + as * L::A_SLOT, &maps.a[sg], &a_full[as], ch * 64, wk.x0 - 1, wk.y0 - 1, wk.n0);
                         if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
-                        for (int tap = 0; tap < taps && !RES; ++tap) {
-                            // weights are K-major [Cout][tap][cin]: K block of (tap, ch) = tap*chunks + ch
-                            const int kb = seg == 0 ? tap * p.seg_chunks[0] + ch : kchunk + ch;
+                        for (int tap = 0; tap < sp.taps && !RES; ++tap) {
+                            const int kb = sp.kb_base + tap * sp.kb_stride + ch;
                             mbar_wait(&b_empty[bs], bph ^ 1u);
                             mbar_arrive_expect_tx(&b_full[bs], L::B_TILE);
                             tma_load_2d(smem + L::OFF_B + bs * L::B_TILE, &maps.b, &b_full[bs], kb * 64, wk.nt * BN);
                             if (++bs == L::NB) { bs = 0; bph ^= 1u; }
                         }
                     }
-                    kchunk += (seg == 0 ? 9 : 1) * p.seg_chunks[seg];
                 }
             }
         }
@@ -163,16 +179,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 mbar_wait(&t_empty[tb], tph ^ 1u);                    // epilogue drained this accumulator pair
                 tc_fence_after();
                 uint32_t first = 1;
-                int kchunk = 0;
-                for (int seg = 0; seg < 3; ++seg) {
-                    const int taps = seg == 0 ? 9 : 1;
-                    for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
-                        mbar_wait(&a_full[as], aph);
+                for (int sg = 0; sg < p.n_seg; ++sg) {
+                    const V2Seg sp = p.seg[sg];
+                    for (int ch = 0; ch < sp.chunks; ++ch) {
+                        mbar_wait(&a_ready[as], aph);                 // landed AND transformed
                         tc_fence_after();
                         const uint32_t a_base = smem_u32(smem + as * L::A_SLOT);
-                        for (int tap = 0; tap < taps; ++tap) {
-                            const int dy = seg == 0 ? tap / 3 : 1, dx = seg == 0 ? tap % 3 : 1;
-                            if (RES) bs = seg == 0 ? tap * p.seg_chunks[0] + ch : kchunk + ch;
+                        for (int tap = 0; tap < sp.taps; ++tap) {
+                            const int dy = sp.taps == 9 ? tap / 3 : 1, dx = sp.taps == 9 ? tap % 3 : 1;
+                            if (RES) bs = sp.kb_base + tap * sp.kb_stride + ch;
                             else { mbar_wait(&b_full[bs], bph); tc_fence_after(); }
                             const uint64_t db = make_smem_desc_sw128(smem_u32(smem + L::OFF_B + bs * L::B_TILE));
 #pragma unroll
@@ -191,10 +206,66 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         umma_commit(&a_empty[as]);
                         if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
                     }
-                    kchunk += (seg == 0 ? 9 : 1) * p.seg_chunks[seg];
                 }
                 umma_commit(&t_full[tb]);
                 if (++tb == 2) { tb = 0; tph ^= 1u; }
+            }
+        }
+    } else if (warp >= 6) {
+        // ===================== input transform (warps 6..9): GroupNorm affine (+SiLU) in place =====================
+        const int tt = threadIdx.x - 192, lv = tt & 7, r0 = tt >> 3;      // 8-channel vector, first row
+        const int rows_per_img = p.imgs_per_super == 1 ? 340 : 180;
+        int as = 0; uint32_t aph = 0;
+        for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
+            const V2Work wk = v2_decode(p, w);
+            for (int sg = 0; sg < p.n_seg; ++sg) {
+                const V2Seg sp = p.seg[sg];
+                for (int ch = 0; ch < sp.chunks; ++ch) {
+                    float sc[2][8], sh[2][8];
+                    if (sp.xform) {                                        // in flight while the TMA lands
+#pragma unroll
+                        for (int im = 0; im < 2; ++im) {
+                            if (im < p.imgs_per_super && wk.n0 + im < p.B) {
+                                const float4* ss = reinterpret_cast<const float4*>(
+                                    p.gn_ss + (size_t)(wk.n0 + im) * p.gn_C + sp.ss_off + ch * 64 + lv * 8);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 t = __ldg(ss + j);
+                                    sc[im][2 * j] = t.x; sh[im][2 * j] = t.y; sc[im][2 * j + 1] = t.z; sh[im][2 * j + 1] = t.w;
+                                }
+                            }
+                        }
+                    }
+                    mbar_wait(&a_full[as], aph);
+                    if (sp.xform) {
+                        uint8_t* slot = smem + as * L::A_SLOT;
+#pragma unroll
+                        for (int im = 0; im < 2; ++im) {
+                            if (im >= p.imgs_per_super || wk.n0 + im >= p.B) continue;
+                            for (int rr = r0; rr < rows_per_img; rr += 16) {
+                                const int hy = rr / 10, hx = rr - hy * 10;
+                                const int y = wk.y0 - 1 + hy, x = wk.x0 - 1 + hx;
+                                if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;   // padding stays exactly 0
+                                const int r = im * 180 + rr;
+                                uint4* ptr = reinterpret_cast<uint4*>(slot + r * 128 + ((lv ^ (r & 7)) << 4));
+                                uint4 v = *ptr;
+                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 f = __bfloat1622float2(h2[j]);
+                                    f.x = fmaf(f.x, sc[im][2 * j], sh[im][2 * j]);
+                                    f.y = fmaf(f.y, sc[im][2 * j + 1], sh[im][2 * j + 1]);
+                                    if (sp.xform == 2) { f.x = silu_tanh_v2(f.x); f.y = silu_tanh_v2(f.y); }
+                                    h2[j] = __floats2bfloat162_rn(f.x, f.y);
+                                }
+                                *ptr = v;
+                            }
+                        }
+                        fence_proxy_async();                               // generic-proxy writes -> UMMA (async proxy)
+                    }
+                    mbar_arrive(&a_ready[as]);
+                    if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
+                }
             }
         }
     } else {
@@ -320,9 +391,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
 
 bool conv_tc2_supported(const ConvArgs& a) {
     const bool k3 = a.KH == 3 && a.KW == 3 && a.pad == 1;
-    const bool k1 = a.KH == 1 && a.KW == 1 && a.pad == 0 && a.sc0_C == 0 && a.sc1_C == 0;   // runs as a "shortcut-only" conv
+    const bool k1 = a.KH == 1 && a.KW == 1 && a.pad == 0 && a.sc0_C == 0 && a.sc1_C == 0 && a.Cin1 == 0;   // centre-tap-only conv
     if (!(k3 || k1) || a.stride != 1 || a.sc_stride != 1) return false;
-    if (a.Cin % 64 || a.sc0_C % 64 || a.sc1_C % 64 || a.Cout % 64) return false;
+    if (a.Cin % 64 || a.Cin1 % 64 || a.sc0_C % 64 || a.sc1_C % 64 || a.Cout % 64) return false;
     if (a.W % 8 || a.H % 16) return false;
     if (a.H % 32 != 0 && a.H != 16) return false;
     return true;
@@ -389,17 +460,34 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     const int n_super = ceil_div(a.B, p.imgs_per_super) * p.tiles_x * p.supers_per_img;
     p.n_work = n_super * p.n_ntiles;
     const bool k1 = a.KH == 1;                          // 1x1 conv == centre-tap-only segment of the same machinery
-    p.seg_chunks[0] = k1 ? 0 : a.Cin / 64; p.seg_chunks[1] = k1 ? a.Cin / 64 : a.sc0_C / 64; p.seg_chunks[2] = a.sc1_C / 64;
+    const int Ct = a.Cin + a.Cin1;
+    const void* srcs[4] = {nullptr, nullptr, nullptr, nullptr}; int src_C[4] = {0, 0, 0, 0};
+    p.n_seg = 0;
+    auto add_seg = [&](const void* src, int C, int taps, int kb_base, int kb_stride, int xform, int ss_off) {
+        if (!C) return;
+        srcs[p.n_seg] = src; src_C[p.n_seg] = C;
+        p.seg[p.n_seg++] = V2Seg{C / 64, taps, kb_base, kb_stride, xform, ss_off};
+    };
+    if (k1) {
+        add_seg(a.in, a.Cin, 1, 0, 0, a.gn_mode, 0);
+    } else {
+        add_seg(a.in, a.Cin, 9, 0, Ct / 64, a.gn_mode, 0);
+        add_seg(a.in1, a.Cin1, 9, a.Cin / 64, Ct / 64, a.gn_mode, a.Cin);
+        add_seg(a.sc0, a.sc0_C, 1, 9 * Ct / 64, 0, 0, 0);
+        add_seg(a.sc1, a.sc1_C, 1, 9 * Ct / 64 + a.sc0_C / 64, 0, 0, 0);
+    }
+    SYNT_CHECK(!a.gn_mode || a.gn_ss != nullptr, "conv_tc2: gn_mode without scale/shift");
+    p.gn_ss = a.gn_ss; p.gn_C = Ct;
     p.B = a.B; p.H = a.H; p.W = a.W; p.Cout = a.Cout;
     p.bias = a.bias; p.bias2 = a.bias2; p.residual = (const bf16*)a.residual; p.relu = a.relu;
     p.stats = a.stats_out; p.stats_slots = conv_tc2_stats_slots(a);
     p.chunk = v2_chunk(a, BN);
     V2Maps maps;
     const int bh = a.H == 16 ? 18 : 34, bn = a.H == 16 ? 2 : 1;
-    make_halo_map(&maps.a[0], a.in, a.B, a.H, a.W, a.Cin, bh, bn);
-    if (k1) maps.a[1] = maps.a[0];
-    else if (a.sc0_C) make_halo_map(&maps.a[1], a.sc0, a.B, a.H, a.W, a.sc0_C, bh, bn); else maps.a[1] = maps.a[0];
-    if (a.sc1_C) make_halo_map(&maps.a[2], a.sc1, a.B, a.H, a.W, a.sc1_C, bh, bn); else maps.a[2] = maps.a[0];
+    for (int i = 0; i < 4; ++i) {
+        if (i < p.n_seg) make_halo_map(&maps.a[i], srcs[i], a.B, a.H, a.W, src_C[i], bh, bn);
+        else maps.a[i] = maps.a[0];
+    }
     {
         cuuint64_t dims[2] = {(cuuint64_t)a.ktot(), (cuuint64_t)a.Cout};
         cuuint64_t strides[1] = {(cuuint64_t)a.ktot() * 2};

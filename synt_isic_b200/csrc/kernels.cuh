@@ -20,6 +20,10 @@ struct ConvArgs {
     int B = 0, H = 0, W = 0, Cin = 0;
     int KH = 3, KW = 3, stride = 1, pad = 1;
     int Ho = 0, Wo = 0, Cout = 0;
+    // conv_tc2 only: second main source (channel concat, K order [tap][Cin + Cin1]) and fused input GroupNorm
+    const void* in1 = nullptr; int Cin1 = 0;
+    const float2* gn_ss = nullptr;     // [B][Cin + Cin1] (scale, shift)
+    int gn_mode = 0;                   // 0 raw input, 1 GroupNorm affine, 2 affine + SiLU
     const void* sc0 = nullptr; int sc0_C = 0;    // NHWC [B, Ho*sc_stride, Wo*sc_stride, sc0_C]
     const void* sc1 = nullptr; int sc1_C = 0;
     int sc_stride = 1;
@@ -30,7 +34,7 @@ struct ConvArgs {
     int relu = 0;
     void* out = nullptr;               // NHWC [B, Ho, Wo, Cout]
     float2* stats_out = nullptr;       // conv_tc2 only: per-channel (sum, sumsq) partials [B][slots][Cout] of `out`
-    int ktot() const { return KH * KW * Cin + sc0_C + sc1_C; }
+    int ktot() const { return KH * KW * (Cin + Cin1) + sc0_C + sc1_C; }
 };
 // fp32-FMA implicit GEMM (verification mode and odd shapes); weights are fp32.
 void conv_simt(const ConvArgs& a, int act_dtype, cudaStream_t s);

@@ -177,6 +177,7 @@ struct synt_unet {
     bool use_tc = true;                           // tcgen05 convs (bf16 mode) vs fp32-FMA convs
     bool want_f32_w = false;
     bool use_v2 = true;                           // persistent halo-tile kernel for 3x3 stride-1 convs
+    bool fuse_gn = true;                          // GroupNorm(+SiLU) applied inside conv_tc2 (no normalised tensor in HBM)
     ConvInW conv_in_w;
     ConvOutW conv_out_w;
     DevPtr norm_out_g, norm_out_b;
@@ -420,10 +421,11 @@ struct Fwd {
         ++u->launches;
         return o;
     }
+    bool fused_ok(const ConvArgs& a) const { return u->dt == DT_BF16 && u->use_tc && u->use_v2 && conv_tc2_supported(a); }
     // `out` receives GroupNorm statistics when want_stats: fused in the conv_tc2 epilogue, else stand-alone
     void conv(ConvArgs& a, const WeightDev& w, Act* out = nullptr, bool want_stats = false) {
-        const bool tc = u->dt == DT_BF16 && u->use_tc && conv_tc_supported(a);
-        const bool v2 = tc && u->use_v2 && conv_tc2_supported(a);
+        const bool v2 = fused_ok(a);
+        const bool tc = v2 || (u->dt == DT_BF16 && u->use_tc && conv_tc_supported(a));
         a.weight = w.get(tc);
         if (want_stats && v2) {
             out->stats_slots = conv_tc2_stats_slots(a);
@@ -442,19 +444,31 @@ struct Fwd {
     }
     Act resnet(const ResnetW& r, const Act& x0, const Act* x1) {
         const int H = x0.H, W = x0.W;
-        Act a = gn_act(x0, x1, r.g1, r.b1n, true);
+        // probe: can both convs take their GroupNorm'd input through the in-kernel transform?
+        ConvArgs probe; probe.B = B; probe.H = H; probe.W = W; probe.Ho = H; probe.Wo = W;
+        probe.Cin = x0.C; probe.Cin1 = x1 ? x1->C : 0; probe.Cout = r.cout;
+        const bool fuse = u->fuse_gn && fused_ok(probe);
         Act h1 = make(H, W, r.cout);
         {
-            ConvArgs c; c.in = a.p; c.B = B; c.H = H; c.W = W; c.Cin = r.cin; c.Ho = H; c.Wo = W; c.Cout = r.cout;
+            ConvArgs c; c.B = B; c.H = H; c.W = W; c.Ho = H; c.Wo = W; c.Cout = r.cout;
             c.bias = (const float*)r.bias1->p; c.bias2 = (const float*)u->temb_cur->p + r.temb_off; c.out = h1.p;
-            conv(c, r.w1, &h1, true);
+            if (fuse) {
+                float2* ss = gn_scale_shift(x0, x1, r.g1, r.b1n);
+                c.in = x0.p; c.Cin = x0.C;
+                if (x1) { c.in1 = x1->p; c.Cin1 = x1->C; }
+                c.gn_ss = ss; c.gn_mode = 2;
+                conv(c, r.w1, &h1, true);
+                u->pool.release(ss);
+            } else {
+                Act a = gn_act(x0, x1, r.g1, r.b1n, true);
+                c.in = a.p; c.Cin = r.cin;
+                conv(c, r.w1, &h1, true);
+                drop(a);
+            }
         }
-        drop(a);
-        Act a2 = gn_act(h1, nullptr, r.g2, r.b2n, true);
-        drop(h1);
         Act o = make(H, W, r.cout);
         {
-            ConvArgs c; c.in = a2.p; c.B = B; c.H = H; c.W = W; c.Cin = r.cout; c.Ho = H; c.Wo = W; c.Cout = r.cout;
+            ConvArgs c; c.B = B; c.H = H; c.W = W; c.Cin = r.cout; c.Ho = H; c.Wo = W; c.Cout = r.cout;
             c.bias = (const float*)r.bias2->p; c.out = o.p;
             if (r.shortcut) {
                 c.sc0 = x0.p; c.sc0_C = x0.C;
@@ -463,23 +477,41 @@ struct Fwd {
                 SYNT_CHECK(x1 == nullptr, "identity residual with a concatenated input");
                 c.residual = x0.p;
             }
-            conv(c, r.w2, &o, true);
+            if (fuse) {
+                float2* ss = gn_scale_shift(h1, nullptr, r.g2, r.b2n);
+                c.in = h1.p; c.gn_ss = ss; c.gn_mode = 2;
+                conv(c, r.w2, &o, true);
+                u->pool.release(ss);
+            } else {
+                Act a2 = gn_act(h1, nullptr, r.g2, r.b2n, true);
+                c.in = a2.p;
+                conv(c, r.w2, &o, true);
+                drop(a2);
+            }
         }
-        drop(a2);
+        drop(h1);
         tap(r.name, o);
         return o;
     }
     Act attention(const AttnW& w, const Act& x) {
         const int H = x.H, W = x.W, C = w.C;
-        Act a = gn_act(x, nullptr, w.g, w.b, false);
         const bool tc = u->dt == DT_BF16 && u->use_tc && attention_tc_supported(H * W, C);
         Act qkv = make(H, W, tc ? 5 * C : 3 * C);
         {
-            ConvArgs c; c.in = a.p; c.B = B; c.H = H; c.W = W; c.Cin = C; c.KH = c.KW = 1; c.pad = 0; c.Ho = H; c.Wo = W;
+            ConvArgs c; c.B = B; c.H = H; c.W = W; c.Cin = C; c.KH = c.KW = 1; c.pad = 0; c.Ho = H; c.Wo = W;
             c.Cout = qkv.C; c.bias = (const float*)(tc ? w.bqkv_tc : w.bqkv)->p; c.out = qkv.p;
-            conv(c, tc ? w.wqkv_tc : w.wqkv);
+            if (u->fuse_gn && fused_ok(c)) {
+                float2* ss = gn_scale_shift(x, nullptr, w.g, w.b);
+                c.in = x.p; c.gn_ss = ss; c.gn_mode = 1;
+                conv(c, tc ? w.wqkv_tc : w.wqkv);
+                u->pool.release(ss);
+            } else {
+                Act a = gn_act(x, nullptr, w.g, w.b, false);
+                c.in = a.p;
+                conv(c, tc ? w.wqkv_tc : w.wqkv);
+                drop(a);
+            }
         }
-        drop(a);
         Act o = make(H, W, C);
         {
             ProfScope ps(u, s, PC_ATTN, 4.0 * B * (double)(H * W) * (H * W) * C);
@@ -634,6 +666,8 @@ int synt_unet_create(const float* params_host, long long n_params, int dtype, sy
     u->use_tc = dtype == DT_BF16 && !(force && force[0] == '1');
     const char* v2 = getenv("SYNT_CONV_V2");
     u->use_v2 = !(v2 && v2[0] == '0');
+    const char* fg = getenv("SYNT_FUSE_GN");
+    u->fuse_gn = !(fg && fg[0] == '0');
     SYNT_CUDA(cudaStreamCreateWithFlags(&u->own_stream, cudaStreamNonBlocking));
     SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_in, cudaEventDisableTiming));
     SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_out, cudaEventDisableTiming));
@@ -933,5 +967,23 @@ extern "C" int synt_debug_attention(int use_tc, int act_dtype, const void* qkv, 
     } else {
         attention_simt(qkv, act_dtype, B, N, C, out, (cudaStream_t)stream);
     }
+    SYNT_CATCH
+}
+
+// conv_tc2 with its fused-input features: channel-concat main input (in | in1) and GroupNorm scale/shift
+// (+SiLU) applied inside the kernel.  gn_ss: [B][Cin+Cin1] float2 (scale, shift); gn_mode 0/1/2.
+extern "C" int synt_debug_conv_gn(const void* in, int Cin, const void* in1, int Cin1, const void* gn_ss, int gn_mode,
+                                  int B, int H, int W, int K, const void* sc0, int sc0_C, const void* weight,
+                                  const float* bias, const void* residual, void* out, int Cout, void* stats_out,
+                                  int* stats_slots, void* stream) {
+    SYNT_TRY
+    ConvArgs a;
+    a.in = in; a.Cin = Cin; a.in1 = in1; a.Cin1 = Cin1; a.gn_ss = (const float2*)gn_ss; a.gn_mode = gn_mode;
+    a.B = B; a.H = H; a.W = W; a.KH = a.KW = K; a.pad = K / 2; a.Ho = H; a.Wo = W; a.Cout = Cout;
+    a.sc0 = sc0; a.sc0_C = sc0_C; a.weight = weight; a.bias = bias; a.residual = residual; a.out = out;
+    a.stats_out = (float2*)stats_out;
+    SYNT_CHECK(conv_tc2_supported(a), "conv_tc2: unsupported");
+    if (stats_slots) *stats_slots = conv_tc2_stats_slots(a);
+    conv_tc2(a, (cudaStream_t)stream);
     SYNT_CATCH
 }

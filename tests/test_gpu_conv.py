@@ -1,5 +1,7 @@
 """Kernel-level parity of the two GEMM carriers (tcgen05 implicit GEMM, fp32-FMA implicit GEMM)
 against torch.nn.functional.conv2d on the same (bf16-rounded) operands, through the C ABI."""
+import ctypes as C
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -116,3 +118,64 @@ def test_conv_tcgen05_persistent_halo(cuda_dev, case):
     B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2 = case
     rel, mx = run_conv(cuda_dev, 6, B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2)
     assert rel < 4e-3, (rel, mx)
+
+
+GN_CASES = [
+    # B, H, W, Cin, Cin1, Cout, K, gn_mode, sc0_C, residual
+    (2, 32, 32, 64, 0, 64, 3, 2, 0, True),          # resnet conv2 (identity residual), resident weights
+    (3, 16, 16, 256, 256, 256, 3, 2, 0, False),     # up_blocks.0 conv1: concat input, 2 images / super-tile, odd B
+    (2, 64, 64, 128, 64, 128, 3, 2, 0, False),      # up_blocks.2.resnets.2 conv1: 192-channel concat
+    (2, 32, 32, 256, 0, 256, 3, 2, 128, False),     # conv2 + raw (untransformed) 1x1 shortcut segment
+    (2, 32, 32, 256, 0, 1280, 1, 1, 0, False),      # attention qkv projection: GroupNorm without SiLU
+    (1, 128, 128, 64, 0, 64, 3, 2, 0, True),        # 128x128: padding rows/cols must stay zero after the transform
+]
+
+
+@pytest.mark.parametrize("case", GN_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_tcgen05_fused_groupnorm_input(cuda_dev, case):
+    """conv_tc2 with GroupNorm(+SiLU) applied to the input inside the kernel and fused output statistics."""
+    B, H, W, Cin, Cin1, Cout, K, mode, scC, res = case
+    dev = cuda_dev
+    g = torch.Generator().manual_seed(sum(case))
+    Ct = Cin + Cin1
+    x = torch.randn(B, Ct, H, W, generator=g) * 1.5 + 0.3
+    sc = 0.5 + torch.rand(B, Ct, generator=g)
+    sh = torch.randn(B, Ct, generator=g) * 0.5
+    w = torch.randn(Cout, Ct, K, K, generator=g) / (Ct * K * K) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    xs = torch.randn(B, scC, H, W, generator=g) if scC else None
+    ws = torch.randn(Cout, scC, generator=g) / scC ** 0.5 if scC else None
+    r = torch.randn(B, Cout, H, W, generator=g) if res else None
+    q = lambda t: t.to(torch.bfloat16).float()
+    xq = q(x).to(dev)
+    y = xq * sc.to(dev)[:, :, None, None] + sh.to(dev)[:, :, None, None]
+    if mode == 2:
+        y = F.silu(y)
+    y = q(y)                                                       # the kernel rounds the transformed tile to bf16
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = F.conv2d(y, q(w).to(dev), b.to(dev), padding=K // 2)
+    if scC:
+        ref = ref + F.conv2d(q(xs).to(dev), q(ws).to(dev)[:, :, None, None])
+    if res:
+        ref = ref + q(r).to(dev)
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(dev) if t is not None else None
+    x0, x1 = nhwc(x[:, :Cin]), (nhwc(x[:, Cin:]) if Cin1 else None)
+    wp = _pack(w, ws).to(torch.bfloat16).to(dev)
+    ss = torch.stack([sc, sh], dim=2).contiguous().to(dev)        # [B][Ct] float2
+    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros(B * 64 * Cout * 2, dtype=torch.float32, device=dev)
+    slots = C.c_int()
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    _lib.check(_lib.lib().synt_debug_conv_gn(ptr(x0), Cin, ptr(x1), Cin1, ptr(ss), mode, B, H, W, K, ptr(nhwc(xs)), scC, ptr(wp),
+                                             ptr(b.to(dev)), ptr(nhwc(r)), ptr(out), Cout, ptr(stats), C.byref(slots),
+                                             _lib.current_stream_ptr()), "debug_conv_gn")
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2)
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 6e-3, rel                                         # tanh.approx SiLU + bf16 re-rounding of the input
+    # fused output statistics == per-channel sums of the stored bf16 output
+    st = stats[: B * slots.value * Cout * 2].view(B, slots.value, Cout, 2).sum(1)
+    want_s = got.sum(dim=(2, 3)); want_q = (got * got).sum(dim=(2, 3))
+    assert torch.allclose(st[..., 0], want_s, rtol=2e-3, atol=2e-2)
+    assert torch.allclose(st[..., 1], want_q, rtol=2e-3, atol=2e-2)
