@@ -242,23 +242,33 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
 #pragma unroll
                         for (int im = 0; im < 2; ++im) {
                             if (im >= p.imgs_per_super || wk.n0 + im >= p.B) continue;
-                            for (int rr = r0; rr < rows_per_img; rr += 16) {
-                                const int hy = rr / 10, hx = rr - hy * 10;
-                                const int y = wk.y0 - 1 + hy, x = wk.x0 - 1 + hx;
-                                if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;   // padding stays exactly 0
-                                const int r = im * 180 + rr;
-                                uint4* ptr = reinterpret_cast<uint4*>(slot + r * 128 + ((lv ^ (r & 7)) << 4));
-                                uint4 v = *ptr;
-                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v);
+                            constexpr int UR = 4;                          // rows in flight per thread (hides LDS/MUFU latency)
+                            for (int base = r0; base < rows_per_img; base += 16 * UR) {
+                                uint4 v[UR]; uint4* ptr[UR]; bool ok[UR];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float2 f = __bfloat1622float2(h2[j]);
-                                    f.x = fmaf(f.x, sc[im][2 * j], sh[im][2 * j]);
-                                    f.y = fmaf(f.y, sc[im][2 * j + 1], sh[im][2 * j + 1]);
-                                    if (sp.xform == 2) { f.x = silu_tanh_v2(f.x); f.y = silu_tanh_v2(f.y); }
-                                    h2[j] = __floats2bfloat162_rn(f.x, f.y);
+                                for (int uu = 0; uu < UR; ++uu) {
+                                    const int rr = base + 16 * uu;
+                                    const int hy = rr / 10, hx = rr - hy * 10;
+                                    const int y = wk.y0 - 1 + hy, x = wk.x0 - 1 + hx;
+                                    ok[uu] = rr < rows_per_img && y >= 0 && y < p.H && x >= 0 && x < p.W;   // padding stays exactly 0
+                                    const int r = im * 180 + rr;
+                                    ptr[uu] = reinterpret_cast<uint4*>(slot + r * 128 + ((lv ^ (r & 7)) << 4));
+                                    if (ok[uu]) v[uu] = *ptr[uu];
                                 }
-                                *ptr = v;
+#pragma unroll
+                                for (int uu = 0; uu < UR; ++uu) {
+                                    if (!ok[uu]) continue;
+                                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v[uu]);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        float2 f = __bfloat1622float2(h2[j]);
+                                        f.x = fmaf(f.x, sc[im][2 * j], sh[im][2 * j]);
+                                        f.y = fmaf(f.y, sc[im][2 * j + 1], sh[im][2 * j + 1]);
+                                        if (sp.xform == 2) { f.x = silu_tanh_v2(f.x); f.y = silu_tanh_v2(f.y); }
+                                        h2[j] = __floats2bfloat162_rn(f.x, f.y);
+                                    }
+                                    *ptr[uu] = v[uu];
+                                }
                             }
                         }
                         fence_proxy_async();                               // generic-proxy writes -> UMMA (async proxy)

@@ -500,7 +500,7 @@ struct Fwd {
         {
             ConvArgs c; c.B = B; c.H = H; c.W = W; c.Cin = C; c.KH = c.KW = 1; c.pad = 0; c.Ho = H; c.Wo = W;
             c.Cout = qkv.C; c.bias = (const float*)(tc ? w.bqkv_tc : w.bqkv)->p; c.out = qkv.p;
-            if (u->fuse_gn && fused_ok(c)) {
+            if (u->fuse_gn && fused_ok(c) && c.Cout <= 256) {     // many N tiles would re-transform the tile per N tile
                 float2* ss = gn_scale_shift(x, nullptr, w.g, w.b);
                 c.in = x.p; c.gn_ss = ss; c.gn_mode = 1;
                 conv(c, tc ? w.wqkv_tc : w.wqkv);

@@ -164,11 +164,12 @@ def test_conv_tcgen05_fused_groupnorm_input(cuda_dev, case):
     wp = _pack(w, ws).to(torch.bfloat16).to(dev)
     ss = torch.stack([sc, sh], dim=2).contiguous().to(dev)        # [B][Ct] float2
     out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
-    stats = torch.zeros(B * 64 * Cout * 2, dtype=torch.float32, device=dev)
+    stats = torch.zeros(B * 256 * Cout * 2, dtype=torch.float32, device=dev)
     slots = C.c_int()
     ptr = lambda t: t.data_ptr() if t is not None else None
-    _lib.check(_lib.lib().synt_debug_conv_gn(ptr(x0), Cin, ptr(x1), Cin1, ptr(ss), mode, B, H, W, K, ptr(nhwc(xs)), scC, ptr(wp),
-                                             ptr(b.to(dev)), ptr(nhwc(r)), ptr(out), Cout, ptr(stats), C.byref(slots),
+    xs_d, r_d, b_d = nhwc(xs), nhwc(r), b.to(dev)                 # keep the device tensors alive across the call
+    _lib.check(_lib.lib().synt_debug_conv_gn(ptr(x0), Cin, ptr(x1), Cin1, ptr(ss), mode, B, H, W, K, ptr(xs_d), scC, ptr(wp),
+                                             ptr(b_d), ptr(r_d), ptr(out), Cout, ptr(stats), C.byref(slots),
                                              _lib.current_stream_ptr()), "debug_conv_gn")
     torch.cuda.synchronize()
     got = out.float().permute(0, 3, 1, 2)
