@@ -53,19 +53,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max rel. error 7.5e-5, far
-// below the bf16 rounding of P): the kernel is MUFU-bound (N^2 exponentials per head), so 3 of every 8
-// exponentials are computed here while the MUFU pipe works on the other 5.
-__device__ __forceinline__ float ex2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float t = x + 12582912.0f;                  // 1.5 * 2^23: low mantissa bits = round(x)
-    const float r = t - 12582912.0f;
-    const float f = x - r;                            // in [-0.5, 0.5]
-    float p = fmaf(f, 0.05517083779f, 0.24260935187f);
-    p = fmaf(p, f, 0.69326096773f);
-    p = fmaf(p, f, 0.99992817640f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
+// NOTE (measured, B200): moving 3 of every 8 exponentials to an FMA-pipe polynomial (Cody-Waite + degree-3
+// minimax) made the kernel 10% SLOWER (4.09 -> 4.50 ms/step): the softmax warps are issue/FMA-pipe limited
+// next to the MUFU pipe, and packed ex2.approx.{f16,bf16}x2 lowers to two MUFU ops on sm_100a.  All
+// exponentials therefore stay on MUFU.EX2.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -248,10 +239,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
                         for (int i = 0; i < 4; ++i) {
                             const int e = piece * 32 + q * 8 + i * 2;
                             const float x0 = __uint_as_float(v[e]) - mrow, x1 = __uint_as_float(v[e + 1]) - mrow;
-                            // elements 1, 4, 6 of every 8 go to the FMA-pipe polynomial, the rest to MUFU.EX2
-                            const float p0 = (i == 2) ? ex2_poly(x0) : ex2_approx(x0);
-                            const float p1 = (i == 0 || i == 3) ? ex2_poly(x1) : ex2_approx(x1);
-                            w[i] = pack_bf16x2(p0, p1);
+                            w[i] = pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
                         }
                         const int chunk16 = ((piece & 1) * 4 + q) ^ sw;   // SWIZZLE_128B: 16-byte chunk ^ (row & 7)
                         *reinterpret_cast<uint4*>(blk + chunk16 * 16) = make_uint4(w[0], w[1], w[2], w[3]);
