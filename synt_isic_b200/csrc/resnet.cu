@@ -58,6 +58,44 @@ void classifier_preprocess(const float* x, int B, int Hin, int Win, int Hout, in
     SYNT_LAUNCH_CHECK();
 }
 
+// Stem im2col for the tensor-core path: pre [B,224,224,3] bf16 -> A [B,112,112,192] bf16 with
+// k = ky*24 + kx*3 + c (7x7 window, stride 2, pad 3; kx = 7 and k >= 168 are zero padding), so every
+// window row is one 48-byte, 16-byte-aligned segment copied from 21 contiguous input elements.
+// The 7x7/s2 stem then runs as a 1x1 convolution with Cin = 192 on the tcgen05 kernel.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const bf16* __restrict__ pre, long long nseg, bf16* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nseg; i += (long long)gridDim.x * blockDim.x) {
+        const int ky = (int)(i & 7);                       // segment 7 = zero tail
+        long long p = i >> 3;
+        const int ox = (int)(p % 112), oy = (int)((p / 112) % 112);
+        const long long b = p / (112 * 112);
+        __align__(16) unsigned short v[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) v[j] = 0;
+        const int iy = 2 * oy - 3 + ky;
+        if (ky < 7 && iy >= 0 && iy < 224) {
+            const unsigned short* row = reinterpret_cast<const unsigned short*>(pre) + ((b * 224 + iy) * 224) * 3;
+            const int ix0 = 2 * ox - 3;
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
+                const int ix = ix0 + kx;
+                if (ix >= 0 && ix < 224) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[kx * 3 + c] = row[ix * 3 + c];
+                }
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + p * 192 + ky * 24);
+        const uint4* src = reinterpret_cast<const uint4*>(v);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+}
+void stem_im2col(const void* pre, int B, void* out, cudaStream_t s) {
+    const long long nseg = (long long)B * 112 * 112 * 8;
+    const int blocks = (int)((nseg + 255) / 256 < 148 * 32 ? (nseg + 255) / 256 : 148 * 32);
+    stem_im2col_kernel<<<blocks, 256, 0, s>>>((const bf16*)pre, nseg, (bf16*)out);
+    SYNT_LAUNCH_CHECK();
+}
+
 template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ in, int H, int W, int C, int Ho, int Wo, long long nvec_total,
                                T* __restrict__ out) {
@@ -286,7 +324,8 @@ using namespace synt;
 
 struct synt_resnet18 {
     int dt = DT_BF16, num_classes = 7; bool use_tc = true;
-    RConv stem;                              // 7x7 s2, always the fp32-FMA kernel (Cin = 3)
+    RConv stem;                              // 7x7 s2 on the fp32-FMA kernel (fp32 mode)
+    RConv stem_tc;                           // the same stem as a 1x1 conv over the im2col'd input (K 147 -> 192), bf16 tcgen05
     RConv c1[4][2], c2[4][2];
     RPtr fc_w, fc_b;
     Pool pool;
@@ -295,6 +334,8 @@ struct synt_resnet18 {
 };
 
 namespace synt {
+
+void stem_im2col(const void* pre, int B, void* out, cudaStream_t s);
 
 struct RFwd {
     synt_resnet18* r; cudaStream_t s; int B;
@@ -320,7 +361,15 @@ struct RFwd {
         classifier_preprocess(x_nchw, B, 128, 128, 224, 224, pre, 3, r->dt, s);
         tap("preprocess", pre, 224, 224, 3);
         void* c1 = make(112, 112, 64);
-        conv(r->stem, pre, 224, 224, nullptr, 1, nullptr, 1, c1, 112, 112);
+        if (r->use_tc) {
+            void* col = make(112, 112, 192);
+            stem_im2col(pre, B, col, s);
+            ++r->launches;
+            conv(r->stem_tc, col, 112, 112, nullptr, 1, nullptr, 1, c1, 112, 112);
+            r->pool.release(col);
+        } else {
+            conv(r->stem, pre, 224, 224, nullptr, 1, nullptr, 1, c1, 112, 112);
+        }
         r->pool.release(pre);
         tap("relu", c1, 112, 112, 64);
         void* cur = make(56, 56, 64);
@@ -386,6 +435,20 @@ int synt_resnet18_create(const float* P, long long n_params, int num_classes, in
     r->use_tc = dtype == DT_BF16 && !(force && force[0] == '1');
     const bool bf = r->use_tc;
     r->stem = make_rconv(P, m, "conv1", "bn1", 3, 64, 7, 2, "", "", 0, false);
+    if (bf) {                                               // [64][3][7][7] -> K-major [64][ky*24 + kx*3 + c], zero-padded to 192, bf16
+        std::vector<float> sc, sh;
+        fold_bn(P, m, "bn1", 64, sc, sh);
+        const float* w = P + m.find("conv1.weight");        // [64][3][7][7]
+        std::vector<uint16_t> pk((size_t)64 * 192, 0);
+        for (int n = 0; n < 64; ++n)
+            for (int ky = 0; ky < 7; ++ky)
+                for (int kx = 0; kx < 7; ++kx)
+                    for (int c = 0; c < 3; ++c)
+                        pk[(size_t)n * 192 + ky * 24 + kx * 3 + c] = r_f2bf(w[((size_t)n * 3 + c) * 49 + ky * 7 + kx] * sc[n]);
+        r->stem_tc.cin = 192; r->stem_tc.cout = 64; r->stem_tc.k = 1; r->stem_tc.stride = 1; r->stem_tc.bf = true;
+        r->stem_tc.w = r_upload(pk.data(), pk.size() * 2);
+        r->stem_tc.b = r_upload(sh.data(), sh.size() * 4);
+    }
     int cin = 64;
     for (int l = 0; l < 4; ++l) {
         const int c = kStageCh[l];
@@ -411,7 +474,7 @@ int synt_resnet18_logits(synt_resnet18_t* h, const float* x, int B, float* logit
     SYNT_TRY
     SYNT_CHECK(h && x && logits && B > 0, "bad argument");
     const size_t img = (size_t)3 * 128 * 128;
-    const int mb = 64;                                      // bounds the workspace
+    const int mb = 128;                                     // bounds the workspace (im2col of the stem: 4.8 MB per image)
     for (int b0 = 0; b0 < B; b0 += mb) {
         RFwd f{h, (cudaStream_t)stream, B - b0 < mb ? B - b0 : mb};
         f.run(x + b0 * img, logits + (size_t)b0 * h->num_classes);
