@@ -210,9 +210,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&s_free[sb]);                  // S buffer is in registers
-                float cmax = __uint_as_float(v[0]);
+                float cm[8];                               // 8 independent chains instead of one 127-deep dependency
 #pragma unroll
-                for (int i = 1; i < 128; ++i) cmax = fmaxf(cmax, __uint_as_float(v[i]));
+                for (int i = 0; i < 8; ++i) cm[i] = __uint_as_float(v[i]);
+#pragma unroll
+                for (int i = 8; i < 128; ++i) cm[i & 7] = fmaxf(cm[i & 7], __uint_as_float(v[i]));
+                const float cmax = fmaxf(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])), fmaxf(fmaxf(cm[4], cm[5]), fmaxf(cm[6], cm[7])));
                 float alpha = 1.0f;
                 bool moved = false;
                 if (c == 0) { m[jj] = cmax; }

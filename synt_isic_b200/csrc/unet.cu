@@ -191,6 +191,8 @@ struct synt_unet {
     DevPtr timesteps_dev, coef_table_dev; int n_steps = 0;
     std::vector<int> timesteps_host;
     Pool pool;
+    Pool pool2;                                   // second chain (dual-stream sampling)
+    bool dual = false; cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     long long launches = 0;
     // CUDA graph cache for one sampling step
     struct GraphKey {
@@ -214,6 +216,9 @@ struct synt_unet {
     ~synt_unet() {
         if (gexec) cudaGraphExecDestroy(gexec);
         if (own_stream) cudaStreamDestroy(own_stream);
+        if (side_stream) cudaStreamDestroy(side_stream);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
     }
@@ -376,17 +381,17 @@ struct ProfScope {
 };
 
 struct Fwd {
-    synt_unet* u; cudaStream_t s; int B;
+    synt_unet* u; cudaStream_t s; int B; Pool* pool;
     size_t esz() const { return dtype_size(u->dt); }
     Act make(int H, int W, int C) {
-        Act a; a.B = B; a.H = H; a.W = W; a.C = C; a.p = u->pool.alloc(a.numel() * esz()); return a;
+        Act a; a.B = B; a.H = H; a.W = W; a.C = C; a.p = pool->alloc(a.numel() * esz()); return a;
     }
-    void drop(Act& a) { u->pool.release(a.p); u->pool.release(a.stats); a.p = nullptr; a.stats = nullptr; }
+    void drop(Act& a) { pool->release(a.p); pool->release(a.stats); a.p = nullptr; a.stats = nullptr; }
     // per-channel statistics by the stand-alone kernel (tensors whose producer does not fuse them)
     void standalone_stats(Act& a) {
         const int HW = a.H * a.W;
         a.stats_slots = gn_num_chunks(B, HW);
-        a.stats = (float2*)u->pool.alloc((size_t)B * a.stats_slots * a.C * sizeof(float2));
+        a.stats = (float2*)pool->alloc((size_t)B * a.stats_slots * a.C * sizeof(float2));
         ProfScope ps(u, s, PC_GN_STATS);
         gn_stats(a.p, a.C, nullptr, 0, u->dt, B, HW, a.C, a.stats, a.stats_slots, s);
         ++u->launches;
@@ -402,7 +407,7 @@ struct Fwd {
     float2* gn_scale_shift(const Act& x0, const Act* x1, const DevPtr& gamma, const DevPtr& beta) {
         const int C = x0.C + (x1 ? x1->C : 0), HW = x0.H * x0.W;
         SYNT_CHECK(x0.stats && (!x1 || x1->stats), "GroupNorm input without statistics");
-        float2* ss = (float2*)u->pool.alloc((size_t)B * C * sizeof(float2));
+        float2* ss = (float2*)pool->alloc((size_t)B * C * sizeof(float2));
         ProfScope ps(u, s, PC_GN_STATS);
         gn_finalize_channels(x0.stats, x0.stats_slots, x0.C, x1 ? x1->stats : nullptr, x1 ? x1->stats_slots : 0,
                              x1 ? x1->C : 0, B, kGroups, HW, kGnEps, (const float*)gamma->p, (const float*)beta->p, ss, s);
@@ -417,7 +422,7 @@ struct Fwd {
         gn_apply_fused(x0.p, x0.stats, x0.stats_slots, x0.C, x1 ? x1->p : nullptr, x1 ? x1->stats : nullptr,
                        x1 ? x1->stats_slots : 0, x1 ? x1->C : 0, u->dt, B, x0.H * x0.W, kGroups, kGnEps,
                        (const float*)gamma->p, (const float*)beta->p, ss, silu ? 1 : 0, o.p, s);
-        u->pool.release(ss);
+        pool->release(ss);
         ++u->launches;
         return o;
     }
@@ -429,7 +434,7 @@ struct Fwd {
         a.weight = w.get(tc);
         if (want_stats && v2) {
             out->stats_slots = conv_tc2_stats_slots(a);
-            out->stats = (float2*)u->pool.alloc((size_t)B * out->stats_slots * a.Cout * sizeof(float2));
+            out->stats = (float2*)pool->alloc((size_t)B * out->stats_slots * a.Cout * sizeof(float2));
             a.stats_out = out->stats;
         }
         {
@@ -458,7 +463,7 @@ struct Fwd {
                 if (x1) { c.in1 = x1->p; c.Cin1 = x1->C; }
                 c.gn_ss = ss; c.gn_mode = 2;
                 conv(c, r.w1, &h1, true);
-                u->pool.release(ss);
+                pool->release(ss);
             } else {
                 Act a = gn_act(x0, x1, r.g1, r.b1n, true);
                 c.in = a.p; c.Cin = r.cin;
@@ -481,7 +486,7 @@ struct Fwd {
                 float2* ss = gn_scale_shift(h1, nullptr, r.g2, r.b2n);
                 c.in = h1.p; c.gn_ss = ss; c.gn_mode = 2;
                 conv(c, r.w2, &o, true);
-                u->pool.release(ss);
+                pool->release(ss);
             } else {
                 Act a2 = gn_act(h1, nullptr, r.g2, r.b2n, true);
                 c.in = a2.p;
@@ -504,7 +509,7 @@ struct Fwd {
                 float2* ss = gn_scale_shift(x, nullptr, w.g, w.b);
                 c.in = x.p; c.gn_ss = ss; c.gn_mode = 1;
                 conv(c, tc ? w.wqkv_tc : w.wqkv);
-                u->pool.release(ss);
+                pool->release(ss);
             } else {
                 Act a = gn_act(x, nullptr, w.g, w.b, false);
                 c.in = a.p;
@@ -516,9 +521,9 @@ struct Fwd {
         {
             ProfScope ps(u, s, PC_ATTN, 4.0 * B * (double)(H * W) * (H * W) * C);
             if (tc) {
-                void* vt = u->pool.alloc((size_t)B * (C / 8) * 16 * H * W * 2);
+                void* vt = pool->alloc((size_t)B * (C / 8) * 16 * H * W * 2);
                 attention_tc(qkv.p, B, H * W, C, vt, o.p, s);
-                u->pool.release(vt);
+                pool->release(vt);
                 ++u->launches;
             } else {
                 attention_simt(qkv.p, u->dt, B, H * W, C, o.p, s);
@@ -591,7 +596,7 @@ struct Fwd {
         float2* ss = gn_scale_shift(hcur, nullptr, u->norm_out_g, u->norm_out_b);
         { ProfScope ps(u, s, PC_CONV_OUT, 2.0 * B * kImg * kImg * 3.0 * 576); conv_out3(hcur.p, u->dt, ss, u->conv_out_w, B, kImg, kImg, eps_nchw, sch, s); }
         ++u->launches;
-        u->pool.release(ss);
+        pool->release(ss);
         drop(hcur);
     }
 };
@@ -606,9 +611,8 @@ static void sample_step(synt_unet* u, float* x, int B, const float* z, unsigned 
                     (const int*)u->timesteps_dev->p, (const int*)u->step_ctr->p, 0, (float*)u->temb_cur->p,
                     (float*)u->coef_cur->p, s);
     ++u->launches;
-    for (int b0 = 0; b0 < B; b0 += mb) {
-        const int nb = B - b0 < mb ? B - b0 : mb;
-        Fwd f{u, s, nb};
+    auto chain = [&](int b0, int nb, cudaStream_t cs, Pool* pool) {
+        Fwd f{u, cs, nb, pool};
         SchedArgs sch;
         sch.x = x + b0 * img; sch.coef = (const float*)u->coef_cur->p;
         sch.z = z ? z + b0 * img : nullptr; sch.z_step_stride = (long long)B * img;
@@ -617,6 +621,19 @@ static void sample_step(synt_unet* u, float* x, int B, const float* z, unsigned 
         sch.eps_step_stride = (long long)B * img;
         sch.image_offset = image_offset + b0;
         f.run(x + b0 * img, eps_tap ? eps_tap + b0 * img : nullptr, sch);
+    };
+    if (u->dual && B >= 2 && mb >= B) {
+        // two independent half-batch chains on two streams: the tails / small kernels of one chain are
+        // filled by the other (captured as two parallel branches of the step graph)
+        const int h0 = B / 2;
+        SYNT_CUDA(cudaEventRecord(u->ev_fork, s));
+        SYNT_CUDA(cudaStreamWaitEvent(u->side_stream, u->ev_fork, 0));
+        chain(0, h0, s, &u->pool);
+        chain(h0, B - h0, u->side_stream, &u->pool2);
+        SYNT_CUDA(cudaEventRecord(u->ev_join, u->side_stream));
+        SYNT_CUDA(cudaStreamWaitEvent(s, u->ev_join, 0));
+    } else {
+        for (int b0 = 0; b0 < B; b0 += mb) chain(b0, B - b0 < mb ? B - b0 : mb, s, &u->pool);
     }
     advance_step((int*)u->step_ctr->p, s);
     ++u->launches;
@@ -666,6 +683,11 @@ int synt_unet_create(const float* params_host, long long n_params, int dtype, sy
     u->use_tc = dtype == DT_BF16 && !(force && force[0] == '1');
     const char* v2 = getenv("SYNT_CONV_V2");
     u->use_v2 = !(v2 && v2[0] == '0');
+    const char* du = getenv("SYNT_DUAL");
+    u->dual = du && du[0] == '1';
+    SYNT_CUDA(cudaStreamCreateWithFlags(&u->side_stream, cudaStreamNonBlocking));
+    SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_fork, cudaEventDisableTiming));
+    SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_join, cudaEventDisableTiming));
     const char* fg = getenv("SYNT_FUSE_GN");
     u->fuse_gn = !(fg && fg[0] == '0');
     SYNT_CUDA(cudaStreamCreateWithFlags(&u->own_stream, cudaStreamNonBlocking));
@@ -700,7 +722,7 @@ int synt_unet_debug_forward(synt_unet_t* h, const float* x, int B, int t, const 
     for (int b0 = 0; b0 < B; b0 += mb) {
         const int nb = B - b0 < mb ? B - b0 : mb;
         SYNT_CHECK(!dbg || nb == B, "debug taps need B <= 16");
-        Fwd f{h, s, nb};
+        Fwd f{h, s, nb, &h->pool};
         SchedArgs sch;
         f.run(x + b0 * img, dbg ? dbg_eps : eps + b0 * img, sch);
     }
