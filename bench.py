@@ -133,16 +133,36 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _dbg(msg):
+    if os.environ.get("BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
 def run_ours(args):
     import torch
     from synt_isic_b200 import DDPMScheduler, SUPPORTED_CONFIG, UNet2DModel
     from synt_isic_b200.dist import init_from_env, max_over_ranks
     import torch.distributed as dist
 
-    rank, world, local = init_from_env("nccl")
-    assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
-    dev = torch.device(f"cuda:{local}")
-    torch.cuda.set_device(dev)
+    # NCCL prints its version banner on stdout when the first communicator is built: keep stdout for the JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, world, local = init_from_env("nccl")
+        assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+        dev = torch.device(f"cuda:{local}")
+        torch.cuda.set_device(dev)
+        if world > 1:
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     B = args.batch
     peaks = load_peaks()
 
@@ -168,7 +188,9 @@ def run_ours(args):
 
     with torch.cuda.stream(stream):
         x = x_host.to(dev, non_blocking=True)
+        _dbg("model on device")
         run_steps(x, 0, W)                                    # warm-up: pool sizing, graph capture, clocks
+        _dbg("warm-up done")
         stream.synchronize()
         if world > 1:
             dist.barrier()
@@ -187,7 +209,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         clocks = sampler.stop() if rank == 0 else None
         launches = model.launch_count() - l0
-        sec_step = max_over_ranks(ev0.elapsed_time(ev1) / 1e3 / K, dev)
+        _dbg("timed region done")
+        sec_step = max_over_ranks(ev0.elapsed_time(ev1) / 1e3 / K, dev, dist.group.WORLD if world > 1 else None)
+        _dbg("max over ranks done")
         finite = bool(torch.isfinite(x).all().item())
 
         # ---- e2e: public API, pinned host input/output copies inside the timed region, every step
@@ -205,12 +229,14 @@ def run_ours(args):
             out_host.copy_(x, non_blocking=True)
         e1.record(stream)
         stream.synchronize()
-        sec_e2e = max_over_ranks(e0.elapsed_time(e1) / 1e3 / Ke, dev)
+        sec_e2e = max_over_ranks(e0.elapsed_time(e1) / 1e3 / Ke, dev, dist.group.WORLD if world > 1 else None)
+        _dbg("e2e done")
 
         # ---- per-kernel profile of one step (CUDA-event pair around every launch)
         prof = model.profile_step(x, sched, micro_batch=args.micro_batch) if rank == 0 else None
         stream.synchronize()
 
+    _dbg("profile done")
     value = world * B / (T_STEPS * sec_step)
     e2e_value = world * B / (T_STEPS * sec_e2e)
     if rank != 0:

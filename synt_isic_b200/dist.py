@@ -46,7 +46,9 @@ def partition(units, rank: int, world: int):
 
 
 def _world(group):
-    if group is None and not dist.is_initialized():
+    """``group=None`` means "this rank alone" (no collective is issued); pass ``dist.group.WORLD`` (or a
+    sub-group) to shard across ranks.  Every rank of the group must then make the same call."""
+    if group is None or not dist.is_initialized():
         return 0, 1
     return dist.get_rank(group), dist.get_world_size(group)
 

@@ -177,19 +177,21 @@ def fn(x):                      # stand-in for the classifier: row-wise, determi
     return torch.stack([x.sum(dim=(1, 2, 3)), x.mean(dim=(1, 2, 3)) * 3], dim=1)
 g = torch.Generator().manual_seed(5)
 items = torch.randn(13, 3, 4, 4, generator=g)
-out = sharded_eval(fn, items, None, chunk=4)
+out = sharded_eval(fn, items, dist.group.WORLD, chunk=4)
 ref = torch.stack([items.sum(dim=(1, 2, 3)), items.mean(dim=(1, 2, 3)) * 3], dim=1)
 assert torch.allclose(out, ref, atol=1e-6), (out - ref).abs().max()
 lo, hi = shard_bounds(13, rank, world)
 assert sum(calls) == hi - lo                     # each rank evaluated only its slice
 counts = [3, 2]
 mine = torch.full((counts[rank], 2, 2, 3), rank + 1, dtype=torch.uint8)
-allimg = gather_images(mine, counts, None, dst=0)
+allimg = gather_images(mine, counts, dist.group.WORLD, dst=0)
 if rank == 0:
     assert allimg.shape == (5, 2, 2, 3) and allimg[:3].eq(1).all() and allimg[3:].eq(2).all()
 else:
     assert allimg is None
-assert max_over_ranks(float(rank + 1), "cpu") == 2.0
+assert max_over_ranks(float(rank + 1), "cpu", dist.group.WORLD) == 2.0
+solo = sharded_eval(fn, items, None, chunk=4)          # group=None: this rank alone, no collective
+assert torch.allclose(solo, ref, atol=1e-6)
 dist.barrier()
 print("RANK_OK", rank)
 """
