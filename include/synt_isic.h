@@ -130,6 +130,10 @@ int synt_debug_conv_gn(const void* in_dev, int Cin, const void* in1_dev, int Cin
                        int B, int H, int W, int K, const void* sc0_dev, int sc0_C, const void* weight_dev,
                        const float* bias_dev, const void* residual_dev, void* out_dev, int Cout, void* stats_out_dev,
                        int* stats_slots, void* stream);
+/* Upsample2D(nearest 2x) + conv3x3 through the fused sub-pixel path (four 2x2 convolutions on the low-res
+ * input): in [B,H,W,Cin] bf16 (device), w_host the raw [Cout][Cin][3][3] fp32 filter (HOST), out [B,2H,2W,Cout]. */
+int synt_debug_conv_up2x(const void* in_dev, int B, int H, int W, int Cin, const float* w_host, const float* bias_dev,
+                         void* out_dev, int Cout, void* stats_out_dev, int* stats_slots, void* stream);
 /* softmax(q k^T / sqrt(8)) v on caller-provided tensors: use_tc=0: qkv [B,N,3C] (q|k|v); use_tc=1: the
  * zero-interleaved bf16 layout [B,N,5C] consumed by the tcgen05 attention kernel. out: [B,N,C]. */
 int synt_debug_attention(int use_tc, int act_dtype, const void* qkv_dev, int B, int N, int C, void* out_dev,

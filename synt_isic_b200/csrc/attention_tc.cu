@@ -9,19 +9,21 @@
 //   vt   [B*32, 16, N] bf16 = per head V^T padded to 16 rows: rows 0..7 = v dims, row 8 = 1
 //          (so the P.V MMA also produces the softmax denominator), rows 9..15 = 0.
 //
-// One CTA = 128 queries x 4 heads of one image; one pass over the keys in chunks of 128:
-//   S  = Q_h K_h^T     one tcgen05.mma  M128 x N128 x K16  -> TMEM (fp32, log2 domain), 3 S buffers
+// One CTA = 128 queries x 4 heads of one image, TWO CTAs resident per SM; one pass over the keys in chunks of 64:
+//   S  = Q_h K_h^T     one tcgen05.mma  M128 x N64 x K16  -> TMEM (fp32, log2 domain), 3 S buffers
 //   P  = exp2(S - m)   softmax warps: tcgen05.ld -> ex2 -> bf16 -> swizzled st.shared
-//   O_h += P V_h       eight tcgen05.mma M128 x N16 x K16, P from shared memory
+//   O_h += P V_h       four tcgen05.mma M128 x N16 x K16, P from shared memory
 // Online softmax with LAZY rescaling: the running reference m of a row only moves when the chunk
 // maximum exceeds it by more than 2^8; then O_h (16 TMEM columns incl. the denominator column)
 // is scaled in place by the softmax warps (tcgen05.ld/st) while no MMA on O_h is in flight.  The
-// result is mathematically the exact softmax.  d = 8 makes the kernel exp/TMEM-read bound
-// (N^2 ex2 per head; the MMAs are <10% of its time).
+// result is mathematically the exact softmax.  d = 8 makes the kernel MUFU bound (N^2 ex2 per head,
+// 16 ex2/clk/SM; the MMAs are <10% of its time): the design goal is to keep the MUFU pipe busy, hence
+// two co-resident CTAs (256 TMEM columns, ~97 KB smem, 80 registers/thread average each) = 4 softmax
+// warps per SM sub-partition whose load/max/exp phases interleave.
 //
 // Warp roles (384 threads): warp 0 TMA producer, warp 1 TMEM allocator + S-MMA issuer, warp 2
 // P.V-MMA issuer, warp 3 idle, warps 4..7 softmax warpgroup 0 (heads 0,2), warps 8..11 softmax
-// warpgroup 1 (heads 1,3).
+// warpgroup 1 (heads 1,3).  The softmax warps keep only 32 S values live (<= 80 registers/thread).
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -32,21 +34,23 @@ using namespace ptx;
 
 constexpr int ATC_THREADS = 384;
 constexpr int ATC_STAGES = 3;
+constexpr int ATC_KEYS = 64;                           // keys per chunk
 constexpr int ATC_Q_BYTES = 128 * 128;                 // 128 queries x (4 heads x 16) bf16
-constexpr int ATC_K_BYTES = 128 * 128;                 // 128 keys    x (4 heads x 16) bf16
-constexpr int ATC_V_BYTES = 2 * 4 * 16 * 128;          // 2 key blocks x 4 heads x 16 rows x 64 keys
+constexpr int ATC_K_BYTES = ATC_KEYS * 128;            // 64 keys     x (4 heads x 16) bf16
+constexpr int ATC_V_BYTES = 4 * 16 * 128;              // 4 heads x 16 rows x 64 keys
 constexpr int ATC_STAGE_BYTES = ATC_K_BYTES + ATC_V_BYTES;
-constexpr int ATC_P_BYTES = 2 * 128 * 128;             // 128 queries x 128 keys bf16 (2 blocks of 64 keys)
+constexpr int ATC_P_BYTES = 128 * 128;                 // 128 queries x 64 keys bf16
 constexpr int ATC_OFF_STAGE = ATC_Q_BYTES;
 constexpr int ATC_OFF_P = ATC_OFF_STAGE + ATC_STAGES * ATC_STAGE_BYTES;
 constexpr int ATC_OFF_BAR = ATC_OFF_P + 2 * ATC_P_BYTES;
 constexpr int ATC_SMEM = ATC_OFF_BAR + 256 + 1024;
-constexpr uint32_t ATC_TMEM_COLS = 512;                // S buffers [0,384), O_h [384+16h, +16)
-constexpr int ATC_NS = 3;                              // S buffers
-constexpr uint32_t ATC_O_COL = 384;
+constexpr uint32_t ATC_TMEM_COLS = 256;                // S buffers [0,192), O_h [192+16h, +16)
+constexpr int ATC_NS = 3;                              // S buffers (64 columns each)
+constexpr uint32_t ATC_O_COL = 192;
 constexpr float ATC_LAZY = 8.0f;                       // rescale only when the max grows by more than 2^8
+static_assert(2 * (ATC_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit in shared memory");
 
-struct AttnTcMaps { CUtensorMap qk; CUtensorMap vt; };
+struct AttnTcMaps { CUtensorMap q; CUtensorMap k; CUtensorMap vt; };
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -87,7 +91,7 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, int N,
+__global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, int N,
                                                                       int C, bf16* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -105,11 +109,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, hg = blockIdx.y, b = blockIdx.z;
-    const int n_chunks = N / 128;
+    const int n_chunks = N / ATC_KEYS;
     const int n_units = n_chunks * 4;            // unit u = chunk*4 + head
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&maps.qk);
+        prefetch_tmap(&maps.q);
+        prefetch_tmap(&maps.k);
         prefetch_tmap(&maps.vt);
         for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < ATC_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 128); }
@@ -124,26 +129,24 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===================== TMA producer =====================
             mbar_arrive_expect_tx(q_full, ATC_Q_BYTES);
-            tma_load_2d(smem, &maps.qk, q_full, hg * 64, b * N + q0);
+            tma_load_2d(smem, &maps.q, q_full, hg * 64, b * N + q0);
             int stage = 0; uint32_t phase = 0;
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 uint8_t* sk = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES;
                 mbar_arrive_expect_tx(&full_bar[stage], ATC_STAGE_BYTES);
-                tma_load_2d(sk, &maps.qk, &full_bar[stage], 512 + hg * 64, b * N + c * 128);
-                tma_load_3d(sk + ATC_K_BYTES, &maps.vt, &full_bar[stage], c * 128, 0, b * (C / 8) + hg * 4);
-                tma_load_3d(sk + ATC_K_BYTES + ATC_V_BYTES / 2, &maps.vt, &full_bar[stage], c * 128 + 64, 0,
-                            b * (C / 8) + hg * 4);
+                tma_load_2d(sk, &maps.k, &full_bar[stage], 512 + hg * 64, b * N + c * ATC_KEYS);
+                tma_load_3d(sk + ATC_K_BYTES, &maps.vt, &full_bar[stage], c * ATC_KEYS, 0, b * (C / 8) + hg * 4);
                 if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===================== S = Q K^T issuer =====================
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, ATC_KEYS);
             const uint32_t q_addr = smem_u32(smem);
             int stage = 0; uint32_t phase = 0;
             mbar_wait(q_full, 0);
@@ -153,14 +156,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
                 mbar_wait(&s_free[sb], (((uint32_t)(u / ATC_NS)) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES);
-                umma_bf16(tmem + sb * 128, make_smem_desc_sw128(q_addr) + 2 * j, make_smem_desc_sw128(k_addr) + 2 * j,
+                umma_bf16(tmem + sb * ATC_KEYS, make_smem_desc_sw128(q_addr) + 2 * j, make_smem_desc_sw128(k_addr) + 2 * j,
                           idesc_s, 0u);
                 umma_commit(&s_full[sb]);
                 if (j == 3) { if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; } }
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===================== O += P V issuer =====================
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, 16);
             const uint32_t p_addr = smem_u32(smem + ATC_OFF_P);
@@ -171,14 +174,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
                 mbar_wait(&p_full[g], pfull_ph[g]); pfull_ph[g] ^= 1u;
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES + ATC_K_BYTES);
+                const uint64_t dp = make_smem_desc_sw128(p_addr + g * ATC_P_BYTES);
+                const uint64_t dv = make_smem_desc_sw128(v_addr + j * 2048);
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
-                    const uint64_t dp = make_smem_desc_sw128(p_addr + g * ATC_P_BYTES + kb * 16384);
-                    const uint64_t dv = make_smem_desc_sw128(v_addr + kb * (ATC_V_BYTES / 2) + j * 2048);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(tmem + ATC_O_COL + j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv, (c | kb | kk) != 0 ? 1u : 0u);
-                }
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem + ATC_O_COL + j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv, (c | kk) != 0 ? 1u : 0u);
                 umma_commit(&p_free[g]);
                 if (j == 3) {
                     umma_commit(&empty_bar[stage]);                      // all S and P.V reads of this stage are done
@@ -203,19 +203,24 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
                 const int j = g + 2 * jj, u = c * 4 + j, sb = u % ATC_NS;
                 mbar_wait(&s_full[sb], ((uint32_t)(u / ATC_NS)) & 1u);
                 tc_fence_after();
-                uint32_t v[128];
+                // pass 1 over the S tile: row maximum (32 live registers; the exponentials re-read the tile from
+                // TMEM in pass 2 -- TMEM bandwidth is plentiful, registers are what two CTAs per SM compete for)
+                uint32_t v[32];
+                float cm[4];
 #pragma unroll
-                for (int piece = 0; piece < 4; ++piece)
-                    tmem_ld_32x32b_x32(lane_addr + sb * 128 + piece * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[piece * 32]));
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&s_free[sb]);                  // S buffer is in registers
-                float cm[8];                               // 8 independent chains instead of one 127-deep dependency
+                for (int piece = 0; piece < ATC_KEYS / 32; ++piece) {
+                    tmem_ld_32x32b_x32(lane_addr + sb * ATC_KEYS + piece * 32, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) cm[i] = __uint_as_float(v[i]);
-#pragma unroll
-                for (int i = 8; i < 128; ++i) cm[i & 7] = fmaxf(cm[i & 7], __uint_as_float(v[i]));
-                const float cmax = fmaxf(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])), fmaxf(fmaxf(cm[4], cm[5]), fmaxf(cm[6], cm[7])));
+                    for (int i = 0; i < 4; ++i) {
+                        float t = fmaxf(fmaxf(__uint_as_float(v[i]), __uint_as_float(v[4 + i])), __uint_as_float(v[8 + i]));
+                        t = fmaxf(fmaxf(t, __uint_as_float(v[12 + i])), __uint_as_float(v[16 + i]));
+                        t = fmaxf(fmaxf(t, __uint_as_float(v[20 + i])), __uint_as_float(v[24 + i]));
+                        t = fmaxf(t, __uint_as_float(v[28 + i]));
+                        cm[i] = piece == 0 ? t : fmaxf(cm[i], t);
+                    }
+                }
+                const float cmax = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
                 float alpha = 1.0f;
                 bool moved = false;
                 if (c == 0) { m[jj] = cmax; }
@@ -233,19 +238,23 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
                 }
                 const float mrow = m[jj];
 #pragma unroll
-                for (int piece = 0; piece < 4; ++piece) {
-                    uint8_t* blk = p_row + (piece >> 1) * 16384;           // 64-key block
+                for (int piece = 0; piece < ATC_KEYS / 32; ++piece) {
+                    tmem_ld_32x32b_x32(lane_addr + sb * ATC_KEYS + piece * 32, v);
+                    tmem_ld_wait();
+                    if (piece == ATC_KEYS / 32 - 1) {
+                        tc_fence_before();
+                        mbar_arrive(&s_free[sb]);                          // last read of this S buffer
+                    }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 4; ++q) {                          // 16-byte chunk = 8 keys
                         uint32_t w[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int e = piece * 32 + q * 8 + i * 2;
+                            const int e = q * 8 + i * 2;
                             const float x0 = __uint_as_float(v[e]) - mrow, x1 = __uint_as_float(v[e + 1]) - mrow;
                             w[i] = pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
                         }
-                        const int chunk16 = ((piece & 1) * 4 + q) ^ sw;   // SWIZZLE_128B: 16-byte chunk ^ (row & 7)
-                        *reinterpret_cast<uint4*>(blk + chunk16 * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(p_row + (((piece * 4 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // SWIZZLE_128B
                     }
                 }
                 tc_fence_before();
@@ -314,7 +323,9 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
         cuuint64_t dims[2] = {(cuuint64_t)ldq, (cuuint64_t)B * N};
         cuuint64_t strides[1] = {(cuuint64_t)ldq * 2};
         cuuint32_t box[2] = {64, 128};
-        encode_bf16_sw128(&maps.qk, qkv, 2, dims, strides, box, "attention qk");
+        encode_bf16_sw128(&maps.q, qkv, 2, dims, strides, box, "attention q");
+        cuuint32_t boxk[2] = {64, ATC_KEYS};
+        encode_bf16_sw128(&maps.k, qkv, 2, dims, strides, boxk, "attention k");
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)N, 16, (cuuint64_t)B * (C / 8)};

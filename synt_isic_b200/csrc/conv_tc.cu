@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const uint32_t tmem_acc = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===================== TMA producer =====================
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < total_iters; ++it) {
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===================== MMA issuer =====================
             constexpr uint32_t idesc = make_idesc_bf16(128, BN);
             int stage = 0; uint32_t phase = 0;

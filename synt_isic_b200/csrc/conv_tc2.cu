@@ -51,7 +51,7 @@ struct V2Smem {
     static constexpr int TOTAL = OFF_BAR + 512 + 1024;
 };
 
-struct V2Maps { CUtensorMap a[4]; CUtensorMap b; CUtensorMap out; };   // a[i]: activation source of segment i
+struct V2Maps { CUtensorMap a[4]; CUtensorMap b; CUtensorMap out[4]; };   // a[i]: source of segment i; out[phase]
 // A K segment = one source tensor: `chunks` 64-channel blocks x `taps` (9 = 3x3 window, 1 = centre tap);
 // weight K block of (tap, chunk) = kb_base + tap*kb_stride + chunk; xform: 0 raw, 1 GroupNorm affine,
 // 2 affine + SiLU with scale/shift rows gn_ss[n][ss_off + channel].
@@ -59,6 +59,7 @@ struct V2Seg { int chunks, taps, kb_base, kb_stride, xform, ss_off; };
 struct V2Params {
     int n_work;              // super-tiles x N tiles
     int n_ntiles, tiles_x, supers_per_img, imgs_per_super, row_off;
+    int nt_real;             // real N tiles; n_ntiles = nt_real * phases (phase = sub-pixel position of a fused 2x upsample)
     int n_seg; V2Seg seg[4];
     const float2* gn_ss; int gn_C;     // GroupNorm scale/shift [B][gn_C] of the (concatenated) main input
     int B, H, W, Cout;
@@ -87,13 +88,15 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // consecutive items round-robin (chunk c -> CTA c % grid): neighbouring CTAs work on neighbouring tiles
 // (L2/DRAM locality) while each chunk stays inside one (image, N tile), so GroupNorm partial sums are
 // carried in registers across the chunk and written once -- slot = chunk index within the image.
-struct V2Work { int n0, y0, x0, nt, grp; };
+struct V2Work { int n0, y0, x0, nt, grp, phase, ntr; };   // nt: virtual N tile (weights), ntr: real N tile (channels)
 __device__ __forceinline__ V2Work v2_decode(const V2Params& p, int w) {
     V2Work o;
     const int per_img = p.tiles_x * p.supers_per_img;
     const int rem = w % per_img, key = w / per_img;
     o.nt = key % p.n_ntiles;
     o.grp = key / p.n_ntiles;
+    o.phase = o.nt / p.nt_real;
+    o.ntr = o.nt % p.nt_real;
     o.n0 = o.grp * p.imgs_per_super;
     o.y0 = (rem / p.tiles_x) * (p.imgs_per_super == 1 ? 32 : 0);
     o.x0 = (rem % p.tiles_x) * 8;
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     const int a_bytes = p.imgs_per_super == 1 ? 34 * 10 * 128 : 2 * 18 * 10 * 128;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.b); prefetch_tmap(&maps.out);
+        prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.b); prefetch_tmap(&maps.out[0]);
         for (int s = 0; s < V2_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_ready[s], V2_XF_THREADS); }
         for (int s = 0; s < L::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 128); }
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===================== TMA producer =====================
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
             if (RES) {                                                // whole weight matrix, once (n_ntiles == 1)
@@ -170,12 +173,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===================== MMA issuer =====================
             constexpr uint32_t idesc = make_idesc_bf16(128, BN);
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int tb = 0; uint32_t tph = 0;
             if (RES) mbar_wait(&b_full[0], 0);
             for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
+                const V2Work wk = v2_decode(p, w);
                 mbar_wait(&t_empty[tb], tph ^ 1u);                    // epilogue drained this accumulator pair
                 tc_fence_after();
                 uint32_t first = 1;
@@ -186,7 +190,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         tc_fence_after();
                         const uint32_t a_base = smem_u32(smem + as * L::A_SLOT);
                         for (int tap = 0; tap < sp.taps; ++tap) {
-                            const int dy = sp.taps == 9 ? tap / 3 : 1, dx = sp.taps == 9 ? tap % 3 : 1;
+                            // 9 taps: 3x3 window; 4 taps: the 2x2 window of sub-pixel phase (py, px) of a fused nearest-2x
+                            // upsample (rows y+py-1, y+py of the low-res input); 1 tap: centre
+                            const int dy = sp.taps == 9 ? tap / 3 : (sp.taps == 4 ? (wk.phase >> 1) + (tap >> 1) : 1);
+                            const int dx = sp.taps == 9 ? tap % 3 : (sp.taps == 4 ? (wk.phase & 1) + (tap & 1) : 1);
                             if (RES) bs = sp.kb_base + tap * sp.kb_stride + ch;
                             else { mbar_wait(&b_full[bs], bph); tc_fence_after(); }
                             const uint64_t db = make_smem_desc_sw128(smem_u32(smem + L::OFF_B + bs * L::B_TILE));
@@ -284,15 +291,17 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         uint8_t* staging = smem + L::OFF_STAGING;
         float* bias_s = reinterpret_cast<float*>(smem + L::OFF_BIAS);
         const int sw = r & 7;
+        // TMA stores are issued by the elected lane of warp 2 (elect.sync is deterministic for a fixed member mask,
+        // so the same thread owns every bulk group)
         int tb = 0; uint32_t tph = 0; int last_nt = -1;
         float acc1 = 0.f, acc2 = 0.f;                               // GroupNorm partials carried across tiles
         for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
             const V2Work wk = v2_decode(p, w);
-            if (wk.nt != last_nt) {                                  // (bias + time-embedding row) of this N tile -> smem
+            if (wk.ntr != last_nt) {                                  // (bias + time-embedding row) of this N tile -> smem
                 epi_bar_sync();
                 const int et = threadIdx.x - 64;
-                if (et < BN) bias_s[et] = p.bias[wk.nt * BN + et] + (p.bias2 ? p.bias2[wk.nt * BN + et] : 0.f);
-                last_nt = wk.nt;
+                if (et < BN) bias_s[et] = p.bias[wk.ntr * BN + et] + (p.bias2 ? p.bias2[wk.ntr * BN + et] : 0.f);
+                last_nt = wk.ntr;
                 epi_bar_sync();
             }
             mbar_wait(&t_full[tb], tph);
@@ -307,11 +316,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 uint4 rres[BN / 8];                                  // the row's residual, in flight while TMEM drains
                 const bool has_res = p.residual != nullptr && valid;
                 if (has_res) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + wk.nt * BN);
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + wk.ntr * BN);
 #pragma unroll
                     for (int i = 0; i < BN / 8; ++i) rres[i] = __ldg(rp + i);
                 }
-                if (threadIdx.x == 64) tma_store_wait_read();        // previous TMA store has read the staging tile
+                if (warp == 2) { if (elect_one()) tma_store_wait_read(); }   // previous TMA store has read the staging tile
                 epi_bar_sync();
 #pragma unroll
                 for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -352,11 +361,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 if (mt == V2_MT - 1) { tc_fence_before(); mbar_arrive(&t_empty[tb]); }   // accumulators fully read
                 fence_proxy_async();
                 epi_bar_sync();
-                if (threadIdx.x == 64 && valid) {
+                if (warp == 2 && valid) {
+                    if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j)
-                        tma_store_4d(&maps.out, staging + j * 16384, wk.nt * BN + j * 64, wk.x0, ty0, n_img);
-                    tma_store_commit();
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_store_4d(&maps.out[wk.phase], staging + j * 16384, wk.ntr * BN + j * 64, wk.x0, ty0, n_img);
+                        tma_store_commit();
+                    }
                 }
                 if (p.stats && valid) {
                     // fused GroupNorm statistics: per-channel (sum, sumsq) of the bf16 values just staged;
@@ -374,8 +385,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         s1 += x; s2 = fmaf(x, x, s2);
                     }
                     if (p.imgs_per_super == 2) {                      // 16x16 images: one partial row per tile
-                        const int slot = (wk.x0 >> 3) * (128 / BN) + half;
-                        p.stats[((size_t)n_img * p.stats_slots + slot) * p.Cout + wk.nt * BN + col] = make_float2(s1, s2);
+                        const int slot = (wk.phase * p.tiles_x + (wk.x0 >> 3)) * (128 / BN) + half;
+                        p.stats[((size_t)n_img * p.stats_slots + slot) * p.Cout + wk.ntr * BN + col] = make_float2(s1, s2);
                     } else {
                         acc1 += s1; acc2 += s2;
                     }
@@ -385,13 +396,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 // end of this chunk (chunks never straddle an (image, N tile)): one partial row per chunk
                 const int per_img = p.tiles_x * p.supers_per_img;
                 const int et = threadIdx.x - 64, col = et % BN, half = et / BN;
-                const int slot = ((w % per_img) / p.chunk) * (128 / BN) + half;
-                p.stats[((size_t)wk.n0 * p.stats_slots + slot) * p.Cout + wk.nt * BN + col] = make_float2(acc1, acc2);
+                const int slot = (wk.phase * (per_img / p.chunk) + (w % per_img) / p.chunk) * (128 / BN) + half;
+                p.stats[((size_t)wk.n0 * p.stats_slots + slot) * p.Cout + wk.ntr * BN + col] = make_float2(acc1, acc2);
                 acc1 = 0.f; acc2 = 0.f;
             }
             if (++tb == 2) { tb = 0; tph ^= 1u; }
         }
-        if (threadIdx.x == 64) tma_store_wait_all();
+        if (warp == 2) { if (elect_one()) tma_store_wait_all(); }
     }
     tc_fence_before();
     __syncthreads();
@@ -400,6 +411,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
 }
 
 bool conv_tc2_supported(const ConvArgs& a) {
+    if (a.up2x && (a.KH != 3 || a.Cin1 || a.sc0_C || a.sc1_C || a.gn_mode || a.residual)) return false;
     const bool k3 = a.KH == 3 && a.KW == 3 && a.pad == 1;
     const bool k1 = a.KH == 1 && a.KW == 1 && a.pad == 0 && a.sc0_C == 0 && a.sc1_C == 0 && a.Cin1 == 0;   // centre-tap-only conv
     if (!(k3 || k1) || a.stride != 1 || a.sc_stride != 1) return false;
@@ -419,7 +431,7 @@ static int v2_num_sms() {
 static int v2_chunk(const ConvArgs& a, int BN) {
     if (a.H == 16) return 1;
     const int per_img = (a.W / 8) * (a.H / 32);
-    const long long n_work = (long long)a.B * per_img * (a.Cout / BN);
+    const long long n_work = (long long)a.B * per_img * (a.Cout / BN) * (a.up2x ? 4 : 1);
     const long long grid = n_work < v2_num_sms() ? n_work : v2_num_sms();
     int best = 1; long long best_span = -1;
     for (int R = 8; R >= 1; R >>= 1) {
@@ -433,9 +445,10 @@ static int v2_chunk(const ConvArgs& a, int BN) {
 // partial rows per image in stats_out (every row is written exactly once by the kernel)
 int conv_tc2_stats_slots(const ConvArgs& a) {
     const int BN = (a.Cout % 128 == 0) ? 128 : 64;
-    if (a.H == 16) return (a.W / 8) * (128 / BN);
+    const int phases = a.up2x ? 4 : 1;
+    if (a.H == 16) return phases * (a.W / 8) * (128 / BN);
     const int per_img = (a.W / 8) * (a.H / 32);
-    return (per_img / v2_chunk(a, BN)) * (128 / BN);
+    return phases * (per_img / v2_chunk(a, BN)) * (128 / BN);
 }
 
 template <int BN, bool RES>
@@ -466,7 +479,9 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     p.row_off = a.H == 16 ? 18 : 16;
     p.tiles_x = a.W / 8;
     p.supers_per_img = a.H == 16 ? 1 : a.H / 32;
-    p.n_ntiles = a.Cout / BN;
+    const int phases = a.up2x ? 4 : 1;
+    p.nt_real = a.Cout / BN;
+    p.n_ntiles = p.nt_real * phases;
     const int n_super = ceil_div(a.B, p.imgs_per_super) * p.tiles_x * p.supers_per_img;
     p.n_work = n_super * p.n_ntiles;
     const bool k1 = a.KH == 1;                          // 1x1 conv == centre-tap-only segment of the same machinery
@@ -480,6 +495,8 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     };
     if (k1) {
         add_seg(a.in, a.Cin, 1, 0, 0, a.gn_mode, 0);
+    } else if (a.up2x) {
+        add_seg(a.in, a.Cin, 4, 0, a.Cin / 64, 0, 0);     // weights: [4 phases x Cout][4 taps x Cin], see pack_upsample_phases
     } else {
         add_seg(a.in, a.Cin, 9, 0, Ct / 64, a.gn_mode, 0);
         add_seg(a.in1, a.Cin1, 9, a.Cin / 64, Ct / 64, a.gn_mode, a.Cin);
@@ -499,21 +516,27 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
         else maps.a[i] = maps.a[0];
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)a.ktot(), (cuuint64_t)a.Cout};
-        cuuint64_t strides[1] = {(cuuint64_t)a.ktot() * 2};
+        const int kt = a.up2x ? 4 * a.Cin : a.ktot();
+        cuuint64_t dims[2] = {(cuuint64_t)kt, (cuuint64_t)a.Cout * phases};
+        cuuint64_t strides[1] = {(cuuint64_t)kt * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)BN};
         encode_bf16_sw128(&maps.b, a.weight, 2, dims, strides, box, "v2 weight");
     }
-    {
+    for (int ph = 0; ph < 4; ++ph) {
+        if (ph >= phases) { maps.out[ph] = maps.out[0]; continue; }
+        // phase (py, px) of a fused 2x upsample writes output pixels (2y+py, 2x+px): a strided view of `out`
+        const int up = a.up2x ? 2 : 1, py = ph >> 1, px = ph & 1;
+        const int Wo = a.W * up, Ho = a.H * up;
+        const bf16* base = (const bf16*)a.out + ((size_t)py * Wo + px) * a.Cout;
         cuuint64_t dims[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
-        cuuint64_t strides[3] = {(cuuint64_t)a.Cout * 2, (cuuint64_t)a.W * a.Cout * 2, (cuuint64_t)a.H * a.W * a.Cout * 2};
+        cuuint64_t strides[3] = {(cuuint64_t)up * a.Cout * 2, (cuuint64_t)up * Wo * a.Cout * 2, (cuuint64_t)Ho * Wo * a.Cout * 2};
         cuuint32_t box[4] = {64, 8, 16, 1};
-        encode_bf16_sw128(&maps.out, a.out, 4, dims, strides, box, "v2 output");
+        encode_bf16_sw128(&maps.out[ph], base, 4, dims, strides, box, "v2 output");
     }
     const int num_sms = v2_num_sms();
     const int grid = p.n_work < num_sms ? p.n_work : num_sms;
 
-    const bool resident = BN == 64 && p.n_ntiles == 1 && a.ktot() / 64 <= 12;
+    const bool resident = BN == 64 && p.n_ntiles == 1 && !a.up2x && a.ktot() / 64 <= 12;
     if (BN == 128)     launch_v2<128, false>(maps, p, grid, (bf16*)a.out, s);
     else if (resident) launch_v2<64, true>(maps, p, grid, (bf16*)a.out, s);
     else               launch_v2<64, false>(maps, p, grid, (bf16*)a.out, s);

@@ -24,6 +24,10 @@ struct ConvArgs {
     const void* in1 = nullptr; int Cin1 = 0;
     const float2* gn_ss = nullptr;     // [B][Cin + Cin1] (scale, shift)
     int gn_mode = 0;                   // 0 raw input, 1 GroupNorm affine, 2 affine + SiLU
+    // conv_tc2 only: nearest-2x upsample fused into the 3x3 conv as four sub-pixel 2x2 convolutions on the
+    // low-res input (2.25x fewer FLOPs): `in` is [B,H,W,Cin], `out` is [B,2H,2W,Cout], weight is the
+    // phase-stacked matrix [4*Cout][4*Cin] (taps pre-summed); Ho/Wo describe the LOW-res tile grid here
+    int up2x = 0;
     const void* sc0 = nullptr; int sc0_C = 0;    // NHWC [B, Ho*sc_stride, Wo*sc_stride, sc0_C]
     const void* sc1 = nullptr; int sc1_C = 0;
     int sc_stride = 1;

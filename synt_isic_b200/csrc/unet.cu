@@ -134,6 +134,26 @@ static std::vector<float> pack_conv(const float* w, int cout, int cin, int k, co
     }
     return o;
 }
+// Upsample2D (nearest 2x) followed by conv3x3(pad 1) == four 2x2 convolutions on the LOW-res input, one per
+// output sub-pixel phase (py, px): output (2y+py, 2x+px) reads low-res rows y+py-1, y+py and columns x+px-1,
+// x+px; the 3x3 taps that land on the same low-res pixel are summed (in fp32, before the bf16 rounding).
+// [Cout][Cin][3][3] -> phase-stacked K-major [4*Cout][4*Cin]: row = phase*Cout + n, col = (ty*2+tx)*Cin + c.
+static std::vector<float> pack_upsample_phases(const float* w, int cout, int cin) {
+    std::vector<float> o((size_t)16 * cout * cin, 0.f);
+    // low-res tap t of phase p collects 3x3 taps k with (p + k - 1) >> 1 == p - 1 + t (floor division)
+    auto lowtap = [](int p, int k) { const int u = p + k - 1; return (u < 0 ? -1 : u >> 1) - (p - 1); };
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+            for (int n = 0; n < cout; ++n) {
+                float* row = o.data() + ((size_t)(py * 2 + px) * cout + n) * 4 * cin;
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int t = lowtap(py, ky) * 2 + lowtap(px, kx);
+                        for (int c = 0; c < cin; ++c) row[t * cin + c] += w[(((size_t)n * cin + c) * 3 + ky) * 3 + kx];
+                    }
+            }
+    return o;
+}
 struct WeightDev {                                // one GEMM operand on the device
     DevPtr f32, b16;
     const void* get(bool tc) const { return tc ? b16->p : f32->p; }
@@ -166,7 +186,7 @@ struct AttnW {
     DevPtr g, b; WeightDev wqkv, wo; DevPtr bqkv, bo;
     WeightDev wqkv_tc; DevPtr bqkv_tc;            // zero-interleaved (q' | k' | v) projection for attention_tc
 };
-struct ConvW { std::string name; int cin, cout; WeightDev w; DevPtr b; };
+struct ConvW { std::string name; int cin, cout; WeightDev w; DevPtr b; WeightDev w_up; };   // w_up: pack_upsample_phases
 
 }  // namespace synt
 
@@ -178,6 +198,7 @@ struct synt_unet {
     bool want_f32_w = false;
     bool use_v2 = true;                           // persistent halo-tile kernel for 3x3 stride-1 convs
     bool fuse_gn = true;                          // GroupNorm(+SiLU) applied inside conv_tc2 (no normalised tensor in HBM)
+    bool fuse_up = true;                          // Upsample2D folded into its conv (sub-pixel phases)
     ConvInW conv_in_w;
     ConvOutW conv_out_w;
     DevPtr norm_out_g, norm_out_b;
@@ -285,10 +306,11 @@ static AttnW make_attn(const float* P, const std::string& name, int C, bool f32,
     a.bo = dev_upload(P + m.find(name + ".to_out.0.bias"), C * 4);
     return a;
 }
-static ConvW make_conv(const float* P, const std::string& name, int cin, int cout, bool f32, bool b16) {
+static ConvW make_conv(const float* P, const std::string& name, int cin, int cout, bool f32, bool b16, bool upsampler = false) {
     const Manifest& m = manifest();
     ConvW c; c.name = name; c.cin = cin; c.cout = cout;
     c.w = upload_weight(pack_conv(P + m.find(name + ".weight"), cout, cin, 3, nullptr, 0), f32, b16);
+    if (upsampler && b16) c.w_up = upload_weight(pack_upsample_phases(P + m.find(name + ".weight"), cout, cin), false, true);
     c.b = dev_upload(P + m.find(name + ".bias"), cout * 4);
     return c;
 }
@@ -340,7 +362,7 @@ static void build_unet(synt_unet* u, const float* P) {
             u->up_res[i].push_back(add_res(b + ".resnets." + std::to_string(j), ch + cs, cout));
         }
         if (kUpAttn[i]) for (int j = 0; j < 3; ++j) u->up_attn[i].push_back(make_attn(P, b + ".attentions." + std::to_string(j), cout, f32, b16));
-        if (i != 3) u->upsample.push_back(make_conv(P, b + ".upsamplers.0.conv", cout, cout, f32, b16));
+        if (i != 3) u->upsample.push_back(make_conv(P, b + ".upsamplers.0.conv", cout, cout, f32, b16, true));
     }
     u->temb_total = (int)proj_b.size();
 
@@ -438,8 +460,10 @@ struct Fwd {
             a.stats_out = out->stats;
         }
         {
-            ProfScope ps(u, s, tc ? PC_CONV_TC : PC_CONV_SIMT, 2.0 * B * a.Ho * a.Wo * (double)a.Cout * a.ktot(),
-                         B * a.Ho * a.Wo, a.Cout, a.ktot());
+            // up2x: algorithmic FLOPs of the reference's conv3x3 on the upsampled image (executed: 4/9 of that)
+            const int up = a.up2x ? 4 : 1;
+            ProfScope ps(u, s, tc ? PC_CONV_TC : PC_CONV_SIMT, 2.0 * B * a.Ho * a.Wo * up * (double)a.Cout * a.ktot(),
+                         B * a.Ho * a.Wo * up, a.Cout, a.ktot());
             if (v2) conv_tc2(a, s);
             else if (tc) conv_tc(a, s);
             else conv_simt(a, u->dt, s);
@@ -550,6 +574,18 @@ struct Fwd {
         return o;
     }
     Act up(const ConvW& w, const Act& x) {
+        if (u->fuse_up && w.w_up.b16) {
+            // nearest-2x upsample folded into the conv: four sub-pixel 2x2 convolutions on the low-res input
+            ConvArgs c; c.in = x.p; c.B = B; c.H = x.H; c.W = x.W; c.Cin = w.cin; c.Ho = x.H; c.Wo = x.W;
+            c.Cout = w.cout; c.bias = (const float*)w.b->p; c.up2x = 1;
+            if (fused_ok(c)) {
+                Act o = make(x.H * 2, x.W * 2, w.cout);
+                c.out = o.p;
+                conv(c, w.w_up, &o, true);
+                tap(w.name.substr(0, w.name.size() - 5), o);
+                return o;
+            }
+        }
         Act up2 = make(x.H * 2, x.W * 2, x.C);
         { ProfScope ps(u, s, PC_UPSAMPLE); upsample_nearest2x(x.p, u->dt, B, x.H, x.W, x.C, up2.p, s); }
         ++u->launches;
@@ -690,6 +726,8 @@ int synt_unet_create(const float* params_host, long long n_params, int dtype, sy
     SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_join, cudaEventDisableTiming));
     const char* fg = getenv("SYNT_FUSE_GN");
     u->fuse_gn = !(fg && fg[0] == '0');
+    const char* fu = getenv("SYNT_FUSE_UP");
+    u->fuse_up = !(fu && fu[0] == '0');
     SYNT_CUDA(cudaStreamCreateWithFlags(&u->own_stream, cudaStreamNonBlocking));
     SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_in, cudaEventDisableTiming));
     SYNT_CUDA(cudaEventCreateWithFlags(&u->ev_out, cudaEventDisableTiming));
@@ -970,6 +1008,23 @@ extern "C" int synt_debug_conv(int use_tc, int act_dtype, const void* in, int B,
     } else {
         conv_simt(a, act_dtype, (cudaStream_t)stream);
     }
+    SYNT_CATCH
+}
+
+// Upsample2D + conv3x3 through the fused sub-pixel path of conv_tc2: in [B,H,W,Cin] bf16, w_host the raw
+// [Cout][Cin][3][3] fp32 filter (host), out [B,2H,2W,Cout] bf16, optional GroupNorm partials of `out`.
+extern "C" int synt_debug_conv_up2x(const void* in, int B, int H, int W, int Cin, const float* w_host, const float* bias,
+                                    void* out, int Cout, void* stats_out, int* stats_slots, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(in && w_host && bias && out, "bad argument");
+    WeightDev wd = upload_weight(pack_upsample_phases(w_host, Cout, Cin), false, true);
+    ConvArgs a;
+    a.in = in; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Ho = H; a.Wo = W; a.Cout = Cout; a.up2x = 1;
+    a.weight = wd.b16->p; a.bias = bias; a.out = out; a.stats_out = (float2*)stats_out;
+    SYNT_CHECK(conv_tc2_supported(a), "conv_tc2: unsupported");
+    if (stats_slots) *stats_slots = conv_tc2_stats_slots(a);
+    conv_tc2(a, (cudaStream_t)stream);
+    SYNT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));     // wd is freed on return
     SYNT_CATCH
 }
 

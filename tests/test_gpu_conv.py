@@ -180,3 +180,46 @@ def test_conv_tcgen05_fused_groupnorm_input(cuda_dev, case):
     want_s = got.sum(dim=(2, 3)); want_q = (got * got).sum(dim=(2, 3))
     assert torch.allclose(st[..., 0], want_s, rtol=2e-3, atol=2e-2)
     assert torch.allclose(st[..., 1], want_q, rtol=2e-3, atol=2e-2)
+
+
+UP_CASES = [
+    # B, H, W (low-res), Cin, Cout
+    (3, 16, 16, 256, 256),      # up_blocks.0 upsampler: 2 images per super-tile, odd B
+    (2, 32, 32, 256, 256),      # up_blocks.1 upsampler
+    (2, 64, 64, 128, 128),      # up_blocks.2 upsampler
+    (1, 32, 32, 64, 64),        # Cout = 64 (N tile 64)
+]
+
+
+@pytest.mark.parametrize("case", UP_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_tcgen05_fused_upsample(cuda_dev, case):
+    """Upsample2D (nearest 2x) + conv3x3 as four sub-pixel 2x2 convolutions inside conv_tc2
+    (diffusers Upsample2D reached from core/generator/image_generator.py:400) vs F.interpolate + F.conv2d."""
+    B, H, W, Cin, Cout = case
+    dev = cuda_dev
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    q = lambda t: t.to(torch.bfloat16).float()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    # the reference order of operations, fp32 weights (the fused path sums taps in fp32 and rounds once)
+    ref = F.conv2d(F.interpolate(q(x).to(dev), scale_factor=2.0, mode="nearest"), w.to(dev), b.to(dev), padding=1)
+    xin = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(dev)
+    out = torch.empty(B, 2 * H, 2 * W, Cout, dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros(B * 1024 * Cout * 2, dtype=torch.float32, device=dev)
+    slots = C.c_int()
+    wh = w.contiguous()
+    bd = b.to(dev)
+    _lib.check(_lib.lib().synt_debug_conv_up2x(xin.data_ptr(), B, H, W, Cin, wh.data_ptr(), bd.data_ptr(), out.data_ptr(),
+                                               Cout, stats.data_ptr(), C.byref(slots), _lib.current_stream_ptr()),
+               "debug_conv_up2x")
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2)
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 5e-3, rel                                         # bf16 rounding of the (pre-summed) weights and of the output
+    st = stats[: B * slots.value * Cout * 2].view(B, slots.value, Cout, 2).sum(1)
+    want_s = got.sum(dim=(2, 3)); want_q = (got * got).sum(dim=(2, 3))
+    assert torch.allclose(st[..., 0], want_s, rtol=2e-3, atol=5e-2)
+    assert torch.allclose(st[..., 1], want_q, rtol=2e-3, atol=5e-2)
