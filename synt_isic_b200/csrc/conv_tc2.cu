@@ -20,9 +20,12 @@
 //     -- the normalised activation tensor is never materialised in HBM.
 // L2 -> smem bytes per MMA clock: (43.5 KB + 9*BN*128 B) / (36*BN clk) = 42 B/clk for BN = 128.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5
-// epilogue, warps 6..9 input transform.  Rings: A halo slots (2), B weight-tile slots (NB), TMEM
-// accumulator buffers (2).
+// Warp roles (640 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (both one elected
+// lane), warps 4..7 / 8..11 two epilogue warpgroups (warpgroup e owns M tile e of every super-tile, its own
+// staging tile and TMA stores; the residual tile is TMA-loaded INTO the staging tile and updated in place),
+// warps 12..19 input transform.  The roles are latency-bound (one warp per SM sub-partition each would
+// leave the tensor pipe waiting), hence two warps per sub-partition for epilogue and transform.
+// Rings: A halo slots (2), B weight-tile slots (NB), TMEM accumulator buffers (2).
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -31,8 +34,10 @@ namespace synt {
 
 using namespace ptx;
 
-constexpr int V2_THREADS = 320;
-constexpr int V2_XF_THREADS = 128;                         // transform warps 6..9
+constexpr int V2_THREADS = 640;
+constexpr int V2_EPI_BASE = 128;                           // epilogue warps 4..11 (two warpgroups, one per M tile)
+constexpr int V2_XF_BASE = 384;                            // transform warps 12..19
+constexpr int V2_XF_THREADS = 256;
 constexpr int V2_MT = 2;                                   // M tiles (16x8 pixels each) per super-tile
 constexpr int V2_A_STAGES = 2;
 
@@ -42,16 +47,17 @@ template <int BN, bool RES>
 struct V2Smem {
     static constexpr int A_SLOT = 46080;                   // max(34*10, 2*18*10) * 128, already 1 KB aligned
     static constexpr int B_TILE = BN * 128;
-    static constexpr int STAGING = 128 * BN * 2;           // one M tile of bf16 output
-    static constexpr int NB = RES ? 12 : ((BN == 128) ? 6 : 8);
+    static constexpr int STAGING = 128 * BN * 2;           // one M tile of bf16 output (one per epilogue warpgroup)
+    static constexpr int NB = RES ? 12 : ((BN == 128) ? 4 : 8);
     static constexpr int OFF_B = V2_A_STAGES * A_SLOT;
     static constexpr int OFF_STAGING = OFF_B + NB * B_TILE;
-    static constexpr int OFF_BIAS = OFF_STAGING + STAGING;
-    static constexpr int OFF_BAR = OFF_BIAS + BN * 4;
+    static constexpr int OFF_BIAS = OFF_STAGING + V2_MT * STAGING;
+    static constexpr int OFF_BAR = OFF_BIAS + V2_MT * BN * 4;
     static constexpr int TOTAL = OFF_BAR + 512 + 1024;
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-struct V2Maps { CUtensorMap a[4]; CUtensorMap b; CUtensorMap out[4]; };   // a[i]: source of segment i; out[phase]
+struct V2Maps { CUtensorMap a[4]; CUtensorMap b; CUtensorMap out[4]; CUtensorMap res; };   // a[i]: source of segment i; out[phase]
 // A K segment = one source tensor: `chunks` 64-channel blocks x `taps` (9 = 3x3 window, 1 = centre tap);
 // weight K block of (tap, chunk) = kb_base + tap*kb_stride + chunk; xform: 0 raw, 1 GroupNorm affine,
 // 2 affine + SiLU with scale/shift rows gn_ss[n][ss_off + channel].
@@ -63,7 +69,7 @@ struct V2Params {
     int n_seg; V2Seg seg[4];
     const float2* gn_ss; int gn_C;     // GroupNorm scale/shift [B][gn_C] of the (concatenated) main input
     int B, H, W, Cout;
-    const float* bias; const float* bias2; const bf16* residual; int relu;
+    const float* bias; const float* bias2; int has_res; int relu;   // residual tile arrives through maps.res
     float2* stats; int stats_slots;   // optional fused GroupNorm partials [B][stats_slots][Cout]
     int chunk;                         // consecutive work items per CTA turn (divides the super-tiles per image)
 };
@@ -124,7 +130,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     uint64_t* b_empty = b_full + L::NB;             // [NB]
     uint64_t* t_full = b_empty + L::NB;             // [2]
     uint64_t* t_empty = t_full + 2;                 // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    uint64_t* r_full = t_empty + 2;                 // [2] residual tile of epilogue warpgroup e has landed in its staging
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = p.imgs_per_super == 1 ? 34 * 10 * 128 : 2 * 18 * 10 * 128;
 
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.b); prefetch_tmap(&maps.out[0]);
         for (int s = 0; s < V2_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_ready[s], V2_XF_THREADS); }
         for (int s = 0; s < L::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 256); mbar_init(&r_full[s], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -218,9 +225,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 if (++tb == 2) { tb = 0; tph ^= 1u; }
             }
         }
-    } else if (warp >= 6) {
-        // ===================== input transform (warps 6..9): GroupNorm affine (+SiLU) in place =====================
-        const int tt = threadIdx.x - 192, lv = tt & 7, r0 = tt >> 3;      // 8-channel vector, first row
+    } else if (warp >= V2_XF_BASE / 32) {
+        // ===================== input transform (warps 12..19): GroupNorm affine (+SiLU) in place =====================
+        const int tt = threadIdx.x - V2_XF_BASE, lv = tt & 7, r0 = tt >> 3;      // 8-channel vector, first row
         const int rows_per_img = p.imgs_per_super == 1 ? 340 : 180;
         int as = 0; uint32_t aph = 0;
         for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
@@ -250,11 +257,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         for (int im = 0; im < 2; ++im) {
                             if (im >= p.imgs_per_super || wk.n0 + im >= p.B) continue;
                             constexpr int UR = 4;                          // rows in flight per thread (hides LDS/MUFU latency)
-                            for (int base = r0; base < rows_per_img; base += 16 * UR) {
+                            for (int base = r0; base < rows_per_img; base += (V2_XF_THREADS / 8) * UR) {
                                 uint4 v[UR]; uint4* ptr[UR]; bool ok[UR];
 #pragma unroll
                                 for (int uu = 0; uu < UR; ++uu) {
-                                    const int rr = base + 16 * uu;
+                                    const int rr = base + (V2_XF_THREADS / 8) * uu;
                                     const int hy = rr / 10, hx = rr - hy * 10;
                                     const int y = wk.y0 - 1 + hy, x = wk.x0 - 1 + hx;
                                     ok[uu] = rr < rows_per_img && y >= 0 && y < p.H && x >= 0 && x < p.W;   // padding stays exactly 0
@@ -285,94 +292,103 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 }
             }
         }
-    } else {
-        // ===================== epilogue (warps 2..5) =====================
+    } else if (warp >= V2_EPI_BASE / 32) {
+        // ===================== epilogue: warpgroup e (warps 4..7 / 8..11) owns M tile e of every super-tile ==========
+        const int e = (warp - V2_EPI_BASE / 32) >> 2;                // warpgroup = M tile index
         const int q = warp & 3, r = q * 32 + lane;                  // accumulator row = pixel (r/8, r%8) of the 16x8 tile
-        uint8_t* staging = smem + L::OFF_STAGING;
-        float* bias_s = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+        const int et = (threadIdx.x - V2_EPI_BASE) & 127;           // thread index within the warpgroup
+        uint8_t* staging = smem + L::OFF_STAGING + e * L::STAGING;
+        float* bias_s = reinterpret_cast<float*>(smem + L::OFF_BIAS) + e * BN;
         const int sw = r & 7;
-        // TMA stores are issued by the elected lane of warp 2 (elect.sync is deterministic for a fixed member mask,
-        // so the same thread owns every bulk group)
-        int tb = 0; uint32_t tph = 0; int last_nt = -1;
+        const bool lead_warp = q == 0;                              // its elected lane owns this warpgroup's TMA loads/stores
+        const uint32_t bar_id = 1 + e;
+        auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
+        // tile e of work item w: image, first row, validity (B odd with two images per super-tile)
+        auto tile_of = [&](const V2Work& wk, int& n_img, int& ty0) {
+            n_img = wk.n0 + (p.imgs_per_super == 1 ? 0 : e);
+            ty0 = wk.y0 + (p.imgs_per_super == 1 ? 16 * e : 0);
+            return n_img < p.B;                                      // H, W are multiples of the tile
+        };
+        auto load_residual = [&](const V2Work& wk) {               // residual tile -> staging (same swizzled layout as the output)
+            int n_img, ty0;
+            if (!tile_of(wk, n_img, ty0)) return;
+            mbar_arrive_expect_tx(&r_full[e], L::STAGING);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+                tma_load_4d(staging + j * 16384, &maps.res, &r_full[e], wk.ntr * BN + j * 64, wk.x0, ty0, n_img);
+        };
+        int tb = 0; uint32_t tph = 0, rph = 0; int last_nt = -1;
         float acc1 = 0.f, acc2 = 0.f;                               // GroupNorm partials carried across tiles
+        if (p.has_res && lead_warp) {
+            const int w0 = v2_item(p, 0);
+            if (w0 >= 0) { if (elect_one()) load_residual(v2_decode(p, w0)); }
+        }
         for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
             const V2Work wk = v2_decode(p, w);
+            int n_img, ty0;
+            const bool valid = tile_of(wk, n_img, ty0);
             if (wk.ntr != last_nt) {                                  // (bias + time-embedding row) of this N tile -> smem
-                epi_bar_sync();
-                const int et = threadIdx.x - 64;
+                wg_sync();
                 if (et < BN) bias_s[et] = p.bias[wk.ntr * BN + et] + (p.bias2 ? p.bias2[wk.ntr * BN + et] : 0.f);
                 last_nt = wk.ntr;
-                epi_bar_sync();
             }
             mbar_wait(&t_full[tb], tph);
             tc_fence_after();
-#pragma unroll 1
-            for (int mt = 0; mt < V2_MT; ++mt) {
-                const int n_img = wk.n0 + (p.imgs_per_super == 1 ? 0 : mt);
-                const int ty0 = wk.y0 + (p.imgs_per_super == 1 ? 16 * mt : 0);
-                const int oy = ty0 + (r >> 3), ox = wk.x0 + (r & 7);
-                const bool valid = n_img < p.B;                      // H, W are multiples of the tile
-                const size_t pix = ((size_t)n_img * p.H + oy) * p.W + ox;
-                uint4 rres[BN / 8];                                  // the row's residual, in flight while TMEM drains
-                const bool has_res = p.residual != nullptr && valid;
-                if (has_res) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + wk.ntr * BN);
+            const bool has_res = p.has_res && valid;
+            if (has_res) { mbar_wait(&r_full[e], rph); rph ^= 1u; }  // landed; also means the staging tile was free
+            wg_sync();                                               // staging free (leader waited for the previous store), bias visible
 #pragma unroll
-                    for (int i = 0; i < BN / 8; ++i) rres[i] = __ldg(rp + i);
-                }
-                if (warp == 2) { if (elect_one()) tma_store_wait_read(); }   // previous TMA store has read the staging tile
-                epi_bar_sync();
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tb * V2_MT + e) * BN + c0), v);
+                tmem_ld_wait();
+                uint8_t* srow = staging + (c0 >> 6) * 16384 + r * 128;
 #pragma unroll
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tb * V2_MT + mt) * BN + c0), v);
-                    tmem_ld_wait();
-                    uint8_t* srow = staging + (c0 >> 6) * 16384 + r * 128;
+                for (int g = 0; g < 4; ++g) {
+                    float f[8];
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8 + 4);
+                    f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                    f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                    f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                    f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                    uint4* slot = reinterpret_cast<uint4*>(srow + (((((c0 & 63) >> 3) + g) ^ sw) << 4));
+                    if (has_res) {                                   // in-place: this thread's own 16 bytes of the residual tile
+                        const uint4 rv = *slot;
+                        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float f[8];
-                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8);
-                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8 + 4);
-                        f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-                        f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-                        f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-                        f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-                        if (has_res) {
-                            const uint4 rv = rres[(c0 >> 3) + g];
-                            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 t = __bfloat1622float2(rh[j]);
-                                f[2 * j] += t.x; f[2 * j + 1] += t.y;
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 t = __bfloat1622float2(rh[j]);
+                            f[2 * j] += t.x; f[2 * j + 1] += t.y;
                         }
-                        if (p.relu) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-                        }
-                        uint4 pk;
-                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                        const int chunk16 = (((c0 & 63) >> 3) + g) ^ sw;
-                        *reinterpret_cast<uint4*>(srow + chunk16 * 16) = pk;
                     }
-                }
-                if (mt == V2_MT - 1) { tc_fence_before(); mbar_arrive(&t_empty[tb]); }   // accumulators fully read
-                fence_proxy_async();
-                epi_bar_sync();
-                if (warp == 2 && valid) {
-                    if (elect_one()) {
+                    if (p.relu) {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            tma_store_4d(&maps.out[wk.phase], staging + j * 16384, wk.ntr * BN + j * 64, wk.x0, ty0, n_img);
-                        tma_store_commit();
+                        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
                     }
+                    uint4 pk;
+                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                    *slot = pk;
                 }
-                if (p.stats && valid) {
+            }
+            tc_fence_before();
+            mbar_arrive(&t_empty[tb]);                               // this warpgroup's accumulator tile is fully read
+            fence_proxy_async();
+            wg_sync();
+            if (lead_warp && valid) {
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_store_4d(&maps.out[wk.phase], staging + j * 16384, wk.ntr * BN + j * 64, wk.x0, ty0, n_img);
+                    tma_store_commit();
+                }
+            }
+            if (p.stats) {
+                if (valid) {
                     // fused GroupNorm statistics: per-channel (sum, sumsq) of the bf16 values just staged;
                     // thread = one column (x one row half for BN = 64), fixed summation order
-                    const int et = threadIdx.x - 64;                 // 0..127
                     const int col = et % BN, half = et / BN;          // BN = 128: half = 0, all 128 rows
                     constexpr int ROWS = BN;                          // rows per thread: 128 (BN=128) or 64 (BN=64)
                     const uint8_t* sb = staging + (col >> 6) * 16384 + (col & 7) * 2;
@@ -391,18 +407,28 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         acc1 += s1; acc2 += s2;
                     }
                 }
+                if (p.imgs_per_super == 1 && (w + 1) % p.chunk == 0) {
+                    // end of this chunk (chunks never straddle an (image, N tile)): one partial row per chunk and warpgroup
+                    const int per_img = p.tiles_x * p.supers_per_img;
+                    const int col = et % BN, half = et / BN;
+                    const int slot = ((wk.phase * (per_img / p.chunk) + (w % per_img) / p.chunk) * (128 / BN) + half) * V2_MT + e;
+                    p.stats[((size_t)wk.n0 * p.stats_slots + slot) * p.Cout + wk.ntr * BN + col] = make_float2(acc1, acc2);
+                    acc1 = 0.f; acc2 = 0.f;
+                }
             }
-            if (p.stats && p.imgs_per_super == 1 && (w + 1) % p.chunk == 0) {
-                // end of this chunk (chunks never straddle an (image, N tile)): one partial row per chunk
-                const int per_img = p.tiles_x * p.supers_per_img;
-                const int et = threadIdx.x - 64, col = et % BN, half = et / BN;
-                const int slot = (wk.phase * (per_img / p.chunk) + (w % per_img) / p.chunk) * (128 / BN) + half;
-                p.stats[((size_t)wk.n0 * p.stats_slots + slot) * p.Cout + wk.ntr * BN + col] = make_float2(acc1, acc2);
-                acc1 = 0.f; acc2 = 0.f;
+            wg_sync();                                               // every statistics read of the staging tile is done
+            if (lead_warp) {
+                if (elect_one()) {
+                    tma_store_wait_read();                           // ... and so is the TMA store's: the staging tile is free
+                    if (p.has_res) {
+                        const int wn = v2_item(p, it + 1);
+                        if (wn >= 0) load_residual(v2_decode(p, wn));
+                    }
+                }
             }
             if (++tb == 2) { tb = 0; tph ^= 1u; }
         }
-        if (warp == 2) { if (elect_one()) tma_store_wait_all(); }
+        if (lead_warp) { if (elect_one()) tma_store_wait_all(); }
     }
     tc_fence_before();
     __syncthreads();
@@ -448,7 +474,7 @@ int conv_tc2_stats_slots(const ConvArgs& a) {
     const int phases = a.up2x ? 4 : 1;
     if (a.H == 16) return phases * (a.W / 8) * (128 / BN);
     const int per_img = (a.W / 8) * (a.H / 32);
-    return phases * (per_img / v2_chunk(a, BN)) * (128 / BN);
+    return phases * (per_img / v2_chunk(a, BN)) * (128 / BN) * V2_MT;      // one row per chunk and epilogue warpgroup
 }
 
 template <int BN, bool RES>
@@ -506,7 +532,7 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     SYNT_CHECK(!a.gn_mode || a.gn_ss != nullptr, "conv_tc2: gn_mode without scale/shift");
     p.gn_ss = a.gn_ss; p.gn_C = Ct;
     p.B = a.B; p.H = a.H; p.W = a.W; p.Cout = a.Cout;
-    p.bias = a.bias; p.bias2 = a.bias2; p.residual = (const bf16*)a.residual; p.relu = a.relu;
+    p.bias = a.bias; p.bias2 = a.bias2; p.has_res = a.residual != nullptr; p.relu = a.relu;
     p.stats = a.stats_out; p.stats_slots = conv_tc2_stats_slots(a);
     p.chunk = v2_chunk(a, BN);
     V2Maps maps;
@@ -532,6 +558,14 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
         cuuint64_t strides[3] = {(cuuint64_t)up * a.Cout * 2, (cuuint64_t)up * Wo * a.Cout * 2, (cuuint64_t)Ho * Wo * a.Cout * 2};
         cuuint32_t box[4] = {64, 8, 16, 1};
         encode_bf16_sw128(&maps.out[ph], base, 4, dims, strides, box, "v2 output");
+    }
+    if (a.residual) {
+        cuuint64_t dims[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+        cuuint64_t strides[3] = {(cuuint64_t)a.Cout * 2, (cuuint64_t)a.W * a.Cout * 2, (cuuint64_t)a.H * a.W * a.Cout * 2};
+        cuuint32_t box[4] = {64, 8, 16, 1};
+        encode_bf16_sw128(&maps.res, a.residual, 4, dims, strides, box, "v2 residual");
+    } else {
+        maps.res = maps.out[0];
     }
     const int num_sms = v2_num_sms();
     const int grid = p.n_work < num_sms ? p.n_work : num_sms;
