@@ -28,6 +28,7 @@
 // Rings: A halo slots (2), B weight-tile slots (NB), TMEM accumulator buffers (2).
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include <type_traits>
 #include "tmap.cuh"
 
 namespace synt {
@@ -229,62 +230,72 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         // ===================== input transform (warps 12..19): GroupNorm affine (+SiLU) in place =====================
         const int tt = threadIdx.x - V2_XF_BASE, lv = tt & 7, r0 = tt >> 3;      // 8-channel vector, first row
         const int rows_per_img = p.imgs_per_super == 1 ? 340 : 180;
+        const int hy0 = r0 / 10, hx0 = r0 - hy0 * 10;                    // halo coordinates of the first row (10 pixels per halo row)
+        constexpr int RSTEP = V2_XF_THREADS / 8;                         // rows advance by 32 = 3 halo rows + 2 pixels
         int as = 0; uint32_t aph = 0;
         for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
             const V2Work wk = v2_decode(p, w);
             for (int sg = 0; sg < p.n_seg; ++sg) {
                 const V2Seg sp = p.seg[sg];
                 for (int ch = 0; ch < sp.chunks; ++ch) {
-                    float sc[2][8], sh[2][8];
-                    if (sp.xform) {                                        // in flight while the TMA lands
+                    float sc[8], sh[8];                                    // image 0 of the super-tile: in flight while the TMA lands
+                    const float pre = sp.xform == 2 ? 0.5f : 1.0f;         // SiLU works on h = y/2: silu(y) = h + h*tanh(h)
+                    auto load_ss = [&](int im) {
+                        const float4* ss = reinterpret_cast<const float4*>(
+                            p.gn_ss + (size_t)(wk.n0 + im) * p.gn_C + sp.ss_off + ch * 64 + lv * 8);
 #pragma unroll
-                        for (int im = 0; im < 2; ++im) {
-                            if (im < p.imgs_per_super && wk.n0 + im < p.B) {
-                                const float4* ss = reinterpret_cast<const float4*>(
-                                    p.gn_ss + (size_t)(wk.n0 + im) * p.gn_C + sp.ss_off + ch * 64 + lv * 8);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float4 t = __ldg(ss + j);
-                                    sc[im][2 * j] = t.x; sh[im][2 * j] = t.y; sc[im][2 * j + 1] = t.z; sh[im][2 * j + 1] = t.w;
-                                }
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 t = __ldg(ss + j);
+                            sc[2 * j] = pre * t.x; sh[2 * j] = pre * t.y; sc[2 * j + 1] = pre * t.z; sh[2 * j + 1] = pre * t.w;
                         }
-                    }
+                    };
+                    if (sp.xform) load_ss(0);
                     mbar_wait(&a_full[as], aph);
                     if (sp.xform) {
                         uint8_t* slot = smem + as * L::A_SLOT;
+                        auto run = [&](auto silu_tag) {
+                            constexpr bool SILU = decltype(silu_tag)::value;
 #pragma unroll
-                        for (int im = 0; im < 2; ++im) {
-                            if (im >= p.imgs_per_super || wk.n0 + im >= p.B) continue;
-                            constexpr int UR = 4;                          // rows in flight per thread (hides LDS/MUFU latency)
-                            for (int base = r0; base < rows_per_img; base += (V2_XF_THREADS / 8) * UR) {
-                                uint4 v[UR]; uint4* ptr[UR]; bool ok[UR];
+                            for (int im = 0; im < 2; ++im) {
+                                if (im >= p.imgs_per_super || wk.n0 + im >= p.B) continue;
+                                if (im == 1) load_ss(1);                   // 16x16 layers: second image of the super-tile
+                                constexpr int UR = 4;                      // rows in flight per thread (hides LDS/MUFU latency)
+                                int hy = wk.y0 - 1 + hy0, hx = wk.x0 - 1 + hx0;     // image coordinates of the current row
+                                for (int rr = r0; rr < rows_per_img;) {
+                                    uint4 v[UR]; uint4* ptr[UR]; bool ok[UR];
 #pragma unroll
-                                for (int uu = 0; uu < UR; ++uu) {
-                                    const int rr = base + (V2_XF_THREADS / 8) * uu;
-                                    const int hy = rr / 10, hx = rr - hy * 10;
-                                    const int y = wk.y0 - 1 + hy, x = wk.x0 - 1 + hx;
-                                    ok[uu] = rr < rows_per_img && y >= 0 && y < p.H && x >= 0 && x < p.W;   // padding stays exactly 0
-                                    const int r = im * 180 + rr;
-                                    ptr[uu] = reinterpret_cast<uint4*>(slot + r * 128 + ((lv ^ (r & 7)) << 4));
-                                    if (ok[uu]) v[uu] = *ptr[uu];
-                                }
-#pragma unroll
-                                for (int uu = 0; uu < UR; ++uu) {
-                                    if (!ok[uu]) continue;
-                                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v[uu]);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        float2 f = __bfloat1622float2(h2[j]);
-                                        f.x = fmaf(f.x, sc[im][2 * j], sh[im][2 * j]);
-                                        f.y = fmaf(f.y, sc[im][2 * j + 1], sh[im][2 * j + 1]);
-                                        if (sp.xform == 2) { f.x = silu_tanh_v2(f.x); f.y = silu_tanh_v2(f.y); }
-                                        h2[j] = __floats2bfloat162_rn(f.x, f.y);
+                                    for (int uu = 0; uu < UR; ++uu) {
+                                        // out-of-image halo pixels stay exactly 0 (= the padding of the activated tensor)
+                                        ok[uu] = rr < rows_per_img && (unsigned)hy < (unsigned)p.H && (unsigned)hx < (unsigned)p.W;
+                                        const int r = im * 180 + rr;
+                                        ptr[uu] = reinterpret_cast<uint4*>(slot + r * 128 + ((lv ^ (r & 7)) << 4));
+                                        if (ok[uu]) v[uu] = *ptr[uu];
+                                        rr += RSTEP; hy += 3; hx += 2;
+                                        if (hx >= wk.x0 + 9) { hx -= 10; ++hy; }
                                     }
-                                    *ptr[uu] = v[uu];
+#pragma unroll
+                                    for (int uu = 0; uu < UR; ++uu) {
+                                        if (!ok[uu]) continue;
+                                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v[uu]);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            float2 f = __bfloat1622float2(h2[j]);
+                                            f.x = fmaf(f.x, sc[2 * j], sh[2 * j]);
+                                            f.y = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+                                            if (SILU) {
+                                                float t0, t1;
+                                                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(f.x));
+                                                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(f.y));
+                                                f.x = fmaf(f.x, t0, f.x); f.y = fmaf(f.y, t1, f.y);
+                                            }
+                                            h2[j] = __floats2bfloat162_rn(f.x, f.y);
+                                        }
+                                        *ptr[uu] = v[uu];
+                                    }
                                 }
                             }
-                        }
+                        };
+                        if (sp.xform == 2) run(std::true_type{}); else run(std::false_type{});
                         fence_proxy_async();                               // generic-proxy writes -> UMMA (async proxy)
                     }
                     mbar_arrive(&a_ready[as]);
@@ -318,7 +329,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 tma_load_4d(staging + j * 16384, &maps.res, &r_full[e], wk.ntr * BN + j * 64, wk.x0, ty0, n_img);
         };
         int tb = 0; uint32_t tph = 0, rph = 0; int last_nt = -1;
-        float acc1 = 0.f, acc2 = 0.f;                               // GroupNorm partials carried across tiles
+        float acc[8];                                               // GroupNorm partials (4 columns x (sum, sumsq)) carried across tiles
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
         if (p.has_res && lead_warp) {
             const int w0 = v2_item(p, 0);
             if (w0 >= 0) { if (elect_one()) load_residual(v2_decode(p, w0)); }
@@ -386,34 +399,48 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 }
             }
             if (p.stats) {
+                // fused GroupNorm statistics: per-channel (sum, sumsq) of the bf16 values just staged.  Warp q of the
+                // warpgroup owns BN/4 columns; lane = (column quad cq, row part rp): 8-byte loads of 4 columns, the row
+                // parts interleaved so that the lanes of one load phase hit distinct banks of the swizzled tile; the
+                // partials stay in registers across the tiles of a chunk, fixed summation order.
+                constexpr int CQW = BN / 16, RP = 32 / CQW, SUB = 16 / RP;     // BN=128: 8 quads x 4 parts x 4-row runs
+                const int cq = lane % CQW, rp = lane / CQW;
+                const int col0 = q * (BN / 4) + cq * 4;
                 if (valid) {
-                    // fused GroupNorm statistics: per-channel (sum, sumsq) of the bf16 values just staged;
-                    // thread = one column (x one row half for BN = 64), fixed summation order
-                    const int col = et % BN, half = et / BN;          // BN = 128: half = 0, all 128 rows
-                    constexpr int ROWS = BN;                          // rows per thread: 128 (BN=128) or 64 (BN=64)
-                    const uint8_t* sb = staging + (col >> 6) * 16384 + (col & 7) * 2;
-                    const int ck = (col & 63) >> 3;
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                    for (int i = 0; i < ROWS; ++i) {
-                        const int row = half * ROWS + i;
-                        const float x = __bfloat162float(*reinterpret_cast<const bf16*>(sb + row * 128 + ((ck ^ (row & 7)) << 4)));
-                        s1 += x; s2 = fmaf(x, x, s2);
-                    }
-                    if (p.imgs_per_super == 2) {                      // 16x16 images: one partial row per tile
-                        const int slot = (wk.phase * p.tiles_x + (wk.x0 >> 3)) * (128 / BN) + half;
-                        p.stats[((size_t)n_img * p.stats_slots + slot) * p.Cout + wk.ntr * BN + col] = make_float2(s1, s2);
-                    } else {
-                        acc1 += s1; acc2 += s2;
+                    const uint8_t* sb = staging + (col0 >> 6) * 16384 + (col0 & 7) * 2;
+                    const int ck = (col0 & 63) >> 3;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                        for (int j = 0; j < SUB; ++j) {
+                            const int row = (2 * k + rp / (RP / 2)) * 8 + (rp % (RP / 2)) * SUB + j;
+                            const uint2 u = *reinterpret_cast<const uint2*>(sb + row * 128 + ((ck ^ (row & 7)) << 4));
+                            const float x0 = __uint_as_float(u.x << 16), x1 = __uint_as_float(u.x & 0xffff0000u);
+                            const float x2 = __uint_as_float(u.y << 16), x3 = __uint_as_float(u.y & 0xffff0000u);
+                            acc[0] += x0; acc[1] = fmaf(x0, x0, acc[1]); acc[2] += x1; acc[3] = fmaf(x1, x1, acc[3]);
+                            acc[4] += x2; acc[5] = fmaf(x2, x2, acc[5]); acc[6] += x3; acc[7] = fmaf(x3, x3, acc[7]);
+                        }
                     }
                 }
-                if (p.imgs_per_super == 1 && (w + 1) % p.chunk == 0) {
-                    // end of this chunk (chunks never straddle an (image, N tile)): one partial row per chunk and warpgroup
-                    const int per_img = p.tiles_x * p.supers_per_img;
-                    const int col = et % BN, half = et / BN;
-                    const int slot = ((wk.phase * (per_img / p.chunk) + (w % per_img) / p.chunk) * (128 / BN) + half) * V2_MT + e;
-                    p.stats[((size_t)wk.n0 * p.stats_slots + slot) * p.Cout + wk.ntr * BN + col] = make_float2(acc1, acc2);
-                    acc1 = 0.f; acc2 = 0.f;
+                // 16x16 layers: one partial row per tile; otherwise one per chunk (chunks never straddle an (image, N tile))
+                const bool flush = p.imgs_per_super == 2 ? valid : (w + 1) % p.chunk == 0;
+                if (flush) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                        for (int o = CQW; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+                    }
+                    if (rp == 0) {
+                        const int per_img = p.tiles_x * p.supers_per_img;
+                        const int slot = p.imgs_per_super == 2 ? wk.phase * p.tiles_x + (wk.x0 >> 3)
+                                                               : (wk.phase * (per_img / p.chunk) + (w % per_img) / p.chunk) * V2_MT + e;
+                        float4* dst = reinterpret_cast<float4*>(
+                            p.stats + ((size_t)(p.imgs_per_super == 2 ? n_img : wk.n0) * p.stats_slots + slot) * p.Cout + wk.ntr * BN + col0);
+                        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
                 }
             }
             wg_sync();                                               // every statistics read of the staging tile is done
@@ -472,9 +499,9 @@ static int v2_chunk(const ConvArgs& a, int BN) {
 int conv_tc2_stats_slots(const ConvArgs& a) {
     const int BN = (a.Cout % 128 == 0) ? 128 : 64;
     const int phases = a.up2x ? 4 : 1;
-    if (a.H == 16) return phases * (a.W / 8) * (128 / BN);
+    if (a.H == 16) return phases * (a.W / 8);                             // one row per tile
     const int per_img = (a.W / 8) * (a.H / 32);
-    return phases * (per_img / v2_chunk(a, BN)) * (128 / BN) * V2_MT;      // one row per chunk and epilogue warpgroup
+    return phases * (per_img / v2_chunk(a, BN)) * V2_MT;                   // one row per chunk and epilogue warpgroup
 }
 
 template <int BN, bool RES>

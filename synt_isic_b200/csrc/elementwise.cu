@@ -136,7 +136,15 @@ __global__ void __launch_bounds__(256) gn_finalize_channels_kernel(const float2*
         const float2* base = first ? partA + (size_t)b * SA * C0 + c : partB + (size_t)b * SB * C1 + (c - C0);
         const int S = first ? SA : SB, Cs = first ? C0 : C1;
         double ts = 0.0, tq = 0.0;
-        for (int k = slice; k < S; k += nslice) {
+        int k = slice;
+        for (; k + 7 * nslice < S; k += 8 * nslice) {          // 8 independent loads in flight (the chain was latency bound)
+            float2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(base + (size_t)(k + j * nslice) * Cs);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ts += (double)v[j].x; tq += (double)v[j].y; }
+        }
+        for (; k < S; k += nslice) {
             const float2 v = __ldg(base + (size_t)k * Cs);
             ts += (double)v.x; tq += (double)v.y;
         }
@@ -345,7 +353,109 @@ __global__ void __launch_bounds__(128) conv_in3_kernel(const float* __restrict__
         store8<T>(o + n0, acc);
     }
 }
-void conv_in3(const float* x, const ConvInW& w, int B, int H, int W, void* out, int dt, cudaStream_t s) {
+// ---- bf16 production path: register-tiled fp32 FMA (4 pixels x 16 channels per thread, weights broadcast from
+// shared memory) with the GroupNorm statistics of the OUTPUT fused (per-channel sum / sum of squares of the stored
+// bf16 values, one partial row per 8-row band).  Block = 256 threads = one band of 8 rows x W columns of one image,
+// walked in 32-column tiles; warp = (channel quarter cq = warp & 3, row half), lane = pixel group (row, 4 columns): every
+// lane of a warp reads the SAME weights (one shared-memory wavefront per LDS.128) and the input rows are padded to a
+// stride of 65 floats so that the 32 pixel groups of a warp hit 32 different banks.
+constexpr int CI_ROWS = 8, CI_COLS = 32, CI_STRIDE = 65;
+
+__global__ void __launch_bounds__(256) conv_in3_tiled_kernel(const float* __restrict__ x, const __grid_constant__ ConvInW w,
+                                                             int H, int W, bf16* __restrict__ out, float2* __restrict__ stats,
+                                                             int stats_slots) {
+    __shared__ __align__(16) float w_s[27][64];
+    __shared__ float in_s[3][CI_ROWS + 2][CI_STRIDE];
+    __shared__ float2 red_s[2][64];
+    const int b = blockIdx.y, y0 = blockIdx.x * CI_ROWS;
+    for (int i = threadIdx.x; i < 27 * 64; i += 256) w_s[i / 64][i % 64] = w.w[i / 64][i % 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cq = warp & 3, row = (warp >> 2) * 4 + (lane >> 3), xg = lane & 7;
+    float bias[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) bias[j] = w.b[cq * 16 + j];
+    float s1[16], s2[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    const float* xb = x + (size_t)b * 3 * H * W;
+    for (int x0 = 0; x0 < W; x0 += CI_COLS) {
+        __syncthreads();                                             // previous tile fully consumed (and w_s visible)
+        for (int i = threadIdx.x; i < 3 * (CI_ROWS + 2) * (CI_COLS + 2); i += 256) {
+            const int c = i / ((CI_ROWS + 2) * (CI_COLS + 2)), rem = i % ((CI_ROWS + 2) * (CI_COLS + 2));
+            const int hy = rem / (CI_COLS + 2), hx = rem % (CI_COLS + 2);
+            const int iy = y0 + hy - 1, ix = x0 + hx - 1;
+            in_s[c][hy][hx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + ((size_t)c * H + iy) * W + ix) : 0.f;
+        }
+        __syncthreads();
+        float acc[4][16];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[p][j] = bias[j];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float v[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) v[j] = in_s[c][row + dy][xg * 4 + j];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float4* wr = reinterpret_cast<const float4*>(&w_s[(dy * 3 + dx) * 3 + c][cq * 16]);
+                    float wv[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float4 t = wr[j]; wv[4 * j] = t.x; wv[4 * j + 1] = t.y; wv[4 * j + 2] = t.z; wv[4 * j + 3] = t.w; }
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(v[p + dx], wv[j], acc[p][j]);
+                }
+            }
+        const int oy = y0 + row;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int ox = x0 + xg * 4 + p;
+            uint4 pk[2];
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                h2[j] = __floats2bfloat162_rn(acc[p][2 * j], acc[p][2 * j + 1]);
+                const float2 r = __bfloat1622float2(h2[j]);          // statistics of the values the consumers will read
+                s1[2 * j] += r.x; s2[2 * j] = fmaf(r.x, r.x, s2[2 * j]);
+                s1[2 * j + 1] += r.y; s2[2 * j + 1] = fmaf(r.y, r.y, s2[2 * j + 1]);
+            }
+            uint4* o = reinterpret_cast<uint4*>(out + (((size_t)b * H + oy) * W + ox) * 64 + cq * 16);
+            o[0] = pk[0]; o[1] = pk[1];
+        }
+    }
+    // per-channel sums over the band: the 32 lanes of a warp, then the two warps that share cq
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) red_s[warp >> 2][cq * 16 + j] = make_float2(s1[j], s2[j]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && stats)
+        stats[((size_t)b * stats_slots + blockIdx.x) * 64 + threadIdx.x] =
+            make_float2(red_s[0][threadIdx.x].x + red_s[1][threadIdx.x].x, red_s[0][threadIdx.x].y + red_s[1][threadIdx.x].y);
+}
+
+int conv_in3_stats_slots(int H, int W, int dt) { return (dt == DT_BF16 && H % CI_ROWS == 0 && W % CI_COLS == 0) ? H / CI_ROWS : 0; }
+
+void conv_in3(const float* x, const ConvInW& w, int B, int H, int W, void* out, int dt, float2* stats_out, cudaStream_t s) {
+    if (conv_in3_stats_slots(H, W, dt) > 0) {
+        conv_in3_tiled_kernel<<<dim3(H / CI_ROWS, B), 256, 0, s>>>(x, w, H, W, (bf16*)out, stats_out, H / CI_ROWS);
+        SYNT_LAUNCH_CHECK();
+        return;
+    }
+    SYNT_CHECK(stats_out == nullptr, "conv_in3: fused statistics need the tiled bf16 path");
     const long long np = (long long)B * H * W;
     const int blocks = (int)((np + 127) / 128);
     if (dt == DT_F32) conv_in3_kernel<float><<<blocks, 128, 0, s>>>(x, w, B, H, W, (float*)out);
@@ -376,6 +486,43 @@ __device__ __forceinline__ void philox_normal3(unsigned long long seed, unsigned
     __sincosf(6.283185307179586f * u1, &s0, &c0);
     __sincosf(6.283185307179586f * u3, &s1, &c1);
     z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; (void)s1;
+}
+
+// eps of one pixel (3 channels) -> optional eps tap, DDPMScheduler.step on x (in place), optional trajectory frame
+__device__ __forceinline__ void sched_epilogue(const float (&e)[3], int b, int oy, int ox, int H, int W, float* eps_out,
+                                               const SchedArgs& sch) {
+    const size_t plane = (size_t)H * W;
+    const size_t i0 = ((size_t)b * 3) * plane + (size_t)oy * W + ox;
+    const long long step = sch.step_ptr ? (long long)*sch.step_ptr : 0;
+    if (eps_out) {
+        float* eo = eps_out + step * sch.eps_step_stride;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) eo[i0 + j * plane] = e[j];
+    }
+    if (sch.x) {
+        const float sqrt_b = sch.coef[0], sqrt_a = sch.coef[1], c_x0 = sch.coef[2], c_xt = sch.coef[3],
+                    sigma = sch.coef[4];
+        float z[3] = {0.f, 0.f, 0.f};
+        if (sigma != 0.f) {
+            if (sch.z) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) z[j] = sch.z[step * sch.z_step_stride + i0 + j * plane];
+            } else {
+                const unsigned long long elem = (unsigned long long)(sch.image_offset + b) * plane + (size_t)oy * W + ox;
+                philox_normal3(sch.seed, elem, (uint32_t)step, z);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float xv = sch.x[i0 + j * plane];
+            float x0v = (xv - sqrt_b * e[j]) / sqrt_a;
+            x0v = fminf(fmaxf(x0v, -1.f), 1.f);
+            float prev = c_x0 * x0v + c_xt * xv;
+            if (sigma != 0.f) prev = prev + sigma * z[j];
+            sch.x[i0 + j * plane] = prev;
+            if (sch.traj) sch.traj[step * sch.traj_step_stride + i0 + j * plane] = prev;
+        }
+    }
 }
 
 // =============================================================== conv_out (64 -> 3) =
@@ -431,52 +578,136 @@ __global__ void __launch_bounds__(256) conv_out3_kernel(const T* __restrict__ h,
         }
     }
     if (oy >= H || ox >= W) return;
-    const size_t plane = (size_t)H * W;
-    const size_t i0 = ((size_t)b * 3) * plane + (size_t)oy * W + ox;
     const float e[3] = {acc0, acc1, acc2};
-    const long long step = sch.step_ptr ? (long long)*sch.step_ptr : 0;
-    if (eps_out) {
-        float* eo = eps_out + step * sch.eps_step_stride;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) eo[i0 + j * plane] = e[j];
-    }
-    if (sch.x) {
-        const float sqrt_b = sch.coef[0], sqrt_a = sch.coef[1], c_x0 = sch.coef[2], c_xt = sch.coef[3],
-                    sigma = sch.coef[4];
-        float z[3] = {0.f, 0.f, 0.f};
-        if (sigma != 0.f) {
-            if (sch.z) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) z[j] = sch.z[step * sch.z_step_stride + i0 + j * plane];
-            } else {
-                const unsigned long long elem = (unsigned long long)(sch.image_offset + b) * plane + (size_t)oy * W + ox;
-                philox_normal3(sch.seed, elem, (uint32_t)step, z);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float xv = sch.x[i0 + j * plane];
-            float x0v = (xv - sqrt_b * e[j]) / sqrt_a;
-            x0v = fminf(fmaxf(x0v, -1.f), 1.f);
-            float prev = c_x0 * x0v + c_xt * xv;
-            if (sigma != 0.f) prev = prev + sigma * z[j];
-            sch.x[i0 + j * plane] = prev;
-            if (sch.traj) sch.traj[step * sch.traj_step_stride + i0 + j * plane] = prev;
-        }
-    }
+    sched_epilogue(e, b, oy, ox, H, W, eps_out, sch);
 }
 
-void conv_out3(const void* h, int dt, const float2* scale_shift, const ConvOutW& w, int B, int H, int W,
+// ---- bf16 production path: the same tile on the legacy tensor-core path (mma.sync m16n8k16, N = 3 padded to 8).
+// The GroupNorm+SiLU'd 18x18x64 halo tile is staged as bf16 with a 16-byte-chunk XOR swizzle (pixel & 7) so that the
+// ldmatrix rows of 8 consecutive pixels are bank-conflict free; the weights arrive pre-arranged as per-lane B
+// fragments (36 k-steps = 9 taps x 4 sixteen-channel blocks).  Each warp owns two rows of 16 pixels (two m16 tiles).
+// eps goes through shared memory so that one thread owns all three channels of a pixel in the scheduler epilogue.
+constexpr int COT_TILE_BYTES = CO_HALO * CO_HALO * 128;          // 41472
+constexpr int COT_FRAG_BYTES = 36 * 32 * 8;                       // 9216
+constexpr int COT_SMEM_BYTES = COT_TILE_BYTES + COT_FRAG_BYTES + 256 * 3 * 4;
+
+__global__ void __launch_bounds__(256) conv_out3_mma_kernel(const bf16* __restrict__ h, const float2* __restrict__ scale_shift,
+                                                            const uint2* __restrict__ bfrag, float b0, float b1, float b2,
+                                                            int B, int H, int W, float* __restrict__ eps_out,
+                                                            const __grid_constant__ SchedArgs sch) {
+    extern __shared__ __align__(128) uint8_t cot_smem[];
+    uint8_t* tile = cot_smem;
+    uint2* frag_s = reinterpret_cast<uint2*>(cot_smem + COT_TILE_BYTES);
+    float* eps_s = reinterpret_cast<float*>(cot_smem + COT_TILE_BYTES + COT_FRAG_BYTES);
+    const int b = blockIdx.z, y0 = blockIdx.y * CO_TILE, x0 = blockIdx.x * CO_TILE;
+    for (int i = threadIdx.x; i < 36 * 32; i += 256) frag_s[i] = __ldg(bfrag + i);
+    // ---- stage: 324 halo pixels x 8 vectors of 8 channels, GroupNorm affine + SiLU, bf16
+    {
+        const int v = threadIdx.x & 7;                               // this thread's channel vector is fixed
+        float sc[8], sh[8];
+        const float4* ss = reinterpret_cast<const float4*>(scale_shift + (size_t)b * 64 + v * 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldg(ss + j);
+            sc[2 * j] = 0.5f * t.x; sh[2 * j] = 0.5f * t.y; sc[2 * j + 1] = 0.5f * t.z; sh[2 * j + 1] = 0.5f * t.w;   // h = y/2
+        }
+        constexpr int NP = CO_HALO * CO_HALO;
+        for (int hp0 = threadIdx.x >> 3; hp0 < NP; hp0 += 4 * 32) {   // 4 pixels in flight per thread
+            uint4 raw[4]; bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int hp = hp0 + u * 32;
+                const int hy = hp / CO_HALO, hx = hp - hy * CO_HALO;
+                const int iy = y0 + hy - 1, ix = x0 + hx - 1;
+                ok[u] = hp < NP && iy >= 0 && iy < H && ix >= 0 && ix < W;
+                if (ok[u]) raw[u] = __ldg(reinterpret_cast<const uint4*>(h + (((size_t)b * H + iy) * W + ix) * 64 + v * 8));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int hp = hp0 + u * 32;
+                if (hp >= NP) continue;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[u]) {
+                    const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+                    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __bfloat1622float2(x2[j]);
+                        const float h0 = fmaf(f.x, sc[2 * j], sh[2 * j]), h1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+                        float t0, t1;
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                        o2[j] = __floats2bfloat162_rn(fmaf(h0, t0, h0), fmaf(h1, t1, h1));   // silu(y) = h + h tanh(h)
+                    }
+                }
+                *reinterpret_cast<uint4*>(tile + hp * 128 + ((v ^ (hp & 7)) << 4)) = o;
+            }
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    float acc[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        acc[m][0] = acc[m][2] = t == 0 ? b0 : (t == 1 ? b2 : 0.f);
+        acc[m][1] = acc[m][3] = t == 0 ? b1 : 0.f;
+    }
+    const uint32_t tile_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+    const int lm = lane >> 3, lr = lane & 7;                         // ldmatrix: matrix index, row within it
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            const uint2 bf = frag_s[(tap * 4 + kc) * 32 + lane];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int hp = (warp * 2 + m + dy) * CO_HALO + dx + (lm & 1) * 8 + lr;
+                const uint32_t addr = tile_u32 + hp * 128 + (((kc * 2 + (lm >> 1)) ^ (hp & 7)) << 4);
+                uint32_t a0, a1, a2, a3;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                             : "+f"(acc[m][0]), "+f"(acc[m][1]), "+f"(acc[m][2]), "+f"(acc[m][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+            }
+        }
+    }
+    // accumulator fragment -> eps_s[pixel][3]: rows g / g+8 of the m16 tile = pixels tx = g / g+8 of row warp*2+m
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int p0 = (warp * 2 + m) * 16 + g;
+        if (t == 0) {
+            eps_s[p0 * 3 + 0] = acc[m][0]; eps_s[p0 * 3 + 1] = acc[m][1];
+            eps_s[(p0 + 8) * 3 + 0] = acc[m][2]; eps_s[(p0 + 8) * 3 + 1] = acc[m][3];
+        } else if (t == 1) {
+            eps_s[p0 * 3 + 2] = acc[m][0]; eps_s[(p0 + 8) * 3 + 2] = acc[m][2];
+        }
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / CO_TILE, tx = threadIdx.x % CO_TILE;
+    const int oy = y0 + ty, ox = x0 + tx;
+    if (oy >= H || ox >= W) return;
+    const float e[3] = {eps_s[threadIdx.x * 3], eps_s[threadIdx.x * 3 + 1], eps_s[threadIdx.x * 3 + 2]};
+    sched_epilogue(e, b, oy, ox, H, W, eps_out, sch);
+}
+
+void conv_out3(const void* h, int dt, const float2* scale_shift, const ConvOutW& w, const void* bfrag, int B, int H, int W,
                float* eps_nchw, const SchedArgs& sch, cudaStream_t s) {
     dim3 grid(ceil_div(W, CO_TILE), ceil_div(H, CO_TILE), B);
     static bool attr_set = false;
     if (!attr_set) {
         SYNT_CUDA(cudaFuncSetAttribute(conv_out3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, CO_SMEM_BYTES));
         SYNT_CUDA(cudaFuncSetAttribute(conv_out3_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CO_SMEM_BYTES));
+        SYNT_CUDA(cudaFuncSetAttribute(conv_out3_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COT_SMEM_BYTES));
         attr_set = true;
     }
     if (dt == DT_F32)
         conv_out3_kernel<float><<<grid, 256, CO_SMEM_BYTES, s>>>((const float*)h, scale_shift, w, B, H, W, eps_nchw, sch);
+    else if (bfrag)
+        conv_out3_mma_kernel<<<grid, 256, COT_SMEM_BYTES, s>>>((const bf16*)h, scale_shift, (const uint2*)bfrag, w.b[0], w.b[1],
+                                                              w.b[2], B, H, W, eps_nchw, sch);
     else
         conv_out3_kernel<bf16><<<grid, 256, CO_SMEM_BYTES, s>>>((const bf16*)h, scale_shift, w, B, H, W, eps_nchw, sch);
     SYNT_LAUNCH_CHECK();

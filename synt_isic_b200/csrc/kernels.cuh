@@ -55,7 +55,11 @@ void conv_tc_halo(const ConvArgs& a, int variant, cudaStream_t s);
 
 // UNet conv_in: x fp32 NCHW [B,3,H,W] -> NHWC T [B,H,W,64], 3x3 pad 1.
 struct ConvInW { float w[27][64]; float b[64]; };          // k = tap*3 + c
-void conv_in3(const float* x_nchw, const ConvInW& w, int B, int H, int W, void* out, int dt, cudaStream_t s);
+// stats_out (optional, only when conv_in3_stats_slots(H, W, dt) > 0): per-channel (sum, sumsq) partial rows
+// [B][slots][64] of the stored output, for the first GroupNorm
+int conv_in3_stats_slots(int H, int W, int dt);
+void conv_in3(const float* x_nchw, const ConvInW& w, int B, int H, int W, void* out, int dt, float2* stats_out,
+              cudaStream_t s);
 
 // UNet tail: eps = conv_out(SiLU(GN(h))) fused with DDPMScheduler.step.
 struct ConvOutW { float w[9][64][3]; float b[3]; };
@@ -73,7 +77,9 @@ struct SchedArgs {
     long long eps_step_stride = 0;     // stride of the eps tap between steps
     long long image_offset = 0;        // global image index of image 0 of this call (Philox stream id)
 };
-void conv_out3(const void* h, int dt, const float2* scale_shift, const ConvOutW& w, int B, int H, int W,
+// bfrag (bf16 mode, nullable): conv_out weights as per-lane mma.sync m16n8k16 B fragments, uint2[36 k-steps][32 lanes]
+// (k-step = tap*4 + 16-channel block; lane (g = lane/4, t = lane%4): .x = w[k0 + 2t, 2t+1][n = g], .y = same at k0 + 8)
+void conv_out3(const void* h, int dt, const float2* scale_shift, const ConvOutW& w, const void* bfrag, int B, int H, int W,
                float* eps_nchw /*nullable*/, const SchedArgs& sch, cudaStream_t s);
 
 // Stand-alone DDPMScheduler.step on fp32 NCHW tensors (the drop-in scheduler object).

@@ -202,6 +202,7 @@ struct synt_unet {
     ConvInW conv_in_w;
     ConvOutW conv_out_w;
     DevPtr norm_out_g, norm_out_b;
+    DevPtr conv_out_frag;                         // conv_out weights as mma.sync B fragments (bf16 mode)
     std::vector<ResnetW> down_res[4], up_res[4];
     std::vector<AttnW> down_attn[4], up_attn[4];
     std::vector<ConvW> downsample, upsample;      // index = block (3 each)
@@ -331,6 +332,19 @@ static void build_unet(synt_unet* u, const float* P) {
             for (int c = 0; c < 64; ++c)
                 for (int t = 0; t < 9; ++t) u->conv_out_w.w[t][c][n] = wo[((size_t)n * 64 + c) * 9 + t];
         memcpy(u->conv_out_w.b, P + m.find("conv_out.bias"), 3 * 4);
+        if (b16) {                                          // B fragments of mma.sync.m16n8k16 (see kernels.cuh)
+            std::vector<uint32_t> fr((size_t)36 * 32 * 2);
+            auto wv = [&](int tap, int c, int n) -> uint32_t { return n < 3 ? f2bf(wo[((size_t)n * 64 + c) * 9 + tap]) : 0u; };
+            for (int tap = 0; tap < 9; ++tap)
+                for (int kc = 0; kc < 4; ++kc)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, t = lane & 3, k0 = kc * 16 + t * 2;
+                        uint32_t* o = fr.data() + ((size_t)(tap * 4 + kc) * 32 + lane) * 2;
+                        o[0] = wv(tap, k0, g) | (wv(tap, k0 + 1, g) << 16);
+                        o[1] = wv(tap, k0 + 8, g) | (wv(tap, k0 + 9, g) << 16);
+                    }
+            u->conv_out_frag = dev_upload(fr.data(), fr.size() * 4);
+        }
         u->norm_out_g = dev_upload(P + m.find("conv_norm_out.weight"), 64 * 4);
         u->norm_out_b = dev_upload(P + m.find("conv_norm_out.bias"), 64 * 4);
     }
@@ -601,9 +615,14 @@ struct Fwd {
     // eps = UNet(x, t) for one micro-batch; temb_cur must already hold the row of t.
     void run(const float* x_nchw, float* eps_nchw, const SchedArgs& sch) {
         Act h = make(kImg, kImg, 64);
-        { ProfScope ps(u, s, PC_CONV_IN, 2.0 * B * kImg * kImg * 64.0 * 27); conv_in3(x_nchw, u->conv_in_w, B, kImg, kImg, h.p, u->dt, s); }
+        const int in_slots = conv_in3_stats_slots(kImg, kImg, u->dt);
+        if (in_slots > 0) {                                     // statistics of the first GroupNorm fused into conv_in
+            h.stats_slots = in_slots;
+            h.stats = (float2*)pool->alloc((size_t)B * in_slots * 64 * sizeof(float2));
+        }
+        { ProfScope ps(u, s, PC_CONV_IN, 2.0 * B * kImg * kImg * 64.0 * 27); conv_in3(x_nchw, u->conv_in_w, B, kImg, kImg, h.p, u->dt, h.stats, s); }
         ++u->launches;
-        standalone_stats(h);
+        if (in_slots == 0) standalone_stats(h);
         tap("conv_in", h);
         std::vector<Act> skips; skips.push_back(h);
         Act cur = h;                                            // `cur` aliases the top skip
@@ -630,7 +649,7 @@ struct Fwd {
             if (i != 3) { Act o = up(u->upsample[i], hcur); drop(hcur); hcur = o; }
         }
         float2* ss = gn_scale_shift(hcur, nullptr, u->norm_out_g, u->norm_out_b);
-        { ProfScope ps(u, s, PC_CONV_OUT, 2.0 * B * kImg * kImg * 3.0 * 576); conv_out3(hcur.p, u->dt, ss, u->conv_out_w, B, kImg, kImg, eps_nchw, sch, s); }
+        { ProfScope ps(u, s, PC_CONV_OUT, 2.0 * B * kImg * kImg * 3.0 * 576); conv_out3(hcur.p, u->dt, ss, u->conv_out_w, u->conv_out_frag ? u->conv_out_frag->p : nullptr, B, kImg, kImg, eps_nchw, sch, s); }
         ++u->launches;
         pool->release(ss);
         drop(hcur);
