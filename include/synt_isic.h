@@ -134,8 +134,8 @@ int synt_debug_conv_gn(const void* in_dev, int Cin, const void* in1_dev, int Cin
  * input): in [B,H,W,Cin] bf16 (device), w_host the raw [Cout][Cin][3][3] fp32 filter (HOST), out [B,2H,2W,Cout]. */
 int synt_debug_conv_up2x(const void* in_dev, int B, int H, int W, int Cin, const float* w_host, const float* bias_dev,
                          void* out_dev, int Cout, void* stats_out_dev, int* stats_slots, void* stream);
-/* softmax(q k^T / sqrt(8)) v on caller-provided tensors: use_tc=0: qkv [B,N,3C] (q|k|v); use_tc=1: the
- * zero-interleaved bf16 layout [B,N,5C] consumed by the tcgen05 attention kernel. out: [B,N,C]. */
+/* softmax(q k^T / sqrt(8)) v on caller-provided tensors qkv [B,N,3C] (q|k|v), out [B,N,C]; use_tc=1: the tcgen05
+ * kernel, bf16, q already multiplied by log2(e)/sqrt(8). */
 int synt_debug_attention(int use_tc, int act_dtype, const void* qkv_dev, int B, int N, int C, void* out_dev,
                          void* stream);
 

@@ -2,10 +2,12 @@
 // AttnProcessor2_0 reached from core/generator/image_generator.py:400): 32 heads of d = 8,
 // sequence N = 1024 (32x32) or 256 (16x16).
 //
-// Inputs (produced by the qkv projection GEMM with zero-interleaved weights, so no separate
-// padding pass exists):
-//   qkv' [B*N, 1280] bf16 = ( q' 512 | k' 512 | v 256 );  q'/k' hold each head as 16 columns
-//          = 8 real dims + 8 zeros (UMMA_K = 16 for bf16), q' pre-scaled by log2(e)/sqrt(8);
+// Inputs:
+//   qkv  [B*N, 768] bf16 = ( q 256 | k 256 | v 256 ), the plain output of the fused q/k/v projection; q is pre-scaled by
+//          log2(e)/sqrt(8) (folded into the projection weights).  A head is 8 columns, UMMA_K is 16 for bf16, so one
+//          K step covers a PAIR of heads: the key operand is the natural 16-column pair (k_2p | k_2p+1) and the query
+//          operand of head j is (q_j | 0) for even j, (0 | q_j) for odd j -- a zero-masked copy of the 128-query tile
+//          that the softmax warps build once per CTA in shared memory.  No padded tensor exists in HBM.
 //   vt   [B*32, 16, N] bf16 = per head V^T padded to 16 rows: rows 0..7 = v dims, row 8 = 1
 //          (so the P.V MMA also produces the softmax denominator), rows 9..15 = 0.
 //
@@ -18,8 +20,9 @@
 // is scaled in place by the softmax warps (tcgen05.ld/st) while no MMA on O_h is in flight.  The
 // result is mathematically the exact softmax.  d = 8 makes the kernel MUFU bound (N^2 ex2 per head,
 // 16 ex2/clk/SM; the MMAs are <10% of its time): the design goal is to keep the MUFU pipe busy, hence
-// two co-resident CTAs (256 TMEM columns, ~97 KB smem, 80 registers/thread average each) = 4 softmax
-// warps per SM sub-partition whose load/max/exp phases interleave.
+// two co-resident CTAs (256 TMEM columns, 112 KB smem, 80 registers/thread each) = 4 softmax warps per SM
+// sub-partition whose load/max/exp phases interleave, and three rotating P tiles (unit u -> tile u % 3, like the
+// S buffers) so that a softmax warpgroup does not wait for the P.V MMA of its previous unit.
 //
 // Warp roles (384 threads): warp 0 TMA producer, warp 1 TMEM allocator + S-MMA issuer, warp 2
 // P.V-MMA issuer, warp 3 idle, warps 4..7 softmax warpgroup 0 (heads 0,2), warps 8..11 softmax
@@ -35,22 +38,22 @@ using namespace ptx;
 constexpr int ATC_THREADS = 384;
 constexpr int ATC_STAGES = 3;
 constexpr int ATC_KEYS = 64;                           // keys per chunk
-constexpr int ATC_Q_BYTES = 128 * 128;                 // 128 queries x (4 heads x 16) bf16
-constexpr int ATC_K_BYTES = ATC_KEYS * 128;            // 64 keys     x (4 heads x 16) bf16
+constexpr int ATC_NS = 3;                              // S buffers (64 TMEM columns each) and P tiles
+constexpr int ATC_Q_BYTES = 128 * 128;                 // 128 queries x (4 heads x 16) bf16, zero-masked
+constexpr int ATC_K_BYTES = ATC_KEYS * 128;            // 64 keys x 8 heads x 8 dims bf16 (natural layout, this CTA uses 4 heads)
 constexpr int ATC_V_BYTES = 4 * 16 * 128;              // 4 heads x 16 rows x 64 keys
 constexpr int ATC_STAGE_BYTES = ATC_K_BYTES + ATC_V_BYTES;
 constexpr int ATC_P_BYTES = 128 * 128;                 // 128 queries x 64 keys bf16
 constexpr int ATC_OFF_STAGE = ATC_Q_BYTES;
 constexpr int ATC_OFF_P = ATC_OFF_STAGE + ATC_STAGES * ATC_STAGE_BYTES;
-constexpr int ATC_OFF_BAR = ATC_OFF_P + 2 * ATC_P_BYTES;
-constexpr int ATC_SMEM = ATC_OFF_BAR + 256 + 1024;
+constexpr int ATC_OFF_BAR = ATC_OFF_P + ATC_NS * ATC_P_BYTES;   // P tiles rotate with the S buffers (unit u -> u % 3)
+constexpr int ATC_SMEM = ATC_OFF_BAR + 256;            // the dynamic window starts 1 KB aligned (checked in the kernel)
 constexpr uint32_t ATC_TMEM_COLS = 256;                // S buffers [0,192), O_h [192+16h, +16)
-constexpr int ATC_NS = 3;                              // S buffers (64 columns each)
 constexpr uint32_t ATC_O_COL = 192;
 constexpr float ATC_LAZY = 8.0f;                       // rescale only when the max grows by more than 2^8
 static_assert(2 * (ATC_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit in shared memory");
 
-struct AttnTcMaps { CUtensorMap q; CUtensorMap k; CUtensorMap vt; };
+struct AttnTcMaps { CUtensorMap k; CUtensorMap vt; };
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -92,18 +95,18 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
 }
 
 __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, int N,
-                                                                      int C, bf16* __restrict__ out) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+                                                                      int C, const bf16* __restrict__ qkv,
+                                                                      bf16* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();             // SWIZZLE_128B tiles need 1 KB alignment
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_OFF_BAR);
     uint64_t* full_bar = bars;                   // [STAGES]
     uint64_t* empty_bar = bars + ATC_STAGES;     // [STAGES]
     uint64_t* s_full = bars + 2 * ATC_STAGES;    // [NS]
     uint64_t* s_free = s_full + ATC_NS;          // [NS]
-    uint64_t* p_full = s_free + ATC_NS;          // [2]
-    uint64_t* p_free = p_full + 2;               // [2]
-    uint64_t* q_full = p_free + 2;
+    uint64_t* p_full = s_free + ATC_NS;          // [NS] P tiles rotate like the S buffers
+    uint64_t* p_free = p_full + ATC_NS;          // [NS]
+    uint64_t* q_full = p_free + ATC_NS;          // zero-masked Q tile written by the softmax warps
     uint64_t* o_full = q_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
@@ -112,14 +115,20 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
     const int n_chunks = N / ATC_KEYS;
     const int n_units = n_chunks * 4;            // unit u = chunk*4 + head
 
+    // the softmax threads fetch their 32 bytes of the query tile first: the global latency overlaps the set-up below
+    uint4 q_pre[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+    if (warp >= 4) {
+        const int t = threadIdx.x - 128, qrow = t >> 1, hp = t & 1;
+        const uint4* src = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + q0 + qrow) * (3 * C) + hg * 32 + hp * 16);
+        q_pre[0] = __ldg(src); q_pre[1] = __ldg(src + 1);
+    }
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&maps.q);
         prefetch_tmap(&maps.k);
         prefetch_tmap(&maps.vt);
         for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < ATC_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 128); }
-        for (int g = 0; g < 2; ++g) { mbar_init(&p_full[g], 128); mbar_init(&p_free[g], 1); }
-        mbar_init(q_full, 1); mbar_init(o_full, 1);
+        for (int g = 0; g < ATC_NS; ++g) { mbar_init(&p_full[g], 128); mbar_init(&p_free[g], 1); }
+        mbar_init(q_full, 256); mbar_init(o_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<ATC_TMEM_COLS>(tmem_slot);
@@ -131,14 +140,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
     if (warp == 0) {
         if (elect_one()) {
             // ===================== TMA producer =====================
-            mbar_arrive_expect_tx(q_full, ATC_Q_BYTES);
-            tma_load_2d(smem, &maps.q, q_full, hg * 64, b * N + q0);
             int stage = 0; uint32_t phase = 0;
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 uint8_t* sk = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES;
                 mbar_arrive_expect_tx(&full_bar[stage], ATC_STAGE_BYTES);
-                tma_load_2d(sk, &maps.k, &full_bar[stage], 512 + hg * 64, b * N + c * ATC_KEYS);
+                tma_load_2d(sk, &maps.k, &full_bar[stage], C + (hg >> 1) * 64, b * N + c * ATC_KEYS);
                 tma_load_3d(sk + ATC_K_BYTES, &maps.vt, &full_bar[stage], c * ATC_KEYS, 0, b * (C / 8) + hg * 4);
                 if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
             }
@@ -156,8 +163,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 mbar_wait(&s_free[sb], (((uint32_t)(u / ATC_NS)) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES);
-                umma_bf16(tmem + sb * ATC_KEYS, make_smem_desc_sw128(q_addr) + 2 * j, make_smem_desc_sw128(k_addr) + 2 * j,
-                          idesc_s, 0u);
+                // A: zero-masked head j of the Q tile; B: the natural 16-column pair that holds head j of this CTA's 4 heads
+                umma_bf16(tmem + sb * ATC_KEYS, make_smem_desc_sw128(q_addr) + 2 * j,
+                          make_smem_desc_sw128(k_addr) + 4 * (hg & 1) + 2 * (j >> 1), idesc_s, 0u);
                 umma_commit(&s_full[sb]);
                 if (j == 3) { if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; } }
             }
@@ -167,19 +175,19 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
             // ===================== O += P V issuer =====================
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, 16);
             const uint32_t p_addr = smem_u32(smem + ATC_OFF_P);
-            int stage = 0; uint32_t phase = 0; uint32_t pfull_ph[2] = {0, 0};
+            int stage = 0; uint32_t phase = 0;
             for (int u = 0; u < n_units; ++u) {
-                const int j = u & 3, c = u >> 2, g = j & 1;
+                const int j = u & 3, c = u >> 2, pb = u % ATC_NS;
                 if (j == 0) mbar_wait(&full_bar[stage], phase);          // V of this chunk has landed
-                mbar_wait(&p_full[g], pfull_ph[g]); pfull_ph[g] ^= 1u;
+                mbar_wait(&p_full[pb], ((uint32_t)(u / ATC_NS)) & 1u);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES + ATC_K_BYTES);
-                const uint64_t dp = make_smem_desc_sw128(p_addr + g * ATC_P_BYTES);
+                const uint64_t dp = make_smem_desc_sw128(p_addr + pb * ATC_P_BYTES);
                 const uint64_t dv = make_smem_desc_sw128(v_addr + j * 2048);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     umma_bf16(tmem + ATC_O_COL + j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv, (c | kk) != 0 ? 1u : 0u);
-                umma_commit(&p_free[g]);
+                umma_commit(&p_free[pb]);
                 if (j == 3) {
                     umma_commit(&empty_bar[stage]);                      // all S and P.V reads of this stage are done
                     if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
@@ -193,10 +201,23 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
         const int quarter = warp & 3;                      // TMEM lane quarter of this warp
         const int r = quarter * 32 + lane;                 // query row
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-        uint32_t pfree_ph = 0;
         float m[2] = {0.f, 0.f};                           // running softmax reference of heads g and g+2
-        uint8_t* p_row = smem + ATC_OFF_P + g * ATC_P_BYTES + r * 128;
         const int sw = r & 7;
+        {
+            // zero-masked Q tile: thread = (query row, pair of heads); head j keeps its 8 dims in chunk 2j + (j&1) of the
+            // row (16-byte chunks, SWIZZLE_128B: physical chunk = logical ^ (row & 7)), the other chunk of the pair is 0
+            const int t = threadIdx.x - 128, qrow = t >> 1, hp = t & 1;
+            const uint4 h0 = q_pre[0], h1 = q_pre[1];                    // heads 2hp, 2hp+1 (loaded at kernel entry)
+            uint8_t* qr = smem + qrow * 128;
+            const int qs = qrow & 7;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(qr + (((4 * hp + 0) ^ qs) << 4)) = h0;    // head 2hp   -> (q | 0)
+            *reinterpret_cast<uint4*>(qr + (((4 * hp + 1) ^ qs) << 4)) = z;
+            *reinterpret_cast<uint4*>(qr + (((4 * hp + 2) ^ qs) << 4)) = z;     // head 2hp+1 -> (0 | q)
+            *reinterpret_cast<uint4*>(qr + (((4 * hp + 3) ^ qs) << 4)) = h1;
+            fence_proxy_async();
+            mbar_arrive(q_full);
+        }
         for (int c = 0; c < n_chunks; ++c) {
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
@@ -225,8 +246,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 bool moved = false;
                 if (c == 0) { m[jj] = cmax; }
                 else if (cmax > m[jj] + ATC_LAZY) { alpha = ex2_approx(m[jj] - cmax); m[jj] = cmax; moved = true; }
-                mbar_wait(&p_free[g], pfree_ph ^ 1u); pfree_ph ^= 1u;     // P.V of this group's previous unit is complete:
-                                                                          // P[g] is free and O_j has no MMA in flight
+                uint8_t* p_row = smem + ATC_OFF_P + sb * ATC_P_BYTES + r * 128;
+                // P.V of unit u-3 is complete, hence (in-order MMA pipe) so is every earlier one: P[sb] is free and
+                // O_j (last written by unit u-4) has no MMA in flight
+                mbar_wait(&p_free[sb], (((uint32_t)(u / ATC_NS)) & 1u) ^ 1u);
                 if (__any_sync(0xffffffffu, moved)) {
                     tc_fence_after();
                     uint32_t o[16];
@@ -259,7 +282,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 }
                 tc_fence_before();
                 fence_proxy_async();                                       // generic-proxy writes -> async proxy (UMMA)
-                mbar_arrive(&p_full[g]);
+                mbar_arrive(&p_full[sb]);
             }
         }
         // ---- epilogue: O_h / rowsum -> bf16 NHWC
@@ -312,18 +335,16 @@ __global__ void __launch_bounds__(256) build_vt_kernel(const bf16* __restrict__ 
 
 bool attention_tc_supported(int N, int C) { return (N % 128 == 0) && C == 256; }
 
-// qkv: [B, N, 1280] bf16 (q' | k' | v), vt scratch: [B*32, 16, N] bf16, out: [B, N, 256] bf16
+// qkv: [B, N, 768] bf16 (q | k | v, q pre-scaled), vt scratch: [B*32, 16, N] bf16, out: [B, N, 256] bf16
 void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* out, cudaStream_t s) {
     SYNT_CHECK(attention_tc_supported(N, C), "attention_tc: unsupported shape");
-    const int ldq = 5 * C;                                         // 2*2C + C = 1280
-    build_vt_kernel<<<dim3(N / 64, B), 256, 0, s>>>((const bf16*)qkv, N, C, ldq, 4 * C, (bf16*)vt_scratch);
+    const int ldq = 3 * C;
+    build_vt_kernel<<<dim3(N / 64, B), 256, 0, s>>>((const bf16*)qkv, N, C, ldq, 2 * C, (bf16*)vt_scratch);
     SYNT_LAUNCH_CHECK();
     AttnTcMaps maps;
     {
         cuuint64_t dims[2] = {(cuuint64_t)ldq, (cuuint64_t)B * N};
         cuuint64_t strides[1] = {(cuuint64_t)ldq * 2};
-        cuuint32_t box[2] = {64, 128};
-        encode_bf16_sw128(&maps.q, qkv, 2, dims, strides, box, "attention q");
         cuuint32_t boxk[2] = {64, ATC_KEYS};
         encode_bf16_sw128(&maps.k, qkv, 2, dims, strides, boxk, "attention k");
     }
@@ -338,7 +359,7 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
         SYNT_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
         attr = true;
     }
-    attention_tc_kernel<<<dim3(N / 128, C / 32, B), ATC_THREADS, ATC_SMEM, s>>>(maps, N, C, (bf16*)out);
+    attention_tc_kernel<<<dim3(N / 128, C / 32, B), ATC_THREADS, ATC_SMEM, s>>>(maps, N, C, (const bf16*)qkv, (bf16*)out);
     SYNT_LAUNCH_CHECK();
 }
 

@@ -111,8 +111,8 @@ void upsample_nearest2x(const void* in, int dt, int B, int H, int W, int C, void
 // softmax(q k^T / sqrt(8)) v over qkv NHWC-token layout [B, N, 3*C] (q | k | v), heads of 8.
 void attention_simt(const void* qkv, int dt, int B, int N, int C, void* out, cudaStream_t s);
 bool attention_tc_supported(int N, int C);
-// tcgen05 attention: qkv' [B, N, 5C] bf16 = (q' 2C | k' 2C | v C) with every head of q'/k' zero-padded to 16
-// columns and q' pre-scaled by log2(e)/sqrt(8); vt_scratch [B*C/8, 16, N] bf16 is filled by the call.
+// tcgen05 attention: qkv [B, N, 3C] bf16 = (q | k | v) with q pre-scaled by log2(e)/sqrt(8);
+// vt_scratch [B*C/8, 16, N] bf16 is filled by the call.
 void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* out, cudaStream_t s);
 
 // time embedding tables: emb[t] = Linear2(SiLU(Linear1(sincos(t)))) for t in [0,T),

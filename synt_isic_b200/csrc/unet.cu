@@ -184,7 +184,7 @@ struct ResnetW {
 struct AttnW {
     std::string name; int C;
     DevPtr g, b; WeightDev wqkv, wo; DevPtr bqkv, bo;
-    WeightDev wqkv_tc; DevPtr bqkv_tc;            // zero-interleaved (q' | k' | v) projection for attention_tc
+    WeightDev wqkv_tc; DevPtr bqkv_tc;            // (q*log2(e)/sqrt(8) | k | v) projection for attention_tc
 };
 struct ConvW { std::string name; int cin, cout; WeightDev w; DevPtr b; WeightDev w_up; };   // w_up: pack_upsample_phases
 
@@ -283,22 +283,12 @@ static AttnW make_attn(const float* P, const std::string& name, int C, bool f32,
     a.wqkv = upload_weight(wqkv, f32, b16);
     a.bqkv = dev_upload(bqkv.data(), bqkv.size() * 4);
     if (b16) {
-        // q'/k': head h -> 16 rows (8 real + 8 zero) so that one UMMA_K=16 step covers a head; the
-        // softmax scale and the exp->exp2 conversion are folded into q'
+        // attention_tc reads the plain (q | k | v) projection; the softmax scale and the exp->exp2 conversion are
+        // folded into the q rows
         const float qscale = 1.4426950408889634f / std::sqrt(8.0f);
-        std::vector<float> wp((size_t)5 * C * C, 0.f), bp(5 * C, 0.f);
-        for (int h = 0; h < C / 8; ++h)
-            for (int d = 0; d < 8; ++d) {
-                const int src = h * 8 + d, dq = h * 16 + d, dk = 2 * C + h * 16 + d;
-                for (int i = 0; i < C; ++i) {
-                    wp[(size_t)dq * C + i] = wqkv[(size_t)src * C + i] * qscale;
-                    wp[(size_t)dk * C + i] = wqkv[(size_t)(C + src) * C + i];
-                }
-                bp[dq] = bqkv[src] * qscale;
-                bp[dk] = bqkv[C + src];
-            }
-        memcpy(wp.data() + (size_t)4 * C * C, wqkv.data() + (size_t)2 * C * C, (size_t)C * C * 4);
-        memcpy(bp.data() + 4 * C, bqkv.data() + 2 * C, C * 4);
+        std::vector<float> wp(wqkv), bp(bqkv);
+        for (size_t i = 0; i < (size_t)C * C; ++i) wp[i] *= qscale;
+        for (int i = 0; i < C; ++i) bp[i] *= qscale;
         a.wqkv_tc = upload_weight(wp, false, true);
         a.bqkv_tc = dev_upload(bp.data(), bp.size() * 4);
     }
@@ -539,7 +529,7 @@ struct Fwd {
     Act attention(const AttnW& w, const Act& x) {
         const int H = x.H, W = x.W, C = w.C;
         const bool tc = u->dt == DT_BF16 && u->use_tc && attention_tc_supported(H * W, C);
-        Act qkv = make(H, W, tc ? 5 * C : 3 * C);
+        Act qkv = make(H, W, 3 * C);
         {
             ConvArgs c; c.B = B; c.H = H; c.W = W; c.Cin = C; c.KH = c.KW = 1; c.pad = 0; c.Ho = H; c.Wo = W;
             c.Cout = qkv.C; c.bias = (const float*)(tc ? w.bqkv_tc : w.bqkv)->p; c.out = qkv.p;
@@ -1048,7 +1038,7 @@ extern "C" int synt_debug_conv_up2x(const void* in, int B, int H, int W, int Cin
 }
 
 // attention core on caller-provided tensors: use_tc=0 -> qkv [B,N,3C] (q|k|v) of `act_dtype`;
-// use_tc=1 -> qkv' [B,N,5C] bf16 in the zero-interleaved layout of attention_tc (see kernels.cuh)
+// use_tc=1 -> qkv [B,N,3C] bf16 with q pre-scaled by log2(e)/sqrt(8) (see kernels.cuh)
 extern "C" int synt_debug_attention(int use_tc, int act_dtype, const void* qkv, int B, int N, int C, void* out,
                                     void* stream) {
     SYNT_TRY

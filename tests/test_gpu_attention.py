@@ -42,21 +42,19 @@ def test_attention_simt(cuda_dev, N, dt):
 
 @pytest.mark.parametrize("N,B,scale", [(256, 2, 1.0), (1024, 2, 1.0), (1024, 3, 3.0)])
 def test_attention_tcgen05(cuda_dev, N, B, scale):
-    """Inputs in the kernel's own layout: q'/k' zero-interleaved to 16 columns per head, q' pre-scaled by
-    log2(e)/sqrt(8).  scale=3 gives peaky softmax rows (logits up to ~ +-60)."""
+    """Inputs as the fused q/k/v projection writes them: (q | k | v) with q pre-scaled by log2(e)/sqrt(8).
+    scale=3 gives peaky softmax rows (logits up to ~ +-60)."""
     C = 256
     q, k, v = make_qkv(B, N, C, N + B, scale)
     qs = q * (math.log2(math.e) / math.sqrt(8))
-    qp = torch.zeros(B, N, 32, 16); kp = torch.zeros(B, N, 32, 16)
-    qp[..., :8] = qs.view(B, N, 32, 8); kp[..., :8] = k.view(B, N, 32, 8)
-    qkv = torch.cat([qp.view(B, N, 512), kp.view(B, N, 512), v], dim=2).to(torch.bfloat16).to(cuda_dev).contiguous()
+    qkv = torch.cat([qs, k, v], dim=2).to(torch.bfloat16).to(cuda_dev).contiguous()
     out = torch.empty(B, N, C, dtype=torch.bfloat16, device=cuda_dev)
     _lib.check(_lib.lib().synt_debug_attention(1, 1, qkv.data_ptr(), B, N, C, out.data_ptr(), _lib.current_stream_ptr()))
     torch.cuda.synchronize()
     # reference on the bf16-rounded operands the kernel actually saw
-    qr = qkv[..., :512].float().cpu().view(B, N, 32, 16)[..., :8].reshape(B, N, C) / (math.log2(math.e) / math.sqrt(8))
-    kr = qkv[..., 512:1024].float().cpu().view(B, N, 32, 16)[..., :8].reshape(B, N, C)
-    vr = qkv[..., 1024:].float().cpu()
+    qr = qkv[..., :C].float().cpu() / (math.log2(math.e) / math.sqrt(8))
+    kr = qkv[..., C:2 * C].float().cpu()
+    vr = qkv[..., 2 * C:].float().cpu()
     ref = reference(qr, kr, vr)
     err = ((out.float().cpu() - ref).norm() / ref.norm()).item()
     assert err < 6e-3, err            # P and the output are rounded to bf16
