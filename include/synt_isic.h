@@ -134,6 +134,10 @@ int synt_debug_conv_gn(const void* in_dev, int Cin, const void* in1_dev, int Cin
  * input): in [B,H,W,Cin] bf16 (device), w_host the raw [Cout][Cin][3][3] fp32 filter (HOST), out [B,2H,2W,Cout]. */
 int synt_debug_conv_up2x(const void* in_dev, int B, int H, int W, int Cin, const float* w_host, const float* bias_dev,
                          void* out_dev, int Cout, void* stats_out_dev, int* stats_slots, void* stream);
+/* Host-only (no GPU needed): phase-stacked filter of the fused Upsample2D + conv3x3: w [Cout][Cin][3][3] ->
+ * out [4*Cout][4*Cin], row = (py*2+px)*Cout + n, col = (ty*2+tx)*Cin + c; output pixel (2y+py, 2x+px) =
+ * sum over the 2x2 low-res window rows y+py-1+ty, columns x+px-1+tx. */
+int synt_debug_pack_upsample_phases(const float* w_host, int Cout, int Cin, float* out_host);
 /* softmax(q k^T / sqrt(8)) v on caller-provided tensors qkv [B,N,3C] (q|k|v), out [B,N,C]; use_tc=1: the tcgen05
  * kernel, bf16, q already multiplied by log2(e)/sqrt(8). */
 int synt_debug_attention(int use_tc, int act_dtype, const void* qkv_dev, int B, int N, int C, void* out_dev,

@@ -48,14 +48,23 @@ template <int BN, bool RES>
 struct V2Smem {
     static constexpr int A_SLOT = 46080;                   // max(34*10, 2*18*10) * 128, already 1 KB aligned
     static constexpr int B_TILE = BN * 128;
-    static constexpr int STAGING = 128 * BN * 2;           // one M tile of bf16 output (one per epilogue warpgroup)
-    static constexpr int NB = RES ? 12 : ((BN == 128) ? 4 : 8);
+    // BN = 256 (Cout = 256, large K): one UMMA of N = 256 per M tile -- per MMA the tensor core reads 4 KB of A and
+    // BN*32 B of B from shared memory, and that operand traffic (measured ~90 B/clk) is what paces N <= 128 tiles
+    // (98 clk per N = 128 UMMA against a 64 clk floor); N = 256 runs at its 128 clk floor.  The price: the two
+    // accumulators of a super-tile fill all 512 TMEM columns (NBUF = 1, the epilogue does not overlap the next
+    // mainloop) and the epilogue walks the tile in EC = 64-column passes so that the staging tiles stay small.
+    static constexpr int EC = BN == 256 ? 64 : BN;         // columns per epilogue pass
+    static constexpr int NPASS = BN / EC;
+    static constexpr int NBUF = BN == 256 ? 1 : 2;         // TMEM accumulator buffers (each V2_MT x BN columns)
+    static constexpr int STAGING = 128 * EC * 2;           // one pass of one M tile of bf16 output (one per epilogue warpgroup)
+    static constexpr int NB = RES ? 12 : (BN == 256 ? 3 : (BN == 128 ? 4 : 8));
     static constexpr int OFF_B = V2_A_STAGES * A_SLOT;
     static constexpr int OFF_STAGING = OFF_B + NB * B_TILE;
     static constexpr int OFF_BIAS = OFF_STAGING + V2_MT * STAGING;
     static constexpr int OFF_BAR = OFF_BIAS + V2_MT * BN * 4;
     static constexpr int TOTAL = OFF_BAR + 512 + 1024;
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+    static_assert(NBUF * V2_MT * BN <= 512, "TMEM columns");
 };
 
 struct V2Maps { CUtensorMap a[4]; CUtensorMap b; CUtensorMap out[4]; CUtensorMap res; };   // a[i]: source of segment i; out[phase]
@@ -73,6 +82,8 @@ struct V2Params {
     const float* bias; const float* bias2; int has_res; int relu;   // residual tile arrives through maps.res
     float2* stats; int stats_slots;   // optional fused GroupNorm partials [B][stats_slots][Cout]
     int chunk;                         // consecutive work items per CTA turn (divides the super-tiles per image)
+    int exp_nob;                       // EXPERIMENTS (SYNT_EXP_NOB bit mask, wrong results): 1 skip the weight-tile TMA loads after the
+                                       // first ring fill, 2 skip the input transform, 4 skip the statistics pass
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
@@ -166,14 +177,20 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                     const V2Seg sp = p.seg[sg];
                     for (int ch = 0; ch < sp.chunks; ++ch) {
                         mbar_wait(&a_empty[as], aph ^ 1u);
-                        mbar_arrive_expect_tx(&a_full[as], a_bytes);
-                        tma_load_4d(smem + as * L::A_SLOT, &maps.a[sg], &a_full[as], ch * 64, wk.x0 - 1, wk.y0 - 1, wk.n0);
+                        if ((p.exp_nob & 16) && (it > 0 || aph)) { mbar_arrive(&a_full[as]); }
+                        else {
+                            mbar_arrive_expect_tx(&a_full[as], a_bytes);
+                            tma_load_4d(smem + as * L::A_SLOT, &maps.a[sg], &a_full[as], ch * 64, wk.x0 - 1, wk.y0 - 1, wk.n0);
+                        }
                         if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
                         for (int tap = 0; tap < sp.taps && !RES; ++tap) {
                             const int kb = sp.kb_base + tap * sp.kb_stride + ch;
                             mbar_wait(&b_empty[bs], bph ^ 1u);
-                            mbar_arrive_expect_tx(&b_full[bs], L::B_TILE);
-                            tma_load_2d(smem + L::OFF_B + bs * L::B_TILE, &maps.b, &b_full[bs], kb * 64, wk.nt * BN);
+                            if ((p.exp_nob & 1) && (it > 0 || bph)) { mbar_arrive(&b_full[bs]); }
+                            else {
+                                mbar_arrive_expect_tx(&b_full[bs], L::B_TILE);
+                                tma_load_2d(smem + L::OFF_B + bs * L::B_TILE, &maps.b, &b_full[bs], kb * 64, wk.nt * BN);
+                            }
                             if (++bs == L::NB) { bs = 0; bph ^= 1u; }
                         }
                     }
@@ -223,7 +240,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                     }
                 }
                 umma_commit(&t_full[tb]);
-                if (++tb == 2) { tb = 0; tph ^= 1u; }
+                if (++tb == L::NBUF) { tb = 0; tph ^= 1u; }
             }
         }
     } else if (warp >= V2_XF_BASE / 32) {
@@ -251,7 +268,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                     };
                     if (sp.xform) load_ss(0);
                     mbar_wait(&a_full[as], aph);
-                    if (sp.xform) {
+                    if (sp.xform && !(p.exp_nob & 2)) {
                         uint8_t* slot = smem + as * L::A_SLOT;
                         auto run = [&](auto silu_tag) {
                             constexpr bool SILU = decltype(silu_tag)::value;
@@ -307,6 +324,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         // ===================== epilogue: warpgroup e (warps 4..7 / 8..11) owns M tile e of every super-tile ==========
         const int e = (warp - V2_EPI_BASE / 32) >> 2;                // warpgroup = M tile index
         const int q = warp & 3, r = q * 32 + lane;                  // accumulator row = pixel (r/8, r%8) of the 16x8 tile
+        constexpr int EC = L::EC, NPASS = L::NPASS;
         const int et = (threadIdx.x - V2_EPI_BASE) & 127;           // thread index within the warpgroup
         uint8_t* staging = smem + L::OFF_STAGING + e * L::STAGING;
         float* bias_s = reinterpret_cast<float*>(smem + L::OFF_BIAS) + e * BN;
@@ -320,13 +338,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             ty0 = wk.y0 + (p.imgs_per_super == 1 ? 16 * e : 0);
             return n_img < p.B;                                      // H, W are multiples of the tile
         };
-        auto load_residual = [&](const V2Work& wk) {               // residual tile -> staging (same swizzled layout as the output)
+        auto load_residual = [&](const V2Work& wk, int pass) {     // residual tile (one pass) -> staging, same swizzled layout
             int n_img, ty0;
             if (!tile_of(wk, n_img, ty0)) return;
             mbar_arrive_expect_tx(&r_full[e], L::STAGING);
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-                tma_load_4d(staging + j * 16384, &maps.res, &r_full[e], wk.ntr * BN + j * 64, wk.x0, ty0, n_img);
+            for (int j = 0; j < EC / 64; ++j)
+                tma_load_4d(staging + j * 16384, &maps.res, &r_full[e], wk.ntr * BN + pass * EC + j * 64, wk.x0, ty0, n_img);
         };
         int tb = 0; uint32_t tph = 0, rph = 0; int last_nt = -1;
         float acc[8];                                               // GroupNorm partials (4 columns x (sum, sumsq)) carried across tiles
@@ -334,7 +352,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
         if (p.has_res && lead_warp) {
             const int w0 = v2_item(p, 0);
-            if (w0 >= 0) { if (elect_one()) load_residual(v2_decode(p, w0)); }
+            if (w0 >= 0) { if (elect_one()) load_residual(v2_decode(p, w0), 0); }
         }
         for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
             const V2Work wk = v2_decode(p, w);
@@ -342,118 +360,132 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             const bool valid = tile_of(wk, n_img, ty0);
             if (wk.ntr != last_nt) {                                  // (bias + time-embedding row) of this N tile -> smem
                 wg_sync();
-                if (et < BN) bias_s[et] = p.bias[wk.ntr * BN + et] + (p.bias2 ? p.bias2[wk.ntr * BN + et] : 0.f);
+                for (int i = et; i < BN; i += 128) bias_s[i] = p.bias[wk.ntr * BN + i] + (p.bias2 ? p.bias2[wk.ntr * BN + i] : 0.f);
                 last_nt = wk.ntr;
             }
             mbar_wait(&t_full[tb], tph);
             tc_fence_after();
             const bool has_res = p.has_res && valid;
-            if (has_res) { mbar_wait(&r_full[e], rph); rph ^= 1u; }  // landed; also means the staging tile was free
-            wg_sync();                                               // staging free (leader waited for the previous store), bias visible
+#pragma unroll 1
+            for (int pass = 0; pass < NPASS; ++pass) {
+                const int cb = pass * EC;                            // first column of this pass within the N tile
+                if (has_res) { mbar_wait(&r_full[e], rph); rph ^= 1u; }  // landed; also means the staging tile was free
+                wg_sync();                                           // staging free (leader waited for the previous store), bias visible
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tb * V2_MT + e) * BN + c0), v);
-                tmem_ld_wait();
-                uint8_t* srow = staging + (c0 >> 6) * 16384 + r * 128;
+                for (int c0 = 0; c0 < EC; c0 += 32) {
+                    if (p.exp_nob & 32) break;
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tb * V2_MT + e) * BN + cb + c0), v);
+                    tmem_ld_wait();
+                    uint8_t* srow = staging + (c0 >> 6) * 16384 + r * 128;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float f[8];
-                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8);
-                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8 + 4);
-                    f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-                    f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-                    f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-                    f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-                    uint4* slot = reinterpret_cast<uint4*>(srow + (((((c0 & 63) >> 3) + g) ^ sw) << 4));
-                    if (has_res) {                                   // in-place: this thread's own 16 bytes of the residual tile
-                        const uint4 rv = *slot;
-                        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                    for (int g = 0; g < 4; ++g) {
+                        float f[8];
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cb + c0 + g * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cb + c0 + g * 8 + 4);
+                        f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                        f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                        f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                        f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                        uint4* slot = reinterpret_cast<uint4*>(srow + (((((c0 & 63) >> 3) + g) ^ sw) << 4));
+                        if (has_res) {                               // in-place: this thread's own 16 bytes of the residual tile
+                            const uint4 rv = *slot;
+                            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 t = __bfloat1622float2(rh[j]);
-                            f[2 * j] += t.x; f[2 * j + 1] += t.y;
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 t = __bfloat1622float2(rh[j]);
+                                f[2 * j] += t.x; f[2 * j + 1] += t.y;
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        uint4 pk;
+                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                        *slot = pk;
+                    }
+                }
+                if (pass == NPASS - 1) {
+                    tc_fence_before();
+                    mbar_arrive(&t_empty[tb]);                       // this warpgroup's accumulator tile is fully read
+                }
+                fence_proxy_async();
+                wg_sync();
+                if (lead_warp && valid && !(p.exp_nob & 8)) {
+                    if (elect_one()) {
+#pragma unroll
+                        for (int j = 0; j < EC / 64; ++j)
+                            tma_store_4d(&maps.out[wk.phase], staging + j * 16384, wk.ntr * BN + cb + j * 64, wk.x0, ty0, n_img);
+                        tma_store_commit();
+                    }
+                }
+                if (p.stats && !(p.exp_nob & 4)) {
+                    // fused GroupNorm statistics: per-channel (sum, sumsq) of the bf16 values just staged.  Warp q of the
+                    // warpgroup owns EC/4 columns; lane = (column quad cq, row part rp): 8-byte loads of 4 columns, the row
+                    // parts interleaved so that the lanes of one load phase hit distinct banks of the swizzled tile; the
+                    // partials stay in registers across the tiles of a chunk (single-pass tiles), fixed summation order.
+                    constexpr int CQW = EC / 16, RP = 32 / CQW, SUB = 16 / RP;     // EC=128: 8 quads x 4 parts x 4-row runs
+                    const int cq = lane % CQW, rp = lane / CQW;
+                    const int col0 = q * (EC / 4) + cq * 4;
+                    if (valid) {
+                        const uint8_t* sb = staging + (col0 >> 6) * 16384 + (col0 & 7) * 2;
+                        const int ck = (col0 & 63) >> 3;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                            for (int j = 0; j < SUB; ++j) {
+                                const int row = (2 * k + rp / (RP / 2)) * 8 + (rp % (RP / 2)) * SUB + j;
+                                const uint2 u = *reinterpret_cast<const uint2*>(sb + row * 128 + ((ck ^ (row & 7)) << 4));
+                                const float x0 = __uint_as_float(u.x << 16), x1 = __uint_as_float(u.x & 0xffff0000u);
+                                const float x2 = __uint_as_float(u.y << 16), x3 = __uint_as_float(u.y & 0xffff0000u);
+                                acc[0] += x0; acc[1] = fmaf(x0, x0, acc[1]); acc[2] += x1; acc[3] = fmaf(x1, x1, acc[3]);
+                                acc[4] += x2; acc[5] = fmaf(x2, x2, acc[5]); acc[6] += x3; acc[7] = fmaf(x3, x3, acc[7]);
+                            }
                         }
                     }
-                    if (p.relu) {
+                    // one partial row per tile (16x16 layers, multi-pass tiles) or per chunk (chunks never straddle an
+                    // (image, N tile)) and epilogue warpgroup
+                    const bool per_tile = p.imgs_per_super == 2 || NPASS > 1;
+                    const bool flush = per_tile ? valid : (w + 1) % p.chunk == 0;
+                    if (flush) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                            for (int o = CQW; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+                        }
+                        if (rp == 0) {
+                            const int per_img = p.tiles_x * p.supers_per_img;
+                            const int slot = p.imgs_per_super == 2 ? wk.phase * p.tiles_x + (wk.x0 >> 3)
+                                           : NPASS > 1 ? (wk.phase * per_img + w % per_img) * V2_MT + e
+                                                       : (wk.phase * (per_img / p.chunk) + (w % per_img) / p.chunk) * V2_MT + e;
+                            float4* dst = reinterpret_cast<float4*>(
+                                p.stats + ((size_t)(p.imgs_per_super == 2 ? n_img : wk.n0) * p.stats_slots + slot) * p.Cout +
+                                wk.ntr * BN + cb + col0);
+                            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
                     }
-                    uint4 pk;
-                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                    *slot = pk;
                 }
-            }
-            tc_fence_before();
-            mbar_arrive(&t_empty[tb]);                               // this warpgroup's accumulator tile is fully read
-            fence_proxy_async();
-            wg_sync();
-            if (lead_warp && valid) {
-                if (elect_one()) {
-#pragma unroll
-                    for (int j = 0; j < BN / 64; ++j)
-                        tma_store_4d(&maps.out[wk.phase], staging + j * 16384, wk.ntr * BN + j * 64, wk.x0, ty0, n_img);
-                    tma_store_commit();
-                }
-            }
-            if (p.stats) {
-                // fused GroupNorm statistics: per-channel (sum, sumsq) of the bf16 values just staged.  Warp q of the
-                // warpgroup owns BN/4 columns; lane = (column quad cq, row part rp): 8-byte loads of 4 columns, the row
-                // parts interleaved so that the lanes of one load phase hit distinct banks of the swizzled tile; the
-                // partials stay in registers across the tiles of a chunk, fixed summation order.
-                constexpr int CQW = BN / 16, RP = 32 / CQW, SUB = 16 / RP;     // BN=128: 8 quads x 4 parts x 4-row runs
-                const int cq = lane % CQW, rp = lane / CQW;
-                const int col0 = q * (BN / 4) + cq * 4;
-                if (valid) {
-                    const uint8_t* sb = staging + (col0 >> 6) * 16384 + (col0 & 7) * 2;
-                    const int ck = (col0 & 63) >> 3;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-#pragma unroll
-                        for (int j = 0; j < SUB; ++j) {
-                            const int row = (2 * k + rp / (RP / 2)) * 8 + (rp % (RP / 2)) * SUB + j;
-                            const uint2 u = *reinterpret_cast<const uint2*>(sb + row * 128 + ((ck ^ (row & 7)) << 4));
-                            const float x0 = __uint_as_float(u.x << 16), x1 = __uint_as_float(u.x & 0xffff0000u);
-                            const float x2 = __uint_as_float(u.y << 16), x3 = __uint_as_float(u.y & 0xffff0000u);
-                            acc[0] += x0; acc[1] = fmaf(x0, x0, acc[1]); acc[2] += x1; acc[3] = fmaf(x1, x1, acc[3]);
-                            acc[4] += x2; acc[5] = fmaf(x2, x2, acc[5]); acc[6] += x3; acc[7] = fmaf(x3, x3, acc[7]);
+                wg_sync();                                           // every statistics read of the staging tile is done
+                if (lead_warp) {
+                    if (elect_one()) {
+                        tma_store_wait_read();                       // ... and so is the TMA store's: the staging tile is free
+                        if (p.has_res) {
+                            if (pass + 1 < NPASS) load_residual(wk, pass + 1);
+                            else {
+                                const int wn = v2_item(p, it + 1);
+                                if (wn >= 0) load_residual(v2_decode(p, wn), 0);
+                            }
                         }
                     }
                 }
-                // 16x16 layers: one partial row per tile; otherwise one per chunk (chunks never straddle an (image, N tile))
-                const bool flush = p.imgs_per_super == 2 ? valid : (w + 1) % p.chunk == 0;
-                if (flush) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-#pragma unroll
-                        for (int o = CQW; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-                    }
-                    if (rp == 0) {
-                        const int per_img = p.tiles_x * p.supers_per_img;
-                        const int slot = p.imgs_per_super == 2 ? wk.phase * p.tiles_x + (wk.x0 >> 3)
-                                                               : (wk.phase * (per_img / p.chunk) + (w % per_img) / p.chunk) * V2_MT + e;
-                        float4* dst = reinterpret_cast<float4*>(
-                            p.stats + ((size_t)(p.imgs_per_super == 2 ? n_img : wk.n0) * p.stats_slots + slot) * p.Cout + wk.ntr * BN + col0);
-                        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-                }
             }
-            wg_sync();                                               // every statistics read of the staging tile is done
-            if (lead_warp) {
-                if (elect_one()) {
-                    tma_store_wait_read();                           // ... and so is the TMA store's: the staging tile is free
-                    if (p.has_res) {
-                        const int wn = v2_item(p, it + 1);
-                        if (wn >= 0) load_residual(v2_decode(p, wn));
-                    }
-                }
-            }
-            if (++tb == 2) { tb = 0; tph ^= 1u; }
+            if (++tb == L::NBUF) { tb = 0; tph ^= 1u; }
         }
         if (lead_warp) { if (elect_one()) tma_store_wait_all(); }
     }
@@ -472,6 +504,18 @@ bool conv_tc2_supported(const ConvArgs& a) {
     if (a.W % 8 || a.H % 16) return false;
     if (a.H % 32 != 0 && a.H != 16) return false;
     return true;
+}
+
+// N tile: 256 for the Cout = 256 3x3 convolutions at 32x32 and above (K >= 1152: the un-overlapped epilogue of the
+// single-buffered accumulators stays below ~10% of the mainloop; measured 10-18% faster than two N = 128 tiles),
+// else 128, else 64.  The 16x16 layers keep N = 128: with 128 work items on 148 SMs the longer, un-overlapped items
+// measured 30% slower.
+static int v2_bn(const ConvArgs& a) {
+    if (a.Cout % 256 == 0 && a.KH == 3 && !a.up2x && a.H >= 32 && 9 * (a.Cin + a.Cin1) >= 1152) {
+        static const char* e = getenv("SYNT_CONV_BN256");
+        if (!(e && e[0] == '0')) return 256;
+    }
+    return a.Cout % 128 == 0 ? 128 : 64;
 }
 
 static int v2_num_sms() {
@@ -497,10 +541,11 @@ static int v2_chunk(const ConvArgs& a, int BN) {
 }
 // partial rows per image in stats_out (every row is written exactly once by the kernel)
 int conv_tc2_stats_slots(const ConvArgs& a) {
-    const int BN = (a.Cout % 128 == 0) ? 128 : 64;
+    const int BN = v2_bn(a);
     const int phases = a.up2x ? 4 : 1;
     if (a.H == 16) return phases * (a.W / 8);                             // one row per tile
     const int per_img = (a.W / 8) * (a.H / 32);
+    if (BN == 256) return phases * per_img * V2_MT;                        // multi-pass tiles: one row per tile
     return phases * (per_img / v2_chunk(a, BN)) * V2_MT;                   // one row per chunk and epilogue warpgroup
 }
 
@@ -526,7 +571,7 @@ static void make_halo_map(CUtensorMap* m, const void* base, int B, int H, int W,
 void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     SYNT_CHECK(conv_tc2_supported(a), "conv_tc2: unsupported shape");
     SYNT_CHECK(a.bias != nullptr, "conv_tc2: bias required");
-    const int BN = (a.Cout % 128 == 0) ? 128 : 64;
+    const int BN = v2_bn(a);
     V2Params p{};
     p.imgs_per_super = a.H == 16 ? 2 : 1;
     p.row_off = a.H == 16 ? 18 : 16;
@@ -562,6 +607,7 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     p.bias = a.bias; p.bias2 = a.bias2; p.has_res = a.residual != nullptr; p.relu = a.relu;
     p.stats = a.stats_out; p.stats_slots = conv_tc2_stats_slots(a);
     p.chunk = v2_chunk(a, BN);
+    { static const char* e = getenv("SYNT_EXP_NOB"); p.exp_nob = e ? atoi(e) : 0; }
     V2Maps maps;
     const int bh = a.H == 16 ? 18 : 34, bn = a.H == 16 ? 2 : 1;
     for (int i = 0; i < 4; ++i) {
@@ -598,7 +644,8 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     const int grid = p.n_work < num_sms ? p.n_work : num_sms;
 
     const bool resident = BN == 64 && p.n_ntiles == 1 && !a.up2x && a.ktot() / 64 <= 12;
-    if (BN == 128)     launch_v2<128, false>(maps, p, grid, (bf16*)a.out, s);
+    if (BN == 256)     launch_v2<256, false>(maps, p, grid, (bf16*)a.out, s);
+    else if (BN == 128) launch_v2<128, false>(maps, p, grid, (bf16*)a.out, s);
     else if (resident) launch_v2<64, true>(maps, p, grid, (bf16*)a.out, s);
     else               launch_v2<64, false>(maps, p, grid, (bf16*)a.out, s);
 }

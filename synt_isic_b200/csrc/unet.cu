@@ -1037,6 +1037,16 @@ extern "C" int synt_debug_conv_up2x(const void* in, int B, int H, int W, int Cin
     SYNT_CATCH
 }
 
+// Host-only: the phase-stacked filter of the fused Upsample2D + conv3x3 (pack_upsample_phases), for CPU tests of
+// the sub-pixel decomposition.  w [Cout][Cin][3][3] -> out [4*Cout][4*Cin] (row = phase*Cout + n, col = tap*Cin + c).
+extern "C" int synt_debug_pack_upsample_phases(const float* w, int Cout, int Cin, float* out) {
+    SYNT_TRY
+    SYNT_CHECK(w && out && Cout > 0 && Cin > 0, "bad argument");
+    const std::vector<float> o = pack_upsample_phases(w, Cout, Cin);
+    memcpy(out, o.data(), o.size() * sizeof(float));
+    SYNT_CATCH
+}
+
 // attention core on caller-provided tensors: use_tc=0 -> qkv [B,N,3C] (q|k|v) of `act_dtype`;
 // use_tc=1 -> qkv [B,N,3C] bf16 with q pre-scaled by log2(e)/sqrt(8) (see kernels.cuh)
 extern "C" int synt_debug_attention(int use_tc, int act_dtype, const void* qkv, int B, int N, int C, void* out,

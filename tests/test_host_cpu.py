@@ -215,3 +215,28 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_upsample_conv_subpixel_decomposition():
+    """Upsample2D (nearest 2x) + conv3x3(pad 1) == four 2x2 convolutions on the low-res input with pre-summed taps
+    (the weight packing the fused CUDA path uses; diffusers Upsample2D reached from image_generator.py:400).
+    Host-only: the packing routine of the library against torch on the CPU."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from synt_isic_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    cin, cout, H, W = 6, 5, 7, 9
+    w = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64).float().contiguous()
+    x = torch.randn(2, cin, H, W, generator=g)
+    packed = torch.empty(4 * cout, 4 * cin)
+    _lib.check(_lib.lib().synt_debug_pack_upsample_phases(w.data_ptr(), cout, cin, packed.data_ptr()), "pack")
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, padding=1)
+    xp = F.pad(x, (1, 1, 1, 1))                                   # low-res zero padding == padding of the upsampled image
+    out = torch.zeros_like(ref)
+    for py in range(2):
+        for px in range(2):
+            wp = packed[(py * 2 + px) * cout:(py * 2 + px + 1) * cout].view(cout, 2, 2, cin).permute(0, 3, 1, 2)
+            # window rows y+py-1+ty of x == rows y+py+ty of xp
+            win = xp[:, :, py:py + H + 1, px:px + W + 1]
+            out[:, :, py::2, px::2] = F.conv2d(win, wp.contiguous())
+    assert torch.allclose(out, ref, atol=1e-5, rtol=1e-5), (out - ref).abs().max()
