@@ -83,7 +83,8 @@ struct V2Params {
     float2* stats; int stats_slots;   // optional fused GroupNorm partials [B][stats_slots][Cout]
     int chunk;                         // consecutive work items per CTA turn (divides the super-tiles per image)
     int exp_nob;                       // EXPERIMENTS (SYNT_EXP_NOB bit mask, wrong results): 1 skip the weight-tile TMA loads after the
-                                       // first ring fill, 2 skip the input transform, 4 skip the statistics pass
+                                       // first ring fill, 2 skip the input transform, 4 skip the statistics pass, 8 TMA stores, 16 A-tile loads, 32 epilogue
+                                       // body, 64 no producer/transform at all and no operand waits in the MMA issuer (pure MMA issue rate)
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
@@ -164,14 +165,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         if (elect_one()) {
             // ===================== TMA producer =====================
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
-            if (RES) {                                                // whole weight matrix, once (n_ntiles == 1)
+            if (RES && !(p.exp_nob & 64)) {                           // whole weight matrix, once (n_ntiles == 1)
                 int nkb = 0;
                 for (int sg = 0; sg < p.n_seg; ++sg) nkb += p.seg[sg].chunks * p.seg[sg].taps;
                 mbar_arrive_expect_tx(&b_full[0], nkb * L::B_TILE);
                 for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d(smem + L::OFF_B + kb * L::B_TILE, &maps.b, &b_full[0], kb * 64, 0);
             }
-            for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
+            for (int it = 0, w; (w = v2_item(p, it)) >= 0 && !(p.exp_nob & 64); ++it) {
                 const V2Work wk = v2_decode(p, w);
                 for (int sg = 0; sg < p.n_seg; ++sg) {
                     const V2Seg sp = p.seg[sg];
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             // ===================== MMA issuer =====================
             constexpr uint32_t idesc = make_idesc_bf16(128, BN);
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int tb = 0; uint32_t tph = 0;
-            if (RES) mbar_wait(&b_full[0], 0);
+            if (RES && !(p.exp_nob & 64)) mbar_wait(&b_full[0], 0);
             for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
                 const V2Work wk = v2_decode(p, w);
                 mbar_wait(&t_empty[tb], tph ^ 1u);                    // epilogue drained this accumulator pair
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 for (int sg = 0; sg < p.n_seg; ++sg) {
                     const V2Seg sp = p.seg[sg];
                     for (int ch = 0; ch < sp.chunks; ++ch) {
-                        mbar_wait(&a_ready[as], aph);                 // landed AND transformed
+                        if (!(p.exp_nob & 64)) mbar_wait(&a_ready[as], aph);   // landed AND transformed
                         tc_fence_after();
                         const uint32_t a_base = smem_u32(smem + as * L::A_SLOT);
                         for (int tap = 0; tap < sp.taps; ++tap) {
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                             const int dy = sp.taps == 9 ? tap / 3 : (sp.taps == 4 ? (wk.phase >> 1) + (tap >> 1) : 1);
                             const int dx = sp.taps == 9 ? tap % 3 : (sp.taps == 4 ? (wk.phase & 1) + (tap & 1) : 1);
                             if (RES) bs = sp.kb_base + tap * sp.kb_stride + ch;
-                            else { mbar_wait(&b_full[bs], bph); tc_fence_after(); }
+                            else if (!(p.exp_nob & 64)) { mbar_wait(&b_full[bs], bph); tc_fence_after(); }
                             const uint64_t db = make_smem_desc_sw128(smem_u32(smem + L::OFF_B + bs * L::B_TILE));
 #pragma unroll
                             for (int mt = 0; mt < V2_MT; ++mt) {
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         const int hy0 = r0 / 10, hx0 = r0 - hy0 * 10;                    // halo coordinates of the first row (10 pixels per halo row)
         constexpr int RSTEP = V2_XF_THREADS / 8;                         // rows advance by 32 = 3 halo rows + 2 pixels
         int as = 0; uint32_t aph = 0;
-        for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
+        for (int it = 0, w; (w = v2_item(p, it)) >= 0 && !(p.exp_nob & 64); ++it) {
             const V2Work wk = v2_decode(p, w);
             for (int sg = 0; sg < p.n_seg; ++sg) {
                 const V2Seg sp = p.seg[sg];
