@@ -134,6 +134,8 @@ int synt_debug_conv_gn(const void* in_dev, int Cin, const void* in1_dev, int Cin
  * input): in [B,H,W,Cin] bf16 (device), w_host the raw [Cout][Cin][3][3] fp32 filter (HOST), out [B,2H,2W,Cout]. */
 int synt_debug_conv_up2x(const void* in_dev, int B, int H, int W, int Cin, const float* w_host, const float* bias_dev,
                          void* out_dev, int Cout, void* stats_out_dev, int* stats_slots, void* stream);
+/* Experimental: run the N = 128 conv_tc2 launches as CTA pairs (tcgen05 cta_group::2, M = 256 per MMA); off by default. */
+int synt_debug_set_conv_pair(int on);
 /* Host-only (no GPU needed): phase-stacked filter of the fused Upsample2D + conv3x3: w [Cout][Cin][3][3] ->
  * out [4*Cout][4*Cin], row = (py*2+px)*Cout + n, col = (ty*2+tx)*Cin + c; output pixel (2y+py, 2x+px) =
  * sum over the 2x2 low-res window rows y+py-1+ty, columns x+px-1+tx. */

@@ -128,10 +128,23 @@ __device__ __forceinline__ int v2_item(const V2Params& p, int i) {
     return w < p.n_work ? w : -1;
 }
 
-template <int BN, bool RES>
+// PAIR: the two CTAs of a cluster (one TPC) work on two consecutive super-tiles of the same N tile and share every
+// weight tile: each loads HALF of it (BN/2 rows) and the leader issues `tcgen05.mma.cta_group::2` (M = 256) for both,
+// so per MMA an SM fetches 4 KB of A and only BN*16 B of B from shared memory.  The peer's MMA warp is a relay: it
+// forwards "my A tile is transformed / my half of B has landed / my epilogue drained the accumulators" to the leader
+// with remote mbarrier arrives; the leader's commits are multicast to both CTAs' empty / full barriers.
+template <int BN, bool RES, bool PAIR = false>
 __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ V2Maps maps,
                                                                  const __grid_constant__ V2Params p, bf16* __restrict__ out) {
     using L = V2Smem<BN, RES>;
+    static_assert(!PAIR || (!RES && L::NBUF == 2), "pair mode: streamed weights, double-buffered accumulators");
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    // iteration i of this CTA -> work item (or -1 when exhausted); pair mode: cluster c takes pair-items c, c + #clusters, ...
+    auto v2_item = [&](const V2Params& pp, int i) -> int {
+        if (!PAIR) return synt::v2_item(pp, i);
+        const int w = 2 * (i * ((int)gridDim.x >> 1) + ((int)blockIdx.x >> 1)) + (int)rank;
+        return w < pp.n_work ? w : -1;
+    };
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -144,7 +157,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     uint64_t* t_full = b_empty + L::NB;             // [2]
     uint64_t* t_empty = t_full + 2;                 // [2]
     uint64_t* r_full = t_empty + 2;                 // [2] residual tile of epilogue warpgroup e has landed in its staging
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 2);
+    uint64_t* pa_ready = r_full + 2;                // [2]  pair mode, leader: the peer's a_ready / b_full / t_empty, relayed
+    uint64_t* pb_full = pa_ready + V2_A_STAGES;     // [NB]
+    uint64_t* pt_empty = pb_full + L::NB;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pt_empty + 2);
+    static_assert((3 * V2_A_STAGES + 3 * L::NB + 8) * 8 + 4 <= 512, "barrier region");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = p.imgs_per_super == 1 ? 34 * 10 * 128 : 2 * 18 * 10 * 128;
 
@@ -153,11 +170,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         for (int s = 0; s < V2_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_ready[s], V2_XF_THREADS); }
         for (int s = 0; s < L::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 256); mbar_init(&r_full[s], 1); }
+        for (int s = 0; s < V2_A_STAGES; ++s) mbar_init(&pa_ready[s], 1);
+        for (int s = 0; s < L::NB; ++s) mbar_init(&pb_full[s], 1);
+        for (int s = 0; s < 2; ++s) mbar_init(&pt_empty[s], 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();      // pair: both CTAs' barriers exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
@@ -188,7 +208,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                             const int kb = sp.kb_base + tap * sp.kb_stride + ch;
                             mbar_wait(&b_empty[bs], bph ^ 1u);
                             if ((p.exp_nob & 1) && (it > 0 || bph)) { mbar_arrive(&b_full[bs]); }
-                            else {
+                            else if (PAIR) {                             // this CTA's half of the weight tile (maps.b box: BN/2 rows)
+                                mbar_arrive_expect_tx(&b_full[bs], L::B_TILE / 2);
+                                tma_load_2d(smem + L::OFF_B + bs * L::B_TILE, &maps.b, &b_full[bs], kb * 64,
+                                            wk.nt * BN + (int)rank * (BN / 2));
+                            } else {
                                 mbar_arrive_expect_tx(&b_full[bs], L::B_TILE);
                                 tma_load_2d(smem + L::OFF_B + bs * L::B_TILE, &maps.b, &b_full[bs], kb * 64, wk.nt * BN);
                             }
@@ -199,20 +223,49 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {
+        if (PAIR && rank == 1) {
+            if (elect_one()) {
+                // ===================== relay (peer CTA of a pair): forward local readiness to the leader =====================
+                int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int tb = 0; uint32_t tph = 0;
+                for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
+                    mbar_wait(&t_empty[tb], tph ^ 1u);
+                    mbar_arrive_remote(&pt_empty[tb], 0);
+                    for (int sg = 0; sg < p.n_seg && !(p.exp_nob & 64); ++sg) {
+                        const V2Seg sp = p.seg[sg];
+                        for (int ch = 0; ch < sp.chunks; ++ch) {
+                            mbar_wait(&a_ready[as], aph);
+                            mbar_arrive_remote(&pa_ready[as], 0);
+                            for (int tap = 0; tap < sp.taps; ++tap) {
+                                mbar_wait(&b_full[bs], bph);
+                                mbar_arrive_remote(&pb_full[bs], 0);
+                                if (++bs == L::NB) { bs = 0; bph ^= 1u; }
+                            }
+                            if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
+                        }
+                    }
+                    if (++tb == L::NBUF) { tb = 0; tph ^= 1u; }
+                }
+            }
+        } else if (elect_one()) {
             // ===================== MMA issuer =====================
-            constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+            constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN);
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+                if (PAIR) umma_bf16_pair(d, da, db, idesc, acc); else umma_bf16(d, da, db, idesc, acc);
+            };
+            auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int tb = 0; uint32_t tph = 0;
             if (RES && !(p.exp_nob & 64)) mbar_wait(&b_full[0], 0);
             for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
                 const V2Work wk = v2_decode(p, w);
                 mbar_wait(&t_empty[tb], tph ^ 1u);                    // epilogue drained this accumulator pair
+                if (PAIR) mbar_wait_cluster(&pt_empty[tb], tph);      // ... and so did the peer's
                 tc_fence_after();
                 uint32_t first = 1;
                 for (int sg = 0; sg < p.n_seg; ++sg) {
                     const V2Seg sp = p.seg[sg];
                     for (int ch = 0; ch < sp.chunks; ++ch) {
                         if (!(p.exp_nob & 64)) mbar_wait(&a_ready[as], aph);   // landed AND transformed
+                        if (PAIR && !(p.exp_nob & 64)) mbar_wait_cluster(&pa_ready[as], aph);
                         tc_fence_after();
                         const uint32_t a_base = smem_u32(smem + as * L::A_SLOT);
                         for (int tap = 0; tap < sp.taps; ++tap) {
@@ -221,26 +274,34 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                             const int dy = sp.taps == 9 ? tap / 3 : (sp.taps == 4 ? (wk.phase >> 1) + (tap >> 1) : 1);
                             const int dx = sp.taps == 9 ? tap % 3 : (sp.taps == 4 ? (wk.phase & 1) + (tap & 1) : 1);
                             if (RES) bs = sp.kb_base + tap * sp.kb_stride + ch;
-                            else if (!(p.exp_nob & 64)) { mbar_wait(&b_full[bs], bph); tc_fence_after(); }
+                            else if (!(p.exp_nob & 64)) {
+                                mbar_wait(&b_full[bs], bph);
+                                if (PAIR) mbar_wait_cluster(&pb_full[bs], bph);   // (skipped with the b_full wait under mask 64)
+                                tc_fence_after();
+                            }
                             const uint64_t db = make_smem_desc_sw128(smem_u32(smem + L::OFF_B + bs * L::B_TILE));
+                            // the K steps of the two M tiles alternate, so that consecutive MMAs accumulate into different TMEM tiles
+                            uint64_t da[V2_MT];
 #pragma unroll
-                            for (int mt = 0; mt < V2_MT; ++mt) {
-                                const uint64_t da = make_smem_desc_sw128(a_base + ((mt * p.row_off + dy) * 10 + dx) * 128, 1280);
+                            for (int mt = 0; mt < V2_MT; ++mt)
+                                da[mt] = make_smem_desc_sw128(a_base + ((mt * p.row_off + dy) * 10 + dx) * 128, 1280);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_bf16(tmem + (tb * V2_MT + mt) * BN, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+                            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                                for (int mt = 0; mt < V2_MT; ++mt)
+                                    mma(tmem + (tb * V2_MT + mt) * BN, da[mt] + 2 * k, db + 2 * k, (first && k == 0) ? 0u : 1u);
                             }
                             first = 0;
                             if (!RES) {
-                                umma_commit(&b_empty[bs]);
+                                commit(&b_empty[bs]);
                                 if (++bs == L::NB) { bs = 0; bph ^= 1u; }
                             }
                         }
-                        umma_commit(&a_empty[as]);
+                        commit(&a_empty[as]);
                         if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
                     }
                 }
-                umma_commit(&t_full[tb]);
+                commit(&t_full[tb]);
                 if (++tb == L::NBUF) { tb = 0; tph ^= 1u; }
             }
         }
@@ -449,7 +510,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                     }
                     // one partial row per tile (16x16 layers, multi-pass tiles) or per chunk (chunks never straddle an
                     // (image, N tile)) and epilogue warpgroup
-                    const bool per_tile = p.imgs_per_super == 2 || NPASS > 1;
+                    const bool per_tile = p.imgs_per_super == 2 || NPASS > 1 || PAIR;
                     const bool flush = per_tile ? valid : (w + 1) % p.chunk == 0;
                     if (flush) {
 #pragma unroll
@@ -460,7 +521,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         if (rp == 0) {
                             const int per_img = p.tiles_x * p.supers_per_img;
                             const int slot = p.imgs_per_super == 2 ? wk.phase * p.tiles_x + (wk.x0 >> 3)
-                                           : NPASS > 1 ? (wk.phase * per_img + w % per_img) * V2_MT + e
+                                           : (NPASS > 1 || PAIR) ? (wk.phase * per_img + w % per_img) * V2_MT + e
                                                        : (wk.phase * (per_img / p.chunk) + (w % per_img) / p.chunk) * V2_MT + e;
                             float4* dst = reinterpret_cast<float4*>(
                                 p.stats + ((size_t)(p.imgs_per_super == 2 ? n_img : wk.n0) * p.stats_slots + slot) * p.Cout +
@@ -491,8 +552,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         if (lead_warp) { if (elect_one()) tma_store_wait_all(); }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc<512>(tmem);
+    if (PAIR) cluster_sync_all(); else __syncthreads();      // pair: neither CTA may leave while the other's MMAs read its smem
+    if (warp == 1) { if (PAIR) tmem_dealloc_pair<512>(tmem); else tmem_dealloc<512>(tmem); }
     (void)out;
 }
 
@@ -517,6 +578,21 @@ static int v2_bn(const ConvArgs& a) {
         if (!(e && e[0] == '0')) return 256;
     }
     return a.Cout % 128 == 0 ? 128 : 64;
+}
+
+// CTA-pair mode (cta_group::2): N = 128 tiles with streamed weights and an even number of super-tiles per image
+// Off by default: functionally complete (tests run it), but measured SLOWER than the single-CTA kernel (conv total 5.4 ->
+// 6.3 ms/step): the pure MMA rate only improves from 87 to 81 clk per N = 128 K-step (the per-instruction cost is
+// N/2 + ~21 clk, not operand bandwidth) while the relayed barriers lengthen every hand-shake.  SYNT_CONV_PAIR=1 or
+// synt_debug_set_conv_pair(1) switches it on.
+static int g_conv_pair = -1;
+void conv_tc2_set_pair(int on) { g_conv_pair = on; }
+static bool v2_pair(const ConvArgs& a) {
+    if (g_conv_pair < 0) { const char* e = getenv("SYNT_CONV_PAIR"); g_conv_pair = (e && e[0] == '1') ? 1 : 0; }
+    if (!g_conv_pair) return false;
+    if (v2_bn(a) != 128) return false;
+    const int per_img = a.H == 16 ? a.W / 8 : (a.W / 8) * (a.H / 32);
+    return per_img % 2 == 0;
 }
 
 static int v2_num_sms() {
@@ -546,8 +622,26 @@ int conv_tc2_stats_slots(const ConvArgs& a) {
     const int phases = a.up2x ? 4 : 1;
     if (a.H == 16) return phases * (a.W / 8);                             // one row per tile
     const int per_img = (a.W / 8) * (a.H / 32);
-    if (BN == 256) return phases * per_img * V2_MT;                        // multi-pass tiles: one row per tile
+    if (BN == 256 || v2_pair(a)) return phases * per_img * V2_MT;          // multi-pass tiles / pair mode: one row per tile
     return phases * (per_img / v2_chunk(a, BN)) * V2_MT;                   // one row per chunk and epilogue warpgroup
+}
+
+// cluster (2,1,1) launch of the CTA-pair variant
+static void launch_v2_pair(const V2Maps& maps, const V2Params& p, int grid, bf16* out, cudaStream_t s) {
+    using L = V2Smem<128, false>;
+    auto kern = conv_tc2_kernel<128, false, true>;
+    static bool attr = false;
+    if (!attr) {
+        SYNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SYNT_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p, out));
 }
 
 template <int BN, bool RES>
@@ -573,6 +667,7 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     SYNT_CHECK(conv_tc2_supported(a), "conv_tc2: unsupported shape");
     SYNT_CHECK(a.bias != nullptr, "conv_tc2: bias required");
     const int BN = v2_bn(a);
+    const bool pair = v2_pair(a);
     V2Params p{};
     p.imgs_per_super = a.H == 16 ? 2 : 1;
     p.row_off = a.H == 16 ? 18 : 16;
@@ -619,7 +714,7 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
         const int kt = a.up2x ? 4 * a.Cin : a.ktot();
         cuuint64_t dims[2] = {(cuuint64_t)kt, (cuuint64_t)a.Cout * phases};
         cuuint64_t strides[1] = {(cuuint64_t)kt * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)BN};
+        cuuint32_t box[2] = {64, (cuuint32_t)(pair ? BN / 2 : BN)};       // pair mode: each CTA loads half of the N tile
         encode_bf16_sw128(&maps.b, a.weight, 2, dims, strides, box, "v2 weight");
     }
     for (int ph = 0; ph < 4; ++ph) {
@@ -643,6 +738,11 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     }
     const int num_sms = v2_num_sms();
     const int grid = p.n_work < num_sms ? p.n_work : num_sms;
+    if (pair) {
+        const int clusters = (num_sms / 2 < p.n_work / 2) ? num_sms / 2 : p.n_work / 2;
+        launch_v2_pair(maps, p, 2 * clusters, (bf16*)a.out, s);
+        return;
+    }
 
     const bool resident = BN == 64 && p.n_ntiles == 1 && !a.up2x && a.ktot() / 64 <= 12;
     if (BN == 256)     launch_v2<256, false>(maps, p, grid, (bf16*)a.out, s);

@@ -50,6 +50,7 @@ void conv_tc(const ConvArgs& a, cudaStream_t s);
 bool conv_tc2_supported(const ConvArgs& a);
 void conv_tc2(const ConvArgs& a, cudaStream_t s);
 int conv_tc2_stats_slots(const ConvArgs& a);     // partial rows per image written when stats_out != null
+void conv_tc2_set_pair(int on);                  // experimental CTA-pair (cta_group::2) variant of the N = 128 kernel
 // experimental: 3x3 stride-1 conv with one halo-tile load per channel chunk (see conv_tc_halo.cu)
 void conv_tc_halo(const ConvArgs& a, int variant, cudaStream_t s);
 

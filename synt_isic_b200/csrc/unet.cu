@@ -1037,6 +1037,9 @@ extern "C" int synt_debug_conv_up2x(const void* in, int B, int H, int W, int Cin
     SYNT_CATCH
 }
 
+// Switches the experimental CTA-pair (tcgen05 cta_group::2, cluster of two CTAs) variant of conv_tc2 on or off.
+extern "C" int synt_debug_set_conv_pair(int on) { conv_tc2_set_pair(on ? 1 : 0); return 0; }
+
 // Host-only: the phase-stacked filter of the fused Upsample2D + conv3x3 (pack_upsample_phases), for CPU tests of
 // the sub-pixel decomposition.  w [Cout][Cin][3][3] -> out [4*Cout][4*Cin] (row = phase*Cout + n, col = tap*Cin + c).
 extern "C" int synt_debug_pack_upsample_phases(const float* w, int Cout, int Cin, float* out) {

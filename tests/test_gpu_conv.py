@@ -223,3 +223,19 @@ def test_conv_tcgen05_fused_upsample(cuda_dev, case):
     want_s = got.sum(dim=(2, 3)); want_q = (got * got).sum(dim=(2, 3))
     assert torch.allclose(st[..., 0], want_s, rtol=2e-3, atol=5e-2)
     assert torch.allclose(st[..., 1], want_q, rtol=2e-3, atol=5e-2)
+
+
+PAIR_CASES = [c for c in V2_CASES if c[4] % 128 == 0 and not (c[4] % 256 == 0 and c[1] >= 32 and c[5] == 3 and c[3] >= 128)]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=lambda c: "x".join(map(str, c[:8])))
+def test_conv_tcgen05_cta_pair(cuda_dev, case):
+    """Experimental CTA-pair variant of conv_tc2 (cluster of two CTAs, tcgen05.mma.cta_group::2 with M = 256, each CTA
+    loads half of every weight tile, multicast commits, relayed barriers): same results as the single-CTA kernel."""
+    B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2 = case
+    _lib.check(_lib.lib().synt_debug_set_conv_pair(1), "set_conv_pair")
+    try:
+        rel, mx = run_conv(cuda_dev, 6, B, H, W, Cin, Cout, K, s, p, sc, scs, res, relu, b2)
+    finally:
+        _lib.check(_lib.lib().synt_debug_set_conv_pair(0), "set_conv_pair")
+    assert rel < 4e-3, (rel, mx)
