@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
     const int n_chunks = N / ATC_KEYS;
     const int n_units = n_chunks * 4;            // unit u = chunk*4 + head
 
+    pdl_launch_dependents();
+    pdl_wait();                                              // qkv / vt come from the previous kernels
     // the softmax threads fetch their 32 bytes of the query tile first: the global latency overlaps the set-up below
     uint4 q_pre[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
     if (warp >= 4) {
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
 __global__ void __launch_bounds__(256) build_vt_kernel(const bf16* __restrict__ qkv, int N, int C, int ldq, int voff,
                                                        bf16* __restrict__ vt) {
     __shared__ bf16 tile[64][256 + 8];
+    pdl_enter();
     const int b = blockIdx.y, t0 = blockIdx.x * 64;
     const int H = C / 8;
     for (int i = threadIdx.x; i < 64 * (C / 8); i += 256) {
@@ -339,8 +342,7 @@ bool attention_tc_supported(int N, int C) { return (N % 128 == 0) && C == 256; }
 void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* out, cudaStream_t s) {
     SYNT_CHECK(attention_tc_supported(N, C), "attention_tc: unsupported shape");
     const int ldq = 3 * C;
-    build_vt_kernel<<<dim3(N / 64, B), 256, 0, s>>>((const bf16*)qkv, N, C, ldq, 2 * C, (bf16*)vt_scratch);
-    SYNT_LAUNCH_CHECK();
+    launch_pdl(build_vt_kernel, dim3(N / 64, B), dim3(256), 0, s, (const bf16*)qkv, N, C, ldq, 2 * C, (bf16*)vt_scratch);
     AttnTcMaps maps;
     {
         cuuint64_t dims[2] = {(cuuint64_t)ldq, (cuuint64_t)B * N};
@@ -359,8 +361,8 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
         SYNT_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
         attr = true;
     }
-    attention_tc_kernel<<<dim3(N / 128, C / 32, B), ATC_THREADS, ATC_SMEM, s>>>(maps, N, C, (const bf16*)qkv, (bf16*)out);
-    SYNT_LAUNCH_CHECK();
+    launch_pdl(attention_tc_kernel, dim3(N / 128, C / 32, B), dim3(ATC_THREADS), ATC_SMEM, s, maps, N, C, (const bf16*)qkv,
+               (bf16*)out);
 }
 
 }  // namespace synt

@@ -84,4 +84,28 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------
+// The ~140 kernels of one sampling step form a chain.  Launched with the programmatic-stream-serialization attribute,
+// kernel k+1 may be scheduled as soon as every CTA of kernel k has executed `griddepcontrol.launch_dependents` (first
+// statement of every kernel here): its CTAs take the SMs that kernel k's tail frees, run their prologue (barrier
+// init, TMEM allocation, descriptor prefetch) and block in `griddepcontrol.wait` until kernel k has completed and its
+// writes are visible.  Rule for every kernel launched through launch_pdl: no global-memory access before pdl_wait(),
+// and every CTA executes pdl_wait() (so "k+1 complete" implies "k complete" along the chain).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
+
+bool pdl_enabled();                                  // SYNT_PDL=1 switches the attribute on (default: plain stream order, which measured faster)
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SYNT_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+}
+
 }  // namespace synt

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int n0 = tn * p.TN, y0 = (trem / p.tiles_x) * p.TH, x0 = (trem % p.tiles_x) * p.TW;
     const int nt0 = blockIdx.y * BN;
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a[0]);
         prefetch_tmap(&maps.b);
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
+    pdl_wait();                                              // prologue done; the inputs come from the previous kernel
 
     if (warp == 0) {
         if (elect_one()) {
@@ -258,7 +260,7 @@ static void launch_tc(const ConvTcMaps& maps, const ConvTcParams& p, dim3 grid, 
         SYNT_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr = true;
     }
-    conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, L::TOTAL, s>>>(maps, p);
+    launch_pdl(conv_tc_kernel<BN, STAGES>, grid, dim3(TC_THREADS), L::TOTAL, s, maps, p);
     SYNT_LAUNCH_CHECK();
 }
 

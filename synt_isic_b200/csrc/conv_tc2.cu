@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = p.imgs_per_super == 1 ? 34 * 10 * 128 : 2 * 18 * 10 * 128;
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.b); prefetch_tmap(&maps.out[0]);
         for (int s = 0; s < V2_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_ready[s], V2_XF_THREADS); }
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     if (PAIR) cluster_sync_all(); else __syncthreads();      // pair: both CTAs' barriers exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                                              // prologue done; every input comes from earlier kernels of the chain
 
     if (warp == 0) {
         if (elect_one()) {
@@ -652,8 +654,7 @@ static void launch_v2(const V2Maps& maps, const V2Params& p, int grid, bf16* out
         SYNT_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr = true;
     }
-    conv_tc2_kernel<BN, RES><<<grid, V2_THREADS, L::TOTAL, s>>>(maps, p, out);
-    SYNT_LAUNCH_CHECK();
+    launch_pdl(conv_tc2_kernel<BN, RES, false>, dim3(grid), dim3(V2_THREADS), L::TOTAL, s, maps, p, out);
 }
 
 static void make_halo_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_h, int box_n) {
