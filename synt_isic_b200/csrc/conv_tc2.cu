@@ -565,10 +565,13 @@ bool conv_tc2_supported(const ConvArgs& a) {
     const bool k1 = a.KH == 1 && a.KW == 1 && a.pad == 0 && a.sc0_C == 0 && a.sc1_C == 0 && a.Cin1 == 0;   // centre-tap-only conv
     if (!(k3 || k1) || a.stride != 1 || a.sc_stride != 1) return false;
     if (a.Cin % 64 || a.Cin1 % 64 || a.sc0_C % 64 || a.sc1_C % 64 || a.Cout % 64) return false;
-    if (a.W % 8 || a.H % 16) return false;
-    if (a.H % 32 != 0 && a.H != 16) return false;
-    return true;
+    if (a.W % 8 == 0 && (a.H % 32 == 0 || a.H == 16)) return true;
+    // ragged planes (ResNet18: 56x56, 28x28): the tile grid is rounded up, TMA zero-fills the loads and clips the stores
+    // beyond the plane.  Not with fused statistics / transformed input / upsampling (out-of-plane pixels would count).
+    return a.H > 16 && a.W >= 8 && a.stats_out == nullptr && a.gn_mode == 0 && !a.up2x;
 }
+static inline int v2_tiles_x(const ConvArgs& a) { return (a.W + 7) / 8; }
+static inline int v2_supers(const ConvArgs& a) { return a.H == 16 ? 1 : (a.H + 31) / 32; }
 
 // N tile: 256 for the Cout = 256 3x3 convolutions at 32x32 and above (K >= 1152: the un-overlapped epilogue of the
 // single-buffered accumulators stays below ~10% of the mainloop; measured 10-18% faster than two N = 128 tiles),
@@ -593,7 +596,7 @@ static bool v2_pair(const ConvArgs& a) {
     if (g_conv_pair < 0) { const char* e = getenv("SYNT_CONV_PAIR"); g_conv_pair = (e && e[0] == '1') ? 1 : 0; }
     if (!g_conv_pair) return false;
     if (v2_bn(a) != 128) return false;
-    const int per_img = a.H == 16 ? a.W / 8 : (a.W / 8) * (a.H / 32);
+    const int per_img = v2_tiles_x(a) * v2_supers(a);
     return per_img % 2 == 0;
 }
 
@@ -606,7 +609,7 @@ static int v2_num_sms() {
 // makespan ceil(chunks / grid) * R; ties go to the larger R (fewer GroupNorm partial rows)
 static int v2_chunk(const ConvArgs& a, int BN) {
     if (a.H == 16) return 1;
-    const int per_img = (a.W / 8) * (a.H / 32);
+    const int per_img = v2_tiles_x(a) * v2_supers(a);
     const long long n_work = (long long)a.B * per_img * (a.Cout / BN) * (a.up2x ? 4 : 1);
     const long long grid = n_work < v2_num_sms() ? n_work : v2_num_sms();
     int best = 1; long long best_span = -1;
@@ -623,7 +626,7 @@ int conv_tc2_stats_slots(const ConvArgs& a) {
     const int BN = v2_bn(a);
     const int phases = a.up2x ? 4 : 1;
     if (a.H == 16) return phases * (a.W / 8);                             // one row per tile
-    const int per_img = (a.W / 8) * (a.H / 32);
+    const int per_img = v2_tiles_x(a) * v2_supers(a);
     if (BN == 256 || v2_pair(a)) return phases * per_img * V2_MT;          // multi-pass tiles / pair mode: one row per tile
     return phases * (per_img / v2_chunk(a, BN)) * V2_MT;                   // one row per chunk and epilogue warpgroup
 }
@@ -672,8 +675,8 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     V2Params p{};
     p.imgs_per_super = a.H == 16 ? 2 : 1;
     p.row_off = a.H == 16 ? 18 : 16;
-    p.tiles_x = a.W / 8;
-    p.supers_per_img = a.H == 16 ? 1 : a.H / 32;
+    p.tiles_x = v2_tiles_x(a);
+    p.supers_per_img = v2_supers(a);
     const int phases = a.up2x ? 4 : 1;
     p.nt_real = a.Cout / BN;
     p.n_ntiles = p.nt_real * phases;

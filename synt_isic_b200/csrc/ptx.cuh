@@ -52,9 +52,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > SYNT_MBAR_TIMEOUT_CYCLES) __trap();
+    // try_wait itself suspends the thread for a hardware time slice; the clock is only consulted every 256 retries so
+    // that waiting warps spend few issue slots next to the working ones
+    long long t0 = 0;
+    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
+        if ((spins & 255u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > SYNT_MBAR_TIMEOUT_CYCLES) __trap();
+        }
     }
 }
 
@@ -156,9 +162,13 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait_cluster(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(bar, parity)) {
-        if (clock64() - t0 > SYNT_MBAR_TIMEOUT_CYCLES) __trap();
+    long long t0 = 0;
+    for (uint32_t spins = 1; !mbar_try_wait_cluster(bar, parity); ++spins) {
+        if ((spins & 255u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > SYNT_MBAR_TIMEOUT_CYCLES) __trap();
+        }
     }
 }
 template <uint32_t kCols>

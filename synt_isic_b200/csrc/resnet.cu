@@ -96,6 +96,102 @@ void stem_im2col(const void* pre, int B, void* out, cudaStream_t s) {
     SYNT_LAUNCH_CHECK();
 }
 
+// ---- fused stem: conv 7x7 / stride 2 / pad 3 (3 -> 64, BN folded) + ReLU on the legacy tensor-core path, no im2col tensor.
+// One CTA = 16x16 output pixels of one image.  The 38x38x3 input patch is staged in shared memory with the pixels of a row
+// contiguous (pitch 120 bf16): for k = ky*24 + kx*3 + c the A operand of output pixel (oy, ox) is the contiguous run
+// patch[2*oy + ky][6*ox + (kx*3 + c)], so every mma.sync A register is one aligned 32-bit shared-memory load (the 3 slots
+// per ky beyond the 21 real ones read the neighbouring pixel against zero weights).  K = 168 -> 11 steps of 16; the weights
+// arrive pre-arranged as per-lane B fragments [11][8 n-tiles][32 lanes].  Each warp owns two output rows (two m16 tiles).
+constexpr int ST_TILE = 16, ST_ROWS = 2 * ST_TILE + 6, ST_PITCH = 120, ST_STEPS = 11;
+constexpr int ST_PATCH_BYTES = ST_ROWS * ST_PITCH * 2;                   // 9120
+constexpr int ST_FRAG_BYTES = ST_STEPS * 8 * 32 * 8;                     // 22528
+constexpr int ST_OUT_PITCH = 144;                                        // bytes per staged output pixel (64 bf16 + pad)
+constexpr int ST_SMEM = ST_PATCH_BYTES + ST_FRAG_BYTES + ST_TILE * ST_TILE * ST_OUT_PITCH;
+
+__global__ void __launch_bounds__(256) stem_mma_kernel(const bf16* __restrict__ pre, const uint2* __restrict__ bfrag,
+                                                       const float* __restrict__ bias, bf16* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t st_smem[];
+    unsigned short* patch = reinterpret_cast<unsigned short*>(st_smem);
+    uint2* frag_s = reinterpret_cast<uint2*>(st_smem + ST_PATCH_BYTES);
+    uint8_t* stage = st_smem + ST_PATCH_BYTES + ST_FRAG_BYTES;
+    const int b = blockIdx.z, oy0 = blockIdx.y * ST_TILE, ox0 = blockIdx.x * ST_TILE;
+    for (int i = threadIdx.x; i < ST_STEPS * 8 * 32; i += 256) frag_s[i] = __ldg(bfrag + i);
+    {
+        const unsigned short* src = reinterpret_cast<const unsigned short*>(pre) + (size_t)b * 224 * 224 * 3;
+        const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+        for (int i = threadIdx.x; i < ST_ROWS * ST_PITCH; i += 256) {
+            const int r = i / ST_PITCH, e = i - r * ST_PITCH;            // e = pixel*3 + channel within the patch row
+            const int iy = iy0 + r, ix = ix0 + e / 3;
+            patch[i] = (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) ? __ldg(src + ((size_t)iy * 224 + ix) * 3 + e % 3) : (unsigned short)0;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float acc[2][8][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float b0 = __ldg(bias + nt * 8 + t * 2), b1 = __ldg(bias + nt * 8 + t * 2 + 1);
+            acc[m][nt][0] = b0; acc[m][nt][1] = b1; acc[m][nt][2] = b0; acc[m][nt][3] = b1;
+        }
+#pragma unroll
+    for (int s = 0; s < ST_STEPS; ++s) {
+        // k = 16 s + 2t (+8): window row ky and slot kk within it are compile-time per half of the step
+        constexpr int dummy = 0; (void)dummy;
+        const int k_lo = 16 * s, k_hi = 16 * s + 8;
+        const int off_lo = (k_lo / 24) * ST_PITCH + (k_lo % 24) + 2 * t;
+        const int off_hi = (k_hi / 24) * ST_PITCH + (k_hi % 24) + 2 * t;
+        uint32_t a[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const unsigned short* row = patch + (2 * (warp * 2 + m)) * ST_PITCH;    // output row warp*2 + m
+            a[m][0] = *reinterpret_cast<const uint32_t*>(row + 6 * g + off_lo);
+            a[m][1] = *reinterpret_cast<const uint32_t*>(row + 6 * (g + 8) + off_lo);
+            a[m][2] = *reinterpret_cast<const uint32_t*>(row + 6 * g + off_hi);
+            a[m][3] = *reinterpret_cast<const uint32_t*>(row + 6 * (g + 8) + off_hi);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const uint2 bf = frag_s[(s * 8 + nt) * 32 + lane];
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                             : "+f"(acc[m][nt][0]), "+f"(acc[m][nt][1]), "+f"(acc[m][nt][2]), "+f"(acc[m][nt][3])
+                             : "r"(a[m][0]), "r"(a[m][1]), "r"(a[m][2]), "r"(a[m][3]), "r"(bf.x), "r"(bf.y));
+        }
+    }
+    // ReLU -> bf16 -> staged tile [pixel][64] (pitch 144 B: conflict-free 4-byte writes and 16-byte reads)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int p0 = (warp * 2 + m) * ST_TILE + g;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(acc[m][nt][0], 0.f), fmaxf(acc[m][nt][1], 0.f));
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(acc[m][nt][2], 0.f), fmaxf(acc[m][nt][3], 0.f));
+            *reinterpret_cast<__nv_bfloat162*>(stage + p0 * ST_OUT_PITCH + nt * 16 + t * 4) = lo;
+            *reinterpret_cast<__nv_bfloat162*>(stage + (p0 + 8) * ST_OUT_PITCH + nt * 16 + t * 4) = hi;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ST_TILE * ST_TILE * 8; i += 256) {
+        const int px = i >> 3, ch = i & 7;
+        const int oy = oy0 + px / ST_TILE, ox = ox0 + px % ST_TILE;
+        if (oy < 112 && ox < 112)
+            *reinterpret_cast<uint4*>(out + (((size_t)b * 112 + oy) * 112 + ox) * 64 + ch * 8) =
+                *reinterpret_cast<const uint4*>(stage + px * ST_OUT_PITCH + ch * 16);
+    }
+}
+void stem_mma(const void* pre, int B, const void* bfrag, const float* bias, void* out, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        SYNT_CUDA(cudaFuncSetAttribute(stem_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        attr = true;
+    }
+    stem_mma_kernel<<<dim3(112 / ST_TILE, 112 / ST_TILE, B), 256, ST_SMEM, s>>>((const bf16*)pre, (const uint2*)bfrag, bias, (bf16*)out);
+    SYNT_LAUNCH_CHECK();
+}
+
 template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ in, int H, int W, int C, int Ho, int Wo, long long nvec_total,
                                T* __restrict__ out) {
@@ -324,8 +420,10 @@ using namespace synt;
 
 struct synt_resnet18 {
     int dt = DT_BF16, num_classes = 7; bool use_tc = true;
+    bool use_v2 = true;                      // conv_tc2 where its shape rules allow (SYNT_RESNET_V2=0: conv_tc everywhere)
     RConv stem;                              // 7x7 s2 on the fp32-FMA kernel (fp32 mode)
     RConv stem_tc;                           // the same stem as a 1x1 conv over the im2col'd input (K 147 -> 192), bf16 tcgen05
+    RPtr stem_frag;                          // stem weights as mma.sync B fragments (fused stem kernel, default in bf16 mode)
     RConv c1[4][2], c2[4][2];
     RPtr fc_w, fc_b;
     Pool pool;
@@ -336,6 +434,7 @@ struct synt_resnet18 {
 namespace synt {
 
 void stem_im2col(const void* pre, int B, void* out, cudaStream_t s);
+void stem_mma(const void* pre, int B, const void* bfrag, const float* bias, void* out, cudaStream_t s);
 
 struct RFwd {
     synt_resnet18* r; cudaStream_t s; int B;
@@ -353,7 +452,11 @@ struct RFwd {
         a.pad = c.k / 2; a.Ho = Ho; a.Wo = Wo; a.Cout = c.cout;
         if (c.csc) { a.sc0 = sc; a.sc0_C = c.csc; a.sc_stride = sc_stride; }
         a.weight = c.w->p; a.bias = (const float*)c.b->p; a.residual = residual; a.relu = relu; a.out = out;
-        if (c.bf) conv_tc(a, s); else conv_simt(a, r->dt, s);
+        // stride-1 3x3 convs on the 56x56 / 28x28 planes: the persistent halo-tile kernel (ragged tile grid); the rest
+        // (stride 2, strided 1x1 shortcut segments, 14x14 and 7x7 planes): one TMA box per tap
+        if (c.bf && r->use_v2 && conv_tc2_supported(a)) conv_tc2(a, s);
+        else if (c.bf) conv_tc(a, s);
+        else conv_simt(a, r->dt, s);
         ++r->launches;
     }
     void run(const float* x_nchw, float* logits) {
@@ -361,7 +464,10 @@ struct RFwd {
         classifier_preprocess(x_nchw, B, 128, 128, 224, 224, pre, 3, r->dt, s);
         tap("preprocess", pre, 224, 224, 3);
         void* c1 = make(112, 112, 64);
-        if (r->use_tc) {
+        if (r->use_tc && r->stem_frag) {                     // fused 7x7/s2 stem on mma.sync, no im2col tensor
+            stem_mma(pre, B, r->stem_frag->p, (const float*)r->stem_tc.b->p, c1, s);
+            ++r->launches;
+        } else if (r->use_tc) {
             void* col = make(112, 112, 192);
             stem_im2col(pre, B, col, s);
             ++r->launches;
@@ -434,6 +540,7 @@ int synt_resnet18_create(const float* P, long long n_params, int num_classes, in
     const char* force = getenv("SYNT_FORCE_SIMT");
     r->use_tc = dtype == DT_BF16 && !(force && force[0] == '1');
     const bool bf = r->use_tc;
+    { const char* v2 = getenv("SYNT_RESNET_V2"); r->use_v2 = !(v2 && v2[0] == '0'); }
     r->stem = make_rconv(P, m, "conv1", "bn1", 3, 64, 7, 2, "", "", 0, false);
     if (bf) {                                               // [64][3][7][7] -> K-major [64][ky*24 + kx*3 + c], zero-padded to 192, bf16
         std::vector<float> sc, sh;
@@ -448,6 +555,20 @@ int synt_resnet18_create(const float* P, long long n_params, int num_classes, in
         r->stem_tc.cin = 192; r->stem_tc.cout = 64; r->stem_tc.k = 1; r->stem_tc.stride = 1; r->stem_tc.bf = true;
         r->stem_tc.w = r_upload(pk.data(), pk.size() * 2);
         r->stem_tc.b = r_upload(sh.data(), sh.size() * 4);
+        const char* sm = getenv("SYNT_STEM_IM2COL");
+        if (!(sm && sm[0] == '1')) {                         // per-lane mma.sync B fragments [11 k-steps][8 n-tiles][32 lanes]
+            std::vector<uint32_t> fr((size_t)11 * 8 * 32 * 2);
+            auto wv = [&](int k, int n) -> uint32_t { return pk[(size_t)n * 192 + k]; };
+            for (int st = 0; st < 11; ++st)
+                for (int nt = 0; nt < 8; ++nt)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, t = lane & 3, k0 = st * 16 + t * 2, n = nt * 8 + g;
+                        uint32_t* o = fr.data() + ((size_t)(st * 8 + nt) * 32 + lane) * 2;
+                        o[0] = wv(k0, n) | (wv(k0 + 1, n) << 16);
+                        o[1] = wv(k0 + 8, n) | (wv(k0 + 9, n) << 16);
+                    }
+            r->stem_frag = r_upload(fr.data(), fr.size() * 4);
+        }
     }
     int cin = 64;
     for (int l = 0; l < 4; ++l) {

@@ -109,6 +109,9 @@ V2_CASES = [c for c in CASES if c[5] in (1, 3) and c[6] == 1 and c[1] % 16 == 0 
     (3, 16, 16, 512, 256, 3, 1, 1, (256, 256), 1, False, False, True),     # up_blocks.0: concat shortcut, odd B, 2 images/super-tile
     (5, 64, 64, 192, 128, 3, 1, 1, (128, 64), 1, False, False, True),      # up_blocks.2.resnets.2 conv2-like
     (2, 128, 128, 128, 64, 3, 1, 1, (0, 0), 1, True, False, False),        # persistent: 256 super-tiles on 148 CTAs
+    (3, 56, 56, 64, 64, 3, 1, 1, (0, 0), 1, True, True, False),            # ResNet18 layer1: ragged 56x56 plane (tile grid rounded up)
+    (3, 28, 28, 128, 128, 3, 1, 1, (0, 0), 1, True, True, False),          # ResNet18 layer2: ragged 28x28 plane
+    (2, 40, 24, 64, 128, 3, 1, 1, (64, 0), 1, False, False, True),         # ragged in both directions + shortcut segment
 ]
 
 
