@@ -21,31 +21,42 @@ namespace synt {
 extern thread_local std::string g_last_error;
 
 // =============================================================== kernels ============
+// classifier preprocess of one output pixel (xai/XAI.py:399-431): clamp((x+1)/2, 0, 1) -> bilinear Hin x Win -> Hout x Wout
+// (align_corners=False; antialias is a no-op when upsampling) -> ImageNet normalise.  One definition, used by the
+// stand-alone kernel and by the fused stem, so both produce bit-identical values.
+__device__ __forceinline__ void preprocess_pixel(const float* __restrict__ img /* [3][Hin][Win] */, int Hin, int Win, float sy, float sx,
+                                                 int oy, int ox, float (&v3)[3]) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    float fy = ((float)oy + 0.5f) * sy - 0.5f; if (fy < 0.f) fy = 0.f;
+    float fx = ((float)ox + 0.5f) * sx - 0.5f; if (fx < 0.f) fx = 0.f;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* pl = img + (long long)c * Hin * Win;
+        auto px = [&](int yy, int xx) {
+            float v = (pl[yy * Win + xx] + 1.0f) / 2.0f;
+            return fminf(fmaxf(v, 0.f), 1.f);
+        };
+        const float top = px(y0, x0) * (1.f - lx) + px(y0, x1) * lx;
+        const float bot = px(y1, x0) * (1.f - lx) + px(y1, x1) * lx;
+        const float v = top * (1.f - ly) + bot * ly;
+        v3[c] = (v - mean[c]) / stdv[c];
+    }
+}
+
 template <typename T>
 __global__ void preprocess_kernel(const float* __restrict__ x, int Hin, int Win, int Hout, int Wout, long long npix,
                                   T* __restrict__ out) {
-    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
     const float sy = (float)Hin / (float)Hout, sx = (float)Win / (float)Wout;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
         const int ox = (int)(i % Wout), oy = (int)((i / Wout) % Hout);
         const long long b = i / ((long long)Wout * Hout);
-        float fy = ((float)oy + 0.5f) * sy - 0.5f; if (fy < 0.f) fy = 0.f;
-        float fx = ((float)ox + 0.5f) * sx - 0.5f; if (fx < 0.f) fx = 0.f;
-        const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
-        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        float v3[3];
+        preprocess_pixel(x + b * 3 * (long long)Hin * Win, Hin, Win, sy, sx, oy, ox, v3);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* pl = x + (b * 3 + c) * (long long)Hin * Win;
-            auto px = [&](int yy, int xx) {
-                float v = (pl[yy * Win + xx] + 1.0f) / 2.0f;
-                return fminf(fmaxf(v, 0.f), 1.f);
-            };
-            const float top = px(y0, x0) * (1.f - lx) + px(y0, x1) * lx;
-            const float bot = px(y1, x0) * (1.f - lx) + px(y1, x1) * lx;
-            const float v = top * (1.f - ly) + bot * ly;
-            out[i * 3 + c] = from_f<T>((v - mean[c]) / stdv[c]);
-        }
+        for (int c = 0; c < 3; ++c) out[i * 3 + c] = from_f<T>(v3[c]);
     }
 }
 void classifier_preprocess(const float* x, int B, int Hin, int Win, int Hout, int Wout, void* out, int Cpad, int dt,
@@ -189,6 +200,127 @@ void stem_mma(const void* pre, int B, const void* bfrag, const float* bias, void
         attr = true;
     }
     stem_mma_kernel<<<dim3(112 / ST_TILE, 112 / ST_TILE, B), 256, ST_SMEM, s>>>((const bf16*)pre, (const uint2*)bfrag, bias, (bf16*)out);
+    SYNT_LAUNCH_CHECK();
+}
+
+// ---- fused classifier front-end (bf16 mode): preprocess -> conv 7x7/s2 (+BN, ReLU) -> maxpool 3x3/s2, one kernel.
+// One CTA = 8x8 pooled pixels of one image = 17x17 conv pixels (one row/column of overlap with the neighbours) = a 40x40x3
+// patch of the 224x224 preprocessed image, which is SAMPLED ON THE FLY from the 128x128 source (preprocess_pixel) into
+// shared memory; the conv tile (ReLU'd, bf16) stays in shared memory and is pooled there: neither the 224x224 image nor the
+// 112x112x64 conv output ever exists in HBM.  Out-of-plane conv pixels are written as 0, which equals the -inf padding of
+// the max-pool because every window holds at least one in-plane value and all values are >= 0 after the ReLU.
+// 320 threads = 10 warps x 2 m16 tiles = 320 row slots for the 289 conv pixels (row slot -> pixel is a free mapping because
+// the A operand is fetched with per-thread 32-bit loads, see stem_mma_kernel).
+constexpr int SF_POOL = 8, SF_CONV = 2 * SF_POOL + 1, SF_NPIX = SF_CONV * SF_CONV;          // 8, 17, 289
+constexpr int SF_ROWS = 2 * SF_CONV + 6, SF_PITCH = 126;                                     // 40 patch rows (39 + the k-padding row)
+constexpr int SF_PATCH_BYTES = SF_ROWS * SF_PITCH * 2;                                       // 10080
+constexpr int SF_SMEM = SF_PATCH_BYTES + SF_NPIX * ST_OUT_PITCH;                             // + 41616
+
+__global__ void __launch_bounds__(320, 2) stem_fused_kernel(const float* __restrict__ x /* [B,3,128,128] */, const uint2* __restrict__ bfrag,
+                                                         const float* __restrict__ bias, bf16* __restrict__ out /* [B,56,56,64] */) {
+    extern __shared__ __align__(16) uint8_t sf_smem[];
+    unsigned short* patch = reinterpret_cast<unsigned short*>(sf_smem);
+    uint8_t* tile = sf_smem + SF_PATCH_BYTES;
+    const int b = blockIdx.z, py0 = blockIdx.y * SF_POOL, px0 = blockIdx.x * SF_POOL;
+    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;                       // conv-plane origin of the tile
+    {
+        const float* img = x + (size_t)b * 3 * 128 * 128;
+        const float sc = 128.0f / 224.0f;
+        const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;                  // preprocessed-image origin of the patch
+        constexpr int PW = SF_PITCH / 3;                                 // 42 pixel slots per patch row
+        for (int i = threadIdx.x; i < SF_ROWS * PW; i += 320) {
+            const int r = i / PW, c = i - r * PW;
+            const int iy = iy0 + r, ix = ix0 + c;
+            float v3[3] = {0.f, 0.f, 0.f};
+            if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) preprocess_pixel(img, 128, 128, sc, sc, iy, ix, v3);
+            unsigned short* dst = patch + r * SF_PITCH + c * 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) dst[ch] = __bfloat16_as_ushort(__float2bfloat16_rn(v3[ch]));
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    // row slots of this thread: pixels p = (warp*2 + m)*16 + g (+8); slots >= 289 compute pixel 0 and are discarded
+    int pbase[2][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int p = (warp * 2 + m) * 16 + g + 8 * h;
+            if (p >= SF_NPIX) p = 0;
+            pbase[m][h] = (2 * (p / SF_CONV)) * SF_PITCH + 6 * (p % SF_CONV);
+        }
+    float acc[2][8][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float b0 = __ldg(bias + nt * 8 + t * 2), b1 = __ldg(bias + nt * 8 + t * 2 + 1);
+            acc[m][nt][0] = b0; acc[m][nt][1] = b1; acc[m][nt][2] = b0; acc[m][nt][3] = b1;
+        }
+#pragma unroll
+    for (int s = 0; s < ST_STEPS; ++s) {
+        const int k_lo = 16 * s, k_hi = 16 * s + 8;
+        const int off_lo = (k_lo / 24) * SF_PITCH + (k_lo % 24) + 2 * t;
+        const int off_hi = (k_hi / 24) * SF_PITCH + (k_hi % 24) + 2 * t;
+        uint32_t a[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            a[m][0] = *reinterpret_cast<const uint32_t*>(patch + pbase[m][0] + off_lo);
+            a[m][1] = *reinterpret_cast<const uint32_t*>(patch + pbase[m][1] + off_lo);
+            a[m][2] = *reinterpret_cast<const uint32_t*>(patch + pbase[m][0] + off_hi);
+            a[m][3] = *reinterpret_cast<const uint32_t*>(patch + pbase[m][1] + off_hi);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const uint2 bf = __ldg(bfrag + (s * 8 + nt) * 32 + lane);    // 22.5 KB table, L1-resident
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                             : "+f"(acc[m][nt][0]), "+f"(acc[m][nt][1]), "+f"(acc[m][nt][2]), "+f"(acc[m][nt][3])
+                             : "r"(a[m][0]), "r"(a[m][1]), "r"(a[m][2]), "r"(a[m][3]), "r"(bf.x), "r"(bf.y));
+        }
+    }
+    // ReLU -> bf16 -> conv tile in shared memory; pixels outside the 112x112 conv plane become 0
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int p = (warp * 2 + m) * 16 + g + 8 * h;
+            if (p >= SF_NPIX) continue;
+            const int cy = cy0 + p / SF_CONV, cx = cx0 + p % SF_CONV;
+            const bool in = cy >= 0 && cy < 112 && cx >= 0 && cx < 112;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float v0 = in ? fmaxf(acc[m][nt][2 * h], 0.f) : 0.f, v1 = in ? fmaxf(acc[m][nt][2 * h + 1], 0.f) : 0.f;
+                *reinterpret_cast<__nv_bfloat162*>(tile + p * ST_OUT_PITCH + nt * 16 + t * 4) = __floats2bfloat162_rn(v0, v1);
+            }
+        }
+    __syncthreads();
+    // maxpool 3x3 / stride 2 / pad 1 over the tile: pooled (py, px) <- conv tile rows 2py..2py+2, cols 2px..2px+2 (tile coords)
+    for (int i = threadIdx.x; i < SF_POOL * SF_POOL * 8; i += 320) {
+        const int pp = i >> 3, ch = i & 7, py = pp / SF_POOL, px = pp % SF_POOL;
+        if (py0 + py >= 56 || px0 + px >= 56) continue;
+        __nv_bfloat162 mx[4];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const uint4 v = *reinterpret_cast<const uint4*>(tile + ((2 * py + dy) * SF_CONV + 2 * px + dx) * ST_OUT_PITCH + ch * 16);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mx[j] = (dy == 0 && dx == 0) ? h2[j] : __hmax2(mx[j], h2[j]);
+            }
+        *reinterpret_cast<uint4*>(out + (((size_t)b * 56 + py0 + py) * 56 + px0 + px) * 64 + ch * 8) = *reinterpret_cast<const uint4*>(mx);
+    }
+}
+void stem_fused(const float* x_nchw, int B, const void* bfrag, const float* bias, void* out, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        SYNT_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+        attr = true;
+    }
+    stem_fused_kernel<<<dim3(56 / SF_POOL, 56 / SF_POOL, B), 320, SF_SMEM, s>>>(x_nchw, (const uint2*)bfrag, bias, (bf16*)out);
     SYNT_LAUNCH_CHECK();
 }
 
@@ -421,6 +553,7 @@ using namespace synt;
 struct synt_resnet18 {
     int dt = DT_BF16, num_classes = 7; bool use_tc = true;
     bool use_v2 = true;                      // conv_tc2 where its shape rules allow (SYNT_RESNET_V2=0: conv_tc everywhere)
+    bool fuse_front = true;                  // preprocess + stem + maxpool in one kernel (SYNT_RESNET_FUSE_FRONT=0: three kernels)
     RConv stem;                              // 7x7 s2 on the fp32-FMA kernel (fp32 mode)
     RConv stem_tc;                           // the same stem as a 1x1 conv over the im2col'd input (K 147 -> 192), bf16 tcgen05
     RPtr stem_frag;                          // stem weights as mma.sync B fragments (fused stem kernel, default in bf16 mode)
@@ -435,6 +568,7 @@ namespace synt {
 
 void stem_im2col(const void* pre, int B, void* out, cudaStream_t s);
 void stem_mma(const void* pre, int B, const void* bfrag, const float* bias, void* out, cudaStream_t s);
+void stem_fused(const float* x_nchw, int B, const void* bfrag, const float* bias, void* out, cudaStream_t s);
 
 struct RFwd {
     synt_resnet18* r; cudaStream_t s; int B;
@@ -460,29 +594,37 @@ struct RFwd {
         ++r->launches;
     }
     void run(const float* x_nchw, float* logits) {
-        void* pre = make(224, 224, 3);
-        classifier_preprocess(x_nchw, B, 128, 128, 224, 224, pre, 3, r->dt, s);
-        tap("preprocess", pre, 224, 224, 3);
-        void* c1 = make(112, 112, 64);
-        if (r->use_tc && r->stem_frag) {                     // fused 7x7/s2 stem on mma.sync, no im2col tensor
-            stem_mma(pre, B, r->stem_frag->p, (const float*)r->stem_tc.b->p, c1, s);
+        void* cur = nullptr;
+        if (r->use_tc && r->stem_frag && r->fuse_front && !r->tap_out) {
+            // preprocess + stem + maxpool in one kernel (the debug taps "preprocess" / "relu" / "maxpool" use the unfused path)
+            cur = make(56, 56, 64);
+            stem_fused(x_nchw, B, r->stem_frag->p, (const float*)r->stem_tc.b->p, cur, s);
             ++r->launches;
-        } else if (r->use_tc) {
-            void* col = make(112, 112, 192);
-            stem_im2col(pre, B, col, s);
-            ++r->launches;
-            conv(r->stem_tc, col, 112, 112, nullptr, 1, nullptr, 1, c1, 112, 112);
-            r->pool.release(col);
         } else {
-            conv(r->stem, pre, 224, 224, nullptr, 1, nullptr, 1, c1, 112, 112);
+            void* pre = make(224, 224, 3);
+            classifier_preprocess(x_nchw, B, 128, 128, 224, 224, pre, 3, r->dt, s);
+            tap("preprocess", pre, 224, 224, 3);
+            void* c1 = make(112, 112, 64);
+            if (r->use_tc && r->stem_frag) {                     // fused 7x7/s2 stem on mma.sync, no im2col tensor
+                stem_mma(pre, B, r->stem_frag->p, (const float*)r->stem_tc.b->p, c1, s);
+                ++r->launches;
+            } else if (r->use_tc) {
+                void* col = make(112, 112, 192);
+                stem_im2col(pre, B, col, s);
+                ++r->launches;
+                conv(r->stem_tc, col, 112, 112, nullptr, 1, nullptr, 1, c1, 112, 112);
+                r->pool.release(col);
+            } else {
+                conv(r->stem, pre, 224, 224, nullptr, 1, nullptr, 1, c1, 112, 112);
+            }
+            r->pool.release(pre);
+            tap("relu", c1, 112, 112, 64);
+            cur = make(56, 56, 64);
+            maxpool3x3s2(c1, r->dt, B, 112, 112, 64, cur, s);
+            r->pool.release(c1);
+            tap("maxpool", cur, 56, 56, 64);
+            r->launches += 2;
         }
-        r->pool.release(pre);
-        tap("relu", c1, 112, 112, 64);
-        void* cur = make(56, 56, 64);
-        maxpool3x3s2(c1, r->dt, B, 112, 112, 64, cur, s);
-        r->pool.release(c1);
-        tap("maxpool", cur, 56, 56, 64);
-        r->launches += 2;
         int H = 56;
         for (int l = 0; l < 4; ++l) {
             const int c = kStageCh[l];
@@ -541,6 +683,7 @@ int synt_resnet18_create(const float* P, long long n_params, int num_classes, in
     r->use_tc = dtype == DT_BF16 && !(force && force[0] == '1');
     const bool bf = r->use_tc;
     { const char* v2 = getenv("SYNT_RESNET_V2"); r->use_v2 = !(v2 && v2[0] == '0'); }
+    { const char* ff = getenv("SYNT_RESNET_FUSE_FRONT"); r->fuse_front = !(ff && ff[0] == '0'); }
     r->stem = make_rconv(P, m, "conv1", "bn1", 3, 64, 7, 2, "", "", 0, false);
     if (bf) {                                               // [64][3][7][7] -> K-major [64][ky*24 + kx*3 + c], zero-padded to 192, bf16
         std::vector<float> sc, sh;

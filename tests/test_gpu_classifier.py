@@ -170,3 +170,25 @@ def test_integrated_analyzer_runs(cuda_dev, frames):
     assert any(k.startswith("t_5/top_k/blur") for k in res["cfi"])
     import json
     json.dumps(res)
+
+
+def test_fused_front_end_is_bit_identical_to_the_three_kernels(oc, cuda_dev, frames, monkeypatch):
+    """bf16 mode: preprocess + 7x7/s2 stem + maxpool in ONE kernel (default) against the unfused chain
+    (SYNT_RESNET_FUSE_FRONT=0) and against the im2col + tcgen05 stem (SYNT_STEM_IM2COL=1): same arithmetic per output
+    element, hence identical logits for the first two and bf16-level agreement with the third
+    (classifier of xai/XAI.py:357-471)."""
+    def build(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c = MelanomaClassifierAdaptive(num_classes=7, pretrained=False, precision="bf16")
+        c.model.load_state_dict(oc.model.state_dict())
+        c = c.to(cuda_dev).eval()
+        y = c(frames.to(cuda_dev)).cpu()                      # creates the native handle under this environment
+        for k in env:
+            monkeypatch.delenv(k)
+        return y
+    fused = build({})
+    chain = build({"SYNT_RESNET_FUSE_FRONT": "0"})
+    im2col = build({"SYNT_RESNET_FUSE_FRONT": "0", "SYNT_STEM_IM2COL": "1"})
+    assert torch.equal(fused, chain)
+    assert rel(im2col, fused) < 5e-3
