@@ -284,7 +284,7 @@ def run_ours(args):
                      "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
                      "peak_source": peaks["source"] + ", sustained bf16", "traffic": traffic, "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
                      "traffic_source": traffic_src,
-                     "algorithmic": "2*M*N*K of the reference's convolutions (67.02 GFLOP/image/step), summed over the conv launches of "
+                     "algorithmic": "2*M*N*K of the reference's convolutions incl. the 1x1 attention projections (69.7 GFLOP/image/step), summed over the conv launches of "
                                     "one step / their summed CUDA-event durations; the fused Upsample2D convs execute 4/9 of their share",
                      "launches_per_step": conv["launches"], "flops_per_step": conv["flops"], "ms_per_step": conv["ms"],
                      "whole_step_tflops": B * GFLOP_PER_IMAGE_STEP * 1e9 / sec_step / 1e12,
