@@ -371,38 +371,60 @@ __global__ void __launch_bounds__(128) conv_in3_kernel(const float* __restrict__
 // stride of 65 floats so that the 32 pixel groups of a warp hit 32 different banks.
 constexpr int CI_ROWS = 8, CI_COLS = 32, CI_STRIDE = 65;
 
-__global__ void __launch_bounds__(256) conv_in3_tiled_kernel(const float* __restrict__ x, const __grid_constant__ ConvInW w,
+__global__ void __launch_bounds__(256, 2) conv_in3_tiled_kernel(const float* __restrict__ x, const __grid_constant__ ConvInW w,
                                                              int H, int W, bf16* __restrict__ out, float2* __restrict__ stats,
                                                              int stats_slots) {
     pdl_enter();
     __shared__ __align__(16) float w_s[27][64];
     __shared__ float in_s[3][CI_ROWS + 2][CI_STRIDE];
+    __shared__ __align__(16) float b_s[64];
     __shared__ float2 red_s[2][64];
     const int b = blockIdx.y, y0 = blockIdx.x * CI_ROWS;
     for (int i = threadIdx.x; i < 27 * 64; i += 256) w_s[i / 64][i % 64] = w.w[i / 64][i % 64];
+    if (threadIdx.x < 64) b_s[threadIdx.x] = w.b[threadIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cq = warp & 3, row = (warp >> 2) * 4 + (lane >> 3), xg = lane & 7;
-    float bias[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) bias[j] = w.b[cq * 16 + j];
     float s1[16], s2[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
     const float* xb = x + (size_t)b * 3 * H * W;
-    for (int x0 = 0; x0 < W; x0 += CI_COLS) {
-        __syncthreads();                                             // previous tile fully consumed (and w_s visible)
-        for (int i = threadIdx.x; i < 3 * (CI_ROWS + 2) * (CI_COLS + 2); i += 256) {
+    // input halo of one tile: 3 x 10 x 34 floats = 1020 elements, 4 per thread; the NEXT tile's elements are fetched into
+    // registers before the FMAs of the current tile and stored to shared memory after them (global latency hidden)
+    constexpr int NEL = 3 * (CI_ROWS + 2) * (CI_COLS + 2), PER = (NEL + 255) / 256;
+    float nxt[PER];
+    auto fetch = [&](int x0) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = threadIdx.x + u * 256;
             const int c = i / ((CI_ROWS + 2) * (CI_COLS + 2)), rem = i % ((CI_ROWS + 2) * (CI_COLS + 2));
             const int hy = rem / (CI_COLS + 2), hx = rem % (CI_COLS + 2);
             const int iy = y0 + hy - 1, ix = x0 + hx - 1;
-            in_s[c][hy][hx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + ((size_t)c * H + iy) * W + ix) : 0.f;
+            nxt[u] = (i < NEL && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + ((size_t)c * H + iy) * W + ix) : 0.f;
         }
+    };
+    auto commit = [&]() {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = threadIdx.x + u * 256;
+            if (i < NEL) {
+                const int c = i / ((CI_ROWS + 2) * (CI_COLS + 2)), rem = i % ((CI_ROWS + 2) * (CI_COLS + 2));
+                in_s[c][rem / (CI_COLS + 2)][rem % (CI_COLS + 2)] = nxt[u];
+            }
+        }
+    };
+    fetch(0);
+    for (int x0 = 0; x0 < W; x0 += CI_COLS) {
+        __syncthreads();                                             // previous tile fully consumed (and w_s visible)
+        commit();
         __syncthreads();
+        if (x0 + CI_COLS < W) fetch(x0 + CI_COLS);
         float acc[4][16];
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int j = 0; j < 4; ++j) {
+            const float4 bv = *reinterpret_cast<const float4*>(&b_s[cq * 16 + 4 * j]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[p][j] = bias[j];
+            for (int p = 0; p < 4; ++p) { acc[p][4 * j] = bv.x; acc[p][4 * j + 1] = bv.y; acc[p][4 * j + 2] = bv.z; acc[p][4 * j + 3] = bv.w; }
+        }
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
