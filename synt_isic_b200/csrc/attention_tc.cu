@@ -96,7 +96,7 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
 
 __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, int N,
                                                                       int C, const bf16* __restrict__ qkv,
-                                                                      bf16* __restrict__ out) {
+                                                                      bf16* __restrict__ out, int exp_skip) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();             // SWIZZLE_128B tiles need 1 KB alignment
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_OFF_BAR);
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
         const int r = quarter * 32 + lane;                 // query row
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
         float m[2] = {0.f, 0.f};                           // running softmax reference of heads g and g+2
+        float mnext[2] = {0.f, 0.f};                       // sampled maximum seen in the previous chunk
         const int sw = r & 7;
         {
             // zero-masked Q tile: thread = (query row, pair of heads); head j keeps its 8 dims in chunk 2j + (j&1) of the
@@ -226,28 +227,33 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 const int j = g + 2 * jj, u = c * 4 + j, sb = u % ATC_NS;
                 mbar_wait(&s_full[sb], ((uint32_t)(u / ATC_NS)) & 1u);
                 tc_fence_after();
-                // pass 1 over the S tile: row maximum (32 live registers; the exponentials re-read the tile from
-                // TMEM in pass 2 -- TMEM bandwidth is plentiful, registers are what two CTAs per SM compete for)
+                // Softmax reference m of this row and head.  Any m within the bf16/fp32 exponent range of the true maximum
+                // gives the exact softmax after the final division, so only the FIRST chunk pays for an exact row maximum
+                // (a second pass over the S tile); afterwards m follows a SAMPLED maximum (every 4th key) of the previous
+                // chunk, picked up while its exponentials were computed, and moves only when that exceeds m by more than
+                // 2^8 (lazy rescale).  P may therefore exceed 2^8 for a chunk; bf16 P / fp32 accumulators have the range.
                 uint32_t v[32];
-                float cm[4];
-#pragma unroll
-                for (int piece = 0; piece < ATC_KEYS / 32; ++piece) {
-                    tmem_ld_32x32b_x32(lane_addr + sb * ATC_KEYS + piece * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float t = fmaxf(fmaxf(__uint_as_float(v[i]), __uint_as_float(v[4 + i])), __uint_as_float(v[8 + i]));
-                        t = fmaxf(fmaxf(t, __uint_as_float(v[12 + i])), __uint_as_float(v[16 + i]));
-                        t = fmaxf(fmaxf(t, __uint_as_float(v[20 + i])), __uint_as_float(v[24 + i]));
-                        t = fmaxf(t, __uint_as_float(v[28 + i]));
-                        cm[i] = piece == 0 ? t : fmaxf(cm[i], t);
-                    }
-                }
-                const float cmax = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
                 float alpha = 1.0f;
                 bool moved = false;
-                if (c == 0) { m[jj] = cmax; }
-                else if (cmax > m[jj] + ATC_LAZY) { alpha = ex2_approx(m[jj] - cmax); m[jj] = cmax; moved = true; }
+                if (c == 0) {
+                    float cm[4];
+#pragma unroll
+                    for (int piece = 0; piece < ATC_KEYS / 32; ++piece) {
+                        tmem_ld_32x32b_x32(lane_addr + sb * ATC_KEYS + piece * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float t = fmaxf(fmaxf(__uint_as_float(v[i]), __uint_as_float(v[4 + i])), __uint_as_float(v[8 + i]));
+                            t = fmaxf(fmaxf(t, __uint_as_float(v[12 + i])), __uint_as_float(v[16 + i]));
+                            t = fmaxf(fmaxf(t, __uint_as_float(v[20 + i])), __uint_as_float(v[24 + i]));
+                            t = fmaxf(t, __uint_as_float(v[28 + i]));
+                            cm[i] = piece == 0 ? t : fmaxf(cm[i], t);
+                        }
+                    }
+                    m[jj] = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
+                } else if (mnext[jj] > m[jj] + ATC_LAZY) {
+                    alpha = ex2_approx(m[jj] - mnext[jj]); m[jj] = mnext[jj]; moved = true;
+                }
                 uint8_t* p_row = smem + ATC_OFF_P + sb * ATC_P_BYTES + r * 128;
                 // P.V of unit u-3 is complete, hence (in-order MMA pipe) so is every earlier one: P[sb] is free and
                 // O_j (last written by unit u-4) has no MMA in flight
@@ -262,6 +268,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                     tmem_st_x16(lane_addr + ATC_O_COL + j * 16, o);
                 }
                 const float mrow = m[jj];
+                float smp = mrow;                                          // sampled maximum of this chunk (raw logits)
 #pragma unroll
                 for (int piece = 0; piece < ATC_KEYS / 32; ++piece) {
                     tmem_ld_32x32b_x32(lane_addr + sb * ATC_KEYS + piece * 32, v);
@@ -271,17 +278,22 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                         mbar_arrive(&s_free[sb]);                          // last read of this S buffer
                     }
 #pragma unroll
+                    for (int i = 0; i < 32; i += 8)
+                        smp = fmaxf(fmaxf(smp, __uint_as_float(v[i])), __uint_as_float(v[i + 4]));
+#pragma unroll
                     for (int q = 0; q < 4; ++q) {                          // 16-byte chunk = 8 keys
                         uint32_t w[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int e = q * 8 + i * 2;
                             const float x0 = __uint_as_float(v[e]) - mrow, x1 = __uint_as_float(v[e + 1]) - mrow;
-                            w[i] = pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+                            // exp_skip: EXPERIMENT (SYNT_ATT_NOEXP=1, wrong results): no MUFU, to time everything else
+                            w[i] = exp_skip ? pack_bf16x2(x0 * 1e-3f, x1 * 1e-3f) : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
                         }
                         *reinterpret_cast<uint4*>(p_row + (((piece * 4 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // SWIZZLE_128B
                     }
                 }
+                mnext[jj] = smp;
                 tc_fence_before();
                 fence_proxy_async();                                       // generic-proxy writes -> async proxy (UMMA)
                 mbar_arrive(&p_full[sb]);
@@ -361,8 +373,9 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
         SYNT_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
         attr = true;
     }
+    static const int exp_skip = [] { const char* e = getenv("SYNT_ATT_NOEXP"); return (e && e[0] == '1') ? 1 : 0; }();
     launch_pdl(attention_tc_kernel, dim3(N / 128, C / 32, B), dim3(ATC_THREADS), ATC_SMEM, s, maps, N, C, (const bf16*)qkv,
-               (bf16*)out);
+               (bf16*)out, exp_skip);
 }
 
 }  // namespace synt
