@@ -269,28 +269,35 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 }
                 const float mrow = m[jj];
                 float smp = mrow;                                          // sampled maximum of this chunk (raw logits)
+                // 16-column pieces, double-buffered in registers: the TMEM load of piece p+1 is in flight while the
+                // exponentials of piece p are computed (tcgen05.wait::ld waits for ALL loads, so it sits after the compute)
+                uint32_t vv[2][16];
+                tmem_ld_x16(lane_addr + sb * ATC_KEYS, vv[0]);
+                tmem_ld_wait();
 #pragma unroll
-                for (int piece = 0; piece < ATC_KEYS / 32; ++piece) {
-                    tmem_ld_32x32b_x32(lane_addr + sb * ATC_KEYS + piece * 32, v);
-                    tmem_ld_wait();
-                    if (piece == ATC_KEYS / 32 - 1) {
-                        tc_fence_before();
-                        mbar_arrive(&s_free[sb]);                          // last read of this S buffer
-                    }
+                for (int piece = 0; piece < ATC_KEYS / 16; ++piece) {
+                    uint32_t (&cur)[16] = vv[piece & 1];
+                    if (piece + 1 < ATC_KEYS / 16) tmem_ld_x16(lane_addr + sb * ATC_KEYS + (piece + 1) * 16, vv[(piece + 1) & 1]);
+                    smp = fmaxf(fmaxf(smp, __uint_as_float(cur[0])), __uint_as_float(cur[4]));
+                    smp = fmaxf(fmaxf(smp, __uint_as_float(cur[8])), __uint_as_float(cur[12]));
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8)
-                        smp = fmaxf(fmaxf(smp, __uint_as_float(v[i])), __uint_as_float(v[i + 4]));
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {                          // 16-byte chunk = 8 keys
+                    for (int q = 0; q < 2; ++q) {                          // 16-byte chunk = 8 keys
                         uint32_t w[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int e = q * 8 + i * 2;
-                            const float x0 = __uint_as_float(v[e]) - mrow, x1 = __uint_as_float(v[e + 1]) - mrow;
+                            const float x0 = __uint_as_float(cur[e]) - mrow, x1 = __uint_as_float(cur[e + 1]) - mrow;
                             // exp_skip: EXPERIMENT (SYNT_ATT_NOEXP=1, wrong results): no MUFU, to time everything else
                             w[i] = exp_skip ? pack_bf16x2(x0 * 1e-3f, x1 * 1e-3f) : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
                         }
-                        *reinterpret_cast<uint4*>(p_row + (((piece * 4 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // SWIZZLE_128B
+                        *reinterpret_cast<uint4*>(p_row + (((piece * 2 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // SWIZZLE_128B
+                    }
+                    if (piece + 1 < ATC_KEYS / 16) {
+                        tmem_ld_wait();
+                        if (piece + 2 == ATC_KEYS / 16) {                  // the last load of this S buffer has completed
+                            tc_fence_before();
+                            mbar_arrive(&s_free[sb]);
+                        }
                     }
                 }
                 mnext[jj] = smp;
