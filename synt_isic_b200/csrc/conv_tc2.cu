@@ -568,10 +568,12 @@ bool conv_tc2_supported(const ConvArgs& a) {
     if (a.W % 8 == 0 && (a.H % 32 == 0 || a.H == 16)) return true;
     // ragged planes (ResNet18: 56x56, 28x28): the tile grid is rounded up, TMA zero-fills the loads and clips the stores
     // beyond the plane.  Not with fused statistics / transformed input / upsampling (out-of-plane pixels would count).
-    return a.H > 16 && a.W >= 8 && a.stats_out == nullptr && a.gn_mode == 0 && !a.up2x;
+    // planes of 9..16 rows (ResNet18 14x14) use the two-images-per-super-tile mode of the 16x16 layers
+    return a.H > 8 && a.W >= 8 && a.stats_out == nullptr && a.gn_mode == 0 && !a.up2x;
 }
+static inline bool v2_two_img(const ConvArgs& a) { return a.H <= 16; }      // one 16-row M tile per image, two images per super-tile
 static inline int v2_tiles_x(const ConvArgs& a) { return (a.W + 7) / 8; }
-static inline int v2_supers(const ConvArgs& a) { return a.H == 16 ? 1 : (a.H + 31) / 32; }
+static inline int v2_supers(const ConvArgs& a) { return v2_two_img(a) ? 1 : (a.H + 31) / 32; }
 
 // N tile: 256 for the Cout = 256 3x3 convolutions at 32x32 and above (K >= 1152: the un-overlapped epilogue of the
 // single-buffered accumulators stays below ~10% of the mainloop; measured 10-18% faster than two N = 128 tiles),
@@ -608,7 +610,7 @@ static int v2_num_sms() {
 // consecutive work items per CTA turn: the divisor of the super-tiles per image (<= 8) with the smallest
 // makespan ceil(chunks / grid) * R; ties go to the larger R (fewer GroupNorm partial rows)
 static int v2_chunk(const ConvArgs& a, int BN) {
-    if (a.H == 16) return 1;
+    if (v2_two_img(a)) return 1;
     const int per_img = v2_tiles_x(a) * v2_supers(a);
     const long long n_work = (long long)a.B * per_img * (a.Cout / BN) * (a.up2x ? 4 : 1);
     const long long grid = n_work < v2_num_sms() ? n_work : v2_num_sms();
@@ -625,7 +627,7 @@ static int v2_chunk(const ConvArgs& a, int BN) {
 int conv_tc2_stats_slots(const ConvArgs& a) {
     const int BN = v2_bn(a);
     const int phases = a.up2x ? 4 : 1;
-    if (a.H == 16) return phases * (a.W / 8);                             // one row per tile
+    if (v2_two_img(a)) return phases * v2_tiles_x(a);                      // one row per tile
     const int per_img = v2_tiles_x(a) * v2_supers(a);
     if (BN == 256 || v2_pair(a)) return phases * per_img * V2_MT;          // multi-pass tiles / pair mode: one row per tile
     return phases * (per_img / v2_chunk(a, BN)) * V2_MT;                   // one row per chunk and epilogue warpgroup
@@ -673,8 +675,8 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     const int BN = v2_bn(a);
     const bool pair = v2_pair(a);
     V2Params p{};
-    p.imgs_per_super = a.H == 16 ? 2 : 1;
-    p.row_off = a.H == 16 ? 18 : 16;
+    p.imgs_per_super = v2_two_img(a) ? 2 : 1;
+    p.row_off = v2_two_img(a) ? 18 : 16;
     p.tiles_x = v2_tiles_x(a);
     p.supers_per_img = v2_supers(a);
     const int phases = a.up2x ? 4 : 1;
@@ -709,7 +711,7 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     p.chunk = v2_chunk(a, BN);
     { static const char* e = getenv("SYNT_EXP_NOB"); p.exp_nob = e ? atoi(e) : 0; }
     V2Maps maps;
-    const int bh = a.H == 16 ? 18 : 34, bn = a.H == 16 ? 2 : 1;
+    const int bh = v2_two_img(a) ? 18 : 34, bn = v2_two_img(a) ? 2 : 1;
     for (int i = 0; i < 4; ++i) {
         if (i < p.n_seg) make_halo_map(&maps.a[i], srcs[i], a.B, a.H, a.W, src_C[i], bh, bn);
         else maps.a[i] = maps.a[0];

@@ -112,6 +112,7 @@ V2_CASES = [c for c in CASES if c[5] in (1, 3) and c[6] == 1 and c[1] % 16 == 0 
     (3, 56, 56, 64, 64, 3, 1, 1, (0, 0), 1, True, True, False),            # ResNet18 layer1: ragged 56x56 plane (tile grid rounded up)
     (3, 28, 28, 128, 128, 3, 1, 1, (0, 0), 1, True, True, False),          # ResNet18 layer2: ragged 28x28 plane
     (2, 40, 24, 64, 128, 3, 1, 1, (64, 0), 1, False, False, True),         # ragged in both directions + shortcut segment
+    (3, 14, 14, 256, 256, 3, 1, 1, (0, 0), 1, True, True, False),          # ResNet18 layer3: 14x14 in the two-images-per-super-tile mode
 ]
 
 

@@ -13,7 +13,7 @@ python tools/ncu_target.py --steps 1 > gpurun_out/plain_$TAG.log 2>&1 || { echo 
 # conv_tc2 launches of one eager step: 0-3 = N 64 at 128x128, 4-7 = N 128 at 64x64, 8,9 = N 256 at 32x32, 10 = qkv 1x1, 11 = out-proj
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:conv_tc2 -c 12 -o /tmp/prof_conv_$TAG \
     python tools/ncu_target.py --steps 1 > gpurun_out/ncu_conv_$TAG.log 2>&1
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:"attention_tc_kernel|conv_out3_mma|conv_in3_tiled|gn_finalize_channels" -c 6 -o /tmp/prof_misc_$TAG \
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"attention_tc_kernel|conv_out3_mma|conv_in3_tiled" -c 4 -o /tmp/prof_misc_$TAG \
     python tools/ncu_target.py --steps 1 > gpurun_out/ncu_misc_$TAG.log 2>&1
 for k in conv misc; do
     f=/tmp/prof_${k}_$TAG.ncu-rep
