@@ -738,7 +738,11 @@ int synt_resnet18_logits(synt_resnet18_t* h, const float* x, int B, float* logit
     SYNT_TRY
     SYNT_CHECK(h && x && logits && B > 0, "bad argument");
     const size_t img = (size_t)3 * 128 * 128;
-    const int mb = 128;                                     // bounds the workspace (im2col of the stem: 4.8 MB per image)
+    // micro-batch: bounds the workspace.  Fused front-end: ~1.3 MB per image (largest tensors: 56x56x64 bf16) -> 512 images
+    // per pass keep the 14x14 / 7x7 layers' grids full; unfused paths materialise the 224x224 image / the stem output
+    const bool fused = h->use_tc && h->stem_frag && h->fuse_front && !h->tap_out;
+    static const int mb_env = [] { const char* e = getenv("SYNT_RESNET_MB"); return e ? atoi(e) : 0; }();
+    const int mb = mb_env > 0 ? mb_env : (fused ? 512 : 128);
     for (int b0 = 0; b0 < B; b0 += mb) {
         RFwd f{h, (cudaStream_t)stream, B - b0 < mb ? B - b0 : mb};
         f.run(x + b0 * img, logits + (size_t)b0 * h->num_classes);
