@@ -359,7 +359,7 @@ def run_ours(args):
             sec_dev = t0.elapsed_time(t1) / 3e3
             w0 = time.perf_counter()                                             # e2e: pinned host frames in, scores out
             for _ in range(3):
-                xai.compute_time_shap(clf, traj_host.to(dev, non_blocking=True), list(range(T_STEPS)), 0)
+                xai.compute_time_shap(clf, traj_host, list(range(T_STEPS)), 0)      # streams the pinned frames in chunks
             stream.synchronize()
             sec_e2e_ts = (time.perf_counter() - w0) / 3
         line["time_shap"] = {"sec_per_image": sec_dev, "e2e_sec_per_image": sec_e2e_ts, "frames": T_STEPS, "unit": "s/image",

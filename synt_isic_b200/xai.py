@@ -44,13 +44,50 @@ def _probs(classifier, images: torch.Tensor, group=None) -> torch.Tensor:
     return F.softmax(logits, dim=1)
 
 
+def _probs_from_host(classifier, frames_cpu: torch.Tensor, dev, chunk: int = 256) -> torch.Tensor:
+    """softmax(logits) of frames that live in (ideally pinned) HOST memory: the frames are copied in chunks on a side
+    stream so that the H2D copy of chunk i+1 overlaps the classifier kernels of chunk i."""
+    n = frames_cpu.shape[0]
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty((min(chunk, n), 3, 128, 128), dtype=torch.float32, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    used = [torch.cuda.Event() for _ in range(2)]
+    out = []
+    side.wait_stream(main)
+
+    def issue(i):
+        b, lo = i & 1, i * chunk
+        with torch.cuda.stream(side):
+            side.wait_event(used[b])
+            bufs[b][: min(chunk, n - lo)].copy_(frames_cpu[lo: lo + chunk], non_blocking=True)
+            ready[b].record(side)
+
+    n_chunks = (n + chunk - 1) // chunk
+    issue(0)
+    with torch.no_grad():
+        for i in range(n_chunks):
+            if i + 1 < n_chunks:
+                issue(i + 1)
+            b, lo = i & 1, i * chunk
+            main.wait_event(ready[b])
+            out.append(classifier(bufs[b][: min(chunk, n - lo)]))
+            used[b].record(main)
+    main.wait_stream(side)
+    return F.softmax(torch.cat(out), dim=1)
+
+
 # ------------------------------------------------------------------ Time-SHAP -----------
 def compute_time_shap(classifier, trajectory, timesteps, target_class, group=None, verbose=False):
     """xai/XAI.py:1179-1234.  ``trajectory``: list of [1,3,128,128] tensors or one [T,3,128,128]."""
     dev = _dev(classifier)
     frames = trajectory if torch.is_tensor(trajectory) else torch.cat([f.to(dev).reshape(-1, 3, 128, 128) for f in trajectory])
-    frames = frames.to(dev).reshape(-1, 3, 128, 128)
-    p = _probs(classifier, frames, group)[:, target_class]
+    if frames.device.type == "cpu" and dev.type == "cuda" and group is None and frames.shape[0] > 256:
+        # a host-resident trajectory: stream it through the classifier (copies overlap the kernels)
+        p = _probs_from_host(classifier, frames.reshape(-1, 3, 128, 128).float(), dev)[:, target_class]
+    else:
+        frames = frames.to(dev).reshape(-1, 3, 128, 128)
+        p = _probs(classifier, frames, group)[:, target_class]
     prob_scores = p.double().cpu().numpy()                      # get_confidence(...).item()
     confidence_scores = torch.log(p + 1e-8).double().cpu().numpy()   # get_per_class_score(...).item()
     if len(confidence_scores) > 1 and (confidence_scores.max() - confidence_scores.min()) > 1e-6:

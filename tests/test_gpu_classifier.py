@@ -192,3 +192,14 @@ def test_fused_front_end_is_bit_identical_to_the_three_kernels(oc, cuda_dev, fra
     im2col = build({"SYNT_RESNET_FUSE_FRONT": "0", "SYNT_STEM_IM2COL": "1"})
     assert torch.equal(fused, chain)
     assert rel(im2col, fused) < 5e-3
+
+
+def test_time_shap_streams_a_host_trajectory(clfs, cuda_dev):
+    """A host-resident (pinned) trajectory of more than 256 frames is streamed through the classifier in chunks with the
+    copies on a side stream: same importances and raw scores as the on-device call (xai/XAI.py:1179-1234)."""
+    g = torch.Generator().manual_seed(5)
+    traj = torch.tanh(torch.randn(300, 3, 128, 128, generator=g)).pin_memory()
+    imp_h, raw_h = xai.compute_time_shap(clfs["bf16"], traj, list(range(300)), 3)
+    imp_d, raw_d = xai.compute_time_shap(clfs["bf16"], traj.to(cuda_dev), list(range(300)), 3)
+    assert np.allclose(raw_h["confidence_scores"], raw_d["confidence_scores"], atol=1e-6)
+    assert np.allclose(imp_h, imp_d, atol=1e-6)
