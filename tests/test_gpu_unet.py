@@ -217,3 +217,26 @@ def test_philox_noise_is_standard_normal(models, cuda_dev):
     zhat = (a - mu) / sigma
     assert abs(zhat.mean().item()) < 0.01 and abs(zhat.std().item() - 1.0) < 0.01
     assert abs((zhat ** 4).mean().item() - 3.0) < 0.1
+
+
+def test_bulk_dataset_driver_writes_the_reference_formats(cuda_dev, tmp_path):
+    """SURVEY 8f row 1 end to end on the GPU: batched sampling of two classes through ImageGenerator, image files with the
+    ISIC numbering, JSON side-cars and the one-hot ground-truth CSV (diffusion/console_generator_server.py:405-467);
+    the batched images equal what generate_single_image produces for the same seed."""
+    import csv
+    import json
+    from PIL import Image
+    from synt_isic_b200 import bulk
+    from synt_isic_b200.generator import ImageGenerator, image_seed
+    gen = ImageGenerator(device=str(cuda_dev), inference_steps=4, base_seed=7, batch_size=4)
+    res = bulk.generate_dataset(gen, [("MEL", 3), ("DF", 2)], str(tmp_path), layout="flat", postprocess=False, batch_size=4)
+    assert res["total"] == 5 and res["generated"] == {"MEL": 3, "DF": 2}
+    folder = tmp_path / bulk.SYNTHETIC_DIR
+    names = sorted(p.name for p in folder.glob("*.jpg"))
+    assert names == [bulk.isic_name(bulk.LAST_REAL_ISIC_NUMBER + i) for i in range(1, 6)]
+    meta = json.load(open(folder / "ISIC_0034324.json"))
+    assert meta["class"] == "DF" and meta["seed"] == image_seed(7, "DF", 0) and meta["inference_steps"] == 4
+    rows = list(csv.reader(open(res["files"]["ground_truth_csv"])))
+    assert rows[0] == bulk.ground_truth_header() and rows[4][0] == "ISIC_0034324.jpg" and rows[4][6] == "1.0"
+    img = np.asarray(Image.open(folder / "ISIC_0034321.jpg"))
+    assert img.shape == (128, 128, 3) and img.dtype == np.uint8

@@ -192,6 +192,24 @@ else:
 assert max_over_ranks(float(rank + 1), "cpu", dist.group.WORLD) == 2.0
 solo = sharded_eval(fn, items, None, chunk=4)          # group=None: this rank alone, no collective
 assert torch.allclose(solo, ref, atol=1e-6)
+# bulk-dataset driver (SURVEY 8f row 1): units round-robin over the ranks, ONE gather_object of the rows, CSV on rank 0
+import numpy as np, csv, tempfile
+from synt_isic_b200 import bulk
+class FakeGen:
+    base_seed = 42; color_statistics = {}; stop_requested = False
+    def generate_batch(self, class_name, seeds, noise_seed=None, image_offset=0):
+        return np.zeros((len(seeds), 128, 128, 3), np.uint8), None, ["h"] * len(seeds)
+out_dir = sys.argv[2]
+written = []
+res = bulk.generate_dataset(FakeGen(), [("MEL", 70), ("DF", 5), ("NV", 130)], out_dir, layout="flat", postprocess=False,
+                            batch_size=64, group=dist.group.WORLD, save_fn=lambda img, fp, c, s, h: written.append(fp.name))
+units = bulk.plan_units([("MEL", 70), ("DF", 5), ("NV", 130)], 64, "flat")
+assert len(written) == sum(u.count for i, u in enumerate(units) if i % world == rank)
+if rank == 0:
+    assert res["total"] == 205 and res["generated"] == {"MEL": 70, "DF": 5, "NV": 130}
+    rows = list(csv.reader(open(res["files"]["ground_truth_csv"])))
+    assert len(rows) == 206 and rows[1][0] == "ISIC_0034321.jpg" and rows[-1][0] == "ISIC_0034525.jpg"
+    assert [r[0] for r in rows[1:]] == sorted(r[0] for r in rows[1:])          # same file as a single-rank run would write
 dist.barrier()
 print("RANK_OK", rank)
 """
@@ -202,7 +220,7 @@ def test_world_size_2_gloo(tmp_path):
     script.write_text(_WORKER)
     port = 29500 + (os.getpid() % 400)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), str(script), ROOT]
+           "127.0.0.1", "--master-port", str(port), str(script), ROOT, str(tmp_path / "dataset")]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -240,3 +258,60 @@ def test_upsample_conv_subpixel_decomposition():
             win = xp[:, :, py:py + H + 1, px:px + W + 1]
             out[:, :, py::2, px::2] = F.conv2d(win, wp.contiguous())
     assert torch.allclose(out, ref, atol=1e-5, rtol=1e-5), (out - ref).abs().max()
+
+
+class _FakeGenerator:
+    """Stands in for ImageGenerator on a box without GPU: deterministic 'images', records what it was asked for."""
+    base_seed = 42
+    color_statistics = {}
+    stop_requested = False
+
+    def __init__(self):
+        self.calls = []
+
+    def generate_batch(self, class_name, seeds, noise_seed=None, image_offset=0):
+        self.calls.append((class_name, list(seeds), image_offset))
+        imgs = np.zeros((len(seeds), 128, 128, 3), np.uint8)
+        for j, s in enumerate(seeds):
+            imgs[j] = s % 251
+        return imgs, None, [f"h{s:08x}" for s in seeds]
+
+
+def test_bulk_dataset_formats_and_numbering(tmp_path):
+    """ISIC numbering, one-hot ground-truth CSV (console_generator_server.py:50,83-125) and metadata
+    CSV (image_generator.py:742-782, path_manager.py:94-96) of the batched bulk driver; the numbering and the rank
+    partition are pure functions of (class order, index)."""
+    import csv as _csv
+    from synt_isic_b200 import bulk
+    from synt_isic_b200.generator import image_seed
+    cfg = [("MEL", 70), ("VASC", 3), ("NV", 64)]
+    units = bulk.plan_units(cfg, batch_size=64, layout="flat")
+    assert [(u.class_name, u.first_index, u.count, u.first_number) for u in units] == [
+        ("MEL", 0, 64, 34321), ("MEL", 64, 6, 34385), ("VASC", 0, 3, 34391), ("NV", 0, 64, 34394)]
+    assert bulk.isic_name(34321) == "ISIC_0034321.jpg" and bulk.isic_name(1, "png") == "ISIC_0000001.png"
+    assert bulk.ground_truth_header() == ["image", "MEL", "NV", "BCC", "AKIEC", "BKL", "DF", "VASC"]
+    assert bulk.ground_truth_row("ISIC_0034391.jpg", "VASC") == ["ISIC_0034391.jpg", 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+    # two ranks cover every unit exactly once, numbering unchanged
+    from synt_isic_b200.dist import partition
+    r0, r1 = partition(units, 0, 2), partition(units, 1, 2)
+    assert sorted(r0 + r1, key=lambda u: u.first_number) == units and not set(r0) & set(r1)
+
+    saved = []
+    gen = _FakeGenerator()
+    res = bulk.generate_dataset(gen, cfg, str(tmp_path), layout="flat", postprocess=False,
+                                save_fn=lambda img, fp, c, s, h: saved.append((fp.name, c, s, int(img[0, 0, 0]))))
+    assert res["total"] == 137 and res["generated"] == {"MEL": 70, "VASC": 3, "NV": 64}
+    assert gen.calls[1] == ("MEL", [image_seed(42, "MEL", 64 + j) for j in range(6)], 64)     # seeds of image_generator.py:626-637
+    assert saved[0] == ("ISIC_0034321.jpg", "MEL", image_seed(42, "MEL", 0), image_seed(42, "MEL", 0) % 251)
+    rows = list(_csv.reader(open(res["files"]["ground_truth_csv"])))
+    assert rows[0] == bulk.ground_truth_header() and len(rows) == 138
+    assert rows[1] == ["ISIC_0034321.jpg", "1.0", "0.0", "0.0", "0.0", "0.0", "0.0", "0.0"]
+    assert rows[71] == ["ISIC_0034391.jpg", "0.0", "0.0", "0.0", "0.0", "0.0", "0.0", "1.0"]
+    assert rows[-1][0] == "ISIC_0034457.jpg" and rows[-1][2] == "1.0"
+
+    res2 = bulk.generate_dataset(_FakeGenerator(), [("BCC", 2), ("DF", 1)], str(tmp_path / "gui"), layout="per_class",
+                                 postprocess=False, save_fn=lambda *a: None)
+    rows2 = list(_csv.DictReader(open(res2["files"]["metadata_csv"])))
+    assert [r["filename"] for r in rows2] == ["ISIC_0000001.png", "ISIC_0000002.png", "ISIC_0000001.png"]
+    assert [r["class"] for r in rows2] == ["BCC", "BCC", "DF"] and rows2[0]["source"] == "synthetic"
+    assert list(rows2[0].keys()) == ["filename", "class", "isic_number", "source", "generated_at"]
