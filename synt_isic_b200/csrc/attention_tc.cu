@@ -8,8 +8,9 @@
 //          K step covers a PAIR of heads: the key operand is the natural 16-column pair (k_2p | k_2p+1) and the query
 //          operand of head j is (q_j | 0) for even j, (0 | q_j) for odd j -- a zero-masked copy of the 128-query tile
 //          that the softmax warps build once per CTA in shared memory.  No padded tensor exists in HBM.
-//   vt   [B*32, 16, N] bf16 = per head V^T padded to 16 rows: rows 0..7 = v dims, row 8 = 1
-//          (so the P.V MMA also produces the softmax denominator), rows 9..15 = 0.
+//   The P.V operand of a head is V^T padded to 16 rows: rows 0..7 = v dims, row 8 = 1 (so the P.V MMA also produces the
+//          softmax denominator), rows 9..15 = 0.  Warp 3 builds it per 64-key stage directly in shared memory from the v
+//          columns of qkv (registers -> swizzled 32-bit stores, next stage prefetched); no V^T tensor exists in HBM.
 //
 // One CTA = 128 queries x 4 heads of one image, TWO CTAs resident per SM; one pass over the keys in chunks of 64:
 //   S  = Q_h K_h^T     one tcgen05.mma  M128 x N64 x K16  -> TMEM (fp32, log2 domain), 3 S buffers
@@ -25,7 +26,7 @@
 // S buffers) so that a softmax warpgroup does not wait for the P.V MMA of its previous unit.
 //
 // Warp roles (384 threads): warp 0 TMA producer, warp 1 TMEM allocator + S-MMA issuer, warp 2
-// P.V-MMA issuer, warp 3 idle, warps 4..7 softmax warpgroup 0 (heads 0,2), warps 8..11 softmax
+// P.V-MMA issuer, warp 3 V^T builder, warps 4..7 softmax warpgroup 0 (heads 0,2), warps 8..11 softmax
 // warpgroup 1 (heads 1,3).  The softmax warps keep only 32 S values live (<= 80 registers/thread).
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -53,7 +54,7 @@ constexpr uint32_t ATC_O_COL = 192;
 constexpr float ATC_LAZY = 8.0f;                       // rescale only when the max grows by more than 2^8
 static_assert(2 * (ATC_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit in shared memory");
 
-struct AttnTcMaps { CUtensorMap k; CUtensorMap vt; };
+struct AttnTcMaps { CUtensorMap k; };
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -126,8 +127,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
     }
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.k);
-        prefetch_tmap(&maps.vt);
-        for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        // full: the TMA producer's arrive.expect_tx (K tile) + the V^T builder's arrive
+        for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < ATC_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 128); }
         for (int g = 0; g < ATC_NS; ++g) { mbar_init(&p_full[g], 128); mbar_init(&p_free[g], 1); }
         mbar_init(q_full, 256); mbar_init(o_full, 1);
@@ -146,11 +147,55 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 uint8_t* sk = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES;
-                mbar_arrive_expect_tx(&full_bar[stage], ATC_STAGE_BYTES);
+                mbar_arrive_expect_tx(&full_bar[stage], ATC_K_BYTES);
                 tma_load_2d(sk, &maps.k, &full_bar[stage], C + (hg >> 1) * 64, b * N + c * ATC_KEYS);
-                tma_load_3d(sk + ATC_K_BYTES, &maps.vt, &full_bar[stage], c * ATC_KEYS, 0, b * (C / 8) + hg * 4);
                 if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
             }
+        }
+    } else if (warp == 3) {
+        // ===================== V^T builder =====================
+        // stage tile: [4 heads][16 rows][64 keys] bf16, SWIZZLE_128B (row = 128 B, 16-byte chunk ^= row & 7).  Lane l owns keys
+        // 2l, 2l+1 of the chunk: their 4 x 8 v values arrive as 2 x 64 B from global memory and leave as 32 aligned 32-bit
+        // stores (two adjacent keys of one row).  Rows 8 (ones) and 9..15 (zeros) are constant: written once per slot.
+        for (int i = lane; i < ATC_STAGES * 4 * 8 * 32; i += 32) {            // rows 8..15 of every head of every slot
+            const int word = i & 31, row = 8 + ((i >> 5) & 7), h = (i >> 8) & 3, st = i >> 10;
+            uint8_t* base = smem + ATC_OFF_STAGE + st * ATC_STAGE_BYTES + ATC_K_BYTES + h * 2048 + row * 128;
+            *reinterpret_cast<uint32_t*>(base + ((((word >> 2) ^ (row & 7)) << 4) | ((word & 3) << 2))) = row == 8 ? 0x3F803F80u : 0u;
+        }
+        const uint4* vsrc = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + 2 * lane) * (3 * C) + 2 * C + hg * 32);
+        const size_t key_stride = (size_t)(3 * C) / 8;                        // uint4 per token row
+        uint4 nx[2][4];
+        auto fetch = [&](int c) {
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                for (int h = 0; h < 4; ++h) nx[kk][h] = __ldg(vsrc + ((size_t)c * ATC_KEYS + kk) * key_stride + h);
+        };
+        fetch(0);
+        int stage = 0; uint32_t phase = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            uint4 cur[2][4];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                for (int h = 0; h < 4; ++h) cur[kk][h] = nx[kk][h];
+            if (c + 1 < n_chunks) fetch(c + 1);
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sv = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES + ATC_K_BYTES;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const uint16_t* a = reinterpret_cast<const uint16_t*>(&cur[0][h]);    // key 2l:   dims 0..7 of head h
+                const uint16_t* bq = reinterpret_cast<const uint16_t*>(&cur[1][h]);   // key 2l+1
+#pragma unroll
+                for (int d = 0; d < 8; ++d) {
+                    const uint32_t pair = (uint32_t)a[d] | ((uint32_t)bq[d] << 16);
+                    *reinterpret_cast<uint32_t*>(sv + h * 2048 + d * 128 + ((((lane >> 2) ^ d) << 4) | ((lane & 3) << 2))) = pair;
+                }
+            }
+            fence_proxy_async();                                              // generic-proxy writes -> UMMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
         }
     } else if (warp == 1) {
         if (elect_one()) {
@@ -361,19 +406,13 @@ bool attention_tc_supported(int N, int C) { return (N % 128 == 0) && C == 256; }
 void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* out, cudaStream_t s) {
     SYNT_CHECK(attention_tc_supported(N, C), "attention_tc: unsupported shape");
     const int ldq = 3 * C;
-    launch_pdl(build_vt_kernel, dim3(N / 64, B), dim3(256), 0, s, (const bf16*)qkv, N, C, ldq, 2 * C, (bf16*)vt_scratch);
+    (void)vt_scratch;                                               // V^T is built inside the kernel
     AttnTcMaps maps;
     {
         cuuint64_t dims[2] = {(cuuint64_t)ldq, (cuuint64_t)B * N};
         cuuint64_t strides[1] = {(cuuint64_t)ldq * 2};
         cuuint32_t boxk[2] = {64, ATC_KEYS};
         encode_bf16_sw128(&maps.k, qkv, 2, dims, strides, boxk, "attention k");
-    }
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)N, 16, (cuuint64_t)B * (C / 8)};
-        cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)N * 32};
-        cuuint32_t box[3] = {64, 16, 4};
-        encode_bf16_sw128(&maps.vt, vt_scratch, 3, dims, strides, box, "attention vt");
     }
     static bool attr = false;
     if (!attr) {

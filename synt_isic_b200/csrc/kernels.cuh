@@ -113,7 +113,7 @@ void upsample_nearest2x(const void* in, int dt, int B, int H, int W, int C, void
 void attention_simt(const void* qkv, int dt, int B, int N, int C, void* out, cudaStream_t s);
 bool attention_tc_supported(int N, int C);
 // tcgen05 attention: qkv [B, N, 3C] bf16 = (q | k | v) with q pre-scaled by log2(e)/sqrt(8);
-// vt_scratch [B*C/8, 16, N] bf16 is filled by the call.
+// vt_scratch is unused (the padded V^T operand is built in shared memory by the kernel) and may be null.
 void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* out, cudaStream_t s);
 
 // time embedding tables: emb[t] = Linear2(SiLU(Linear1(sincos(t)))) for t in [0,T),

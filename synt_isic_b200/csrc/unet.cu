@@ -549,10 +549,7 @@ struct Fwd {
         {
             ProfScope ps(u, s, PC_ATTN, 4.0 * B * (double)(H * W) * (H * W) * C);
             if (tc) {
-                void* vt = pool->alloc((size_t)B * (C / 8) * 16 * H * W * 2);
-                attention_tc(qkv.p, B, H * W, C, vt, o.p, s);
-                pool->release(vt);
-                ++u->launches;
+                attention_tc(qkv.p, B, H * W, C, nullptr, o.p, s);     // V^T is built inside the kernel
             } else {
                 attention_simt(qkv.p, u->dt, B, H * W, C, o.p, s);
             }
@@ -1058,11 +1055,7 @@ extern "C" int synt_debug_attention(int use_tc, int act_dtype, const void* qkv, 
     SYNT_CHECK(qkv && out && B > 0, "bad argument");
     if (use_tc) {
         SYNT_CHECK(act_dtype == DT_BF16 && attention_tc_supported(N, C), "attention_tc: unsupported");
-        void* vt = nullptr;
-        SYNT_CUDA(cudaMalloc(&vt, (size_t)B * (C / 8) * 16 * N * 2));
-        try { attention_tc(qkv, B, N, C, vt, out, (cudaStream_t)stream); } catch (...) { cudaFree(vt); throw; }
-        SYNT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-        cudaFree(vt);
+        attention_tc(qkv, B, N, C, nullptr, out, (cudaStream_t)stream);
     } else {
         attention_simt(qkv, act_dtype, B, N, C, out, (cudaStream_t)stream);
     }
