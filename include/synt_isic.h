@@ -63,6 +63,11 @@ int synt_unet_set_schedule(synt_unet_t* h, int n_steps, const int* timesteps_hos
 int synt_unet_sample(synt_unet_t* h, float* x_dev, int B, const float* z_dev, unsigned long long seed,
                      long long image_offset, float* traj_dev, float* eps_tap_dev, int step_begin, int step_end,
                      int micro_batch, int use_graph, void* stream);
+/* Coalition decoding for the permutation Time-SHAP over denoising steps (README.md:171-221 of the reference; no code
+ * in the reference): with mask_dev != NULL (uint8 [n_steps][B], device) image b takes the transition of step s of the
+ * following synt_unet_sample calls only if mask[s*B + b] != 0 and is frozen otherwise; noise_shared != 0 makes every
+ * image of the batch draw the same in-kernel noise field (common random numbers across coalitions).  NULL / 0 resets. */
+int synt_unet_set_step_mask(synt_unet_t* h, const unsigned char* mask_dev, int noise_shared);
 /* host-buffer form of the same call (what a non-PyTorch caller binds): H2D of x_T, all steps of
  * the current schedule, uint8 HWC conversion (image_generator.py:441-447), D2H of the images.
  * x_final_host (optional) receives the fp32 result. */

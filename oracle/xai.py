@@ -8,6 +8,7 @@ exposes ``get_confidence / get_per_class_score / get_probabilities``:
 * ``patch_shap``           -- ``compute_shap_approximation``           xai/XAI.py:1111-1177
 * ``intervene``            -- ``counterfactual_intervention_advanced`` xai/XAI.py:1454-1597
 * ``causal_shift``         -- ``compute_causal_shift_comprehensive``   xai/XAI.py:1600-1700
+* ``time_shap_permutation`` -- permutation Shapley over denoising steps, README.md:171-221 (spec only, no reference code)
 
 Randomness the reference draws from global RNGs (patch masks ``torch.rand(8,8)``, noise
 ``randn_like``, ``randperm``) is INJECTED here so the CUDA path can be compared exactly.
@@ -121,3 +122,57 @@ def causal_shift(classifier, original, modified, target_class):
         "js_divergence": float(0.5 * (F.kl_div(mid, po, reduction="sum") + F.kl_div(mid, pm, reduction="sum"))),
         "total_variation": float(0.5 * (po - pm).abs().sum()),
     }
+
+
+# ------------------------------------------------------------------ permutation Time-SHAP over denoising steps
+# README.md:171-221 of the reference specifies it (players = steps, v(S) = logit after a decode that applies the
+# transition only on the steps of S, phi_hat = mean over permutations of the marginal contribution of a step to its
+# prefix); the reference ships NO code for it, so this oracle is the definition the CUDA path is held to: plain Python
+# loops, one B=1 decode per coalition.
+def step_permutations(n_steps: int, n_perm: int, seed: int) -> np.ndarray:
+    """n_perm permutations of 0..n_steps-1 drawn one after the other from numpy.random.default_rng(seed)."""
+    rng = np.random.default_rng(int(seed))
+    return np.stack([rng.permutation(n_steps) for _ in range(n_perm)]).astype(np.int64)
+
+
+def coalition_value(unet, scheduler, classifier, x_T, coalition, noise, target_class) -> float:
+    """v(S): decode x_T applying the scheduler transition only on step indices in ``coalition`` (frozen elsewhere),
+    same noise realisation ``noise`` [n,1,3,128,128] for every coalition; value = target logit of the classifier."""
+    x = x_T.clone()
+    with torch.no_grad():
+        for i, t in enumerate(scheduler.timesteps):
+            if i in coalition:
+                eps = unet(x, t).sample
+                x = scheduler.step(eps, t, x, noise=noise[i]).prev_sample
+        return float(classifier(x)[0, target_class])
+
+
+def time_shap_permutation(unet, scheduler, classifier, x_T, target_class, n_perm, seed, noise):
+    """phi_hat[t] = (1/M) sum_m [ v(Pref_m(t) + {t}) - v(Pref_m(t)) ]; returns (phi [n], prefix values [M, n+1])."""
+    n = len(scheduler.timesteps)
+    perms = step_permutations(n, n_perm, seed)
+    phi = np.zeros(n, np.float64)
+    values = np.zeros((n_perm, n + 1), np.float64)
+    for m in range(n_perm):
+        coalition = set()
+        values[m, 0] = coalition_value(unet, scheduler, classifier, x_T, coalition, noise, target_class)
+        for k in range(n):
+            player = int(perms[m, k])
+            coalition = coalition | {player}
+            values[m, k + 1] = coalition_value(unet, scheduler, classifier, x_T, coalition, noise, target_class)
+            phi[player] += values[m, k + 1] - values[m, k]
+    return phi / n_perm, values
+
+
+def exact_shapley(value_fn, n: int) -> np.ndarray:
+    """Brute-force Shapley values of a set function on n players (for checking the permutation estimator)."""
+    import itertools
+    import math
+    phi = np.zeros(n, np.float64)
+    for t in range(n):
+        others = [p for p in range(n) if p != t]
+        for r in range(n):
+            for S in itertools.combinations(others, r):
+                w = math.factorial(r) * math.factorial(n - r - 1) / math.factorial(n)
+                phi[t] += w * (value_fn(set(S) | {t}) - value_fn(set(S)))
+    return phi

@@ -52,6 +52,7 @@ SIGNATURES = {
     "synt_debug_conv_gn": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int,
                                      vp, vp, vp, vp, C.c_int, vp, c_i32p, vp]),
     "synt_debug_conv_up2x": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, c_i32p, vp]),
+    "synt_unet_set_step_mask": (C.c_int, [vp, vp, C.c_int]),
     "synt_debug_set_conv_pair": (C.c_int, [C.c_int]),
     "synt_debug_pack_upsample_phases": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "synt_debug_attention": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp]),

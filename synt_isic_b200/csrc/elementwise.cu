@@ -532,6 +532,13 @@ __device__ __forceinline__ void sched_epilogue(const float (&e)[3], int b, int o
         for (int j = 0; j < 3; ++j) eo[i0 + j * plane] = e[j];
     }
     if (sch.x) {
+        if (sch.step_mask && sch.step_mask[step * sch.mask_stride + b] == 0) {   // this image skips the step: x frozen
+            if (sch.traj) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) sch.traj[step * sch.traj_step_stride + i0 + j * plane] = sch.x[i0 + j * plane];
+            }
+            return;
+        }
         const float sqrt_b = sch.coef[0], sqrt_a = sch.coef[1], c_x0 = sch.coef[2], c_xt = sch.coef[3],
                     sigma = sch.coef[4];
         float z[3] = {0.f, 0.f, 0.f};
@@ -540,7 +547,9 @@ __device__ __forceinline__ void sched_epilogue(const float (&e)[3], int b, int o
 #pragma unroll
                 for (int j = 0; j < 3; ++j) z[j] = sch.z[step * sch.z_step_stride + i0 + j * plane];
             } else {
-                const unsigned long long elem = (unsigned long long)(sch.image_offset + b) * plane + (size_t)oy * W + ox;
+                const unsigned long long img = sch.noise_shared ? (unsigned long long)sch.image_offset
+                                                                : (unsigned long long)(sch.image_offset + b);
+                const unsigned long long elem = img * plane + (size_t)oy * W + ox;
                 philox_normal3(sch.seed, elem, (uint32_t)step, z);
             }
         }

@@ -77,6 +77,12 @@ struct SchedArgs {
     long long traj_step_stride = 0;
     long long eps_step_stride = 0;     // stride of the eps tap between steps
     long long image_offset = 0;        // global image index of image 0 of this call (Philox stream id)
+    // coalition decoding (permutation Time-SHAP over denoising steps, README.md:171-221 of the reference): image b takes
+    // the transition of step s only if step_mask[s * mask_stride + b] != 0, otherwise x_b is frozen for that step;
+    // noise_shared: every image of the batch draws the SAME Philox noise field (common random numbers across coalitions)
+    const unsigned char* step_mask = nullptr;
+    int mask_stride = 0;
+    int noise_shared = 0;
 };
 // bfrag (bf16 mode, nullable): conv_out weights as per-lane mma.sync m16n8k16 B fragments, uint2[36 k-steps][32 lanes]
 // (k-step = tap*4 + 16-channel block; lane (g = lane/4, t = lane%4): .x = w[k0 + 2t, 2t+1][n = g], .y = same at k0 + 8)

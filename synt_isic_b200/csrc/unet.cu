@@ -211,6 +211,7 @@ struct synt_unet {
     DevPtr temb_table;                            // [1000][temb_total]
     DevPtr temb_cur, coef_cur, step_ctr;          // fixed per-step buffers (graph friendly)
     DevPtr timesteps_dev, coef_table_dev; int n_steps = 0;
+    const unsigned char* step_mask = nullptr; int noise_shared = 0;   // coalition decoding (synt_unet_set_step_mask)
     std::vector<int> timesteps_host;
     Pool pool;
     Pool pool2;                                   // second chain (dual-stream sampling)
@@ -219,8 +220,10 @@ struct synt_unet {
     // CUDA graph cache for one sampling step
     struct GraphKey {
         float* x; int B; const float* z; float* traj; float* eps; int mb; unsigned long long seed; long long off;
+        const unsigned char* mask; int shared;
         bool operator==(const GraphKey& o) const {
-            return x == o.x && B == o.B && z == o.z && traj == o.traj && eps == o.eps && mb == o.mb && seed == o.seed && off == o.off;
+            return x == o.x && B == o.B && z == o.z && traj == o.traj && eps == o.eps && mb == o.mb && seed == o.seed &&
+                   off == o.off && mask == o.mask && shared == o.shared;
         }
     } gkey{};
     cudaGraphExec_t gexec = nullptr;
@@ -661,7 +664,8 @@ static void sample_step(synt_unet* u, float* x, int B, const float* z, unsigned 
         sch.seed = seed; sch.step_ptr = (const int*)u->step_ctr->p;
         sch.traj = traj ? traj + b0 * img : nullptr; sch.traj_step_stride = (long long)B * img;
         sch.eps_step_stride = (long long)B * img;
-        sch.image_offset = image_offset + b0;
+        sch.image_offset = u->noise_shared ? image_offset : image_offset + b0;
+        sch.step_mask = u->step_mask ? u->step_mask + b0 : nullptr; sch.mask_stride = B; sch.noise_shared = u->noise_shared;
         f.run(x + b0 * img, eps_tap ? eps_tap + b0 * img : nullptr, sch);
     };
     if (u->dual && B >= 2 && mb >= B) {
@@ -819,7 +823,7 @@ int synt_unet_sample(synt_unet_t* h, float* x, int B, const float* z, unsigned l
         for (int i = 0; i < n; ++i) sample_step(h, x, B, z, seed, image_offset, traj, eps_tap, mb, s);
         return 0;
     }
-    synt_unet::GraphKey key{x, B, z, traj, eps_tap, mb, seed, image_offset};
+    synt_unet::GraphKey key{x, B, z, traj, eps_tap, mb, seed, image_offset, h->step_mask, h->noise_shared};
     int done = 0;
     if (!h->gexec || !(key == h->gkey)) {
         if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
@@ -850,6 +854,13 @@ int synt_unet_sample(synt_unet_t* h, float* x, int B, const float* z, unsigned l
         SYNT_CUDA(cudaGraphLaunch(h->gexec, s));
         h->launches += h->graph_nodes;
     }
+    SYNT_CATCH
+}
+
+int synt_unet_set_step_mask(synt_unet_t* h, const unsigned char* mask_dev, int noise_shared) {
+    SYNT_TRY
+    SYNT_CHECK(h, "bad argument");
+    h->step_mask = mask_dev; h->noise_shared = noise_shared ? 1 : 0;
     SYNT_CATCH
 }
 

@@ -220,9 +220,13 @@ class UNet2DModel(nn.Module):
 
     def sample(self, x: torch.Tensor, scheduler, noise: torch.Tensor | None = None, seed: int = 0,
                image_offset: int = 0, trajectory: torch.Tensor | None = None, eps_tap: torch.Tensor | None = None,
-               step_begin: int = 0, step_end: int | None = None, micro_batch: int = 0, use_graph: bool = True):
+               step_begin: int = 0, step_end: int | None = None, micro_batch: int = 0, use_graph: bool = True,
+               step_mask: torch.Tensor | None = None, shared_noise: bool = False):
         """Runs steps [step_begin, step_end) of the loop at image_generator.py:395-403 IN PLACE on
-        ``x`` (fp32 CUDA [B,3,128,128], contiguous).  ``noise`` [n_steps,B,3,128,128] injects z."""
+        ``x`` (fp32 CUDA [B,3,128,128], contiguous).  ``noise`` [n_steps,B,3,128,128] injects z.
+        ``step_mask`` (uint8 CUDA [n_steps, B]): image b takes the transition of step s only where the mask is
+        non-zero and stays frozen otherwise (coalition decoding of the permutation Time-SHAP); ``shared_noise``:
+        all images of the batch draw the same in-kernel noise field."""
         if not (x.is_cuda and x.is_contiguous() and x.dtype == torch.float32):
             raise ValueError("x must be a contiguous fp32 CUDA tensor")
         self.set_schedule(scheduler)
@@ -232,14 +236,28 @@ class UNet2DModel(nn.Module):
             if t_ is not None and not (t_.is_cuda and t_.is_contiguous() and t_.dtype == torch.float32
                                        and tuple(t_.shape) == (n,) + tuple(x.shape)):
                 raise ValueError(f"{nm} must be a contiguous fp32 CUDA tensor of shape [n_steps, *x.shape]")
+        if step_mask is not None and not (step_mask.is_cuda and step_mask.is_contiguous() and step_mask.dtype == torch.uint8
+                                          and tuple(step_mask.shape) == (n, x.shape[0])):
+            raise ValueError("step_mask must be a contiguous uint8 CUDA tensor of shape [n_steps, B]")
         with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().synt_unet_sample(
-                self._handle(), x.data_ptr(), x.shape[0], noise.data_ptr() if noise is not None else None,
-                int(seed) & 0xFFFFFFFFFFFFFFFF, int(image_offset),
-                trajectory.data_ptr() if trajectory is not None else None,
-                eps_tap.data_ptr() if eps_tap is not None else None, step_begin, step_end, micro_batch,
-                1 if use_graph else 0, _lib.current_stream_ptr()), "unet_sample")
+            masked = step_mask is not None or shared_noise
+            if masked:
+                _lib.check(_lib.lib().synt_unet_set_step_mask(self._handle(), step_mask.data_ptr() if step_mask is not None else None,
+                                                              1 if shared_noise else 0), "unet_set_step_mask")
+            try:
+                self._sample_call(x, noise, seed, image_offset, trajectory, eps_tap, step_begin, step_end, micro_batch, use_graph)
+            finally:
+                if masked:
+                    _lib.lib().synt_unet_set_step_mask(self._handle(), None, 0)
         return x
+
+    def _sample_call(self, x, noise, seed, image_offset, trajectory, eps_tap, step_begin, step_end, micro_batch, use_graph):
+        _lib.check(_lib.lib().synt_unet_sample(
+            self._handle(), x.data_ptr(), x.shape[0], noise.data_ptr() if noise is not None else None,
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(image_offset),
+            trajectory.data_ptr() if trajectory is not None else None,
+            eps_tap.data_ptr() if eps_tap is not None else None, step_begin, step_end, micro_batch,
+            1 if use_graph else 0, _lib.current_stream_ptr()), "unet_sample")
 
     PROFILE_CATEGORIES = ("conv_tcgen05", "conv_fp32", "groupnorm_stats", "groupnorm_apply", "attention", "upsample",
                           "conv_in", "conv_out_sched", "misc")

@@ -101,6 +101,71 @@ def compute_time_shap(classifier, trajectory, timesteps, target_class, group=Non
     return imp, raw
 
 
+# ------------------------------------------------------------------ permutation Time-SHAP
+def draw_step_permutations(n_steps: int, n_perm: int, seed: int) -> np.ndarray:
+    """The coalition enumeration: ``n_perm`` permutations of the step indices 0..n_steps-1 (index into
+    ``scheduler.timesteps``, i.e. 0 = the noisiest step), drawn one after the other from
+    ``numpy.random.default_rng(seed)``.  Deterministic in (n_steps, n_perm, seed); int64 [n_perm, n_steps]."""
+    rng = np.random.default_rng(int(seed))
+    return np.stack([rng.permutation(n_steps) for _ in range(n_perm)]).astype(np.int64)
+
+
+def prefix_coalitions(perm: np.ndarray) -> np.ndarray:
+    """Prefix coalitions of one permutation as a mask [n_steps + 1, n_steps]: row k holds the first k players."""
+    n = len(perm)
+    m = np.zeros((n + 1, n), np.uint8)
+    for k in range(n):
+        m[k + 1] = m[k]
+        m[k + 1, perm[k]] = 1
+    return m
+
+
+def shapley_from_prefix_values(perms: np.ndarray, values: np.ndarray) -> np.ndarray:
+    """phi_hat[t] = mean over permutations of v(Pref(t) + {t}) - v(Pref(t)) (README.md:199-207 of the reference).
+    ``values`` [n_perm, n_steps + 1]: value of every prefix coalition, float64."""
+    n_perm, n = perms.shape
+    phi = np.zeros(n, np.float64)
+    for m in range(n_perm):
+        phi[perms[m]] += values[m, 1:] - values[m, :-1]
+    return phi / n_perm
+
+
+def compute_time_shap_permutation(model, scheduler, classifier, x_T: torch.Tensor, target_class: int, n_perm: int = 8,
+                                  seed: int = 0, noise: torch.Tensor | None = None, noise_seed: int = 0, group=None):
+    """Permutation estimate of the Shapley value of every denoising step (README.md:171-221 of the reference; the
+    reference ships no code for it, so the enumeration order is defined here: ``draw_step_permutations``).
+
+    Players: the ``n`` steps of ``scheduler.timesteps``.  v(S) = logit_target(classifier(Dec(x_T; S))) where Dec runs the
+    sampling loop and applies the transition only at steps in S (the image is frozen on the others); all coalitions share
+    one noise realisation (``noise`` [n,1,3,128,128] injected, else the in-kernel Philox field of ``noise_seed``).
+    Per permutation the n+1 prefix coalitions are decoded as ONE batch of the CUDA sampler (per-image step mask) and
+    scored in one classifier call; with ``group`` the permutations are split over the ranks and the partial sums are
+    combined by one all_reduce.  Returns (phi [n] float64, raw dict)."""
+    import torch.distributed as dist
+    dev = x_T.device
+    n = len(scheduler.timesteps)
+    perms = draw_step_permutations(n, n_perm, seed)
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if (group is not None and dist.is_initialized()) else (0, 1)
+    values = np.zeros((n_perm, n + 1), np.float64)
+    B = n + 1
+    z = noise.to(dev).float().expand(n, B, 3, 128, 128).contiguous() if noise is not None else None
+    for m in range(rank, n_perm, world):
+        mask = torch.from_numpy(np.ascontiguousarray(prefix_coalitions(perms[m]).T)).to(dev)      # [n_steps, B]
+        x = x_T.to(dev).float().reshape(1, 3, 128, 128).repeat(B, 1, 1, 1).contiguous()
+        model.sample(x, scheduler, noise=z, seed=noise_seed, step_mask=mask, shared_noise=True)
+        with torch.no_grad():
+            logits = classifier(x)
+        values[m] = logits[:, target_class].double().cpu().numpy()
+    if world > 1:
+        t = torch.from_numpy(values).to(dev)
+        dist.all_reduce(t, group=group)                                  # rows of other ranks are zero here
+        values = t.cpu().numpy()
+    phi = shapley_from_prefix_values(perms, values)
+    raw = {"permutations": perms, "prefix_values": values, "v_empty": float(values[0, 0]), "v_full": float(values[0, -1]),
+           "efficiency_gap": float(phi.sum() - (values[:, -1] - values[:, 0]).mean())}
+    return phi, raw
+
+
 # ------------------------------------------------------------------ patch-SHAP ----------
 def draw_patch_masks(n_samples: int, n_h: int = 8, n_w: int = 8) -> torch.Tensor:
     """The coalition masks exactly as the reference draws them: one ``torch.rand(n_h, n_w) > 0.5``

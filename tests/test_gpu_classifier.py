@@ -203,3 +203,39 @@ def test_time_shap_streams_a_host_trajectory(clfs, cuda_dev):
     imp_d, raw_d = xai.compute_time_shap(clfs["bf16"], traj.to(cuda_dev), list(range(300)), 3)
     assert np.allclose(raw_h["confidence_scores"], raw_d["confidence_scores"], atol=1e-6)
     assert np.allclose(imp_h, imp_d, atol=1e-6)
+
+
+def test_permutation_time_shap_matches_the_oracle(oc, clfs, cuda_dev):
+    """Permutation Shapley over denoising steps (README.md:171-221 of the reference): per permutation the n+1 prefix
+    coalitions are decoded as ONE batch with a per-image step mask in the fused scheduler epilogue and scored in one
+    classifier call; against the oracle's one-decode-per-coalition loops on the same weights, x_T and noise (fp32 mode).
+    Also: efficiency (sum phi = v(all) - v(empty)) and the in-kernel shared noise field (bf16 path runs)."""
+    from oracle.ddpm import DDPMSchedulerOracle
+    from oracle.unet2d import build_unet
+    from synt_isic_b200 import DDPMScheduler, SUPPORTED_CONFIG, UNet2DModel
+    n, M, target = 3, 2, 1
+    ounet = build_unet(0)
+    osched = DDPMSchedulerOracle(); osched.set_timesteps(n)
+    g = torch.Generator().manual_seed(11)
+    x_T = torch.randn(1, 3, 128, 128, generator=g)
+    noise = torch.randn(n, 1, 3, 128, 128, generator=g)
+    phi_ref, val_ref = oxai.time_shap_permutation(ounet, osched, oc, x_T, target, M, 5, noise)
+    model = UNet2DModel(precision="fp32", **SUPPORTED_CONFIG)
+    model.load_state_dict(ounet.state_dict())
+    model = model.to(cuda_dev)
+    sched = DDPMScheduler(num_train_timesteps=1000, beta_schedule="squaredcos_cap_v2", prediction_type="epsilon")
+    sched.set_timesteps(n)
+    phi, raw = xai.compute_time_shap_permutation(model, sched, clfs["fp32"], x_T.to(cuda_dev), target, n_perm=M, seed=5,
+                                                 noise=noise.to(cuda_dev))
+    assert np.array_equal(raw["permutations"], oxai.step_permutations(n, M, 5))
+    assert np.allclose(raw["prefix_values"], val_ref, atol=2e-3), np.abs(raw["prefix_values"] - val_ref).max()
+    assert np.allclose(phi, phi_ref, atol=2e-3)
+    assert abs(raw["efficiency_gap"]) < 1e-9
+    assert np.allclose(raw["prefix_values"][:, 0], raw["prefix_values"][0, 0])           # v(empty) = F(x_T), no decode
+    # production path: bf16 tensor kernels, in-kernel Philox noise shared by all coalitions
+    mb = UNet2DModel(precision="bf16", **SUPPORTED_CONFIG)
+    mb.load_state_dict(ounet.state_dict())
+    mb = mb.to(cuda_dev)
+    phi_b, raw_b = xai.compute_time_shap_permutation(mb, sched, clfs["bf16"], x_T.to(cuda_dev), target, n_perm=M, seed=5, noise_seed=3)
+    assert np.isfinite(phi_b).all() and abs(raw_b["efficiency_gap"]) < 1e-9
+    assert abs(raw_b["prefix_values"][0, 0] - val_ref[0, 0]) < 5e-2                       # v(empty) does not depend on the sampler

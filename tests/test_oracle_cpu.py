@@ -156,3 +156,29 @@ def test_xai_oracle_golden():
     np.testing.assert_allclose(blur[0, :, ::8, ::8].numpy(), gold["blur_sub"], atol=1e-6)
     cs = oxai.causal_shift(c, traj[-1], blur, 0)
     np.testing.assert_allclose([cs["cfi"], cs["delta"], cs["kl_divergence"]], gold["cfi"], atol=1e-4)
+
+
+def test_permutation_shapley_estimator_and_enumeration():
+    """Permutation Time-SHAP (README.md:171-221 of the reference, spec only): the coalition enumeration is a pure function
+    of (n, M, seed) and identical in the oracle and in the product; with ALL n! permutations the estimator equals the
+    brute-force Shapley values of a set function with interactions; efficiency holds for any M."""
+    import itertools
+    from oracle import xai as oxai
+    from synt_isic_b200 import xai
+    p1, p2 = oxai.step_permutations(7, 5, 123), xai.draw_step_permutations(7, 5, 123)
+    assert p1.dtype == np.int64 and np.array_equal(p1, p2)                       # bit-exact enumeration
+    assert np.array_equal(p1[0], np.random.default_rng(123).permutation(7))
+    assert all(sorted(r) == list(range(7)) for r in p1.tolist())
+    m = xai.prefix_coalitions(p1[0])
+    assert m.shape == (8, 7) and m[0].sum() == 0 and m[7].sum() == 7 and all(m[k + 1, p1[0][k]] == 1 for k in range(7))
+    w = np.array([0.5, -1.0, 2.0, 0.25])
+    def v(S):                                                                    # additive part + one pairwise interaction
+        return float(sum(w[i] for i in S) + (3.0 if {1, 2} <= set(S) else 0.0))
+    exact = oxai.exact_shapley(v, 4)
+    assert np.allclose(exact, [0.5, 0.5, 3.5, 0.25])
+    perms = np.array(list(itertools.permutations(range(4))), np.int64)
+    values = np.array([[v(set(p[:k])) for k in range(5)] for p in perms])
+    assert np.allclose(xai.shapley_from_prefix_values(perms, values), exact)
+    few = xai.draw_step_permutations(4, 3, 9)
+    vals = np.array([[v(set(p[:k])) for k in range(5)] for p in few])
+    assert abs(xai.shapley_from_prefix_values(few, vals).sum() - (v({0, 1, 2, 3}) - v(set()))) < 1e-12
