@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--csi-batch", type=int, default=256)
     ap.add_argument("--out", default="gpurun_out/xai.json")
     ap.add_argument("--cpu-frames", type=int, default=16)
+    ap.add_argument("--perm", type=int, default=4, help="permutations of the permutation Time-SHAP (0 = skip)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     clf = MelanomaClassifierAdaptive(num_classes=7, pretrained=False, precision="bf16").to(dev).eval()
@@ -51,6 +52,21 @@ def main():
                         "evals_per_s": a.csi_batch * 5 / t}
     attr_t = timed(lambda: xai.compute_shap_approximation(clf, imgs[:1], 0, n_samples=512), reps=3)
     res["patch_shap_512"] = {"sec_per_image": attr_t}
+    # permutation Time-SHAP over the denoising steps (README.md:171-221): T = 50 steps, M permutations, 51 coalitions/batch
+    if a.perm > 0:
+        from synt_isic_b200 import DDPMScheduler, SUPPORTED_CONFIG, UNet2DModel
+        model = UNet2DModel(precision="bf16", **SUPPORTED_CONFIG).to(dev)
+        sched = DDPMScheduler(num_train_timesteps=1000, beta_schedule="squaredcos_cap_v2", prediction_type="epsilon")
+        sched.set_timesteps(50)
+        x_T = torch.randn(1, 3, 128, 128, generator=g).to(dev)
+        xai.compute_time_shap_permutation(model, sched, clf, x_T, 0, n_perm=1, seed=1)          # warm-up (graph capture)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        phi, raw = xai.compute_time_shap_permutation(model, sched, clf, x_T, 0, n_perm=a.perm, seed=1)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        res["time_shap_permutation"] = {"steps": 50, "permutations": a.perm, "coalitions": a.perm * 51, "sec_per_image": dt,
+                                        "unet_steps_per_s": a.perm * 51 * 50 / dt, "efficiency_gap": raw["efficiency_gap"]}
     # CPU oracle beside it (reference issues 2 forwards per frame at B=1)
     from oracle import xai as oxai
     from oracle.classifier import build_classifier
