@@ -9,6 +9,7 @@ $CMD > gpurun_out/bench_plain_$TAG.json 2> gpurun_out/bench_plain_$TAG.err &&
 timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     -c 900 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "launch list rc=$?"; wc -l gpurun_out/launches_$TAG.csv
+[ "$2" = "launches-only" ] && exit 0
 python tools/ncu_target.py --steps 1 > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain target failed"; exit 1; }
 # conv_tc2 launches of one eager step: 0-3 = N 64 at 128x128, 4-7 = N 128 at 64x64, 8,9 = N 256 at 32x32, 10 = qkv 1x1, 11 = out-proj
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:conv_tc2 -c 12 -o /tmp/prof_conv_$TAG \
