@@ -22,6 +22,7 @@ LIB = PKG / "libsynt_isic_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+CFLAGS += os.environ.get("SYNT_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DSYNT_ATT_TIMELINE_BUILD for tools/att_timeline.py
 
 
 def _sources():

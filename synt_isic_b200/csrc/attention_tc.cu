@@ -31,6 +31,8 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
+#include <cstdio>
+#include <vector>
 
 namespace synt {
 
@@ -97,7 +99,8 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
 
 __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, int N,
                                                                       int C, const bf16* __restrict__ qkv,
-                                                                      bf16* __restrict__ out, int exp_skip) {
+                                                                      bf16* __restrict__ out, int exp_skip,
+                                                                      long long* __restrict__ tl) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();             // SWIZZLE_128B tiles need 1 KB alignment
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_OFF_BAR);
@@ -124,6 +127,24 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
         const int t = threadIdx.x - 128, qrow = t >> 1, hp = t & 1;
         const uint4* src = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + q0 + qrow) * (3 * C) + hg * 32 + hp * 16);
         q_pre[0] = __ldg(src); q_pre[1] = __ldg(src + 1);
+    }
+    // V^T builder (warp 3): constant rows and the first chunk's v values before the set-up barrier (latency overlap)
+    uint4 nx[2][4];
+    const uint4* vsrc = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + 2 * lane) * (3 * C) + 2 * C + hg * 32);
+    const size_t key_stride = (size_t)(3 * C) / 8;                            // uint4 per token row
+    auto fetch = [&](int c) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+            for (int h = 0; h < 4; ++h) nx[kk][h] = __ldg(vsrc + ((size_t)c * ATC_KEYS + kk) * key_stride + h);
+    };
+    if (warp == 3) {
+        fetch(0);
+        for (int i = lane; i < ATC_STAGES * 4 * 8 * 32; i += 32) {            // rows 8..15 of every head of every slot
+            const int word = i & 31, row = 8 + ((i >> 5) & 7), h = (i >> 8) & 3, st = i >> 10;
+            uint8_t* base = smem + ATC_OFF_STAGE + st * ATC_STAGE_BYTES + ATC_K_BYTES + h * 2048 + row * 128;
+            *reinterpret_cast<uint32_t*>(base + ((((word >> 2) ^ (row & 7)) << 4) | ((word & 3) << 2))) = row == 8 ? 0x3F803F80u : 0u;
+        }
     }
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.k);
@@ -157,21 +178,6 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
         // stage tile: [4 heads][16 rows][64 keys] bf16, SWIZZLE_128B (row = 128 B, 16-byte chunk ^= row & 7).  Lane l owns keys
         // 2l, 2l+1 of the chunk: their 4 x 8 v values arrive as 2 x 64 B from global memory and leave as 32 aligned 32-bit
         // stores (two adjacent keys of one row).  Rows 8 (ones) and 9..15 (zeros) are constant: written once per slot.
-        for (int i = lane; i < ATC_STAGES * 4 * 8 * 32; i += 32) {            // rows 8..15 of every head of every slot
-            const int word = i & 31, row = 8 + ((i >> 5) & 7), h = (i >> 8) & 3, st = i >> 10;
-            uint8_t* base = smem + ATC_OFF_STAGE + st * ATC_STAGE_BYTES + ATC_K_BYTES + h * 2048 + row * 128;
-            *reinterpret_cast<uint32_t*>(base + ((((word >> 2) ^ (row & 7)) << 4) | ((word & 3) << 2))) = row == 8 ? 0x3F803F80u : 0u;
-        }
-        const uint4* vsrc = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + 2 * lane) * (3 * C) + 2 * C + hg * 32);
-        const size_t key_stride = (size_t)(3 * C) / 8;                        // uint4 per token row
-        uint4 nx[2][4];
-        auto fetch = [&](int c) {
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                for (int h = 0; h < 4; ++h) nx[kk][h] = __ldg(vsrc + ((size_t)c * ATC_KEYS + kk) * key_stride + h);
-        };
-        fetch(0);
         int stage = 0; uint32_t phase = 0;
         for (int c = 0; c < n_chunks; ++c) {
             uint4 cur[2][4];
@@ -270,7 +276,16 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int j = g + 2 * jj, u = c * 4 + j, sb = u % ATC_NS;
+                // tl (debug, SYNT_ATT_TIMELINE): clock64 of {unit start, S ready, P tile free, unit done} per softmax warp
+#ifdef SYNT_ATT_TIMELINE_BUILD
+                const bool rec = tl != nullptr && lane == 0 && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 1;
+#else
+                constexpr bool rec = false;                                // compile with -DSYNT_ATT_TIMELINE_BUILD for tools/att_timeline.py
+#endif
+                long long* trow = rec ? tl + ((size_t)(warp - 4) * n_units + (c * 2 + jj) * 2) * 4 : nullptr;   // [8 warps][n_units/2 per group..]
+                if (rec) trow[0] = clock64();
                 mbar_wait(&s_full[sb], ((uint32_t)(u / ATC_NS)) & 1u);
+                if (rec) trow[1] = clock64();
                 tc_fence_after();
                 // Softmax reference m of this row and head.  Any m within the bf16/fp32 exponent range of the true maximum
                 // gives the exact softmax after the final division, so only the FIRST chunk pays for an exact row maximum
@@ -303,6 +318,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 // P.V of unit u-3 is complete, hence (in-order MMA pipe) so is every earlier one: P[sb] is free and
                 // O_j (last written by unit u-4) has no MMA in flight
                 mbar_wait(&p_free[sb], (((uint32_t)(u / ATC_NS)) & 1u) ^ 1u);
+                if (rec) trow[2] = clock64();
                 if (__any_sync(0xffffffffu, moved)) {
                     tc_fence_after();
                     uint32_t o[16];
@@ -349,6 +365,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 tc_fence_before();
                 fence_proxy_async();                                       // generic-proxy writes -> async proxy (UMMA)
                 mbar_arrive(&p_full[sb]);
+                if (rec) trow[3] = clock64();
             }
         }
         // ---- epilogue: O_h / rowsum -> bf16 NHWC
@@ -420,8 +437,20 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
         attr = true;
     }
     static const int exp_skip = [] { const char* e = getenv("SYNT_ATT_NOEXP"); return (e && e[0] == '1') ? 1 : 0; }();
+    // debug: SYNT_ATT_TIMELINE=<file> dumps the softmax warps' clock64 samples of CTA (1,1,1) of every 1024-token launch
+    static const char* tl_path = getenv("SYNT_ATT_TIMELINE");
+    long long* tl = nullptr;
+    const size_t tl_n = (size_t)8 * (N / ATC_KEYS) * 4 * 4;
+    if (tl_path && N == 1024 && B > 1) { SYNT_CUDA(cudaMalloc(&tl, tl_n * 8)); SYNT_CUDA(cudaMemsetAsync(tl, 0, tl_n * 8, s)); }
     launch_pdl(attention_tc_kernel, dim3(N / 128, C / 32, B), dim3(ATC_THREADS), ATC_SMEM, s, maps, N, C, (const bf16*)qkv,
-               (bf16*)out, exp_skip);
+               (bf16*)out, exp_skip, tl);
+    if (tl) {
+        std::vector<long long> h(tl_n);
+        SYNT_CUDA(cudaMemcpyAsync(h.data(), tl, tl_n * 8, cudaMemcpyDeviceToHost, s));
+        SYNT_CUDA(cudaStreamSynchronize(s));
+        cudaFree(tl);
+        if (FILE* f = fopen(tl_path, "ab")) { fwrite(h.data(), 8, tl_n, f); fclose(f); }
+    }
 }
 
 }  // namespace synt
