@@ -110,6 +110,23 @@ int synt_resnet18_debug(synt_resnet18_t* h, const float* x_dev, int B, const cha
                         long long out_cap, int* C, int* H, int* W, void* stream);
 long long synt_resnet18_launch_count(synt_resnet18_t* h);
 
+/* Input gradient of the per-class score s = log(softmax(logits)[target_class] + 1e-8) (get_per_class_score,
+ * XAI.py:443-459): replaces the autograd pass that captum's IntegratedGradients (XAI.py:1039-1085) and the plain gradient
+ * attribution (XAI.py:1087-1109) run through the classifier.  score_dev [B] (nullable), grad_dev [B,3,128,128] fp32. */
+int synt_resnet18_score_grad(synt_resnet18_t* h, const float* x_dev, int B, int target_class, float* score_dev,
+                             float* grad_dev, void* stream);
+/* test hook: gradient at an intermediate tensor ("grad:layer4.1" ... "grad:layer1.0" = at the block's pre-ReLU output,
+ * "grad:maxpool", "grad:relu" (stem output, ReLU-masked), "grad:preprocess"), NCHW fp32; B <= 32 */
+int synt_resnet18_grad_debug(synt_resnet18_t* h, const float* x_dev, int B, int target_class, const char* tap,
+                             float* out_dev, long long out_cap, int* C, int* H, int* W, void* stream);
+/* Integrated-Gradients path points and reduction (captum method='riemann_right', XAI.py:1069-1074):
+ *   out[k] = baseline + (k+1)/n_steps * (x - baseline), k = 0..n_steps-1            out [n_steps][per_image]
+ *   out    = (x - baseline) * sum_k grads[k] / n_steps                               out [per_image]            */
+int synt_ig_interpolate(const float* x_dev, const float* baseline_dev, int n_steps, long long per_image, float* out_dev,
+                        void* stream);
+int synt_ig_reduce(const float* grads_dev, const float* x_dev, const float* baseline_dev, int n_steps, long long per_image,
+                   float* out_dev, void* stream);
+
 /* replaces counterfactual_intervention_advanced (XAI.py:1454-1597):
  *   out = clamp(x*(1-M) + I*M, -1, 1); type 0 zero, 1 per-channel mean, 2 5x5 box blur,
  *   3 noise (aux = injected N(0,1) tensor, scaled by noise_std), 4 aux is the intervention itself */

@@ -9,6 +9,10 @@ exposes ``get_confidence / get_per_class_score / get_probabilities``:
 * ``intervene``            -- ``counterfactual_intervention_advanced`` xai/XAI.py:1454-1597
 * ``causal_shift``         -- ``compute_causal_shift_comprehensive``   xai/XAI.py:1600-1700
 * ``time_shap_permutation`` -- permutation Shapley over denoising steps, README.md:171-221 (spec only, no reference code)
+* ``integrated_gradients`` -- ``compute_integrated_gradients`` xai/XAI.py:1039-1085: captum (>=0.6.0, requirements.txt, NOT
+  installed here) ``IntegratedGradients.attribute(method='riemann_right')`` restated from its published algorithm
+  (Sundararajan et al. 2017 eq. 3 with right Riemann sums: alphas = linspace(1/n, 1, n), step sizes 1/n), gradients from
+  torch autograd through the REAL torchvision classifier oracle; ``gradient_attribution`` xai/XAI.py:1087-1109
 
 Randomness the reference draws from global RNGs (patch masks ``torch.rand(8,8)``, noise
 ``randn_like``, ``randperm``) is INJECTED here so the CUDA path can be compared exactly.
@@ -176,3 +180,52 @@ def exact_shapley(value_fn, n: int) -> np.ndarray:
                 w = math.factorial(r) * math.factorial(n - r - 1) / math.factorial(n)
                 phi[t] += w * (value_fn(set(S) | {t}) - value_fn(set(S)))
     return phi
+
+
+# ------------------------------------------------------------------ gradient attributions
+def gradient_attribution(classifier, image, target_class):
+    """XAI.py:1087-1109 -- d get_per_class_score(x, c) / dx by autograd."""
+    x = image.detach().clone().requires_grad_(True)
+    score = classifier.get_per_class_score(x, target_class)
+    score.sum().backward()
+    return x.grad.detach().clone()
+
+
+def integrated_gradients(classifier, image, target_class, baseline, n_steps=50, chunk=10):
+    """XAI.py:1039-1085 with the baseline injected.  captum's ``riemann_right`` builder: ``alphas = linspace(1/n, 1, n)``,
+    ``step_sizes = [1/n] * n``; ``scaled_features = baseline + alpha * (input - baseline)``; the gradients of the scalar
+    forward are multiplied by the step sizes, summed over the path and multiplied by ``input - baseline``.
+    Returns (attribution, convergence delta = sum(attr) - (F(x) - F(x')))."""
+    alphas = np.linspace(1.0 / n_steps, 1.0, n_steps)
+    total = torch.zeros_like(image)
+    for i in range(0, n_steps, chunk):
+        pts = torch.cat([baseline + float(a) * (image - baseline) for a in alphas[i:i + chunk]])
+        total += gradient_attribution(classifier, pts, target_class).sum(0, keepdim=True) * (1.0 / n_steps)
+    attr = total * (image - baseline)
+    with torch.no_grad():
+        delta = attr.sum() - (classifier.get_per_class_score(image, target_class)
+                              - classifier.get_per_class_score(baseline, target_class)).sum()
+    return attr, float(delta)
+
+
+def classifier_gradient_taps(classifier, image, target_class):
+    """Gradients of the score at the intermediate tensors of the classifier (test diagnostics for the CUDA adjoint chain):
+    {'preprocess', 'relu', 'maxpool', 'layerL.J'} -> (activation, d score / d activation), plus 'input'."""
+    m = classifier.model
+    x = image.detach().clone().requires_grad_(True)
+    taps = {}
+    z = classifier.preprocess_for_classifier(x); taps["preprocess"] = z
+    z = F.relu(m.bn1(m.conv1(z))); taps["relu"] = z
+    z = m.maxpool(z); taps["maxpool"] = z
+    for l in range(1, 5):
+        for j in range(2):
+            z = getattr(m, f"layer{l}")[j](z)
+            taps[f"layer{l}.{j}"] = z
+    logits = m.fc(torch.flatten(m.avgpool(z), 1))
+    for t in taps.values():
+        t.retain_grad()
+    score = torch.log(F.softmax(logits, dim=1)[:, target_class] + 1e-8)
+    score.sum().backward()
+    out = {k: (t.detach(), t.grad.detach()) for k, t in taps.items()}
+    out["input"] = (x.detach(), x.grad.detach())
+    return out, score.detach()

@@ -120,6 +120,38 @@ class MelanomaClassifierAdaptive(nn.Module):
         with torch.no_grad():
             return self.get_probabilities(x)[:, target_class]
 
+    # ------------------------------------------------------------------ input gradient -
+    def score_and_input_gradient(self, x, target_class: int):
+        """``(s, ds/dx)`` with ``s = get_per_class_score(x, target_class)`` (XAI.py:443-459): the backward pass that
+        captum's IntegratedGradients (XAI.py:1039-1085) and ``_compute_gradient_attribution`` (XAI.py:1087-1109) obtain from
+        autograd, here as the adjoint chain of the CUDA path (data-gradient convolutions on the same tcgen05 kernels)."""
+        dev = next(self.parameters()).device
+        if x.device != dev:
+            x = x.to(dev)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 128, 128):
+            raise ValueError(f"expected [B,3,128,128] in [-1,1], got {tuple(x.shape)}")
+        h = self._handle()
+        x = x.detach().contiguous().float()
+        score = torch.empty(x.shape[0], dtype=torch.float32, device=dev)
+        grad = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().synt_resnet18_score_grad(h, x.data_ptr(), x.shape[0], int(target_class), score.data_ptr(),
+                                                           grad.data_ptr(), _lib.current_stream_ptr()), "resnet18_score_grad")
+        return score, grad
+
+    def grad_debug_tap(self, x, target_class: int, tap: str):
+        h = self._handle()
+        x = x.contiguous().float()
+        B = x.shape[0]
+        buf = torch.empty(B * 64 * 112 * 112, dtype=torch.float32, device=x.device)
+        c, hh, ww = C.c_int(), C.c_int(), C.c_int()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().synt_resnet18_grad_debug(h, x.data_ptr(), B, int(target_class), tap.encode(), buf.data_ptr(),
+                                                           buf.numel(), C.byref(c), C.byref(hh), C.byref(ww),
+                                                           _lib.current_stream_ptr()), "resnet18_grad_debug")
+        n = B * c.value * hh.value * ww.value
+        return buf[:n].view(B, c.value, hh.value, ww.value).clone()
+
     def debug_tap(self, x, tap: str):
         h = self._handle()
         x = x.contiguous().float()

@@ -146,6 +146,21 @@ void classifier_preprocess(const float* x_nchw, int B, int Hin, int Win, int Hou
 void maxpool3x3s2(const void* in, int dt, int B, int H, int W, int C, void* out, cudaStream_t s);
 void avgpool_fc(const void* in, int dt, int B, int HW, int C, const float* w, const float* b, int nout,
                 float* logits, cudaStream_t s);
+// ---- input-gradient path (resnet_grad.cu): d log(p_c + 1e-8) / dx for Integrated Gradients, xai/XAI.py:1039-1109 ----
+void score_grad(const float* logits, int B, int nc, int target, float* score /*nullable*/, float* dlogits, cudaStream_t s);
+void avgpool_fc_bwd(const float* dlogits, const float* w, const void* feat, int dt, int B, int HW, int C, int nc, void* out,
+                    cudaStream_t s);                                           // ReLU mask (feat > 0) fused
+void relu_mask(const void* g, const void* act, int dt, long long n, void* out /* may alias g */, cudaStream_t s);
+void zero_insert2x(const void* g, const void* act /*nullable ReLU mask*/, int dt, int B, int Ho, int Wo, int C, void* out,
+                   cudaStream_t s);
+void maxpool3x3s2_bwd(const void* dpool, const void* act, int dt, int B, int H, int W, int C, void* dact, cudaStream_t s);
+void stem_dgrad(const void* g, int dt, int B, const float* w /*[64][147] fp32*/, float* dpre /*[B,224,224,3]*/, cudaStream_t s);
+void classifier_preprocess_bwd(const float* dpre, const float* x, int B, int Hin, int Win, int Hout, int Wout, float* dx,
+                               cudaStream_t s);
+void dgrad_weights(const void* src, int src_ld, int src_off, int cin_f, int cout_f, int taps, int bf, void* dst, int dst_ld,
+                   int dst_off, cudaStream_t s);
+void ig_interpolate(const float* x, const float* base, int n_steps, long long per, float* out, cudaStream_t s);
+void ig_reduce(const float* grads, const float* x, const float* base, int n_steps, long long per, float* out, cudaStream_t s);
 // interventions (xai/XAI.py:1495-1575): type 0=zero 1=mean 2=blur5 3=noise(injected) 4=given tensor
 void intervene_blend(const float* x, const float* mask, const float* aux, int type, float noise_std, int B, int C,
                      int H, int W, float* out, cudaStream_t s);

@@ -558,6 +558,10 @@ struct synt_resnet18 {
     RConv stem_tc;                           // the same stem as a 1x1 conv over the im2col'd input (K 147 -> 192), bf16 tcgen05
     RPtr stem_frag;                          // stem weights as mma.sync B fragments (fused stem kernel, default in bf16 mode)
     RConv c1[4][2], c2[4][2];
+    // data-gradient convolutions of the same layers (built on first use by ensure_bwd): d2 = dgrad of conv2 (c -> c),
+    // d1 = dgrad of conv1 (c -> block input channels; the stride-2 blocks carry the 1x1 downsample dgrad as shortcut segment)
+    RConv d1[4][2], d2[4][2];
+    RPtr zero_bias; bool bwd_ready = false;
     RPtr fc_w, fc_b;
     Pool pool;
     long long launches = 0;
@@ -581,14 +585,14 @@ struct RFwd {
         r->tap_C = C; r->tap_H = H; r->tap_W = W; r->tap_hit = true;
     }
     void conv(const RConv& c, const void* in, int H, int W, const void* sc, int sc_stride, const void* residual, int relu,
-              void* out, int Ho, int Wo) {
+              void* out, int Ho, int Wo, bool allow_v2 = true) {
         ConvArgs a; a.in = in; a.B = B; a.H = H; a.W = W; a.Cin = c.cin; a.KH = a.KW = c.k; a.stride = c.stride;
         a.pad = c.k / 2; a.Ho = Ho; a.Wo = Wo; a.Cout = c.cout;
         if (c.csc) { a.sc0 = sc; a.sc0_C = c.csc; a.sc_stride = sc_stride; }
         a.weight = c.w->p; a.bias = (const float*)c.b->p; a.residual = residual; a.relu = relu; a.out = out;
         // stride-1 3x3 convs on the 56x56 / 28x28 planes: the persistent halo-tile kernel (ragged tile grid); the rest
         // (stride 2, strided 1x1 shortcut segments, 14x14 and 7x7 planes): one TMA box per tap
-        if (c.bf && r->use_v2 && conv_tc2_supported(a)) conv_tc2(a, s);
+        if (c.bf && r->use_v2 && allow_v2 && conv_tc2_supported(a)) conv_tc2(a, s);
         else if (c.bf) conv_tc(a, s);
         else conv_simt(a, r->dt, s);
         ++r->launches;
@@ -644,6 +648,150 @@ struct RFwd {
         avgpool_fc(cur, r->dt, B, H * H, 512, (const float*)r->fc_w->p, (const float*)r->fc_b->p, r->num_classes, logits, s);
         ++r->launches;
         r->pool.release(cur);
+    }
+};
+
+// ---- input gradient: forward with every activation kept, then the adjoint chain (kernels: resnet_grad.cu) --------------
+static RPtr r_alloc(size_t bytes) {
+    auto b = std::make_shared<RDev>();
+    SYNT_CUDA(cudaMalloc(&b->p, bytes));
+    return b;
+}
+static void ensure_bwd(synt_resnet18* r, cudaStream_t s) {
+    if (r->bwd_ready) return;
+    const bool bf = r->use_tc;
+    const size_t es = bf ? 2 : 4;
+    std::vector<float> z(512, 0.f);
+    r->zero_bias = r_upload(z.data(), z.size() * 4);
+    int cin = 64;
+    for (int l = 0; l < 4; ++l) {
+        const int c = kStageCh[l];
+        for (int j = 0; j < 2; ++j) {
+            const bool down = j == 0 && l > 0;
+            const int ci = j == 0 ? cin : c;
+            const RConv& f1 = r->c1[l][j];
+            const RConv& f2 = r->c2[l][j];
+            RConv& d2 = r->d2[l][j];                           // gradient at conv2's output [c] -> conv2's input [c]
+            d2.cin = c; d2.cout = c; d2.k = 3; d2.stride = 1; d2.csc = 0; d2.bf = bf; d2.b = r->zero_bias;
+            d2.w = r_alloc((size_t)c * 9 * c * es);
+            dgrad_weights(f2.w->p, 9 * c + f2.csc, 0, c, c, 9, bf, d2.w->p, 9 * c, 0, s);
+            RConv& d1 = r->d1[l][j];                           // gradient at conv1's output [c] -> block input [ci]
+            d1.cin = c; d1.cout = ci; d1.k = 3; d1.stride = 1; d1.csc = down ? c : 0; d1.bf = bf; d1.b = r->zero_bias;
+            const int ld = 9 * c + d1.csc;
+            d1.w = r_alloc((size_t)ci * ld * es);
+            dgrad_weights(f1.w->p, 9 * ci, 0, ci, c, 9, bf, d1.w->p, ld, 0, s);
+            if (down) dgrad_weights(f2.w->p, 9 * c + f2.csc, 9 * c, ci, c, 1, bf, d1.w->p, ld, 9 * c, s);
+        }
+        cin = c;
+    }
+    SYNT_CUDA(cudaStreamSynchronize(s));
+    r->bwd_ready = true;
+}
+
+struct RGrad {
+    synt_resnet18* r; cudaStream_t s; int B;
+    void gtap(const std::string& name, const void* p, int dt, int H, int W, int C) {
+        if (!r->tap_out || name != r->tap_name) return;
+        SYNT_CHECK((long long)B * H * W * C <= r->tap_cap, "debug tap buffer too small");
+        nhwc_to_nchw_f32(p, dt, B, H * W, C, r->tap_out, s);
+        r->tap_C = C; r->tap_H = H; r->tap_W = W; r->tap_hit = true;
+    }
+    // score[b] = log(softmax(logits)[target] + 1e-8) (nullable), dx[b] = d score[b] / d x[b]  (fp32 NCHW like x)
+    void run(const float* x_nchw, int target, float* score, float* dx) {
+        ensure_bwd(r, s);
+        RFwd f{r, s, B};
+        const int dt = r->dt;
+        Pool& pool = r->pool;
+        // ---------------- forward, activations kept ----------------
+        void* pre = f.make(224, 224, 3);
+        classifier_preprocess(x_nchw, B, 128, 128, 224, 224, pre, 3, dt, s);
+        void* a1 = f.make(112, 112, 64);                            // stem output (post-ReLU)
+        if (r->use_tc && r->stem_frag) {
+            stem_mma(pre, B, r->stem_frag->p, (const float*)r->stem_tc.b->p, a1, s);
+        } else if (r->use_tc) {
+            void* col = f.make(112, 112, 192);
+            stem_im2col(pre, B, col, s);
+            f.conv(r->stem_tc, col, 112, 112, nullptr, 1, nullptr, 1, a1, 112, 112);
+            pool.release(col);
+        } else {
+            f.conv(r->stem, pre, 224, 224, nullptr, 1, nullptr, 1, a1, 112, 112);
+        }
+        pool.release(pre);
+        void* x0 = f.make(56, 56, 64);
+        maxpool3x3s2(a1, dt, B, 112, 112, 64, x0, s);
+        void* h1[4][2]; void* o[4][2];
+        const void* cur = x0;
+        int H = 56;
+        for (int l = 0; l < 4; ++l) {
+            const int c = kStageCh[l];
+            for (int j = 0; j < 2; ++j) {
+                const int stride = (j == 0 && l > 0) ? 2 : 1;
+                const int Ho = H / stride;
+                h1[l][j] = f.make(Ho, Ho, c);
+                f.conv(r->c1[l][j], cur, H, H, nullptr, 1, nullptr, 1, h1[l][j], Ho, Ho);
+                o[l][j] = f.make(Ho, Ho, c);
+                if (r->c2[l][j].csc) f.conv(r->c2[l][j], h1[l][j], Ho, Ho, cur, stride, nullptr, 1, o[l][j], Ho, Ho);
+                else                 f.conv(r->c2[l][j], h1[l][j], Ho, Ho, nullptr, 1, cur, 1, o[l][j], Ho, Ho);
+                cur = o[l][j]; H = Ho;
+            }
+        }
+        const int nc = r->num_classes;
+        float* logits = (float*)pool.alloc((size_t)B * nc * 4);
+        float* dlog = (float*)pool.alloc((size_t)B * nc * 4);
+        avgpool_fc(cur, dt, B, H * H, 512, (const float*)r->fc_w->p, (const float*)r->fc_b->p, nc, logits, s);
+        score_grad(logits, B, nc, target, score, dlog, s);
+        // ---------------- backward ----------------
+        // g is always the gradient at a block's PRE-ReLU output (the ReLU mask of the tensor it arrives at is applied)
+        void* g = f.make(7, 7, 512);
+        avgpool_fc_bwd(dlog, (const float*)r->fc_w->p, o[3][1], dt, B, 49, 512, nc, g, s);
+        pool.release(logits); pool.release(dlog);
+        r->launches += 5;
+        for (int l = 3; l >= 0; --l) {
+            const int c = kStageCh[l];
+            const int Ho = 56 >> l;
+            for (int j = 1; j >= 0; --j) {
+                const bool down = j == 0 && l > 0;
+                const int ci = down ? kStageCh[l - 1] : c;
+                const int Hin = down ? 2 * Ho : Ho;
+                gtap("grad:layer" + std::to_string(l + 1) + "." + std::to_string(j), g, dt, Ho, Ho, c);
+                void* t = f.make(Ho, Ho, c);
+                f.conv(r->d2[l][j], g, Ho, Ho, nullptr, 1, nullptr, 0, t, Ho, Ho);
+                void* dxb = f.make(Hin, Hin, ci);
+                if (!down) {
+                    relu_mask(t, h1[l][j], dt, (long long)B * Ho * Ho * c, t, s);
+                    f.conv(r->d1[l][j], t, Ho, Ho, nullptr, 1, /*identity shortcut*/ g, 0, dxb, Ho, Ho);
+                } else {
+                    // stride-2 block: conv1 (3x3/s2) and the 1x1/s2 downsample both read the block input; their data
+                    // gradients are stride-1 convolutions over the zero-inserted gradient planes, fused as main + shortcut
+                    void* tz = f.make(Hin, Hin, c);
+                    void* gz = f.make(Hin, Hin, c);
+                    zero_insert2x(t, h1[l][j], dt, B, Ho, Ho, c, tz, s);
+                    zero_insert2x(g, nullptr, dt, B, Ho, Ho, c, gz, s);
+                    f.conv(r->d1[l][j], tz, Hin, Hin, gz, 1, nullptr, 0, dxb, Hin, Hin, /*allow_v2=*/false);
+                    pool.release(tz); pool.release(gz);
+                    ++r->launches;
+                }
+                ++r->launches;
+                pool.release(t); pool.release(g);
+                pool.release(h1[l][j]); pool.release(o[l][j]);
+                // the block input is the previous block's ReLU output (or, for layer1.0, the max-pool output: no mask)
+                const void* xin = (l == 0 && j == 0) ? nullptr : (j == 1 ? o[l][0] : o[l - 1][1]);
+                if (xin) { relu_mask(dxb, xin, dt, (long long)B * Hin * Hin * ci, dxb, s); ++r->launches; }
+                g = dxb;
+            }
+        }
+        gtap("grad:maxpool", g, dt, 56, 56, 64);
+        void* da1 = f.make(112, 112, 64);
+        maxpool3x3s2_bwd(g, a1, dt, B, 112, 112, 64, da1, s);
+        gtap("grad:relu", da1, dt, 112, 112, 64);
+        pool.release(g); pool.release(a1); pool.release(x0);
+        float* dpre = (float*)pool.alloc((size_t)B * 224 * 224 * 3 * 4);
+        stem_dgrad(da1, dt, B, (const float*)r->stem.w->p, dpre, s);
+        gtap("grad:preprocess", dpre, DT_F32, 224, 224, 3);
+        pool.release(da1);
+        classifier_preprocess_bwd(dpre, x_nchw, B, 128, 128, 224, 224, dx, s);
+        pool.release(dpre);
+        r->launches += 3;
     }
 };
 
@@ -782,6 +930,51 @@ int synt_resnet18_debug(synt_resnet18_t* h, const float* x, int B, const char* t
     SYNT_CATCH
 }
 long long synt_resnet18_launch_count(synt_resnet18_t* h) { return h ? h->launches : 0; }
+
+int synt_resnet18_score_grad(synt_resnet18_t* h, const float* x, int B, int target_class, float* score, float* grad,
+                             void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(h && x && grad && B > 0, "bad argument");
+    SYNT_CHECK(target_class >= 0 && target_class < h->num_classes, "target class out of range");
+    const size_t img = (size_t)3 * 128 * 128;
+    // every activation of the micro-batch stays resident until its adjoint has run: ~5.3 MB (bf16) per image
+    const int mb = h->dt == DT_BF16 ? 64 : 32;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+        RGrad g{h, (cudaStream_t)stream, B - b0 < mb ? B - b0 : mb};
+        g.run(x + b0 * img, target_class, score ? score + b0 : nullptr, grad + b0 * img);
+    }
+    SYNT_CATCH
+}
+int synt_resnet18_grad_debug(synt_resnet18_t* h, const float* x, int B, int target_class, const char* tap, float* out,
+                             long long cap, int* C, int* H, int* W, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(h && x && tap && out && B > 0 && B <= 32, "bad argument");
+    SYNT_CHECK(target_class >= 0 && target_class < h->num_classes, "target class out of range");
+    h->tap_name = tap; h->tap_out = out; h->tap_cap = cap; h->tap_hit = false;
+    float* dx = (float*)h->pool.alloc((size_t)B * 3 * 128 * 128 * 4);
+    RGrad g{h, (cudaStream_t)stream, B};
+    try { g.run(x, target_class, nullptr, dx); } catch (...) { h->tap_out = nullptr; h->pool.release(dx); throw; }
+    h->pool.release(dx);
+    h->tap_out = nullptr;
+    SYNT_CHECK(h->tap_hit, std::string("unknown gradient tap: ") + tap);
+    if (C) *C = h->tap_C;
+    if (H) *H = h->tap_H;
+    if (W) *W = h->tap_W;
+    SYNT_CATCH
+}
+int synt_ig_interpolate(const float* x, const float* baseline, int n_steps, long long per_image, float* out, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(x && baseline && out && n_steps > 0 && per_image > 0, "bad argument");
+    ig_interpolate(x, baseline, n_steps, per_image, out, (cudaStream_t)stream);
+    SYNT_CATCH
+}
+int synt_ig_reduce(const float* grads, const float* x, const float* baseline, int n_steps, long long per_image, float* out,
+                   void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(grads && x && baseline && out && n_steps > 0 && per_image > 0, "bad argument");
+    ig_reduce(grads, x, baseline, n_steps, per_image, out, (cudaStream_t)stream);
+    SYNT_CATCH
+}
 
 int synt_intervene_blend(const float* x, const float* mask, const float* aux, int type, float noise_std, int B, int C,
                          int H, int W, float* out, void* stream) {

@@ -10,10 +10,12 @@ of the CUDA classifier and (optionally) sharded across ranks with a single all_g
   compute_shap_approximation            xai/XAI.py:1111-1177   (513 forwards -> 1 batched)
   counterfactual_intervention_advanced  xai/XAI.py:1454-1597
   compute_causal_shift_comprehensive    xai/XAI.py:1600-1700   (18 forwards -> 1 batch of 2)
+  compute_integrated_gradients          xai/XAI.py:1039-1085   (captum autograd -> batched CUDA adjoint)
+  compute_gradient_attribution          xai/XAI.py:1087-1109
+  compute_combined_attribution          xai/XAI.py:1236-1291
   IntegratedXAIAnalyzer                 xai/xai_integration.py:75-132
 
-Out of scope: Integrated Gradients, Grad-CAM (autograd), region
-morphology, statistics and plots.
+Out of scope: Grad-CAM, region morphology, statistics and plots.
 """
 from __future__ import annotations
 
@@ -29,6 +31,7 @@ SHAP_N_SAMPLES = 512       # xai/XAI.py:240
 NOISE_STD = 0.5            # xai/XAI.py:262
 BLUR_KERNEL_SIZE = 5       # xai/XAI.py:263
 TOP_K_PERCENT = 10         # xai/XAI.py:238
+IG_N_STEPS = 50            # xai/XAI.py:240
 _TYPE_CODES = {"zero": 0, "mean": 1, "blur": 2, "inpaint": 2, "noise": 3, "gaussian_noise": 3, "shuffle": 4}
 
 
@@ -198,6 +201,74 @@ def compute_shap_approximation(classifier, image, target_class, n_samples=SHAP_N
     return full[None, None].expand(1, ch, height, width).contiguous()
 
 
+# ------------------------------------------------------------------ gradient attributions
+def get_baseline(image: torch.Tensor, baseline_type: str = "noise", generator=None) -> torch.Tensor:
+    """xai/XAI.py:1008-1037: 'noise' = 0.1 N(0,1), 'blur' = 31x31 box blur, anything else zeros.  (The reference caches
+    one baseline per (type, shape, device) for the life of the analyzer; pass ``baseline=`` to the callers for that.)"""
+    if baseline_type == "noise":
+        return torch.randn(image.shape, device=image.device, dtype=image.dtype, generator=generator) * 0.1
+    if baseline_type == "blur":
+        return F.avg_pool2d(image, kernel_size=31, stride=1, padding=15)
+    return torch.zeros_like(image)
+
+
+def compute_gradient_attribution(classifier, image, target_class):
+    """xai/XAI.py:1087-1109: d get_per_class_score(x, c) / dx, one call of the CUDA adjoint chain."""
+    dev = _dev(classifier)
+    x = image.to(dev).float().reshape(-1, 3, 128, 128)
+    return classifier.score_and_input_gradient(x, target_class)[1]
+
+
+def compute_integrated_gradients(classifier, image, target_class, n_steps=IG_N_STEPS, baseline_type="noise",
+                                 baseline=None, generator=None, return_convergence_delta=False):
+    """xai/XAI.py:1039-1085 = captum ``IntegratedGradients(forward).attribute(x, baselines=x', n_steps=n,
+    method='riemann_right')`` with forward = ``get_per_class_score(., c)``:
+
+        IG = (x - x') * sum_{k=1..n} (1/n) * ds/dx (x' + (k/n) (x - x'))
+
+    The reference runs the n path points through autograd (captum's default internal batching); here they are ONE batch
+    of the CUDA classifier's score + input-gradient pass.  ``baseline`` injects x' (tests; the reference caches its
+    random baseline).  With ``return_convergence_delta`` also returns sum(IG) - (s(x) - s(x')) (captum's delta)."""
+    dev = _dev(classifier)
+    x = image.to(dev).float().reshape(1, 3, 128, 128).contiguous()
+    base = (get_baseline(x, baseline_type, generator) if baseline is None else baseline.to(dev).float()).reshape(1, 3, 128, 128).contiguous()
+    per = x.numel()
+    pts = torch.empty(n_steps, 3, 128, 128, dtype=torch.float32, device=dev)
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        st = _lib.current_stream_ptr()
+        _lib.check(_lib.lib().synt_ig_interpolate(x.data_ptr(), base.data_ptr(), n_steps, per, pts.data_ptr(), st), "ig_interpolate")
+        _, grads = classifier.score_and_input_gradient(pts, target_class)
+        _lib.check(_lib.lib().synt_ig_reduce(grads.data_ptr(), x.data_ptr(), base.data_ptr(), n_steps, per, out.data_ptr(), st), "ig_reduce")
+    if return_convergence_delta:
+        s = classifier.get_per_class_score(torch.cat([x, base]), target_class)
+        return out, float(out.sum() - (s[0] - s[1]))
+    return out
+
+
+def compute_combined_attribution(classifier, image, target_class, methods=("ig", "shap"), weights=None, **kwargs):
+    """xai/XAI.py:1236-1291: weighted sum of the attribution maps + per-method |attr| mean / max."""
+    methods = list(methods)
+    if weights is None:
+        weights = [1.0 / len(methods)] * len(methods)
+    total, details = None, {}
+    for method, weight in zip(methods, weights):
+        if method == "ig":
+            attr = compute_integrated_gradients(classifier, image, target_class, **kwargs.get("ig", {}))
+        elif method == "shap":
+            attr = compute_shap_approximation(classifier, image, target_class, **kwargs.get("shap", {}))
+        elif method == "gradient":
+            attr = compute_gradient_attribution(classifier, image, target_class)
+        else:
+            continue                                             # unknown method: skipped like the reference (XAI.py:1270-1272)
+        total = attr * weight if total is None else total + attr * weight
+        details[method] = {"weight": weight, "mean_attribution": float(attr.abs().mean()),
+                           "max_attribution": float(attr.abs().max())}
+    if total is None:
+        raise RuntimeError("no attribution could be computed")
+    return total, details
+
+
 # ------------------------------------------------------------------ interventions -------
 def counterfactual_intervention_advanced(image, mask, intervention_type="noise", **kwargs):
     """xai/XAI.py:1454-1597: x~ = clamp(x (1-M) + I M, -1, 1).  Extra kwargs: ``noise`` injects the
@@ -351,7 +422,8 @@ class IntegratedXAIAnalyzer:
                                                      precision=precision).to(self.device).eval()
 
     def analyze_trajectory(self, trajectory, class_name, seed, inference_steps, filename, file_path, timesteps=None,
-                           shap_samples: int = SHAP_N_SAMPLES, intervention_types=("blur",)):
+                           shap_samples: int = SHAP_N_SAMPLES, intervention_types=("blur",), methods=("ig", "shap"),
+                           ig_steps: int = IG_N_STEPS):
         if not trajectory:
             return None
         T = len(trajectory)
@@ -363,7 +435,10 @@ class IntegratedXAIAnalyzer:
         cfi = {}
         for k in key_frames:
             frame = trajectory[k].to(self.device).reshape(1, 3, 128, 128)
-            attr = compute_shap_approximation(self.classifier, frame, target, n_samples=shap_samples, group=self.group)
+            # stage 1 of the reference pipeline (XAI.py:2746-2751): IG + SHAP combined 0.5 / 0.5
+            attr, _ = compute_combined_attribution(self.classifier, frame, target, methods=methods,
+                                                   shap={"n_samples": shap_samples, "group": self.group},
+                                                   ig={"n_steps": ig_steps})
             top, bot = select_regions_topk(attr)
             for rname, mask in (("top_k", top), ("bottom_k", bot)):
                 for it in intervention_types:
@@ -378,7 +453,8 @@ class IntegratedXAIAnalyzer:
                           "probability_scores": [float(v) for v in raw["probability_scores"]],
                           "timesteps": [int(t) for t in timesteps]},
             "cfi": cfi,
-            "skipped_stages": ["integrated_gradients", "grad_cam", "statistics", "plots"],
+            "attribution_methods": list(methods),
+            "skipped_stages": ["grad_cam", "statistics", "plots"],
         }
 
 

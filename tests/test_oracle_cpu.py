@@ -182,3 +182,24 @@ def test_permutation_shapley_estimator_and_enumeration():
     few = xai.draw_step_permutations(4, 3, 9)
     vals = np.array([[v(set(p[:k])) for k in range(5)] for p in few])
     assert abs(xai.shapley_from_prefix_values(few, vals).sum() - (v({0, 1, 2, 3}) - v(set()))) < 1e-12
+
+
+def test_oracle_integrated_gradients_completeness_and_gradient_taps():
+    """captum riemann_right restatement (oracle/xai.py): completeness axiom sum(IG) ~= F(x) - F(x') up to the Riemann error,
+    IG of x' == x is zero, and the tap helper's input gradient equals plain autograd."""
+    from oracle import xai as oxai
+    from oracle.classifier import build_classifier
+    m = build_classifier()
+    g = torch.Generator().manual_seed(3)
+    x = torch.tanh(torch.randn(1, 3, 128, 128, generator=g))
+    base = torch.randn(1, 3, 128, 128, generator=g) * 0.1
+    attr, delta = oxai.integrated_gradients(m, x, 2, base, n_steps=20)
+    with torch.no_grad():
+        diff = float(m.get_per_class_score(x, 2) - m.get_per_class_score(base, 2))
+    assert abs(delta) < 0.15 * abs(diff) + 0.02
+    assert abs(float(attr.sum()) - diff - delta) < 1e-4
+    zero, _ = oxai.integrated_gradients(m, x, 2, x.clone(), n_steps=4)
+    assert float(zero.abs().max()) == 0.0
+    taps, score = oxai.classifier_gradient_taps(m, x, 2)
+    assert torch.allclose(taps["input"][1], oxai.gradient_attribution(m, x, 2), atol=1e-7)
+    assert set(taps) >= {"preprocess", "relu", "maxpool", "layer1.0", "layer4.1", "input"}
