@@ -20,12 +20,25 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--out", default="gpurun_out/ig.json")
+    ap.add_argument("--one", action="store_true",
+                    help="one score + input-gradient pass at --batch between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     clf = MelanomaClassifierAdaptive(num_classes=7, pretrained=False, precision="bf16").to(dev).eval()
     g = torch.Generator().manual_seed(0)
     imgs = torch.tanh(torch.randn(a.batch, 3, 128, 128, generator=g)).to(dev)
     base = (torch.randn(1, 3, 128, 128, generator=g) * 0.1).to(dev)
+
+    if a.one:
+        for _ in range(2):
+            clf.score_and_input_gradient(imgs, 0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        clf.score_and_input_gradient(imgs, 0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print("one pass done")
+        return
 
     def timed(fn, reps=10):
         for _ in range(3):
