@@ -153,7 +153,10 @@ void avgpool_fc_bwd(const float* dlogits, const float* w, const void* feat, int 
 void relu_mask(const void* g, const void* act, int dt, long long n, void* out /* may alias g */, cudaStream_t s);
 void zero_insert2x(const void* g, const void* act /*nullable ReLU mask*/, int dt, int B, int Ho, int Wo, int C, void* out,
                    cudaStream_t s);
-void maxpool3x3s2_bwd(const void* dpool, const void* act, int dt, int B, int H, int W, int C, void* dact, cudaStream_t s);
+// max-pool that also records the winning window element (code = dy*3 + dx, one byte per output element) and its adjoint
+void maxpool3x3s2_idx(const void* in, int dt, int B, int H, int W, int C, void* out, unsigned char* idx, cudaStream_t s);
+void maxpool3x3s2_bwd(const void* dpool, const unsigned char* idx, const void* act, int dt, int B, int H, int W, int C, void* dact,
+                      cudaStream_t s);
 void stem_dgrad(const void* g, int dt, int B, const float* w /*[64][147] fp32*/, float* dpre /*[B,224,224,3]*/, cudaStream_t s);
 void classifier_preprocess_bwd(const float* dpre, const float* x, int B, int Hin, int Win, int Hout, int Wout, float* dx,
                                cudaStream_t s);

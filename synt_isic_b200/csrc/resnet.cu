@@ -718,7 +718,8 @@ struct RGrad {
         }
         pool.release(pre);
         void* x0 = f.make(56, 56, 64);
-        maxpool3x3s2(a1, dt, B, 112, 112, 64, x0, s);
+        unsigned char* pool_idx = (unsigned char*)pool.alloc((size_t)B * 56 * 56 * 64);
+        maxpool3x3s2_idx(a1, dt, B, 112, 112, 64, x0, pool_idx, s);
         void* h1[4][2]; void* o[4][2];
         const void* cur = x0;
         int H = 56;
@@ -782,9 +783,9 @@ struct RGrad {
         }
         gtap("grad:maxpool", g, dt, 56, 56, 64);
         void* da1 = f.make(112, 112, 64);
-        maxpool3x3s2_bwd(g, a1, dt, B, 112, 112, 64, da1, s);
+        maxpool3x3s2_bwd(g, pool_idx, a1, dt, B, 112, 112, 64, da1, s);
         gtap("grad:relu", da1, dt, 112, 112, 64);
-        pool.release(g); pool.release(a1); pool.release(x0);
+        pool.release(g); pool.release(a1); pool.release(x0); pool.release(pool_idx);
         float* dpre = (float*)pool.alloc((size_t)B * 224 * 224 * 3 * 4);
         stem_dgrad(da1, dt, B, (const float*)r->stem.w->p, dpre, s);
         gtap("grad:preprocess", dpre, DT_F32, 224, 224, 3);

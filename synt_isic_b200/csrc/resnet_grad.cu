@@ -11,7 +11,8 @@
 //   avgpool_fc_bwd    dlogits -> gradient at the last block output, ReLU mask fused            [B,7,7,512]
 //   relu_mask         g * (act > 0)                                                            (in place)
 //   zero_insert       [B,Ho,Wo,C] -> [B,2Ho,2Wo,C] with the values at even positions (+ optional ReLU mask)
-//   maxpool_bwd       3x3/s2 max-pool adjoint as a gather (first maximum wins, like ATen), ReLU mask of the stem fused
+//   maxpool_idx / maxpool_bwd   3x3/s2 max-pool that records the winning window element (first maximum, like ATen) and its
+//                     adjoint as a gather over the recorded codes, ReLU mask of the stem fused
 //   stem_dgrad        7x7/s2 data gradient 64 -> 3 channels on CUDA cores (0.24 GFLOP per image), fp32 output
 //   preprocess_bwd    adjoint of clamp((x+1)/2) -> bilinear 128->224 -> normalise, as a gather (deterministic)
 //   ig_interpolate / ig_reduce   the Riemann-right path points and the final (x - x') * mean(grad)
@@ -120,12 +121,58 @@ void zero_insert2x(const void* g, const void* act, int dt, int B, int Ho, int Wo
     SYNT_LAUNCH_CHECK();
 }
 
-// Gather form of the 3x3 / stride 2 / pad 1 max-pool adjoint: input pixel (iy, ix) collects dpool of every window in which
-// it is the FIRST maximum in (dy, dx) scan order (ATen's max_pool2d keeps the first maximum: `val > maxval`).  The ReLU
-// mask of the stem output is applied on the way out (a zero activation gets no gradient either way).
+// 3x3 / stride 2 / pad 1 max-pool that also records WHICH window element won: code = dy*3 + dx of the FIRST maximum in
+// scan order (ATen's max_pool2d keeps the first maximum: `val > maxval`), one byte per output element.
 template <typename T>
-__global__ void maxpool_bwd_kernel(const T* __restrict__ dpool, const T* __restrict__ act, int H, int W, int C, int Ho, int Wo,
-                                   long long nvec_total, T* __restrict__ dact) {
+__global__ void maxpool_idx_kernel(const T* __restrict__ in, int H, int W, int C, int Ho, int Wo, long long nvec_total,
+                                   T* __restrict__ out, unsigned char* __restrict__ idx) {
+    const int nvec = C >> 3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % nvec);
+        long long p = i / nvec;
+        const int ox = (int)(p % Wo); p /= Wo;
+        const int oy = (int)(p % Ho);
+        const long long b = p / Ho;
+        float m[8];
+        unsigned int code[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; code[j] = 0; }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = oy * 2 - 1 + dy;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = ox * 2 - 1 + dx;
+                if (ix < 0 || ix >= W) continue;
+                float x[8];
+                load8<T>(in + ((b * H + iy) * W + ix) * C + v * 8, x);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (x[j] > m[j]) { m[j] = x[j]; code[j] = dy * 3 + dx; }
+            }
+        }
+        store8<T>(out + i * 8, m);
+        uint2 pk;
+        pk.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+        pk.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+        *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    }
+}
+void maxpool3x3s2_idx(const void* in, int dt, int B, int H, int W, int C, void* out, unsigned char* idx, cudaStream_t s) {
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long nv = (long long)B * Ho * Wo * (C / 8);
+    if (dt == DT_F32) maxpool_idx_kernel<float><<<ew_blocks(nv), 256, 0, s>>>((const float*)in, H, W, C, Ho, Wo, nv, (float*)out, idx);
+    else              maxpool_idx_kernel<bf16><<<ew_blocks(nv), 256, 0, s>>>((const bf16*)in, H, W, C, Ho, Wo, nv, (bf16*)out, idx);
+    SYNT_LAUNCH_CHECK();
+}
+
+// Adjoint of the max-pool as a gather: input pixel (iy, ix) collects dpool of each of the (at most four) windows whose
+// recorded winner is this pixel.  The ReLU mask of the stem output is applied on the way out (a zero activation gets no
+// gradient either way).  Per thread: one 16-byte activation load, <= 4 x (8-byte code + 16-byte gradient) loads.
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restrict__ idx, const T* __restrict__ act,
+                                   int H, int W, int C, int Ho, int Wo, long long nvec_total, T* __restrict__ dact) {
     const int nvec = C >> 3;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_total; i += (long long)gridDim.x * blockDim.x) {
         const int v = (int)(i % nvec);
@@ -134,7 +181,7 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dpool, const T* __restr
         const int iy = (int)(p % H);
         const long long b = p / H;
         float self[8], acc[8];
-        load8<T>(act + ((b * H + iy) * W + ix) * C + v * 8, self);
+        load8<T>(act + i * 8, self);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         const int oy_lo = iy >> 1, oy_hi = (iy + 1) >> 1;           // windows 2*oy-1 .. 2*oy+1 that contain iy
@@ -143,29 +190,16 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dpool, const T* __restr
             if (oy >= Ho) continue;
             for (int ox = ox_lo; ox <= ox_hi; ++ox) {
                 if (ox >= Wo) continue;
-                // is (iy, ix) the first maximum of window (oy, ox)?  earlier positions must be strictly smaller,
-                // later positions smaller or equal
-                bool win[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) win[j] = true;
-                const int my = iy - (2 * oy - 1), mx = ix - (2 * ox - 1);
-                for (int dy = 0; dy < 3; ++dy) {
-                    const int yy = 2 * oy - 1 + dy;
-                    if (yy < 0 || yy >= H) continue;
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int xx = 2 * ox - 1 + dx;
-                        if (xx < 0 || xx >= W || (dy == my && dx == mx)) continue;
-                        float o[8];
-                        load8<T>(act + ((b * H + yy) * W + xx) * C + v * 8, o);
-                        const bool before = dy < my || (dy == my && dx < mx);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) win[j] = win[j] && (before ? o[j] < self[j] : o[j] <= self[j]);
-                    }
-                }
+                const unsigned int mine = (unsigned int)((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));
+                const long long o = ((b * Ho + oy) * Wo + ox) * C + v * 8;
+                const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
                 float d[8];
-                load8<T>(dpool + ((b * Ho + oy) * Wo + ox) * C + v * 8, d);
+                load8<T>(dpool + o, d);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += win[j] ? d[j] : 0.f;
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned int code = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xffu;
+                    acc[j] += code == mine ? d[j] : 0.f;
+                }
             }
         }
 #pragma unroll
@@ -173,63 +207,87 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dpool, const T* __restr
         store8<T>(dact + i * 8, acc);
     }
 }
-void maxpool3x3s2_bwd(const void* dpool, const void* act, int dt, int B, int H, int W, int C, void* dact, cudaStream_t s) {
+void maxpool3x3s2_bwd(const void* dpool, const unsigned char* idx, const void* act, int dt, int B, int H, int W, int C, void* dact,
+                      cudaStream_t s) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long nv = (long long)B * H * W * (C / 8);
-    if (dt == DT_F32) maxpool_bwd_kernel<float><<<ew_blocks(nv), 256, 0, s>>>((const float*)dpool, (const float*)act, H, W, C, Ho, Wo, nv, (float*)dact);
-    else              maxpool_bwd_kernel<bf16><<<ew_blocks(nv), 256, 0, s>>>((const bf16*)dpool, (const bf16*)act, H, W, C, Ho, Wo, nv, (bf16*)dact);
+    if (dt == DT_F32) maxpool_bwd_kernel<float><<<ew_blocks(nv), 256, 0, s>>>((const float*)dpool, idx, (const float*)act, H, W, C, Ho, Wo, nv, (float*)dact);
+    else              maxpool_bwd_kernel<bf16><<<ew_blocks(nv), 256, 0, s>>>((const bf16*)dpool, idx, (const bf16*)act, H, W, C, Ho, Wo, nv, (bf16*)dact);
     SYNT_LAUNCH_CHECK();
 }
 
 // Data gradient of the 7x7 / stride 2 / pad 3 stem (3 -> 64 channels, BN folded): dpre[iy, ix, c] =
 // sum over (ky, kx, co) with 2*oy = iy + 3 - ky, 2*ox = ix + 3 - kx of g[oy, ox, co] * w[co][(ky*7 + kx)*3 + c].
-// One CTA = 256 pixels of ONE parity class (iy % 2, ix % 2): every thread of the CTA then uses the same 3x3 .. 4x4 subset of
-// taps, so the weights are a shared-memory broadcast.  g is already masked by the stem's ReLU.
+// One CTA works on ONE parity class (iy % 2, ix % 2): every thread then uses the same 3x3 .. 4x4 subset of taps, so the
+// weights are a shared-memory broadcast (one LDS.128 per output channel and tap).  A thread owns FOUR horizontally adjacent
+// pixels of the class, so each broadcast weight feeds 12 FMAs (0.24 GFLOP per image on CUDA cores; with one pixel per
+// thread the kernel was bound by the LDS issue rate: 1.55 ms -> see profiles/r01f).  g is already masked by the stem's ReLU.
+constexpr int SD_PX = 4, SD_GROUPS = 112 / SD_PX;                       // 28 pixel groups per row of a parity class
 template <typename T>
 __global__ void __launch_bounds__(256) stem_dgrad_kernel(const T* __restrict__ g, const float* __restrict__ w /* [64][147] */,
                                                          float* __restrict__ dpre /* [B,224,224,3] */) {
-    __shared__ float ws[16][64][3];
+    __shared__ float4 ws[16][64];
     const int par_y = blockIdx.y >> 1, par_x = blockIdx.y & 1;
     const long long b = blockIdx.z;
     // taps of this parity class: ky = ky0 + 2a with (iy + 3 - ky) even  ->  ky0 = (par_y + 1) & 1
     const int ky0 = (par_y + 1) & 1, kx0 = (par_x + 1) & 1;
     const int nky = ky0 ? 3 : 4, nkx = kx0 ? 3 : 4;
-    for (int i = threadIdx.x; i < nky * nkx * 64 * 3; i += 256) {
-        const int c = i % 3, co = (i / 3) % 64, t = i / 192;
+    for (int i = threadIdx.x; i < nky * nkx * 64; i += 256) {
+        const int co = i % 64, t = i / 64;
         const int ky = ky0 + 2 * (t / nkx), kx = kx0 + 2 * (t % nkx);
-        ws[t][co][c] = w[co * 147 + (ky * 7 + kx) * 3 + c];
+        const float* wp = w + co * 147 + (ky * 7 + kx) * 3;
+        ws[t][co] = make_float4(wp[0], wp[1], wp[2], 0.f);
     }
     __syncthreads();
     const int q = blockIdx.x * 256 + threadIdx.x;
-    if (q >= 112 * 112) return;
-    const int iy = 2 * (q / 112) + par_y, ix = 2 * (q % 112) + par_x;
-    float acc[3] = {0.f, 0.f, 0.f};
+    if (q >= 112 * SD_GROUPS) return;
+    const int qy = q / SD_GROUPS, qx0 = (q % SD_GROUPS) * SD_PX;
+    const int iy = 2 * qy + par_y;
+    float acc[SD_PX][3];
+#pragma unroll
+    for (int j = 0; j < SD_PX; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
     for (int a = 0; a < nky; ++a) {
-        const int oy = (iy + 3 - (ky0 + 2 * a)) >> 1;              // numerator is even and >= -3 -> shift is exact for >= 0
-        if (iy + 3 - (ky0 + 2 * a) < 0 || oy >= 112) continue;
+        const int ny = iy + 3 - (ky0 + 2 * a);                        // even by construction
+        if (ny < 0 || (ny >> 1) >= 112) continue;
+        const int oy = ny >> 1;
         for (int e = 0; e < nkx; ++e) {
-            const int ox = (ix + 3 - (kx0 + 2 * e)) >> 1;
-            if (ix + 3 - (kx0 + 2 * e) < 0 || ox >= 112) continue;
-            const T* gp = g + ((b * 112 + oy) * 112 + ox) * 64;
-            const float (*wt)[3] = ws[a * nkx + e];
+            // ox of pixel j = (2*(qx0 + j) + par_x + 3 - kx) / 2 = qx0 + j + sh, sh = (par_x + 3 - kx) / 2 (exact, may be -1)
+            const int sh = (par_x + 3 - (kx0 + 2 * e)) >> 1;
+            const int ox0 = qx0 + sh;
+            const T* gp = g + ((b * 112 + oy) * 112 + ox0) * 64;
+            const float4* wt = ws[a * nkx + e];
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
-                float x[8];
-                load8<T>(gp + v * 8, x);
+                float x[SD_PX][8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    acc[0] = fmaf(x[j], wt[v * 8 + j][0], acc[0]);
-                    acc[1] = fmaf(x[j], wt[v * 8 + j][1], acc[1]);
-                    acc[2] = fmaf(x[j], wt[v * 8 + j][2], acc[2]);
+                for (int j = 0; j < SD_PX; ++j) {
+                    if (ox0 + j >= 0 && ox0 + j < 112) load8<T>(gp + j * 64 + v * 8, x[j]);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) x[j][k] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 wv = wt[v * 8 + k];
+#pragma unroll
+                    for (int j = 0; j < SD_PX; ++j) {
+                        acc[j][0] = fmaf(x[j][k], wv.x, acc[j][0]);
+                        acc[j][1] = fmaf(x[j][k], wv.y, acc[j][1]);
+                        acc[j][2] = fmaf(x[j][k], wv.z, acc[j][2]);
+                    }
                 }
             }
         }
     }
-    float* o = dpre + ((b * 224 + iy) * 224 + ix) * 3;
-    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+#pragma unroll
+    for (int j = 0; j < SD_PX; ++j) {
+        float* o = dpre + ((b * 224 + iy) * 224 + 2 * (qx0 + j) + par_x) * 3;
+        o[0] = acc[j][0]; o[1] = acc[j][1]; o[2] = acc[j][2];
+    }
 }
 void stem_dgrad(const void* g, int dt, int B, const float* w, float* dpre, cudaStream_t s) {
-    dim3 grid((112 * 112 + 255) / 256, 4, B);
+    dim3 grid((112 * SD_GROUPS + 255) / 256, 4, B);
     if (dt == DT_F32) stem_dgrad_kernel<float><<<grid, 256, 0, s>>>((const float*)g, w, dpre);
     else              stem_dgrad_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)g, w, dpre);
     SYNT_LAUNCH_CHECK();
