@@ -17,6 +17,7 @@
 //   preprocess_bwd    adjoint of clamp((x+1)/2) -> bilinear 128->224 -> normalise, as a gather (deterministic)
 //   ig_interpolate / ig_reduce   the Riemann-right path points and the final (x - x') * mean(grad)
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace synt {
 
@@ -286,7 +287,107 @@ __global__ void __launch_bounds__(256) stem_dgrad_kernel(const T* __restrict__ g
         o[0] = acc[j][0]; o[1] = acc[j][1]; o[2] = acc[j][2];
     }
 }
+// bf16 production variant: the kernel above re-reads every g row once per tap and parity class (49x in total, ~10 GB of
+// L2 -> L1 traffic per 64 images: 1.36 ms, L2-bandwidth bound).  Here one CTA owns a 32x32 block of dpre (all four parity
+// classes, 16x16 pixels each), stages the 19x19x64 g tile it needs ONCE in shared memory (zero-filled outside the plane, so
+// the tap loops need no bounds checks) next to the 49 x 64 weight triples, and every tap reads from there.
+// Pixel pitch 144 B and row pitch 2752 B (= 4 mod 8 sixteen-byte units) keep the LDS.128 of 8 adjacent lanes (4 pixels x 2
+// rows) on distinct bank groups; a thread owns 4 pixels of one class at column stride 4; warps are class-pure, so the weight
+// reads are broadcasts.  102 KB of shared memory -> two CTAs per SM.
+constexpr int SDT_PITCH = 144, SDT_ROW = 19 * SDT_PITCH + 16, SDT_TILE_BYTES = 19 * SDT_ROW;      // 2752, 52288
+constexpr int SDT_W_BYTES = 49 * 64 * 16, SDT_SMEM = SDT_TILE_BYTES + SDT_W_BYTES;                   // 50176, 102464
+__device__ __forceinline__ int sdt_class_base(int cls) { return cls == 0 ? 0 : (cls == 1 ? 9 : (cls == 2 ? 21 : 33)); }
+__global__ void __launch_bounds__(256, 2) stem_dgrad_tiled_kernel(const bf16* __restrict__ g, const float* __restrict__ w,
+                                                                  float* __restrict__ dpre) {
+    extern __shared__ __align__(16) unsigned char sdt_smem[];
+    unsigned char* tile = sdt_smem;
+    float4* ws = reinterpret_cast<float4*>(sdt_smem + SDT_TILE_BYTES);
+    const int tyi = blockIdx.x / 7, txi = blockIdx.x % 7;
+    const long long b = blockIdx.y;
+    const int oy_base = tyi * 16 - 1, ox_base = txi * 16 - 1;
+    // weights: class cls = 2*(iy%2) + (ix%2) uses taps ky = ky0 + 2a, kx = kx0 + 2e, stored at [base(cls) + a*nkx + e][co]
+    for (int i = threadIdx.x; i < 49 * 64; i += 256) {
+        const int co = i & 63, t = i >> 6;
+        const int cls = t < 9 ? 0 : (t < 21 ? 1 : (t < 33 ? 2 : 3));
+        const int tl = t - sdt_class_base(cls);
+        const int ky0 = ((cls >> 1) + 1) & 1, kx0 = ((cls & 1) + 1) & 1, nkx = kx0 ? 3 : 4;
+        const int ky = ky0 + 2 * (tl / nkx), kx = kx0 + 2 * (tl % nkx);
+        const float* wp = w + co * 147 + (ky * 7 + kx) * 3;
+        ws[i] = make_float4(wp[0], wp[1], wp[2], 0.f);
+    }
+    for (int i = threadIdx.x; i < 19 * 19 * 8; i += 256) {
+        const int ch = i & 7, p = i >> 3;
+        const int ly = p / 19, lx = p - ly * 19;
+        const int oy = oy_base + ly, ox = ox_base + lx;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (oy >= 0 && oy < 112 && ox >= 0 && ox < 112)
+            val = *reinterpret_cast<const uint4*>(g + ((b * 112 + oy) * 112 + ox) * 64 + ch * 8);
+        *reinterpret_cast<uint4*>(tile + ly * SDT_ROW + lx * SDT_PITCH + ch * 16) = val;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cls = warp >> 1, par_y = cls >> 1, par_x = cls & 1;
+    const int t = (warp & 1) * 32 + lane;                           // 64 threads per class: 16 rows x 4 column phases
+    const int qy = t >> 2, qxg = t & 3;                             // the thread's pixels: class row qy, columns qxg + 4j
+    const int ky0 = (par_y + 1) & 1, kx0 = (par_x + 1) & 1;
+    const int nky = ky0 ? 3 : 4, nkx = kx0 ? 3 : 4;
+    const float4* wcls = ws + sdt_class_base(cls) * 64;
+    float acc[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
+    for (int a = 0; a < nky; ++a) {
+        const int ly = qy + ((par_y + 3 - (ky0 + 2 * a)) >> 1) + 1;                 // oy - oy_base, 0..18
+        for (int e = 0; e < nkx; ++e) {
+            const int lx = qxg + ((par_x + 3 - (kx0 + 2 * e)) >> 1) + 1;             // column of pixel j = 0
+            const unsigned char* src = tile + ly * SDT_ROW + lx * SDT_PITCH;
+            const float4* wt = wcls + (a * nkx + e) * 64;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                float x[4][8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 r = *reinterpret_cast<const uint4*>(src + j * 4 * SDT_PITCH + v * 16);
+                    const unsigned int u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        x[j][2 * k] = __uint_as_float(u[k] << 16);
+                        x[j][2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 wv = wt[v * 8 + k];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[j][0] = fmaf(x[j][k], wv.x, acc[j][0]);
+                        acc[j][1] = fmaf(x[j][k], wv.y, acc[j][1]);
+                        acc[j][2] = fmaf(x[j][k], wv.z, acc[j][2]);
+                    }
+                }
+            }
+        }
+    }
+    const int iy = tyi * 32 + 2 * qy + par_y;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ix = txi * 32 + 2 * (qxg + 4 * j) + par_x;
+        float* o = dpre + ((b * 224 + iy) * 224 + ix) * 3;
+        o[0] = acc[j][0]; o[1] = acc[j][1]; o[2] = acc[j][2];
+    }
+}
+
 void stem_dgrad(const void* g, int dt, int B, const float* w, float* dpre, cudaStream_t s) {
+    static const bool tiled = [] { const char* e = getenv("SYNT_STEM_DGRAD_TILED"); return !(e && e[0] == '0'); }();
+    if (dt == DT_BF16 && tiled) {
+        static bool attr = false;
+        if (!attr) {
+            SYNT_CUDA(cudaFuncSetAttribute(stem_dgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDT_SMEM));
+            attr = true;
+        }
+        stem_dgrad_tiled_kernel<<<dim3(49, B), 256, SDT_SMEM, s>>>((const bf16*)g, w, dpre);
+        SYNT_LAUNCH_CHECK();
+        return;
+    }
     dim3 grid((112 * SD_GROUPS + 255) / 256, 4, B);
     if (dt == DT_F32) stem_dgrad_kernel<float><<<grid, 256, 0, s>>>((const float*)g, w, dpre);
     else              stem_dgrad_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)g, w, dpre);
