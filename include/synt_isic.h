@@ -137,6 +137,15 @@ int synt_intervene_blend(const float* x_dev, const float* mask_dev, const float*
 int synt_patch_mask_apply(const float* x_dev, const unsigned char* patch_masks_dev, int n_masks, int C, int H, int W,
                           int patch, float* out_dev, void* stream);
 
+/* replaces select_regions_advanced (XAI.py:1340-1451; numpy percentile + scipy.ndimage closing x2 / opening / label /
+ * small-component removal) for n_maps attribution maps at once, one CTA per map, H*W <= 16384:
+ *   attr_dev [n_maps][C][H][W] fp32 (saliency = channel L2 norm) or, with use_abs, [n_maps][H][W] (saliency = |x|);
+ *   top-k (bottom = 0: saliency >= percentile(100 - k)) or bottom-k (bottom = 1: saliency <= percentile(k));
+ *   mask_dev [n_maps][H][W] bytes 0/1; stats_dev [n_maps][8] fp64 = selected pixels, threshold, mean, std of the saliency,
+ *   mean, std, max, min of the saliency over the selection (0 when nothing is selected) */
+int synt_select_regions(const float* attr_dev, int n_maps, int C, int H, int W, int use_abs, double k_percent, int bottom,
+                        int morphology_cleanup, int connectivity, unsigned char* mask_dev, double* stats_dev, void* stream);
+
 /* ---------------- test hook (kernel-level parity tests; not a reference entry point) ------ */
 /* one convolution on caller-provided NHWC tensors: use_tc=1 tcgen05 (bf16), 0 fp32-FMA carrier.
  * weight is K-major [Cout][K*K*Cin + sc0_C + sc1_C], bf16 for use_tc else fp32. */

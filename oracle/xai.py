@@ -9,6 +9,8 @@ exposes ``get_confidence / get_per_class_score / get_probabilities``:
 * ``intervene``            -- ``counterfactual_intervention_advanced`` xai/XAI.py:1454-1597
 * ``causal_shift``         -- ``compute_causal_shift_comprehensive``   xai/XAI.py:1600-1700
 * ``time_shap_permutation`` -- permutation Shapley over denoising steps, README.md:171-221 (spec only, no reference code)
+* ``select_regions``       -- ``select_regions_advanced`` xai/XAI.py:1340-1451 on the REAL numpy ``percentile`` and scipy
+  ``ndimage`` calls the reference makes (pinned by construction)
 * ``integrated_gradients`` -- ``compute_integrated_gradients`` xai/XAI.py:1039-1085: captum (>=0.6.0, requirements.txt, NOT
   installed here) ``IntegratedGradients.attribute(method='riemann_right')`` restated from its published algorithm
   (Sundararajan et al. 2017 eq. 3 with right Riemann sums: alphas = linspace(1/n, 1, n), step sizes 1/n), gradients from
@@ -229,3 +231,40 @@ def classifier_gradient_taps(classifier, image, target_class):
     out = {k: (t.detach(), t.grad.detach()) for k, t in taps.items()}
     out["input"] = (x.detach(), x.grad.detach())
     return out, score.detach()
+
+
+# ------------------------------------------------------------------ region selection ----
+def select_regions(attribution_map, k_percent=10, region_type="top", morphology_cleanup=True, connectivity=8):
+    """XAI.py:1340-1451.  Saliency = channel L2 norm (3-D / 4-D input, batch entry 0) or |x| (2-D); mask = saliency beyond
+    the (100-k)-th / k-th numpy percentile; clean-up = closing x2, opening x1 (scipy defaults: outside of the image counts
+    as background), then drop connected components smaller than max(10, 1% of the pixels)."""
+    from scipy import ndimage
+    a = attribution_map.detach().cpu().numpy() if torch.is_tensor(attribution_map) else np.array(attribution_map)
+    shape = a.shape
+    a = a[0] if a.ndim == 4 else a
+    sal = np.linalg.norm(a, axis=0) if a.ndim == 3 else np.abs(a)
+    if region_type == "top":
+        thr = np.percentile(sal.ravel(), 100 - k_percent)
+        mask = sal >= thr
+    elif region_type == "bottom":
+        thr = np.percentile(sal.ravel(), k_percent)
+        mask = sal <= thr
+    else:
+        raise ValueError(f"unknown region_type {region_type!r}")
+    if morphology_cleanup:
+        st = ndimage.generate_binary_structure(2, 1 if connectivity == 4 else 2)
+        mask = ndimage.binary_opening(ndimage.binary_closing(mask, structure=st, iterations=2), structure=st, iterations=1)
+        lab, n = ndimage.label(mask, structure=st)
+        if n > 0:
+            sizes = ndimage.sum(mask, lab, range(1, n + 1))
+            keep = np.where(sizes >= max(10, int(0.01 * mask.size)))[0] + 1
+            mask = np.isin(lab, keep)
+    sel = sal[mask]
+    stats = {"total_pixels": sal.size, "selected_pixels": int(mask.sum()), "target_percentage": k_percent,
+             "actual_percentage": mask.sum() / sal.size * 100, "threshold_value": thr,
+             "mean_attribution": np.mean(sal), "std_attribution": np.std(sal),
+             "mean_attribution_selected": np.mean(sel) if sel.size else 0, "std_attribution_selected": np.std(sel) if sel.size else 0,
+             "max_attribution_selected": np.max(sel) if sel.size else 0, "min_attribution_selected": np.min(sel) if sel.size else 0}
+    return {"mask": mask, "threshold": thr, "statistics": stats,
+            "metadata": {"region_type": region_type, "morphology_cleanup": morphology_cleanup, "connectivity": connectivity,
+                         "original_shape": shape}}

@@ -48,6 +48,8 @@ SIGNATURES = {
     "synt_resnet18_launch_count": (C.c_longlong, [vp]),
     "synt_resnet18_score_grad": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp]),
     "synt_resnet18_grad_debug": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_char_p, vp, C.c_longlong, c_i32p, c_i32p, c_i32p, vp]),
+    "synt_select_regions": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                      vp, vp, vp]),
     "synt_ig_interpolate": (C.c_int, [vp, vp, C.c_int, C.c_longlong, vp, vp]),
     "synt_ig_reduce": (C.c_int, [vp, vp, vp, C.c_int, C.c_longlong, vp, vp]),
     "synt_intervene_blend": (C.c_int, [vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),

@@ -13,9 +13,10 @@ of the CUDA classifier and (optionally) sharded across ranks with a single all_g
   compute_integrated_gradients          xai/XAI.py:1039-1085   (captum autograd -> batched CUDA adjoint)
   compute_gradient_attribution          xai/XAI.py:1087-1109
   compute_combined_attribution          xai/XAI.py:1236-1291
+  select_regions_advanced               xai/XAI.py:1340-1451   (numpy percentile + scipy.ndimage -> one CTA per map)
   IntegratedXAIAnalyzer                 xai/xai_integration.py:75-132
 
-Out of scope: Grad-CAM, region morphology, statistics and plots.
+Out of scope: Grad-CAM, statistics and plots.
 """
 from __future__ import annotations
 
@@ -31,6 +32,7 @@ SHAP_N_SAMPLES = 512       # xai/XAI.py:240
 NOISE_STD = 0.5            # xai/XAI.py:262
 BLUR_KERNEL_SIZE = 5       # xai/XAI.py:263
 TOP_K_PERCENT = 10         # xai/XAI.py:238
+BOTTOM_K_PERCENT = 10      # xai/XAI.py:239
 IG_N_STEPS = 50            # xai/XAI.py:240
 _TYPE_CODES = {"zero": 0, "mean": 1, "blur": 2, "inpaint": 2, "noise": 3, "gaussian_noise": 3, "shuffle": 4}
 
@@ -396,17 +398,53 @@ def csi_batch(classifier, images: torch.Tensor, masks: torch.Tensor, interventio
 
 
 # ------------------------------------------------------------------ analyzer ------------
-def select_regions_topk(attribution: torch.Tensor, percent: float = TOP_K_PERCENT):
-    """Top / bottom ``percent`` % masks of an attribution map (threshold part of
-    select_regions_advanced, xai/XAI.py:1340-1451; the scipy morphology clean-up is out of scope)."""
-    a = attribution.float().mean(dim=1)[0] if attribution.dim() == 4 else attribution.float()
-    flat = a.reshape(-1)
-    k = max(1, int(flat.numel() * percent / 100.0))
-    top = torch.zeros_like(flat, dtype=torch.bool)
-    bot = torch.zeros_like(flat, dtype=torch.bool)
-    top[flat.topk(k).indices] = True
-    bot[(-flat).topk(k).indices] = True
-    return top.view_as(a), bot.view_as(a)
+def select_regions_batch(attributions: torch.Tensor, k_percent=TOP_K_PERCENT, region_type: str = "top",
+                         morphology_cleanup: bool = True, connectivity: int = 8):
+    """``select_regions_advanced`` for a stack of maps in one launch: ``attributions`` [n,C,H,W] (saliency = channel L2 norm)
+    or [n,H,W] (saliency = |x|), H*W <= 16384.  Returns (mask bool [n,H,W], stats float64 [n,8]) on the device; stats
+    columns: selected pixels, threshold, mean, std, mean / std / max / min over the selection."""
+    if region_type not in ("top", "bottom"):
+        raise ValueError(f"unknown region_type {region_type!r}")                    # XAI.py:1384-1385
+    if not attributions.is_cuda:
+        raise RuntimeError("region selection runs on CUDA tensors (no CPU fallback)")
+    a = attributions.detach().float().contiguous()
+    use_abs = a.dim() == 3
+    n, C = a.shape[0], (1 if use_abs else a.shape[1])
+    H, W = a.shape[-2], a.shape[-1]
+    mask = torch.empty(n, H, W, dtype=torch.uint8, device=a.device)
+    stats = torch.empty(n, 8, dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().synt_select_regions(a.data_ptr(), n, C, H, W, int(use_abs), float(k_percent),
+                                                  int(region_type == "bottom"), int(bool(morphology_cleanup)), int(connectivity),
+                                                  mask.data_ptr(), stats.data_ptr(), _lib.current_stream_ptr()), "select_regions")
+    return mask.bool(), stats
+
+
+def select_regions_advanced(attribution_map, k_percent=TOP_K_PERCENT, region_type="top", morphology_cleanup=True,
+                            connectivity=8):
+    """xai/XAI.py:1340-1451 with the reference's result dictionary: ``mask`` is a numpy bool array like the reference's
+    (its consumers accept it), ``mask_tensor`` the same mask on the device for the GPU consumers.  A 4-D input uses batch
+    entry 0, a 3-D input is [C,H,W], a 2-D input is taken by absolute value (XAI.py:1366-1373)."""
+    a = attribution_map if torch.is_tensor(attribution_map) else torch.as_tensor(np.asarray(attribution_map))
+    shape = tuple(a.shape)
+    if not a.is_cuda:
+        raise RuntimeError("region selection runs on CUDA tensors (no CPU fallback)")
+    if a.dim() == 4:
+        a = a[0]
+    mask, stats = select_regions_batch(a[None], k_percent, region_type, morphology_cleanup, connectivity)
+    st = stats[0].cpu().numpy()
+    total = int(a.shape[-1] * a.shape[-2])
+    return {
+        "mask": mask[0].cpu().numpy(), "mask_tensor": mask[0], "threshold": np.float32(st[1]),
+        "statistics": {
+            "total_pixels": total, "selected_pixels": int(st[0]), "target_percentage": k_percent,
+            "actual_percentage": st[0] / total * 100, "threshold_value": np.float32(st[1]),
+            "mean_attribution": st[2], "std_attribution": st[3], "mean_attribution_selected": st[4],
+            "std_attribution_selected": st[5], "max_attribution_selected": st[6], "min_attribution_selected": st[7],
+        },
+        "metadata": {"region_type": region_type, "morphology_cleanup": morphology_cleanup, "connectivity": connectivity,
+                     "original_shape": shape},
+    }
 
 
 class IntegratedXAIAnalyzer:
@@ -439,7 +477,9 @@ class IntegratedXAIAnalyzer:
             attr, _ = compute_combined_attribution(self.classifier, frame, target, methods=methods,
                                                    shap={"n_samples": shap_samples, "group": self.group},
                                                    ig={"n_steps": ig_steps})
-            top, bot = select_regions_topk(attr)
+            # XAI.py:2753-2760: top / bottom 10 % regions of the combined map, morphology clean-up included
+            top = select_regions_advanced(attr, TOP_K_PERCENT, "top")["mask_tensor"]
+            bot = select_regions_advanced(attr, BOTTOM_K_PERCENT, "bottom")["mask_tensor"]
             for rname, mask in (("top_k", top), ("bottom_k", bot)):
                 for it in intervention_types:
                     mod = counterfactual_intervention_advanced(frame, mask, it)["modified_image"]
