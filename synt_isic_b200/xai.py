@@ -465,7 +465,7 @@ class IntegratedXAIAnalyzer:
         if not trajectory:
             return None
         T = len(trajectory)
-        if timesteps is None:
+        if timesteps is None or len(timesteps) != T:
             timesteps = list(range(T))                           # xai_integration.py:94-95
         target = CLASS_NAMES.index(class_name) if class_name in CLASS_NAMES else 0
         imp, raw = compute_time_shap(self.classifier, trajectory, timesteps, target, self.group, self.verbose)
@@ -501,3 +501,25 @@ class IntegratedXAIAnalyzer:
 def create_integrated_xai_analyzer(device: str = "cuda"):
     """xai/xai_integration.py:134"""
     return IntegratedXAIAnalyzer(device=device)
+
+
+PREVIEW_PATTERNS = ("xai_step_*.png", "gradcam_most_important_*.png", "time_shap_analysis.png")
+
+
+def run_xai_analysis(image_path, device=None, classifier_path=None, save_dir=None):
+    """xai/xai_integration.py:137-159 -- the GUI preview hook: returns ``(PIL RGB image, path)`` of the first stored XAI
+    artifact of this image (looked up under ``<two levels above the class folder>/xai_results/<class>/<stem>_*/`` in the
+    reference's priority order: step map, Grad-CAM, Time-SHAP plot), else the image itself.  No computation happens here
+    (``device`` / ``classifier_path`` / ``save_dir`` are accepted and unused, like in the reference)."""
+    from pathlib import Path
+    from PIL import Image
+    img_path = Path(image_path)
+    parents = img_path.parents
+    # the reference indexes parents[2] whenever there are >= 2 parents (IndexError for "folder/file.png"); >= 3 here
+    root = (parents[2] if len(parents) >= 3 else Path.cwd()) / "xai_results" / img_path.parent.name
+    if root.exists():
+        for pattern in PREVIEW_PATTERNS:
+            hits = sorted(root.glob(f"{img_path.stem}_*/{pattern}"))
+            if hits:
+                return Image.open(hits[0]).convert("RGB"), str(hits[0])
+    return Image.open(img_path).convert("RGB"), str(img_path)

@@ -315,3 +315,25 @@ def test_bulk_dataset_formats_and_numbering(tmp_path):
     assert [r["filename"] for r in rows2] == ["ISIC_0000001.png", "ISIC_0000002.png", "ISIC_0000001.png"]
     assert [r["class"] for r in rows2] == ["BCC", "BCC", "DF"] and rows2[0]["source"] == "synthetic"
     assert list(rows2[0].keys()) == ["filename", "class", "isic_number", "source", "generated_at"]
+
+
+def test_run_xai_analysis_preview_lookup(tmp_path):
+    """xai_integration.py:137-159: stored artifacts win in the order step map > Grad-CAM > Time-SHAP plot, else the image."""
+    from PIL import Image
+    from synt_isic_b200 import xai
+    img_dir = tmp_path / "out" / "synthetic" / "MEL"
+    img_dir.mkdir(parents=True)
+    img = img_dir / "ISIC_0000007.png"
+    Image.new("RGB", (8, 8), (10, 20, 30)).save(img)
+    pil, path = xai.run_xai_analysis(str(img))
+    assert path == str(img) and pil.mode == "RGB" and pil.size == (8, 8)
+    art = tmp_path / "out" / "xai_results" / "MEL" / "ISIC_0000007_20250101"
+    art.mkdir(parents=True)
+    Image.new("L", (4, 4), 7).save(art / "time_shap_analysis.png")
+    assert xai.run_xai_analysis(str(img))[1] == str(art / "time_shap_analysis.png")
+    Image.new("RGB", (4, 4)).save(art / "gradcam_most_important_t_0.png")
+    assert xai.run_xai_analysis(str(img))[1] == str(art / "gradcam_most_important_t_0.png")
+    Image.new("RGB", (4, 4)).save(art / "xai_step_t_980.png")
+    Image.new("RGB", (4, 4)).save(art / "xai_step_t_0.png")
+    pil, path = xai.run_xai_analysis(str(img), device=None, classifier_path=None, save_dir=None)
+    assert path == str(art / "xai_step_t_0.png") and pil.mode == "RGB"
