@@ -211,7 +211,8 @@ if rank == 0:
     assert len(rows) == 206 and rows[1][0] == "ISIC_0034321.jpg" and rows[-1][0] == "ISIC_0034525.jpg"
     assert [r[0] for r in rows[1:]] == sorted(r[0] for r in rows[1:])          # same file as a single-rank run would write
 dist.barrier()
-print("RANK_OK", rank)
+sys.stdout.write(f"RANK_OK {rank}\n")          # ONE write per rank: both ranks share the pipe, print() may interleave its pieces
+sys.stdout.flush()
 """
 
 
