@@ -11,6 +11,7 @@ of the CUDA classifier and (optionally) sharded across ranks with a single all_g
   counterfactual_intervention_advanced  xai/XAI.py:1454-1597
   compute_causal_shift_comprehensive    xai/XAI.py:1600-1700   (18 forwards -> 1 batch of 2)
   compute_integrated_gradients          xai/XAI.py:1039-1085   (captum autograd -> batched CUDA adjoint)
+  compute_integrated_gradients_batch    the same for every frame of a trajectory (pipeline stage 1, xai/XAI.py:2740-2751)
   compute_gradient_attribution          xai/XAI.py:1087-1109
   compute_combined_attribution          xai/XAI.py:1236-1291
   select_regions_advanced               xai/XAI.py:1340-1451   (numpy percentile + scipy.ndimage -> one CTA per map)
@@ -245,6 +246,39 @@ def compute_integrated_gradients(classifier, image, target_class, n_steps=IG_N_S
     if return_convergence_delta:
         s = classifier.get_per_class_score(torch.cat([x, base]), target_class)
         return out, float(out.sum() - (s[0] - s[1]))
+    return out
+
+
+def compute_integrated_gradients_batch(classifier, images, target_class, n_steps=IG_N_STEPS, baseline_type="noise",
+                                        baselines=None, generator=None, images_per_pass: int = 8):
+    """Integrated Gradients for a stack of images [n,3,128,128] -- what stage 1 of the reference pipeline computes frame by
+    frame for the WHOLE trajectory (XAI.py:2740-2751).  ``images_per_pass * n_steps`` path points go through one score +
+    input-gradient call.  ``baselines``: [1,3,128,128] shared by all images (the reference caches ONE baseline per shape,
+    XAI.py:1021-1037) or [n,3,128,128]; drawn once with ``baseline_type`` when omitted.  Returns [n,3,128,128]."""
+    dev = _dev(classifier)
+    x = images.to(dev).float().reshape(-1, 3, 128, 128).contiguous()
+    n, per = x.shape[0], 3 * 128 * 128
+    if baselines is None:
+        baselines = get_baseline(x[:1], baseline_type, generator)
+    base = baselines.to(dev).float().reshape(-1, 3, 128, 128).contiguous()
+    if base.shape[0] not in (1, n):
+        raise ValueError(f"baselines must have 1 or {n} entries, got {base.shape[0]}")
+    out = torch.empty_like(x)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        st = _lib.current_stream_ptr()
+        for i0 in range(0, n, images_per_pass):
+            m = min(images_per_pass, n - i0)
+            pts = torch.empty(m * n_steps, 3, 128, 128, dtype=torch.float32, device=dev)
+            for j in range(m):
+                b = base[i0 + j] if base.shape[0] == n else base[0]
+                _lib.check(L.synt_ig_interpolate(x[i0 + j].data_ptr(), b.data_ptr(), n_steps, per,
+                                                 pts[j * n_steps:(j + 1) * n_steps].data_ptr(), st), "ig_interpolate")
+            _, grads = classifier.score_and_input_gradient(pts, target_class)
+            for j in range(m):
+                b = base[i0 + j] if base.shape[0] == n else base[0]
+                _lib.check(L.synt_ig_reduce(grads[j * n_steps:(j + 1) * n_steps].data_ptr(), x[i0 + j].data_ptr(), b.data_ptr(),
+                                            n_steps, per, out[i0 + j].data_ptr(), st), "ig_reduce")
     return out
 
 

@@ -338,3 +338,65 @@ def test_run_xai_analysis_preview_lookup(tmp_path):
     Image.new("RGB", (4, 4)).save(art / "xai_step_t_0.png")
     pil, path = xai.run_xai_analysis(str(img), device=None, classifier_path=None, save_dir=None)
     assert path == str(art / "xai_step_t_0.png") and pil.mode == "RGB"
+
+
+def test_batched_integrated_gradients_plumbing(monkeypatch):
+    """Host logic of xai.compute_integrated_gradients_batch (slicing of the path-point / gradient stacks, shared vs
+    per-image baselines, ragged last pass) with the two C entry points and the classifier replaced by closed forms:
+    F(x) = sum x^2 -> dF/dx = 2x -> IG = (x - b) * mean_k 2 (b + a_k (x - b))."""
+    import contextlib
+    import ctypes as C
+    import numpy as np
+    import torch
+    from synt_isic_b200 import _lib, xai
+
+    def arr(ptr, n):
+        return np.ctypeslib.as_array((C.c_float * n).from_address(ptr))
+
+    class FakeLib:
+        def synt_ig_interpolate(self, x, b, n, per, out, st):
+            X, B, O = arr(x, per), arr(b, per), arr(out, n * per).reshape(n, per)
+            for k in range(n):
+                O[k] = B + np.float32((k + 1) / n) * (X - B)
+            return 0
+
+        def synt_ig_reduce(self, g, x, b, n, per, out, st):
+            arr(out, per)[:] = (arr(x, per) - arr(b, per)) * arr(g, n * per).reshape(n, per).sum(0) / n
+            return 0
+
+    class FakeClassifier:
+        calls = []
+
+        def parameters(self):
+            yield torch.zeros(1)
+
+        def score_and_input_gradient(self, pts, target):
+            self.calls.append(pts.shape[0])
+            return pts.flatten(1).pow(2).sum(1), 2 * pts
+
+    monkeypatch.setattr(_lib, "lib", lambda: FakeLib())
+    monkeypatch.setattr(_lib, "current_stream_ptr", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(5, 3, 128, 128, generator=g)
+    alphas = [(k + 1) / 4 for k in range(4)]
+
+    def closed_form(xx, bb):
+        return (xx - bb) * sum(2 * (bb + a * (xx - bb)) for a in alphas) / 4
+
+    shared = torch.randn(1, 3, 128, 128, generator=g) * 0.1
+    clf = FakeClassifier()
+    out = xai.compute_integrated_gradients_batch(clf, x, 0, n_steps=4, baselines=shared, images_per_pass=2)
+    assert clf.calls == [8, 8, 4]                                           # 2 + 2 + 1 images x 4 path points
+    assert torch.allclose(out, closed_form(x, shared), atol=1e-5)
+    own = torch.randn(5, 3, 128, 128, generator=g) * 0.1
+    out = xai.compute_integrated_gradients_batch(clf, x, 0, n_steps=4, baselines=own, images_per_pass=3)
+    assert torch.allclose(out, closed_form(x, own), atol=1e-5)
+    import pytest
+    with pytest.raises(ValueError):
+        xai.compute_integrated_gradients_batch(clf, x, 0, n_steps=4, baselines=own[:2])
+    assert xai.get_baseline(x[:1], "zero").abs().max() == 0 and xai.get_baseline(x[:1], "anything").abs().max() == 0
+    blur = xai.get_baseline(x[:1], "blur")
+    assert blur.shape == x[:1].shape and blur.abs().max() < x[:1].abs().max()
+    noise = xai.get_baseline(x[:1], "noise", generator=torch.Generator().manual_seed(1))
+    assert 0.05 < noise.std() < 0.15                                        # 0.1 * N(0,1), XAI.py:1024
