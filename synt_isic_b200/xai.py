@@ -250,11 +250,12 @@ def compute_integrated_gradients(classifier, image, target_class, n_steps=IG_N_S
 
 
 def compute_integrated_gradients_batch(classifier, images, target_class, n_steps=IG_N_STEPS, baseline_type="noise",
-                                        baselines=None, generator=None, images_per_pass: int = 8):
+                                        baselines=None, generator=None, images_per_pass: int = 8, group=None):
     """Integrated Gradients for a stack of images [n,3,128,128] -- what stage 1 of the reference pipeline computes frame by
     frame for the WHOLE trajectory (XAI.py:2740-2751).  ``images_per_pass * n_steps`` path points go through one score +
     input-gradient call.  ``baselines``: [1,3,128,128] shared by all images (the reference caches ONE baseline per shape,
-    XAI.py:1021-1037) or [n,3,128,128]; drawn once with ``baseline_type`` when omitted.  Returns [n,3,128,128]."""
+    XAI.py:1021-1037) or [n,3,128,128]; drawn once with ``baseline_type`` when omitted.  ``group``: split the images over
+    the ranks of a torch.distributed group (one all_gather).  Returns [n,3,128,128]."""
     dev = _dev(classifier)
     x = images.to(dev).float().reshape(-1, 3, 128, 128).contiguous()
     n, per = x.shape[0], 3 * 128 * 128
@@ -263,6 +264,14 @@ def compute_integrated_gradients_batch(classifier, images, target_class, n_steps
     base = baselines.to(dev).float().reshape(-1, 3, 128, 128).contiguous()
     if base.shape[0] not in (1, n):
         raise ValueError(f"baselines must have 1 or {n} entries, got {base.shape[0]}")
+    if group is not None:
+        # unit = one image: contiguous split over the ranks (weights replicated), ONE all_gather of the maps.  Every rank
+        # must pass the same images AND baselines (draw a random baseline once and broadcast it, or inject it).
+        both = torch.cat([x, base.expand(n, -1, -1, -1)], dim=1)
+        flat = sharded_eval(lambda t: compute_integrated_gradients_batch(
+            classifier, t[:, :3], target_class, n_steps, baselines=t[:, 3:], images_per_pass=images_per_pass).flatten(1),
+            both, group)
+        return flat.view(n, 3, 128, 128)
     out = torch.empty_like(x)
     L = _lib.lib()
     with torch.cuda.device(dev):

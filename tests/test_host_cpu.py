@@ -210,6 +210,39 @@ if rank == 0:
     rows = list(csv.reader(open(res["files"]["ground_truth_csv"])))
     assert len(rows) == 206 and rows[1][0] == "ISIC_0034321.jpg" and rows[-1][0] == "ISIC_0034525.jpg"
     assert [r[0] for r in rows[1:]] == sorted(r[0] for r in rows[1:])          # same file as a single-rank run would write
+# Integrated Gradients over a stack of frames, images split over the ranks (closed-form stand-ins for the CUDA entry points)
+import contextlib, ctypes as C
+from synt_isic_b200 import _lib, xai
+def arr(ptr, n):
+    return np.ctypeslib.as_array((C.c_float * n).from_address(ptr))
+class FakeLib:
+    def synt_ig_interpolate(self, x, b, n, per, out, st):
+        X, B, O = arr(x, per), arr(b, per), arr(out, n * per).reshape(n, per)
+        for k in range(n):
+            O[k] = B + np.float32((k + 1) / n) * (X - B)
+        return 0
+    def synt_ig_reduce(self, g, x, b, n, per, out, st):
+        arr(out, per)[:] = (arr(x, per) - arr(b, per)) * arr(g, n * per).reshape(n, per).sum(0) / n
+        return 0
+class FakeClassifier:
+    seen = 0
+    def parameters(self):
+        yield torch.zeros(1)
+    def score_and_input_gradient(self, pts, target):
+        FakeClassifier.seen += pts.shape[0]
+        return pts.flatten(1).pow(2).sum(1), 2 * pts
+_lib.lib = lambda: FakeLib()
+_lib.current_stream_ptr = lambda: 0
+torch.cuda.device = lambda d: contextlib.nullcontext()
+gi = torch.Generator().manual_seed(11)
+frames = torch.randn(5, 3, 128, 128, generator=gi)
+base = torch.randn(1, 3, 128, 128, generator=gi) * 0.1
+ig = xai.compute_integrated_gradients_batch(FakeClassifier(), frames, 0, n_steps=4, baselines=base, images_per_pass=2,
+                                            group=dist.group.WORLD)
+want = (frames - base) * sum(2 * (base + a * (frames - base)) for a in (0.25, 0.5, 0.75, 1.0)) / 4
+assert ig.shape == (5, 3, 128, 128) and torch.allclose(ig, want, atol=1e-5)
+lo, hi = shard_bounds(5, rank, world)
+assert FakeClassifier.seen == (hi - lo) * 4                      # this rank differentiated only its own frames
 dist.barrier()
 sys.stdout.write(f"RANK_OK {rank}\n")          # ONE write per rank: both ranks share the pipe, print() may interleave its pieces
 sys.stdout.flush()
