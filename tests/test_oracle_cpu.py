@@ -203,3 +203,25 @@ def test_oracle_integrated_gradients_completeness_and_gradient_taps():
     taps, score = oxai.classifier_gradient_taps(m, x, 2)
     assert torch.allclose(taps["input"][1], oxai.gradient_attribution(m, x, 2), atol=1e-7)
     assert set(taps) >= {"preprocess", "relu", "maxpool", "layer1.0", "layer4.1", "input"}
+
+
+def test_attribution_golden_fixtures():
+    """tests/golden/attr.npz pins the attribution oracles: gradient / Integrated Gradients of the torchvision classifier and
+    the numpy-percentile / scipy-morphology region selection (a numpy or scipy upgrade that changes a mask shows up here)."""
+    import sys
+    sys.path.insert(0, G)
+    import make_golden_attr as mg
+    from oracle import xai as oxai
+    from oracle.classifier import build_classifier
+    fx = np.load(os.path.join(G, "attr.npz"))
+    for i, (seed, sigma, kind, conn, k) in enumerate(mg.REGION_CASES):
+        r = oxai.select_regions(mg.region_map(seed, sigma), k, kind, True, conn)
+        assert np.array_equal(np.packbits(r["mask"]), fx[f"region_mask_{i}"]), i
+        assert r["threshold"] == fx[f"region_thr_{i}"] and r["statistics"]["selected_pixels"] == int(fx[f"region_count_{i}"])
+    m = build_classifier()
+    x, base = mg.attribution_inputs()
+    grad = oxai.gradient_attribution(m, x, 2)[0, :, ::8, ::8].numpy()
+    assert np.abs(grad - fx["grad_sub"]).max() <= 1e-4 * np.abs(fx["grad_sub"]).max()
+    ig, delta = oxai.integrated_gradients(m, x, 2, base, n_steps=20)
+    assert np.abs(ig[0, :, ::8, ::8].numpy() - fx["ig_sub"]).max() <= 1e-4 * np.abs(fx["ig_sub"]).max()
+    assert abs(delta - float(fx["ig_delta"])) < 1e-4
