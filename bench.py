@@ -44,6 +44,8 @@ def load_conv_traffic():
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
         try:
             k = json.load(open(path))["kernels"]
+            if not any(n.startswith("attention_tc") for n in k):
+                continue                                         # not a sampling-step capture (e.g. the classifier gradient pass)
             tot = sum(v["avg_dram_bytes_per_launch"] * v["launches"] for n, v in k.items()
                       if n.startswith("conv_tc") and v["avg_dram_bytes_per_launch"])
             cnt = sum(v["launches"] for n, v in k.items() if n.startswith("conv_tc") and v["avg_dram_bytes_per_launch"])
