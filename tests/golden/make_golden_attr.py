@@ -4,7 +4,7 @@
 
   grad_sub / ig_sub   d log(p_c + 1e-8)/dx and the 20-step riemann_right Integrated Gradients map of the oracle classifier
                       (seed-7 weights, torch autograd) for a seeded image and baseline, sub-sampled [::8, ::8]; ig_delta
-  region_*            select_regions (the reference's numpy.percentile / scipy.ndimage calls) on four seeded smooth maps:
+  region_*            select_regions (the reference's numpy.percentile / scipy.ndimage calls) on five seeded maps:
                       bit-packed masks, float32 thresholds, selected-pixel counts
 """
 import os
@@ -20,7 +20,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import xai as oxai  # noqa: E402
 from oracle.classifier import build_classifier  # noqa: E402
 
-REGION_CASES = [(0, 2.0, "top", 8, 10), (1, 1.0, "bottom", 8, 10), (2, 3.0, "top", 4, 25), (3, 0.0, "bottom", 4, 5)]
+REGION_CASES = [(0, 5.0, "top", 8, 10), (1, 1.0, "bottom", 8, 10), (2, 3.0, "top", 4, 25), (3, 6.0, "bottom", 4, 5),
+                (4, 0.0, "top", 8, 5)]                      # (seed, gaussian sigma, region_type, connectivity, k_percent); last: nothing survives
 
 
 def region_map(seed, sigma):
