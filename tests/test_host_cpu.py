@@ -433,3 +433,35 @@ def test_batched_integrated_gradients_plumbing(monkeypatch):
     assert blur.shape == x[:1].shape and blur.abs().max() < x[:1].abs().max()
     noise = xai.get_baseline(x[:1], "noise", generator=torch.Generator().manual_seed(1))
     assert 0.05 < noise.std() < 0.15                                        # 0.1 * N(0,1), XAI.py:1024
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/synt_isic.h must compile as C99 (no C++-isms, no torch types) and a plain C
+    program must link against libsynt_isic_b200.so and reach the host-only entry points (no GPU needed for these)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc, pkg = os.path.join(root, "include"), os.path.join(root, "synt_isic_b200")
+    hdr = os.path.join(inc, "synt_isic.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c", hdr], check=True)
+    src = tmp_path / "demo.c"
+    src.write_text(r"""
+#include "synt_isic.h"
+#include <stdio.h>
+int main(void) {
+    char name[256];
+    long long numel = 0, off = -1;
+    int n = synt_resnet18_num_params();
+    if (n <= 0) return 1;
+    if (synt_resnet18_param_info(7, 0, name, 256, &numel, &off) != 0) return 2;
+    printf("%d %s %lld %lld\n", n, name, numel, off);
+    if (synt_resnet18_param_info(7, -1, name, 256, &numel, &off) >= 0) return 3;      /* error path: negative code ... */
+    if (!synt_last_error() || !synt_last_error()[0]) return 4;                         /* ... and a message */
+    return 0;
+}
+""")
+    exe = tmp_path / "demo"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(src), "-I", inc, "-L", pkg, "-lsynt_isic_b200",
+                    f"-Wl,-rpath,{pkg}", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    n, name, numel, off = r.stdout.split()
+    assert int(n) == 102 and name == "conv1.weight" and int(numel) == 64 * 3 * 49 and int(off) == 0
