@@ -22,6 +22,7 @@ from __future__ import annotations
 import hashlib
 import json
 import os
+import time
 from pathlib import Path
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
@@ -137,10 +138,61 @@ class ImageGenerator:
         self.batch_size = batch_size
         self.xai_analyzer = None
         self.xai_frequency = 0
+        self.xai_hook = None
+        self.xai_every_n = 10
+        self.log_callback = None
         self.progress_every = 5                                               # image_generator.py:435
 
     def stop_generation(self):                                                # :784-786
         self.stop_requested = True
+
+    # ---- the setters the GUI / console callers use (image_generator.py:84-122) ---------------
+    def set_progress_callback(self, callback: Optional[Callable[[int, int, str], None]]):
+        self.progress_callback = callback
+
+    def set_log_callback(self, callback: Optional[Callable[[str], None]]):
+        self.log_callback = callback
+
+    def set_xai_frequency(self, frequency: int):
+        """Every N-th image of a class gets the integrated XAI analysis (>= 1)."""
+        self.xai_frequency = max(1, int(frequency))
+
+    def set_save_trajectory(self, save: bool):
+        self.save_trajectory = bool(save)
+
+    def set_xai_analyzer(self, analyzer):
+        self.xai_analyzer = analyzer
+        if analyzer is not None and not self.xai_frequency:
+            self.xai_frequency = 3                                            # the reference's default (:51)
+
+    def set_xai_hook(self, callback: Optional[Callable[[str, str], None]], every_n: int = 10):
+        """Legacy hook (:93-98).  The reference only STORES it -- nothing in its generation loops ever calls it -- so the
+        drop-in stores it too."""
+        self.xai_hook = callback
+        self.xai_every_n = max(1, int(every_n))
+
+    def set_generation_seed(self, seed: Optional[int]):
+        self.base_seed = int(seed) if seed is not None else None
+
+    def _log_message(self, message: str, level: str = "info"):
+        if self.log_callback:
+            self.log_callback(f"[{level.upper()}] {message}")                 # :129-131
+
+    def _save_xai_results(self, xai_results: Dict[str, Any], class_name: str, filename: str, file_path: str):
+        """:866-886 -- <two levels above the image>/xai_results/<class>/xai_<stem>_<YYYYmmdd_HHMMSS>.json; failures are
+        logged, never raised (the reference swallows them the same way)."""
+        try:
+            xai_dir = Path(file_path).parent.parent / "xai_results" / class_name
+            xai_dir.mkdir(parents=True, exist_ok=True)
+            stamp = time.strftime("%Y%m%d_%H%M%S")
+            target = xai_dir / f"xai_{Path(filename).stem}_{stamp}.json"
+            with open(target, "w", encoding="utf-8") as f:
+                json.dump(xai_results, f, indent=2, ensure_ascii=False)
+            self._log_message(f"XAI results saved: {target}")
+            return str(target)
+        except Exception as e:                                                # noqa: BLE001
+            self._log_message(f"could not save the XAI results: {e}", "warning")
+            return None
 
     def _update_progress(self, cur, total, msg):
         if self.progress_callback:
@@ -266,8 +318,13 @@ class ImageGenerator:
                         done += int(ok)
                         if ok and traj is not None and self.xai_analyzer is not None and self.xai_frequency \
                                 and (i + 1) % self.xai_frequency == 0:
-                            self.xai_analyzer.analyze_trajectory(traj, class_name, s, self.inference_steps,
-                                                                 fp.name, str(fp))
+                            try:                                  # :668-699: analysis errors never stop the generation
+                                res = self.xai_analyzer.analyze_trajectory(traj, class_name, s, self.inference_steps,
+                                                                           fp.name, str(fp))
+                                if res:
+                                    self._save_xai_results(res, class_name, fp.name, str(fp))
+                            except Exception as e:                # noqa: BLE001
+                                self._log_message(f"integrated XAI analysis failed: {e}", "warning")
                         results["rows"].append({"filename": fp.name, "class": class_name, "seed": s})
                 else:
                     for b0 in range(0, count, self.batch_size):

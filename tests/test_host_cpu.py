@@ -465,3 +465,40 @@ int main(void) {
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     n, name, numel, off = r.stdout.split()
     assert int(n) == 102 and name == "conv1.weight" and int(numel) == 64 * 3 * 49 and int(off) == 0
+
+
+def test_image_generator_setters_and_xai_result_files(tmp_path):
+    """image_generator.py:84-122 (setters the GUI calls) and :866-886 (where the integrated-XAI JSON goes)."""
+    import json
+    from synt_isic_b200.generator import ImageGenerator
+
+    class NoModels:
+        inference_steps = 0
+        loaded_models = {}
+
+    gen = ImageGenerator(model_manager=NoModels(), device="cpu", inference_steps=5000)
+    assert gen.inference_steps == 1000                                       # clamp of :75-79
+    logs = []
+    gen.set_log_callback(logs.append)
+    gen.set_progress_callback(None)
+    gen.set_xai_frequency(0)
+    assert gen.xai_frequency == 1
+    gen.set_save_trajectory(1)
+    assert gen.save_trajectory is True
+    gen.set_generation_seed("17")
+    assert gen.base_seed == 17
+    gen.set_generation_seed(None)
+    assert gen.base_seed is None
+    gen.set_xai_hook(lambda p, c: None, every_n=0)
+    assert gen.xai_every_n == 1
+    gen.set_xai_analyzer(object())
+    assert gen.xai_analyzer is not None
+    img = tmp_path / "out" / "MEL" / "ISIC_0000003.png"
+    img.parent.mkdir(parents=True)
+    path = gen._save_xai_results({"time_shap": {"importance": [0.5, 1.0]}, "класс": "MEL"}, "MEL", img.name, str(img))
+    assert path and os.path.dirname(path) == str(tmp_path / "out" / "xai_results" / "MEL")
+    assert os.path.basename(path).startswith("xai_ISIC_0000003_") and path.endswith(".json")
+    assert json.load(open(path, encoding="utf-8"))["класс"] == "MEL"
+    assert any("XAI results saved" in m and m.startswith("[INFO]") for m in logs)
+    assert gen._save_xai_results({"bad": object()}, "MEL", img.name, str(img)) is None     # not JSON-serialisable: logged
+    assert any(m.startswith("[WARNING]") for m in logs)
