@@ -68,6 +68,11 @@ int synt_unet_sample(synt_unet_t* h, float* x_dev, int B, const float* z_dev, un
  * following synt_unet_sample calls only if mask[s*B + b] != 0 and is frozen otherwise; noise_shared != 0 makes every
  * image of the batch draw the same in-kernel noise field (common random numbers across coalitions).  NULL / 0 resets. */
 int synt_unet_set_step_mask(synt_unet_t* h, const unsigned char* mask_dev, int noise_shared);
+/* Per-image noise streams: with keys_dev != NULL (int64 [B], device; must stay valid while sampling) image b of the following
+ * synt_unet_sample calls draws its in-kernel noise from Philox(seed, stream = keys_dev[b], step) instead of stream =
+ * image_offset + b, so the image produced for a key does not depend on the batch it is sampled in (the reference draws
+ * fresh noise per image and step, image_generator.py:403).  NULL resets. */
+int synt_unet_set_image_keys(synt_unet_t* h, const long long* keys_dev);
 /* host-buffer form of the same call (what a non-PyTorch caller binds): H2D of x_T, all steps of
  * the current schedule, uint8 HWC conversion (image_generator.py:441-447), D2H of the images.
  * x_final_host (optional) receives the fp32 result. */
@@ -132,6 +137,12 @@ int synt_ig_reduce(const float* grads_dev, const float* x_dev, const float* base
  *   3 noise (aux = injected N(0,1) tensor, scaled by noise_std), 4 aux is the intervention itself */
 int synt_intervene_blend(const float* x_dev, const float* mask_dev, const float* aux_dev, int type, float noise_std,
                          int B, int C, int H, int W, float* out_dev, void* stream);
+/* the same with the reference's `blur_kernel` kwarg (odd box size of type 2, XAI.py:1474,1511-1527; the plain call uses 5)
+ * and, when intervention_out_dev != NULL, the intervention tensor I itself [B,C,H,W] (result key 'intervention' and
+ * statistics['intervention_strength'] = mean |I|, XAI.py:1584,1592) */
+int synt_intervene_blend_ex(const float* x_dev, const float* mask_dev, const float* aux_dev, int type, float noise_std,
+                            int blur_kernel, int B, int C, int H, int W, float* out_dev, float* intervention_out_dev,
+                            void* stream);
 /* replaces the masking loop of compute_shap_approximation (XAI.py:1143-1161):
  *   out[i] = x with every patch whose mask byte is 0 set to 0; patch_masks [n][H/p][W/p] */
 int synt_patch_mask_apply(const float* x_dev, const unsigned char* patch_masks_dev, int n_masks, int C, int H, int W,

@@ -53,12 +53,14 @@ SIGNATURES = {
     "synt_ig_interpolate": (C.c_int, [vp, vp, C.c_int, C.c_longlong, vp, vp]),
     "synt_ig_reduce": (C.c_int, [vp, vp, vp, C.c_int, C.c_longlong, vp, vp]),
     "synt_intervene_blend": (C.c_int, [vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "synt_intervene_blend_ex": (C.c_int, [vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "synt_debug_conv": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, vp]),
     "synt_debug_conv_gn": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int,
                                      vp, vp, vp, vp, C.c_int, vp, c_i32p, vp]),
     "synt_debug_conv_up2x": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, c_i32p, vp]),
     "synt_unet_set_step_mask": (C.c_int, [vp, vp, C.c_int]),
+    "synt_unet_set_image_keys": (C.c_int, [vp, vp]),
     "synt_debug_set_conv_pair": (C.c_int, [C.c_int]),
     "synt_debug_pack_upsample_phases": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "synt_debug_attention": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp]),

@@ -140,7 +140,7 @@ def generate_dataset(generator, class_configs: Sequence[Tuple[str, int]], output
         folder.mkdir(parents=True, exist_ok=True)
         seeds = [image_seed(generator.base_seed if generator.base_seed is not None else 42, u.class_name, u.first_index + j)
                  for j in range(u.count)]
-        imgs, _, hashes = generator.generate_batch(u.class_name, seeds, image_offset=u.first_index)
+        imgs, _, hashes = generator.generate_batch(u.class_name, seeds)
         for j, (img, r) in enumerate(zip(imgs, unit_rows(u, layout, ext, stamp))):
             if postprocess:
                 img = color_postprocess(img, generator.color_statistics.get(u.class_name))

@@ -34,9 +34,27 @@ class MelanomaClassifierAdaptive(nn.Module):
         if num_classes not in (7, 8):
             raise NotImplementedError("the reference builds 7-way (xai_integration.py:79) or 8-way (XAI.py:490) heads")
         self.num_classes = num_classes
-        # `pretrained=True` asks torchvision for IMAGENET1K_V1 (XAI.py:389); weights are not
-        # downloadable offline, so the container starts random-init and a checkpoint is loaded on top.
-        self.model = models.resnet18(weights=None)
+        # `pretrained=True` asks torchvision for IMAGENET1K_V1 (XAI.py:389).  The weights come from torchvision's cache or
+        # a download; when neither is available (offline box) the network stays random-init and says so LOUDLY -- scores
+        # of an untrained classifier are not the reference's.  ``self.pretrained_loaded`` records what happened.
+        self.pretrained_loaded = False
+        self.model = None
+        if pretrained:
+            import socket
+            old_timeout = socket.getdefaulttimeout()
+            try:
+                socket.setdefaulttimeout(15.0)                       # an unreachable index must not hang the caller
+                self.model = models.resnet18(weights=models.ResNet18_Weights.IMAGENET1K_V1)
+                self.pretrained_loaded = True
+            except Exception as e:                                   # noqa: BLE001  (no network / no cached file)
+                import warnings
+                warnings.warn("MelanomaClassifierAdaptive(pretrained=True): the IMAGENET1K_V1 weights could not be loaded "
+                              f"({type(e).__name__}: {e}); the classifier is RANDOM-INIT until load_state_dict / "
+                              "a classifier checkpoint is applied", RuntimeWarning, stacklevel=2)
+            finally:
+                socket.setdefaulttimeout(old_timeout)
+        if self.model is None:
+            self.model = models.resnet18(weights=None)
         self.model.fc = nn.Linear(self.model.fc.in_features, num_classes)
         self.architecture = "resnet18"
         self.precision = precision
@@ -105,6 +123,18 @@ class MelanomaClassifierAdaptive(nn.Module):
             _lib.check(_lib.lib().synt_resnet18_logits(h, x.data_ptr(), x.shape[0], logits.data_ptr(),
                                                        _lib.current_stream_ptr()), "resnet18_logits")
         return logits
+
+    def logits_host(self, x: np.ndarray) -> np.ndarray:
+        """The host-buffer entry point a non-PyTorch caller binds (``synt_resnet18_logits_host``): HOST array [B,3,128,128]
+        fp32 in [-1,1] -> HOST logits [B, num_classes]; the copies happen inside the call."""
+        h = self._handle()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 4 or x.shape[1:] != (3, 128, 128):
+            raise ValueError(f"expected [B,3,128,128], got {x.shape}")
+        out = np.empty((x.shape[0], self.num_classes), np.float32)
+        with torch.cuda.device(next(self.parameters()).device):
+            _lib.check(_lib.lib().synt_resnet18_logits_host(h, x.ctypes.data, x.shape[0], out.ctypes.data), "resnet18_logits_host")
+        return out
 
     def get_probabilities(self, x):
         return F.softmax(self.forward(x), dim=1)

@@ -548,7 +548,8 @@ __device__ __forceinline__ void sched_epilogue(const float (&e)[3], int b, int o
                 for (int j = 0; j < 3; ++j) z[j] = sch.z[step * sch.z_step_stride + i0 + j * plane];
             } else {
                 const unsigned long long img = sch.noise_shared ? (unsigned long long)sch.image_offset
-                                                                : (unsigned long long)(sch.image_offset + b);
+                                             : sch.image_keys ? (unsigned long long)sch.image_keys[b]
+                                                              : (unsigned long long)(sch.image_offset + b);
                 const unsigned long long elem = img * plane + (size_t)oy * W + ox;
                 philox_normal3(sch.seed, elem, (uint32_t)step, z);
             }
@@ -856,6 +857,11 @@ void select_timestep(const float* table, int ntot, const float* coef_table, cons
                t_direct, temb_cur, coef_cur);
 }
 __global__ void advance_step_kernel(int* p) { pdl_enter(); *p += 1; }
+__global__ void set_step_kernel(int* p, int v) { *p = v; }
+void set_step(int* step_ptr, int value, cudaStream_t s) {
+    set_step_kernel<<<1, 1, 0, s>>>(step_ptr, value);
+    SYNT_LAUNCH_CHECK();
+}
 void advance_step(int* step_ptr, cudaStream_t s) {
     launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, s, step_ptr);
 }

@@ -77,6 +77,8 @@ struct SchedArgs {
     long long traj_step_stride = 0;
     long long eps_step_stride = 0;     // stride of the eps tap between steps
     long long image_offset = 0;        // global image index of image 0 of this call (Philox stream id)
+    const long long* image_keys = nullptr;   // optional device [B]: Philox stream id of image b (replaces image_offset + b),
+                                       // so that an image's noise depends on ITS key only, not on the batch it is sampled in
     // coalition decoding (permutation Time-SHAP over denoising steps, README.md:171-221 of the reference): image b takes
     // the transition of step s only if step_mask[s * mask_stride + b] != 0, otherwise x_b is frozen for that step;
     // noise_shared: every image of the batch draws the SAME Philox noise field (common random numbers across coalitions)
@@ -133,6 +135,7 @@ void select_timestep(const float* table, int ntot, const float* coef_table /*[T]
                      const int* timesteps, const int* step_ptr, int t_direct, float* temb_cur, float* coef_cur,
                      cudaStream_t s);
 void advance_step(int* step_ptr, cudaStream_t s);
+void set_step(int* step_ptr, int value, cudaStream_t s);   // *step_ptr = value (kernel argument: no host buffer to keep alive)
 
 // debug / format helpers
 void nhwc_to_nchw_f32(const void* in, int dt, int B, int HW, int C, float* out, cudaStream_t s);
@@ -165,8 +168,10 @@ void dgrad_weights(const void* src, int src_ld, int src_off, int cin_f, int cout
 void ig_interpolate(const float* x, const float* base, int n_steps, long long per, float* out, cudaStream_t s);
 void ig_reduce(const float* grads, const float* x, const float* base, int n_steps, long long per, float* out, cudaStream_t s);
 // interventions (xai/XAI.py:1495-1575): type 0=zero 1=mean 2=blur5 3=noise(injected) 4=given tensor
-void intervene_blend(const float* x, const float* mask, const float* aux, int type, float noise_std, int B, int C,
-                     int H, int W, float* out, cudaStream_t s);
+// blur_k: odd box size of type 2 (the reference's blur_kernel kwarg, default 5); interv_out (nullable) receives the
+// intervention tensor I itself (the reference returns it and reports mean |I| as intervention_strength, XAI.py:1584,1592)
+void intervene_blend(const float* x, const float* mask, const float* aux, int type, float noise_std, int blur_k, int B, int C,
+                     int H, int W, float* out, float* interv_out, cudaStream_t s);
 void patch_mask_apply(const float* x, const unsigned char* patch_masks, int n_masks, int C, int H, int W,
                       int patch, float* out, cudaStream_t s);
 

@@ -390,8 +390,9 @@ void avgpool_fc(const void* in, int dt, int B, int HW, int C, const float* w, co
 
 // one block per (b, c) plane
 __global__ void __launch_bounds__(256) intervene_kernel(const float* __restrict__ x, const float* __restrict__ mask,
-                                                        const float* __restrict__ aux, int type, float noise_std, int C,
-                                                        int H, int W, float* __restrict__ out) {
+                                                        const float* __restrict__ aux, int type, float noise_std, int blur_k,
+                                                        int C, int H, int W, float* __restrict__ out,
+                                                        float* __restrict__ interv_out) {
     __shared__ float red[256];
     __shared__ float mean_s;
     const int plane = blockIdx.x, b = plane / C, HW = H * W;
@@ -412,26 +413,28 @@ __global__ void __launch_bounds__(256) intervene_kernel(const float* __restrict_
         if (type == 0) iv = 0.f;
         else if (type == 1) iv = mean_s;
         else if (type == 2) {
-            const int y = i / W, xx = i % W;
+            const int y = i / W, xx = i % W, r = blur_k / 2;
             float s = 0.f;
-            for (int dy = -2; dy <= 2; ++dy)
-                for (int dx = -2; dx <= 2; ++dx) {
+            for (int dy = -r; dy <= r; ++dy)
+                for (int dx = -r; dx <= r; ++dx) {
                     const int yy = y + dy, xc = xx + dx;
                     if (yy >= 0 && yy < H && xc >= 0 && xc < W) s += xp[yy * W + xc];
                 }
-            iv = s / 25.f;                                 // avg_pool2d count_include_pad=True
+            iv = s / (float)(blur_k * blur_k);             // avg_pool2d count_include_pad=True
         } else if (type == 3) iv = aux[(size_t)plane * HW + i] * noise_std;
         else iv = aux[(size_t)plane * HW + i];
         const float m = mp[i];
         const float v = xp[i] * (1.f - m) + iv * m;
         op[i] = fminf(fmaxf(v, -1.f), 1.f);
+        if (interv_out) interv_out[(size_t)plane * HW + i] = iv;
     }
 }
-void intervene_blend(const float* x, const float* mask, const float* aux, int type, float noise_std, int B, int C, int H,
-                     int W, float* out, cudaStream_t s) {
+void intervene_blend(const float* x, const float* mask, const float* aux, int type, float noise_std, int blur_k, int B, int C,
+                     int H, int W, float* out, float* interv_out, cudaStream_t s) {
     SYNT_CHECK(type >= 0 && type <= 4, "intervene: unknown type");
     SYNT_CHECK(type < 3 || aux != nullptr, "intervene: aux tensor required");
-    intervene_kernel<<<B * C, 256, 0, s>>>(x, mask, aux, type, noise_std, C, H, W, out);
+    SYNT_CHECK(blur_k >= 1 && (blur_k & 1) && blur_k <= 63, "intervene: blur kernel must be odd, 1..63");
+    intervene_kernel<<<B * C, 256, 0, s>>>(x, mask, aux, type, noise_std, blur_k, C, H, W, out, interv_out);
     SYNT_LAUNCH_CHECK();
 }
 
@@ -979,9 +982,13 @@ int synt_ig_reduce(const float* grads, const float* x, const float* baseline, in
 
 int synt_intervene_blend(const float* x, const float* mask, const float* aux, int type, float noise_std, int B, int C,
                          int H, int W, float* out, void* stream) {
+    return synt_intervene_blend_ex(x, mask, aux, type, noise_std, 5, B, C, H, W, out, nullptr, stream);
+}
+int synt_intervene_blend_ex(const float* x, const float* mask, const float* aux, int type, float noise_std, int blur_kernel,
+                            int B, int C, int H, int W, float* out, float* intervention_out, void* stream) {
     SYNT_TRY
     SYNT_CHECK(x && mask && out && B > 0, "bad argument");
-    intervene_blend(x, mask, aux, type, noise_std, B, C, H, W, out, (cudaStream_t)stream);
+    intervene_blend(x, mask, aux, type, noise_std, blur_kernel, B, C, H, W, out, intervention_out, (cudaStream_t)stream);
     SYNT_CATCH
 }
 int synt_patch_mask_apply(const float* x, const unsigned char* pm, int n_masks, int C, int H, int W, int patch, float* out,

@@ -212,6 +212,7 @@ struct synt_unet {
     DevPtr temb_cur, coef_cur, step_ctr;          // fixed per-step buffers (graph friendly)
     DevPtr timesteps_dev, coef_table_dev; int n_steps = 0;
     const unsigned char* step_mask = nullptr; int noise_shared = 0;   // coalition decoding (synt_unet_set_step_mask)
+    const long long* image_keys = nullptr;        // per-image Philox stream ids (synt_unet_set_image_keys)
     std::vector<int> timesteps_host;
     Pool pool;
     Pool pool2;                                   // second chain (dual-stream sampling)
@@ -220,10 +221,10 @@ struct synt_unet {
     // CUDA graph cache for one sampling step
     struct GraphKey {
         float* x; int B; const float* z; float* traj; float* eps; int mb; unsigned long long seed; long long off;
-        const unsigned char* mask; int shared;
+        const unsigned char* mask; int shared; const long long* keys;
         bool operator==(const GraphKey& o) const {
             return x == o.x && B == o.B && z == o.z && traj == o.traj && eps == o.eps && mb == o.mb && seed == o.seed &&
-                   off == o.off && mask == o.mask && shared == o.shared;
+                   off == o.off && mask == o.mask && shared == o.shared && keys == o.keys;
         }
     } gkey{};
     cudaGraphExec_t gexec = nullptr;
@@ -666,6 +667,7 @@ static void sample_step(synt_unet* u, float* x, int B, const float* z, unsigned 
         sch.eps_step_stride = (long long)B * img;
         sch.image_offset = u->noise_shared ? image_offset : image_offset + b0;
         sch.step_mask = u->step_mask ? u->step_mask + b0 : nullptr; sch.mask_stride = B; sch.noise_shared = u->noise_shared;
+        sch.image_keys = u->image_keys ? u->image_keys + b0 : nullptr;
         f.run(x + b0 * img, eps_tap ? eps_tap + b0 * img : nullptr, sch);
     };
     if (u->dual && B >= 2 && mb >= B) {
@@ -815,15 +817,15 @@ int synt_unet_sample(synt_unet_t* h, float* x, int B, const float* z, unsigned l
         SYNT_CUDA(cudaStreamWaitEvent(s, h->ev_in, 0));
     }
     const int mb = micro_batch > 0 ? (micro_batch < B ? micro_batch : B) : default_micro_batch(B);
-    SYNT_CUDA(cudaMemcpyAsync(h->step_ctr->p, &step_begin, 4, cudaMemcpyHostToDevice, s));
-    SYNT_CUDA(cudaStreamSynchronize(s));                    // &step_begin is a stack temporary
     const int n = step_end - step_begin;
     if (n == 0) return 0;
+    set_step((int*)h->step_ctr->p, step_begin, s);          // kernel argument: no host buffer to outlive, no host sync
+    ++h->launches;
     if (!use_graph) {
         for (int i = 0; i < n; ++i) sample_step(h, x, B, z, seed, image_offset, traj, eps_tap, mb, s);
         return 0;
     }
-    synt_unet::GraphKey key{x, B, z, traj, eps_tap, mb, seed, image_offset, h->step_mask, h->noise_shared};
+    synt_unet::GraphKey key{x, B, z, traj, eps_tap, mb, seed, image_offset, h->step_mask, h->noise_shared, h->image_keys};
     int done = 0;
     if (!h->gexec || !(key == h->gkey)) {
         if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
@@ -861,6 +863,13 @@ int synt_unet_set_step_mask(synt_unet_t* h, const unsigned char* mask_dev, int n
     SYNT_TRY
     SYNT_CHECK(h, "bad argument");
     h->step_mask = mask_dev; h->noise_shared = noise_shared ? 1 : 0;
+    SYNT_CATCH
+}
+
+int synt_unet_set_image_keys(synt_unet_t* h, const long long* keys_dev) {
+    SYNT_TRY
+    SYNT_CHECK(h, "bad argument");
+    h->image_keys = keys_dev;
     SYNT_CATCH
 }
 

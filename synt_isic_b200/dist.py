@@ -62,12 +62,13 @@ def sharded_eval(fn, items: torch.Tensor, group=None, chunk: int = 256) -> torch
     outs = [fn(items[i:min(i + chunk, hi)]) for i in range(lo, hi, chunk)]
     if world == 1:
         return torch.cat(outs) if len(outs) > 1 else outs[0]
-    k = None
     local = torch.cat(outs) if outs else None
-    # every rank must agree on k; rank slices are never empty unless n < world
-    kk = torch.tensor([local.shape[1] if local is not None else 0], device=items.device)
-    dist.all_reduce(kk, op=dist.ReduceOp.MAX, group=group)
-    k = int(kk.item())
+    if n >= world:
+        k = local.shape[1]                                  # no rank slice is empty: every rank knows the row width
+    else:                                                   # fewer rows than ranks: agree on the width (one tiny all_reduce)
+        kk = torch.tensor([local.shape[1] if local is not None else 0], device=items.device)
+        dist.all_reduce(kk, op=dist.ReduceOp.MAX, group=group)
+        k = int(kk.item())
     per = (n + world - 1) // world
     pad = torch.zeros(per, k, dtype=torch.float32, device=items.device)
     if local is not None:
@@ -90,10 +91,13 @@ def gather_images(local_u8: torch.Tensor, counts, group=None, dst: int = 0):
     per = max(counts)
     pad = torch.zeros((per,) + tuple(local_u8.shape[1:]), dtype=local_u8.dtype, device=local_u8.device)
     pad[: local_u8.shape[0]] = local_u8
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
+    # a GATHER to `dst` (only dst receives the images), not an all_gather; `dst` is a rank of `group`
+    dst_global = dist.get_global_rank(group, dst) if group is not None and group is not dist.group.WORLD else dst
     if rank != dst:
+        dist.gather(pad, None, dst=dst_global, group=group)
         return None
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.gather(pad, bufs, dst=dst_global, group=group)
     return torch.cat([bufs[r][: counts[r]] for r in range(world)])
 
 

@@ -81,14 +81,25 @@ def color_postprocess(img: np.ndarray, stats: Optional[dict]) -> np.ndarray:
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
-class ModelManager:
-    """core/generator/model_manager.py: builds the UNet per class, loads ``unet_<CLASS>_best.pth``
-    when present (random-init otherwise -- checkpoints are not shipped), creates the scheduler."""
+class GenerationStopped(RuntimeError):
+    """Raised inside the batched path when ``stop_generation()`` was called (image_generator.py:396)."""
 
-    def __init__(self, checkpoint_dir: Optional[str] = None, device: str = "cuda", precision: str = "bf16"):
+
+SYNTHETIC_CSV_HEADERS = ["filename", "class", "isic_number", "source", "generated_at"]   # image_generator.py:744
+
+
+class ModelManager:
+    """core/generator/model_manager.py: builds the UNet per class, loads ``unet_<CLASS>_best.pth`` and creates the
+    scheduler.  Like the reference (:104-107) ``load_model`` returns False when the checkpoint is missing; random-init
+    weights (benchmarks, tests -- the checkpoints are not shipped) must be asked for with ``allow_random_init=True`` or
+    by passing a ``state_dict``."""
+
+    def __init__(self, checkpoint_dir: Optional[str] = None, device: str = "cuda", precision: str = "bf16",
+                 allow_random_init: bool = False):
         self.checkpoint_dir = Path(checkpoint_dir) if checkpoint_dir else None
         self.device = torch.device(device)
         self.precision = precision
+        self.allow_random_init = bool(allow_random_init)
         self.loaded_models: Dict[str, UNet2DModel] = {}
         self.model_metadata: Dict[str, dict] = {}
         self.inference_steps = 50
@@ -96,13 +107,22 @@ class ModelManager:
     def _create_model_architecture(self) -> UNet2DModel:       # model_manager.py:173-194
         return UNet2DModel(precision=self.precision, **SUPPORTED_CONFIG)
 
-    def load_model(self, class_name: str, state_dict: Optional[dict] = None) -> bool:   # :89-171
-        model = self._create_model_architecture()
+    def load_model(self, class_name: str, state_dict: Optional[dict] = None, force_reload: bool = False) -> bool:   # :89-171
+        if class_name in self.loaded_models and not force_reload and state_dict is None:
+            return True
         meta = {"class": class_name, "source": "random_init"}
         path = self.checkpoint_dir / f"unet_{class_name}_best.pth" if self.checkpoint_dir else None
         if state_dict is None and path is not None and path.exists():
             state_dict = torch.load(str(path), map_location="cpu")
             meta = {"class": class_name, "source": str(path), "bytes": path.stat().st_size}
+        elif state_dict is not None:
+            meta = {"class": class_name, "source": "state_dict"}
+        if state_dict is None and not self.allow_random_init:
+            # model_manager.py:104-107: a missing checkpoint is an error, never a silently random network
+            print(f"model file not found: {path if path is not None else '<no checkpoint_dir>'} "
+                  f"(pass allow_random_init=True for random-init weights)")
+            return False
+        model = self._create_model_architecture()
         if state_dict is not None:
             model.load_state_dict(state_dict)                    # strict (model_manager.py:139)
         self.loaded_models[class_name] = model.to(self.device).eval()
@@ -121,12 +141,35 @@ class ModelManager:
 
 
 class ImageGenerator:
-    def __init__(self, model_manager: Optional[ModelManager] = None, device: str = "cuda",
+    """``ImageGenerator(config_manager)`` is the reference's constructor (image_generator.py:28-78): the first positional
+    argument may be its ``ConfigManager`` (anything with ``get_generation_param`` / ``get_path``), from which
+    ``inference_timesteps`` and the ``checkpoints`` folder are read; everything else of the config is control plane and
+    ignored.  A ``ModelManager`` in that position (or ``model_manager=``) is the native form."""
+
+    def __init__(self, model_manager=None, device: str = "cuda",
                  inference_steps: int = 50, base_seed: Optional[int] = 42, save_trajectory: bool = False,
                  color_statistics: Optional[dict] = None, precision: str = "bf16",
-                 progress_callback: Optional[Callable[[int, int, str], None]] = None, batch_size: int = 64):
+                 progress_callback: Optional[Callable[[int, int, str], None]] = None, batch_size: int = 64,
+                 allow_random_init: bool = False, noise_seed: int = 0):
         self.device = torch.device(device)
-        self.model_manager = model_manager or ModelManager(device=device, precision=precision)
+        self.config_manager = None
+        if model_manager is not None and hasattr(model_manager, "get_generation_param"):
+            self.config_manager = model_manager                               # reference form (image_generator.py:28-29)
+            model_manager = None
+            try:
+                inference_steps = int(self.config_manager.get_generation_param("inference_timesteps"))   # :70-74
+            except Exception:
+                inference_steps = 50
+            ckpt = None
+            try:
+                ckpt = self.config_manager.get_path("checkpoints")            # model_manager.py:97
+            except Exception:
+                ckpt = None
+            model_manager = ModelManager(ckpt, device=device, precision=precision, allow_random_init=allow_random_init)
+            base_seed, save_trajectory = None, True                           # the reference's defaults (:52, :59)
+        self.model_manager = model_manager or ModelManager(device=device, precision=precision,
+                                                           allow_random_init=allow_random_init)
+        self.noise_seed = int(noise_seed)                                     # Philox key of the in-kernel step noise
         self.inference_steps = max(1, min(1000, int(inference_steps)))       # image_generator.py:75-79
         self.model_manager.inference_steps = self.inference_steps
         self.base_seed = base_seed
@@ -220,19 +263,28 @@ class ImageGenerator:
                 xs.append(torch.randn(1, 3, 128, 128, device=self.device))
         return torch.cat(xs)
 
-    def _denoise(self, model, latents, seed_for_noise: int, want_traj: bool, label: str,
+    @staticmethod
+    def noise_keys(seeds: List[Optional[int]]) -> List[int]:
+        """Philox stream id of every image = its seed (a fresh 63-bit draw when the seed is None, like the reference's
+        fresh global-RNG noise, image_generator.py:403): the step noise of an image depends on ITS key only, so the B=1
+        path, any batch composition and ``save_trajectory`` give the same image for the same sidecar seed."""
+        return [int(s) if s is not None else int.from_bytes(os.urandom(8), "little") >> 1 for s in seeds]
+
+    def _denoise(self, model, latents, keys: List[int], want_traj: bool, label: str,
                  progress_offset_units=0, progress_total_units=0):
         """The loop of :395-403 as chunked replays of the fused CUDA-graph step: the stop flag
         (:396) and the progress callback (:435) are honoured between chunks."""
         scheduler = self.model_manager.create_scheduler()
         n = len(scheduler.timesteps)
         traj = torch.empty((n,) + tuple(latents.shape), dtype=torch.float32, device=latents.device) if want_traj else None
+        key_t = torch.tensor(keys, dtype=torch.int64, device=latents.device)
         step = 0
         while step < n:
             if self.stop_requested:
                 return None, None
             end = min(n, step + self.progress_every)
-            model.sample(latents, scheduler, seed=seed_for_noise, trajectory=traj, step_begin=step, step_end=end)
+            model.sample(latents, scheduler, seed=self.noise_seed, image_keys=key_t, trajectory=traj, step_begin=step,
+                         step_end=end)
             step = end
             total = progress_total_units if progress_total_units > 0 else n
             self._update_progress(progress_offset_units + step, total, f"Denoising {label}: {step}/{n} ({int(100 * step / n)}%)")
@@ -250,7 +302,7 @@ class ImageGenerator:
             with torch.no_grad():
                 noise = self.make_noise([seed])
                 nhash = noise_hash(noise)
-                latents, traj = self._denoise(model, noise.clone(), seed if seed is not None else 0,
+                latents, traj = self._denoise(model, noise.clone(), self.noise_keys([seed]),
                                               self.save_trajectory, class_name, progress_offset_units,
                                               progress_total_units)
                 if latents is None:
@@ -279,69 +331,116 @@ class ImageGenerator:
             json.dump(meta, f, indent=2, ensure_ascii=False)
 
     # ---- batched sampling (new) ----------------------------------------------------------
-    def generate_batch(self, class_name: str, seeds: List[int], noise_seed: Optional[int] = None,
-                       image_offset: int = 0) -> Tuple[np.ndarray, torch.Tensor, List[str]]:
-        """Samples len(seeds) images of one class in one fused loop.  Returns (uint8 [B,128,128,3],
-        fp32 finals, x_T hashes)."""
+    def generate_batch(self, class_name: str, seeds: List[Optional[int]]) -> Tuple[np.ndarray, torch.Tensor, List[str]]:
+        """Samples len(seeds) images of one class in one fused loop.  Returns (uint8 [B,128,128,3], fp32 finals, x_T
+        hashes); image i is bit-identical to ``generate_single_image(..., seed=seeds[i])`` in the fp32 mode and equal up
+        to the batch-dependent bf16 rounding of the GEMM tiles in the bf16 mode (same x_T, same step noise).  Raises
+        ``GenerationStopped`` when ``stop_generation()`` was called."""
         model = self._model(class_name)
         with torch.no_grad():
             x = self.make_noise(list(seeds))
             hashes = [noise_hash(x[i:i + 1]) for i in range(x.shape[0])]
-            latents, _ = self._denoise(model, x, noise_seed if noise_seed is not None else int(seeds[0]), False,
-                                       class_name)
+            latents, _ = self._denoise(model, x, self.noise_keys(list(seeds)), False, class_name)
             if latents is None:
-                raise RuntimeError("generation stopped")
+                raise GenerationStopped("generation stopped")
         return to_uint8_image(latents), latents, hashes
 
     # ---- reference signature (image_generator.py:547-548) ---------------------------------
+    def _initialize_synthetic_csv(self, csv_path: Path):                      # :742-758
+        import csv
+        with open(csv_path, "w", newline="", encoding="utf-8") as f:
+            csv.DictWriter(f, fieldnames=SYNTHETIC_CSV_HEADERS).writeheader()
+
+    def _append_to_csv(self, csv_path: Path, data: Dict[str, Any]):           # :760-782
+        import csv
+        with open(csv_path, "a", newline="", encoding="utf-8") as f:
+            csv.DictWriter(f, fieldnames=SYNTHETIC_CSV_HEADERS).writerow({k: data.get(k, "") for k in SYNTHETIC_CSV_HEADERS})
+
     def generate_images(self, class_configs: List[Tuple[str, int]], output_dir: str,
                         postprocess: bool = True) -> Dict[str, Any]:
+        """image_generator.py:547-740.  Result like the reference: ``{"total_generated": n, "stopped": bool}`` or
+        ``{"error": str}`` (nothing propagates); ``synthetic_dataset.csv`` with the reference's columns; ISIC numbering
+        inside the class folder and the XAI cadence count SUCCESSFUL images (``class_image_count``, :609-617, :669).
+        Additions: ``generated`` (per class), ``total`` and ``rows`` (filename / class / seed)."""
         if self.is_generating:
             return {"error": "generation already running"}
-        self.is_generating, self.stop_requested = True, False
-        out = Path(output_dir)
-        out.mkdir(parents=True, exist_ok=True)
+        generated_count = 0
         results: Dict[str, Any] = {"generated": {}, "total": 0, "rows": []}
         try:
+            self.is_generating, self.stop_requested = True, False
+            out = Path(output_dir)
+            out.mkdir(parents=True, exist_ok=True)
+            csv_path = out / "synthetic_dataset.csv"
+            self._initialize_synthetic_csv(csv_path)
+            total_images = sum(c for _, c in class_configs)
+
+            def record(fp: Path, class_name: str, isic_number: int, seed):
+                self._append_to_csv(csv_path, {"filename": fp.name, "class": class_name, "isic_number": isic_number,
+                                               "source": "synthetic", "generated_at": str(fp.stat().st_mtime)})
+                results["rows"].append({"filename": fp.name, "class": class_name, "seed": seed})
+
             for class_name, count in class_configs:
                 if self.stop_requested:
                     break
                 cdir = out / class_name
                 cdir.mkdir(exist_ok=True)
+                # :626-637: seed = base + md5 offset + index; without a base seed a random but recorded 31-bit seed
                 seeds = [image_seed(self.base_seed, class_name, i) if self.base_seed is not None
                          else int.from_bytes(os.urandom(4), "little") & 0x7FFFFFFF for i in range(count)]
-                done = 0
+                class_image_count = 0
                 if self.save_trajectory or self.xai_analyzer is not None:
-                    for i, s in enumerate(seeds):                # B=1 path keeps per-image trajectories
-                        fp = cdir / isic_filename(i + 1)
-                        ok, traj = self.generate_single_image(class_name, str(fp), postprocess, s)
-                        done += int(ok)
-                        if ok and traj is not None and self.xai_analyzer is not None and self.xai_frequency \
-                                and (i + 1) % self.xai_frequency == 0:
+                    for i, sd in enumerate(seeds):               # B=1 path keeps per-image trajectories
+                        if self.stop_requested:
+                            break
+                        fp = cdir / isic_filename(class_image_count + 1)
+                        ok, traj = self.generate_single_image(
+                            class_name, str(fp), postprocess, sd,
+                            progress_offset_units=generated_count * self.inference_steps,
+                            progress_total_units=total_images * self.inference_steps,
+                            overall_index=generated_count + 1, overall_total=total_images)
+                        if not ok:
+                            continue
+                        generated_count += 1
+                        class_image_count += 1
+                        record(fp, class_name, class_image_count, sd)
+                        self._update_progress(generated_count, total_images, f"Generated {generated_count}/{total_images}")
+                        if traj and self.xai_analyzer is not None and self.xai_frequency \
+                                and class_image_count % self.xai_frequency == 0:
                             try:                                  # :668-699: analysis errors never stop the generation
-                                res = self.xai_analyzer.analyze_trajectory(traj, class_name, s, self.inference_steps,
+                                res = self.xai_analyzer.analyze_trajectory(traj, class_name, sd, self.inference_steps,
                                                                            fp.name, str(fp))
                                 if res:
                                     self._save_xai_results(res, class_name, fp.name, str(fp))
                             except Exception as e:                # noqa: BLE001
                                 self._log_message(f"integrated XAI analysis failed: {e}", "warning")
-                        results["rows"].append({"filename": fp.name, "class": class_name, "seed": s})
                 else:
                     for b0 in range(0, count, self.batch_size):
+                        if self.stop_requested:
+                            break
                         chunk = seeds[b0:b0 + self.batch_size]
-                        imgs, _, hashes = self.generate_batch(class_name, chunk, image_offset=b0)
+                        try:
+                            imgs, _, hashes = self.generate_batch(class_name, chunk)
+                        except GenerationStopped:
+                            break
                         for j, img in enumerate(imgs):
-                            fp = cdir / isic_filename(b0 + j + 1)
+                            fp = cdir / isic_filename(class_image_count + 1)
                             if postprocess:
                                 img = color_postprocess(img, self.color_statistics.get(class_name))
                             self._save(img, str(fp), class_name, chunk[j], hashes[j])
-                            results["rows"].append({"filename": fp.name, "class": class_name, "seed": chunk[j]})
-                        done += len(chunk)
-                results["generated"][class_name] = done
-                results["total"] += done
+                            generated_count += 1
+                            class_image_count += 1
+                            record(fp, class_name, class_image_count, chunk[j])
+                        self._update_progress(generated_count, total_images, f"Generated {generated_count}/{total_images}")
+                results["generated"][class_name] = class_image_count
+            results["total"] = generated_count
+            results["total_generated"] = generated_count
+            results["stopped"] = bool(self.stop_requested)
+            return results
+        except Exception as e:                                    # noqa: BLE001  (:730-737)
+            self._log_message(f"generation failed: {e}", "error")
+            return {"error": str(e)}
         finally:
             self.is_generating = False
-        return results
 
 
 class DiffusionGenerator:

@@ -221,12 +221,14 @@ class UNet2DModel(nn.Module):
     def sample(self, x: torch.Tensor, scheduler, noise: torch.Tensor | None = None, seed: int = 0,
                image_offset: int = 0, trajectory: torch.Tensor | None = None, eps_tap: torch.Tensor | None = None,
                step_begin: int = 0, step_end: int | None = None, micro_batch: int = 0, use_graph: bool = True,
-               step_mask: torch.Tensor | None = None, shared_noise: bool = False):
+               step_mask: torch.Tensor | None = None, shared_noise: bool = False,
+               image_keys: torch.Tensor | None = None):
         """Runs steps [step_begin, step_end) of the loop at image_generator.py:395-403 IN PLACE on
         ``x`` (fp32 CUDA [B,3,128,128], contiguous).  ``noise`` [n_steps,B,3,128,128] injects z.
         ``step_mask`` (uint8 CUDA [n_steps, B]): image b takes the transition of step s only where the mask is
         non-zero and stays frozen otherwise (coalition decoding of the permutation Time-SHAP); ``shared_noise``:
-        all images of the batch draw the same in-kernel noise field."""
+        all images of the batch draw the same in-kernel noise field.  ``image_keys`` (int64 CUDA [B]): Philox stream id of
+        every image (default ``image_offset + b``), so that an image's noise depends on its key only."""
         if not (x.is_cuda and x.is_contiguous() and x.dtype == torch.float32):
             raise ValueError("x must be a contiguous fp32 CUDA tensor")
         self.set_schedule(scheduler)
@@ -239,17 +241,42 @@ class UNet2DModel(nn.Module):
         if step_mask is not None and not (step_mask.is_cuda and step_mask.is_contiguous() and step_mask.dtype == torch.uint8
                                           and tuple(step_mask.shape) == (n, x.shape[0])):
             raise ValueError("step_mask must be a contiguous uint8 CUDA tensor of shape [n_steps, B]")
+        if image_keys is not None and not (image_keys.is_cuda and image_keys.is_contiguous() and image_keys.dtype == torch.int64
+                                           and tuple(image_keys.shape) == (x.shape[0],)):
+            raise ValueError("image_keys must be a contiguous int64 CUDA tensor of shape [B]")
         with torch.cuda.device(x.device):
             masked = step_mask is not None or shared_noise
             if masked:
                 _lib.check(_lib.lib().synt_unet_set_step_mask(self._handle(), step_mask.data_ptr() if step_mask is not None else None,
                                                               1 if shared_noise else 0), "unet_set_step_mask")
+            if image_keys is not None:
+                _lib.check(_lib.lib().synt_unet_set_image_keys(self._handle(), image_keys.data_ptr()), "unet_set_image_keys")
             try:
                 self._sample_call(x, noise, seed, image_offset, trajectory, eps_tap, step_begin, step_end, micro_batch, use_graph)
             finally:
                 if masked:
                     _lib.lib().synt_unet_set_step_mask(self._handle(), None, 0)
+                if image_keys is not None:
+                    _lib.lib().synt_unet_set_image_keys(self._handle(), None)
         return x
+
+    def generate_host(self, x_T: np.ndarray, scheduler, seed: int = 0, image_offset: int = 0, micro_batch: int = 0,
+                      want_final: bool = False):
+        """The host-buffer entry point a non-PyTorch caller binds (``synt_unet_generate_host``): ``x_T`` is a HOST array
+        [B,3,128,128] fp32; H2D copy, every step of ``scheduler``, uint8 conversion (image_generator.py:441-447) and the D2H
+        copy happen inside the one call.  Returns uint8 [B,128,128,3] (and the fp32 finals with ``want_final``)."""
+        self.set_schedule(scheduler)
+        x = np.ascontiguousarray(x_T, dtype=np.float32)
+        if x.ndim != 4 or x.shape[1:] != (3, 128, 128):
+            raise ValueError(f"expected [B,3,128,128], got {x.shape}")
+        B = x.shape[0]
+        u8 = np.empty((B, 128, 128, 3), np.uint8)
+        fin = np.empty_like(x) if want_final else None
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().synt_unet_generate_host(self._handle(), x.ctypes.data, B, int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                          int(image_offset), micro_batch, u8.ctypes.data,
+                                                          fin.ctypes.data if fin is not None else None), "unet_generate_host")
+        return (u8, fin) if want_final else u8
 
     def _sample_call(self, x, noise, seed, image_offset, trajectory, eps_tap, step_begin, step_end, micro_batch, use_graph):
         _lib.check(_lib.lib().synt_unet_sample(

@@ -204,6 +204,40 @@ def compute_shap_approximation(classifier, image, target_class, n_samples=SHAP_N
     return full[None, None].expand(1, ch, height, width).contiguous()
 
 
+def compute_shap_approximation_batch(classifier, images, target_class, n_samples=SHAP_N_SAMPLES, patch_size=16,
+                                     patch_masks: torch.Tensor | None = None, frames_per_pass: int = 8, group=None):
+    """``compute_shap_approximation`` for a stack of frames [T,3,128,128] -- what stage 1 of the reference pipeline runs frame
+    by frame over the WHOLE trajectory (XAI.py:2745-2747).  ``patch_masks`` [T,n,H/p,W/p] injects the coalitions; otherwise
+    they are drawn frame after frame from the global CPU RNG in the reference's order (XAI.py:1145).  ``frames_per_pass``
+    frames x (n + 1) masked images go through ONE classifier call.  Returns [T,3,128,128]."""
+    dev = _dev(classifier)
+    x = images.to(dev).float().reshape(-1, 3, 128, 128).contiguous()
+    T, ch, height, width = x.shape
+    n_h, n_w = height // patch_size, width // patch_size
+    if patch_masks is None:
+        patch_masks = torch.stack([draw_patch_masks(n_samples, n_h, n_w) for _ in range(T)])
+    n_samples = patch_masks.shape[1]
+    out = torch.empty_like(x)
+    L = _lib.lib()
+    per = n_samples + 1
+    for t0 in range(0, T, frames_per_pass):
+        g = min(frames_per_pass, T - t0)
+        pm = patch_masks[t0:t0 + g].to(dev).to(torch.uint8).contiguous()
+        batch = torch.empty(g * per, ch, height, width, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.current_stream_ptr()
+            for j in range(g):
+                batch[j * per].zero_()                              # baseline: black image in [-1,1] space
+                _lib.check(L.synt_patch_mask_apply(x[t0 + j].data_ptr(), pm[j].data_ptr(), n_samples, ch, height, width,
+                                                   patch_size, batch[j * per + 1:(j + 1) * per].data_ptr(), st), "patch_mask_apply")
+        scores = torch.log(_probs(classifier, batch, group)[:, target_class] + 1e-8).view(g, per)
+        contrib = scores[:, 1:] - scores[:, :1]                    # masked_score - baseline_score
+        patch_attr = (contrib[:, :, None, None] * pm.float()).sum(1) / n_samples
+        full = patch_attr.repeat_interleave(patch_size, 1).repeat_interleave(patch_size, 2)
+        out[t0:t0 + g] = full[:, None].expand(g, ch, height, width)
+    return out
+
+
 # ------------------------------------------------------------------ gradient attributions
 def get_baseline(image: torch.Tensor, baseline_type: str = "noise", generator=None) -> torch.Tensor:
     """xai/XAI.py:1008-1037: 'noise' = 0.1 N(0,1), 'blur' = 31x31 box blur, anything else zeros.  (The reference caches
@@ -319,6 +353,9 @@ def counterfactual_intervention_advanced(image, mask, intervention_type="noise",
     """xai/XAI.py:1454-1597: x~ = clamp(x (1-M) + I M, -1, 1).  Extra kwargs: ``noise`` injects the
     N(0,1) tensor, ``generator`` seeds it / the shuffle permutation."""
     noise_std = kwargs.get("noise_std", NOISE_STD)
+    blur_kernel = int(kwargs.get("blur_kernel", BLUR_KERNEL_SIZE))
+    if blur_kernel % 2 == 0:
+        blur_kernel += 1                                        # XAI.py:1512-1513
     dev = image.device
     if not image.is_cuda:
         raise RuntimeError("interventions run on CUDA tensors (no CPU fallback)")
@@ -352,15 +389,19 @@ def counterfactual_intervention_advanced(image, mask, intervention_type="noise",
                     perm = idx[torch.randperm(idx.numel(), device=dev, generator=gen)]
                     aux[b, c].view(-1)[idx] = image[b, c].reshape(-1)[perm]
     out = torch.empty_like(image)
+    interv = torch.empty_like(image)
+    # 'inpaint' is the reference's fixed 5x5 grouped box convolution (XAI.py:1529-1539); 'blur' honours blur_kernel
+    bk = blur_kernel if intervention_type == "blur" else 5
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().synt_intervene_blend(image.data_ptr(), m.data_ptr(),
-                                                   aux.contiguous().data_ptr() if aux is not None else None, code,
-                                                   float(noise_std), B, Cc, H, W, out.data_ptr(),
-                                                   _lib.current_stream_ptr()), "intervene_blend")
+        _lib.check(_lib.lib().synt_intervene_blend_ex(image.data_ptr(), m.data_ptr(),
+                                                      aux.contiguous().data_ptr() if aux is not None else None, code,
+                                                      float(noise_std), bk, B, Cc, H, W, out.data_ptr(), interv.data_ptr(),
+                                                      _lib.current_stream_ptr()), "intervene_blend")
     mask_tensor = m[:, None].expand(B, Cc, H, W)
     diff = (image - out).abs()
     return {
         "modified_image": out,
+        "intervention": interv,
         "mask_tensor": mask_tensor,
         "difference": diff,
         "statistics": {
@@ -368,6 +409,7 @@ def counterfactual_intervention_advanced(image, mask, intervention_type="noise",
             "mask_coverage": float(mask_tensor.float().mean()),
             "mean_difference": float(diff.mean()),
             "max_difference": float(diff.max()),
+            "intervention_strength": float(interv.abs().mean()),
         },
         "parameters": {k: v for k, v in kwargs.items() if k not in ("noise", "generator")},
     }
@@ -494,17 +536,35 @@ class IntegratedXAIAnalyzer:
     """xai/xai_integration.py:75-132, hot-path stages only: Time-SHAP over every frame, patch-SHAP
     + top/bottom-k interventions + CFI on the key frames [0, T/2, T-4..T-1] (XAI.py:2822-2896)."""
 
-    def __init__(self, device: str = "cuda", verbose: bool = False, precision: str = "bf16", group=None):
+    def __init__(self, device: str = "cuda", verbose: bool = False, precision: str = "bf16", group=None,
+                 classifier_path: str | None = None, state_dict: dict | None = None, pretrained: bool = True):
+        """``classifier_path`` (a ``torch.save``d state_dict of the classifier or of its ``.model``) / ``state_dict`` load
+        trained weights on top; without them the reference's behaviour is kept (ImageNet-pretrained backbone + fresh
+        7-way head, xai_integration.py:79) and a warning is raised when the pretrained weights are unavailable offline."""
         self.device = torch.device(device)
         self.verbose = verbose
         self.group = group
         # reference: MelanomaClassifierAdaptive(num_classes=7, architecture='auto', pretrained=True)
-        self.classifier = MelanomaClassifierAdaptive(num_classes=7, architecture="auto", pretrained=True,
-                                                     precision=precision).to(self.device).eval()
+        have_weights = classifier_path is not None or state_dict is not None
+        self.classifier = MelanomaClassifierAdaptive(num_classes=7, architecture="auto", pretrained=pretrained and not have_weights,
+                                                     precision=precision)
+        if classifier_path is not None:
+            state_dict = torch.load(classifier_path, map_location="cpu")
+        if state_dict is not None:
+            sd = state_dict.get("model_state_dict", state_dict) if isinstance(state_dict, dict) else state_dict
+            if any(k.startswith("model.") for k in sd):
+                self.classifier.load_state_dict(sd)
+            else:
+                self.classifier.model.load_state_dict(sd)
+        self.classifier = self.classifier.to(self.device).eval()
 
     def analyze_trajectory(self, trajectory, class_name, seed, inference_steps, filename, file_path, timesteps=None,
                            shap_samples: int = SHAP_N_SAMPLES, intervention_types=("blur",), methods=("ig", "shap"),
-                           ig_steps: int = IG_N_STEPS):
+                           ig_steps: int = IG_N_STEPS, stage1_all_frames: bool = True):
+        """Stage 1 (XAI.py:2733-2760) runs on EVERY frame like the reference -- IG and patch-SHAP combined 0.5 / 0.5, top /
+        bottom 10 % regions -- as batched calls (``compute_integrated_gradients_batch``, ``compute_shap_approximation_batch``,
+        ``select_regions_batch``); stage 2 (interventions + CFI, XAI.py:2822-2896) on the key frames [0, T/2, T-4..T-1].
+        ``stage1_all_frames=False`` restricts stage 1 to the key frames (what stage 2 consumes)."""
         if not trajectory:
             return None
         T = len(trajectory)
@@ -513,17 +573,33 @@ class IntegratedXAIAnalyzer:
         target = CLASS_NAMES.index(class_name) if class_name in CLASS_NAMES else 0
         imp, raw = compute_time_shap(self.classifier, trajectory, timesteps, target, self.group, self.verbose)
         key_frames = sorted(set([0, T // 2] + list(range(max(0, T - 4), T))))
+        stage1 = list(range(T)) if stage1_all_frames else key_frames
+        frames = torch.cat([trajectory[k].to(self.device).reshape(1, 3, 128, 128).float() for k in stage1])
+        methods = [m for m in methods if m in ("ig", "shap", "gradient")]     # unknown methods are skipped (XAI.py:1270-1272)
+        if not methods:
+            raise RuntimeError("no attribution could be computed")
+        attr = None
+        for m in methods:                                        # equal weights, XAI.py:2746-2751
+            if m == "ig":
+                a = compute_integrated_gradients_batch(self.classifier, frames, target, n_steps=ig_steps, group=self.group)
+            elif m == "shap":
+                a = compute_shap_approximation_batch(self.classifier, frames, target, n_samples=shap_samples, group=self.group)
+            else:
+                a = compute_gradient_attribution(self.classifier, frames, target)
+            attr = a / len(methods) if attr is None else attr + a / len(methods)
+        # XAI.py:2753-2760: top / bottom 10 % regions of the combined map, morphology clean-up included, all frames per launch
+        top_m, top_s = select_regions_batch(attr, TOP_K_PERCENT, "top")
+        bot_m, bot_s = select_regions_batch(attr, BOTTOM_K_PERCENT, "bottom")
+        top_s, bot_s = top_s.cpu().numpy(), bot_s.cpu().numpy()
+        regions = {f"t_{int(timesteps[k])}": {"top_k": {"selected_pixels": int(top_s[i, 0]), "threshold": float(top_s[i, 1])},
+                                              "bottom_k": {"selected_pixels": int(bot_s[i, 0]), "threshold": float(bot_s[i, 1])},
+                                              "mean_abs_attribution": float(attr[i].abs().mean())}
+                   for i, k in enumerate(stage1)}
         cfi = {}
         for k in key_frames:
-            frame = trajectory[k].to(self.device).reshape(1, 3, 128, 128)
-            # stage 1 of the reference pipeline (XAI.py:2746-2751): IG + SHAP combined 0.5 / 0.5
-            attr, _ = compute_combined_attribution(self.classifier, frame, target, methods=methods,
-                                                   shap={"n_samples": shap_samples, "group": self.group},
-                                                   ig={"n_steps": ig_steps})
-            # XAI.py:2753-2760: top / bottom 10 % regions of the combined map, morphology clean-up included
-            top = select_regions_advanced(attr, TOP_K_PERCENT, "top")["mask_tensor"]
-            bot = select_regions_advanced(attr, BOTTOM_K_PERCENT, "bottom")["mask_tensor"]
-            for rname, mask in (("top_k", top), ("bottom_k", bot)):
+            i = stage1.index(k)
+            frame = frames[i:i + 1]
+            for rname, mask in (("top_k", top_m[i]), ("bottom_k", bot_m[i])):
                 for it in intervention_types:
                     mod = counterfactual_intervention_advanced(frame, mask, it)["modified_image"]
                     r = compute_causal_shift_comprehensive(self.classifier, frame, mod, target, group=self.group)
@@ -535,8 +611,10 @@ class IntegratedXAIAnalyzer:
                           "confidence_scores": [float(v) for v in raw["confidence_scores"]],
                           "probability_scores": [float(v) for v in raw["probability_scores"]],
                           "timesteps": [int(t) for t in timesteps]},
+            "region_analysis": regions,
             "cfi": cfi,
             "attribution_methods": list(methods),
+            "stage1_frames": len(stage1),
             "skipped_stages": ["grad_cam", "statistics", "plots"],
         }
 

@@ -197,7 +197,7 @@ import numpy as np, csv, tempfile
 from synt_isic_b200 import bulk
 class FakeGen:
     base_seed = 42; color_statistics = {}; stop_requested = False
-    def generate_batch(self, class_name, seeds, noise_seed=None, image_offset=0):
+    def generate_batch(self, class_name, seeds):
         return np.zeros((len(seeds), 128, 128, 3), np.uint8), None, ["h"] * len(seeds)
 out_dir = sys.argv[2]
 written = []
@@ -303,8 +303,8 @@ class _FakeGenerator:
     def __init__(self):
         self.calls = []
 
-    def generate_batch(self, class_name, seeds, noise_seed=None, image_offset=0):
-        self.calls.append((class_name, list(seeds), image_offset))
+    def generate_batch(self, class_name, seeds):
+        self.calls.append((class_name, list(seeds)))
         imgs = np.zeros((len(seeds), 128, 128, 3), np.uint8)
         for j, s in enumerate(seeds):
             imgs[j] = s % 251
@@ -335,7 +335,7 @@ def test_bulk_dataset_formats_and_numbering(tmp_path):
     res = bulk.generate_dataset(gen, cfg, str(tmp_path), layout="flat", postprocess=False,
                                 save_fn=lambda img, fp, c, s, h: saved.append((fp.name, c, s, int(img[0, 0, 0]))))
     assert res["total"] == 137 and res["generated"] == {"MEL": 70, "VASC": 3, "NV": 64}
-    assert gen.calls[1] == ("MEL", [image_seed(42, "MEL", 64 + j) for j in range(6)], 64)     # seeds of image_generator.py:626-637
+    assert gen.calls[1] == ("MEL", [image_seed(42, "MEL", 64 + j) for j in range(6)])     # seeds of image_generator.py:626-637
     assert saved[0] == ("ISIC_0034321.jpg", "MEL", image_seed(42, "MEL", 0), image_seed(42, "MEL", 0) % 251)
     rows = list(_csv.reader(open(res["files"]["ground_truth_csv"])))
     assert rows[0] == bulk.ground_truth_header() and len(rows) == 138
@@ -502,3 +502,54 @@ def test_image_generator_setters_and_xai_result_files(tmp_path):
     assert any("XAI results saved" in m and m.startswith("[INFO]") for m in logs)
     assert gen._save_xai_results({"bad": object()}, "MEL", img.name, str(img)) is None     # not JSON-serialisable: logged
     assert any(m.startswith("[WARNING]") for m in logs)
+
+
+def test_image_generator_reference_constructor_and_result_contract(tmp_path):
+    """``ImageGenerator(config_manager)`` (image_generator.py:28-78: inference_timesteps and the checkpoints folder come
+    from the config object) and the result / error contract of ``generate_images`` (:547-740): total_generated + stopped,
+    synthetic_dataset.csv with the reference's columns, numbering by successful images, {"error": ...} instead of raising,
+    a missing checkpoint fails the load (model_manager.py:104-107) unless random init is asked for."""
+    import csv
+    import numpy as np
+    from synt_isic_b200.generator import GenerationStopped, ImageGenerator, ModelManager, SYNTHETIC_CSV_HEADERS
+
+    class Cfg:                                                      # stand-in for core/config/config_manager.py
+        def get_generation_param(self, key, default=None):
+            return {"inference_timesteps": 7}.get(key, default)
+
+        def get_path(self, key):
+            return str(tmp_path / "no_such_checkpoints") if key == "checkpoints" else None
+
+    gen = ImageGenerator(Cfg(), device="cpu")
+    assert gen.inference_steps == 7 and gen.base_seed is None and gen.save_trajectory is True
+    assert gen.model_manager.checkpoint_dir == tmp_path / "no_such_checkpoints"
+    assert gen.model_manager.load_model("MEL") is False               # no checkpoint, no silent random network
+    assert ModelManager(device="cpu", allow_random_init=False).load_model("NV") is False
+
+    # the result contract, with the sampler stubbed out (no GPU here)
+    gen = ImageGenerator(device="cpu", inference_steps=3, base_seed=5, batch_size=2)
+    made = []
+
+    def fake_batch(class_name, seeds):
+        if class_name == "DF" and made:
+            gen.stop_generation()
+            raise GenerationStopped("generation stopped")
+        made.append((class_name, list(seeds)))
+        return np.zeros((len(seeds), 128, 128, 3), np.uint8), None, ["0" * 16] * len(seeds)
+
+    gen.generate_batch = fake_batch
+    res = gen.generate_images([("MEL", 3), ("DF", 2)], str(tmp_path / "out"), postprocess=False)
+    assert res["total_generated"] == 3 and res["stopped"] is True and res["generated"]["MEL"] == 3
+    rows = list(csv.DictReader(open(tmp_path / "out" / "synthetic_dataset.csv", encoding="utf-8")))
+    assert list(rows[0].keys()) == SYNTHETIC_CSV_HEADERS
+    assert [r["filename"] for r in rows] == ["ISIC_0000001.png", "ISIC_0000002.png", "ISIC_0000003.png"]
+    assert [r["isic_number"] for r in rows] == ["1", "2", "3"] and rows[0]["source"] == "synthetic"
+    assert gen.is_generating is False
+
+    def boom(class_name, seeds):
+        raise ValueError("kaboom")
+
+    gen.generate_batch = boom
+    assert gen.generate_images([("MEL", 1)], str(tmp_path / "out2")) == {"error": "kaboom"}
+    keys = ImageGenerator.noise_keys([11, None, 11])
+    assert keys[0] == keys[2] == 11 and 0 <= keys[1] < 2 ** 63
