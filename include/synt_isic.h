@@ -114,6 +114,9 @@ int synt_resnet18_logits_host(synt_resnet18_t* h, const float* x_host, int B, fl
 int synt_resnet18_debug(synt_resnet18_t* h, const float* x_dev, int B, const char* tap, float* out_dev,
                         long long out_cap, int* C, int* H, int* W, void* stream);
 long long synt_resnet18_launch_count(synt_resnet18_t* h);
+/* measurement hook: one warm forward of B <= 512 images with CUDA events between the front end (preprocess + 7x7 stem +
+ * max-pool), the 16 body convolutions and the pool + FC head; ms_out[3] */
+int synt_resnet18_profile(synt_resnet18_t* h, const float* x_dev, int B, float* logits_dev, double* ms_out, void* stream);
 
 /* Input gradient of the per-class score s = log(softmax(logits)[target_class] + 1e-8) (get_per_class_score,
  * XAI.py:443-459): replaces the autograd pass that captum's IntegratedGradients (XAI.py:1039-1085) and the plain gradient

@@ -39,6 +39,9 @@ TIME_EMBED_DIM = BLOCK_OUT_CHANNELS[0] * 4    # 256
 RESNET_TIME_SCALE_SHIFT = "default"     # additive temb (checkpoint-size pin)
 OUTPUT_SCALE_FACTOR = 1.0
 EXPECTED_PARAM_COUNT = 25_304_963
+# "explicit": softmax(q k^T / sqrt(d)) v spelled out (parity runs).  "sdpa": F.scaled_dot_product_attention, what diffusers'
+# AttnProcessor2_0 calls -- used by bench.py's same-box GPU eager baseline so that the baseline gets torch's fused kernels.
+ATTENTION_IMPL = "explicit"
 
 
 def timestep_embedding(timesteps: torch.Tensor, dim: int = BLOCK_OUT_CHANNELS[0]) -> torch.Tensor:
@@ -107,10 +110,13 @@ class Attention(nn.Module):
         q = q.view(b, -1, self.heads, d).transpose(1, 2)
         k = k.view(b, -1, self.heads, d).transpose(1, 2)
         v = v.view(b, -1, self.heads, d).transpose(1, 2)
-        # explicit fp32 softmax(q k^T / sqrt(d)) v  (== F.scaled_dot_product_attention)
-        s = torch.matmul(q, k.transpose(-1, -2)) * (1.0 / math.sqrt(d))
-        p = torch.softmax(s, dim=-1)
-        o = torch.matmul(p, v)
+        if ATTENTION_IMPL == "sdpa":
+            o = F.scaled_dot_product_attention(q, k, v)
+        else:
+            # explicit fp32 softmax(q k^T / sqrt(d)) v  (== F.scaled_dot_product_attention)
+            s = torch.matmul(q, k.transpose(-1, -2)) * (1.0 / math.sqrt(d))
+            p = torch.softmax(s, dim=-1)
+            o = torch.matmul(p, v)
         o = o.transpose(1, 2).reshape(b, -1, c)
         o = self.to_out[0](o)
         o = o.transpose(-1, -2).reshape(b, c, hh, ww)

@@ -46,6 +46,7 @@ SIGNATURES = {
     "synt_resnet18_logits_host": (C.c_int, [vp, vp, C.c_int, vp]),
     "synt_resnet18_debug": (C.c_int, [vp, vp, C.c_int, C.c_char_p, vp, C.c_longlong, c_i32p, c_i32p, c_i32p, vp]),
     "synt_resnet18_launch_count": (C.c_longlong, [vp]),
+    "synt_resnet18_profile": (C.c_int, [vp, vp, C.c_int, vp, C.POINTER(C.c_double), vp]),
     "synt_resnet18_score_grad": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp]),
     "synt_resnet18_grad_debug": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_char_p, vp, C.c_longlong, c_i32p, c_i32p, c_i32p, vp]),
     "synt_select_regions": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,

@@ -195,6 +195,18 @@ class MelanomaClassifierAdaptive(nn.Module):
         n = B * c.value * hh.value * ww.value
         return buf[:n].view(B, c.value, hh.value, ww.value).clone()
 
+    def profile_forward(self, x) -> dict:
+        """Measurement only: device ms of the front end (fused preprocess + stem + max-pool), the body convolutions and
+        the pool + FC head of one warm forward of B <= 512 images."""
+        h = self._handle()
+        x = x.contiguous().float()
+        logits = torch.empty(x.shape[0], self.num_classes, dtype=torch.float32, device=x.device)
+        ms = (C.c_double * 3)()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().synt_resnet18_profile(h, x.data_ptr(), x.shape[0], logits.data_ptr(), ms,
+                                                        _lib.current_stream_ptr()), "resnet18_profile")
+        return {"front_end_ms": ms[0], "body_ms": ms[1], "head_ms": ms[2]}
+
     def launch_count(self) -> int:
         cur = self._handles.get(self.precision)
         return int(_lib.lib().synt_resnet18_launch_count(cur[0])) if cur else 0

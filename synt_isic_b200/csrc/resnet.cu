@@ -579,6 +579,8 @@ void stem_fused(const float* x_nchw, int B, const void* bfrag, const float* bias
 
 struct RFwd {
     synt_resnet18* r; cudaStream_t s; int B;
+    cudaEvent_t* ev = nullptr;               // measurement hook (synt_resnet18_profile): begin / front end / body / head
+    void mark(int i) { if (ev) cudaEventRecord(ev[i], s); }
     size_t esz() const { return dtype_size(r->dt); }
     void* make(int H, int W, int C) { return r->pool.alloc((size_t)B * H * W * C * esz()); }
     void tap(const std::string& name, void* p, int H, int W, int C) {
@@ -602,6 +604,7 @@ struct RFwd {
     }
     void run(const float* x_nchw, float* logits) {
         void* cur = nullptr;
+        mark(0);
         if (r->use_tc && r->stem_frag && r->fuse_front && !r->tap_out) {
             // preprocess + stem + maxpool in one kernel (the debug taps "preprocess" / "relu" / "maxpool" use the unfused path)
             cur = make(56, 56, 64);
@@ -632,6 +635,7 @@ struct RFwd {
             tap("maxpool", cur, 56, 56, 64);
             r->launches += 2;
         }
+        mark(1);
         int H = 56;
         for (int l = 0; l < 4; ++l) {
             const int c = kStageCh[l];
@@ -648,9 +652,11 @@ struct RFwd {
                 tap("layer" + std::to_string(l + 1) + "." + std::to_string(j), cur, H, H, c);
             }
         }
+        mark(2);
         avgpool_fc(cur, r->dt, B, H * H, 512, (const float*)r->fc_w->p, (const float*)r->fc_b->p, r->num_classes, logits, s);
         ++r->launches;
         r->pool.release(cur);
+        mark(3);
     }
 };
 
@@ -899,6 +905,23 @@ int synt_resnet18_logits(synt_resnet18_t* h, const float* x, int B, float* logit
         RFwd f{h, (cudaStream_t)stream, B - b0 < mb ? B - b0 : mb};
         f.run(x + b0 * img, logits + (size_t)b0 * h->num_classes);
     }
+    SYNT_CATCH
+}
+// measurement hook (bench.py roofline_hbm): one warm forward of B <= 512 images with CUDA events between the front end
+// (preprocess + 7x7 stem + max-pool), the 16 body convolutions and the pool + FC head; ms_out[3]
+int synt_resnet18_profile(synt_resnet18_t* h, const float* x, int B, float* logits, double* ms_out, void* stream) {
+    SYNT_TRY
+    SYNT_CHECK(h && x && logits && ms_out && B > 0 && B <= 512, "bad argument (B <= 512)");
+    cudaStream_t s = (cudaStream_t)stream;
+    { RFwd warm{h, s, B}; warm.run(x, logits); }
+    cudaEvent_t ev[4];
+    for (auto& e : ev) SYNT_CUDA(cudaEventCreate(&e));
+    RFwd f{h, s, B};
+    f.ev = ev;
+    f.run(x, logits);
+    SYNT_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < 3; ++i) { float ms = 0.f; SYNT_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); ms_out[i] = ms; }
+    for (auto& e : ev) cudaEventDestroy(e);
     SYNT_CATCH
 }
 int synt_resnet18_logits_host(synt_resnet18_t* h, const float* x_host, int B, float* logits_host) {

@@ -53,9 +53,40 @@ def _world(group):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
+def gather_rows(local: torch.Tensor | None, n: int, group=None, device=None) -> torch.Tensor:
+    """The one exchange of the classifier-evaluation paths: every rank holds the rows [lo, hi) = ``shard_bounds(n, rank,
+    world)`` of an [n, k] result; ONE ``all_gather`` (rows padded to ceil(n / world)) gives every rank the whole table."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    lo, hi = shard_bounds(n, rank, world)
+    if device is None:
+        device = local.device
+    if n >= world:
+        k = local.shape[1]                                  # no rank slice is empty: every rank knows the row width
+    else:                                                   # fewer rows than ranks: agree on the width (one tiny all_reduce)
+        kk = torch.tensor([local.shape[1] if local is not None else 0], device=device)
+        dist.all_reduce(kk, op=dist.ReduceOp.MAX, group=group)
+        k = int(kk.item())
+    per = (n + world - 1) // world
+    pad = torch.zeros(per, k, dtype=torch.float32, device=device)
+    if local is not None and hi > lo:
+        pad[: hi - lo] = local.float()
+    gathered = torch.empty(world * per, k, dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(gathered, pad, group=group)
+    if n == world * per:
+        return gathered
+    parts = []
+    for r in range(world):
+        a, b = shard_bounds(n, r, world)
+        parts.append(gathered[r * per: r * per + (b - a)])
+    return torch.cat(parts)
+
+
 def sharded_eval(fn, items: torch.Tensor, group=None, chunk: int = 256) -> torch.Tensor:
     """``fn(items)`` row-wise (fn maps [n, ...] -> [n, k]) with the rows split across ranks and a
-    single all_gather of the results.  With one rank it is just a chunked call."""
+    single all_gather of the results.  With one rank it is just a chunked call.  ``items`` may live in host memory: every
+    rank then touches (and uploads) only its own rows."""
     rank, world = _world(group)
     n = items.shape[0]
     lo, hi = shard_bounds(n, rank, world) if world > 1 else (0, n)
@@ -63,23 +94,8 @@ def sharded_eval(fn, items: torch.Tensor, group=None, chunk: int = 256) -> torch
     if world == 1:
         return torch.cat(outs) if len(outs) > 1 else outs[0]
     local = torch.cat(outs) if outs else None
-    if n >= world:
-        k = local.shape[1]                                  # no rank slice is empty: every rank knows the row width
-    else:                                                   # fewer rows than ranks: agree on the width (one tiny all_reduce)
-        kk = torch.tensor([local.shape[1] if local is not None else 0], device=items.device)
-        dist.all_reduce(kk, op=dist.ReduceOp.MAX, group=group)
-        k = int(kk.item())
-    per = (n + world - 1) // world
-    pad = torch.zeros(per, k, dtype=torch.float32, device=items.device)
-    if local is not None:
-        pad[: hi - lo] = local.float()
-    gathered = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(gathered, pad, group=group)
-    parts = []
-    for r in range(world):
-        a, b = shard_bounds(n, r, world)
-        parts.append(gathered[r][: b - a])
-    return torch.cat(parts)
+    dev = local.device if local is not None else items.device
+    return gather_rows(local, n, group, dev)
 
 
 def gather_images(local_u8: torch.Tensor, counts, group=None, dst: int = 0):

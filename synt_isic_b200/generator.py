@@ -55,16 +55,22 @@ def noise_hash(x_T: torch.Tensor) -> str:
     return hashlib.sha256(x_T.detach().to("cpu").numpy().tobytes()).hexdigest()[:16]
 
 
-def to_uint8_image(latents: torch.Tensor) -> np.ndarray:
-    """core/generator/image_generator.py:441-447 on the GPU: [B,3,H,W] fp32 -> [B,H,W,3] uint8."""
+def to_uint8_tensor(latents: torch.Tensor, mode: int = 0) -> torch.Tensor:
+    """[B,3,H,W] fp32 -> [B,H,W,3] uint8 ON the device.  mode 0: core/generator/image_generator.py:441-447
+    ((x+1)/2, clamp, *255, truncate); mode 1: diffusion/diffusion_generator.py:147-148 ((x+1)*127.5, clip, truncate)."""
     from . import _lib
     x = latents.contiguous().float()
     B, _, H, W = x.shape
     out = torch.empty(B, H, W, 3, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().synt_to_uint8(x.data_ptr(), B, H, W, 0, out.data_ptr(), _lib.current_stream_ptr()),
+        _lib.check(_lib.lib().synt_to_uint8(x.data_ptr(), B, H, W, int(mode), out.data_ptr(), _lib.current_stream_ptr()),
                    "to_uint8")
-    return out.cpu().numpy()
+    return out
+
+
+def to_uint8_image(latents: torch.Tensor, mode: int = 0) -> np.ndarray:
+    """``to_uint8_tensor`` + the D2H copy of the reference (``image.cpu().numpy()``)."""
+    return to_uint8_tensor(latents, mode).cpu().numpy()
 
 
 def color_postprocess(img: np.ndarray, stats: Optional[dict]) -> np.ndarray:
@@ -448,9 +454,9 @@ class DiffusionGenerator:
     set_timesteps here (:123-128) -> 1000 steps; kept."""
 
     def __init__(self, checkpoint_dir: Optional[str] = None, stats_path: Optional[str] = None, device: str = "cuda",
-                 precision: str = "bf16"):
+                 precision: str = "bf16", allow_random_init: bool = False):
         self.device = torch.device(device)
-        self.manager = ModelManager(checkpoint_dir, device, precision)
+        self.manager = ModelManager(checkpoint_dir, device, precision, allow_random_init=allow_random_init)
         self.color_statistics = {}
         if stats_path and os.path.exists(stats_path):
             with open(stats_path, "r", encoding="utf-8") as f:
@@ -460,13 +466,12 @@ class DiffusionGenerator:
         return DDPMScheduler(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear")
 
     def _run(self, class_name: str, count: int) -> np.ndarray:
-        if class_name not in self.manager.loaded_models:
-            self.manager.load_model(class_name)
+        if class_name not in self.manager.loaded_models and not self.manager.load_model(class_name):
+            raise ValueError(f"no model for class {class_name}")        # diffusion_generator.py:108-109
         model = self.manager.loaded_models[class_name]
         x = torch.randn(count, 3, 128, 128).to(self.device)      # diffusion_generator.py:131 / :211 (CPU global RNG)
         model.sample(x, self._scheduler(), seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
-        img = ((x.permute(0, 2, 3, 1).cpu().numpy() + 1) * 127.5).clip(0, 255).astype(np.uint8)   # :147-148
-        return img
+        return to_uint8_image(x, mode=1)                          # :147-148 ((x+1)*127.5, clip, uint8) on the GPU
 
     def generate_single_image(self, class_name: str, output_path: str, postprocess: bool = True) -> str:
         from PIL import Image

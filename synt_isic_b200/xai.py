@@ -27,7 +27,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .classifier import CLASS_NAMES, MelanomaClassifierAdaptive
-from .dist import sharded_eval
+from .dist import _world, gather_rows, shard_bounds, sharded_eval
 
 SHAP_N_SAMPLES = 512       # xai/XAI.py:240
 NOISE_STD = 0.5            # xai/XAI.py:262
@@ -50,9 +50,16 @@ def _probs(classifier, images: torch.Tensor, group=None) -> torch.Tensor:
     return F.softmax(logits, dim=1)
 
 
-def _probs_from_host(classifier, frames_cpu: torch.Tensor, dev, chunk: int = 256) -> torch.Tensor:
+def _probs_from_host(classifier, frames_cpu: torch.Tensor, dev, chunk: int = 256, group=None) -> torch.Tensor:
     """softmax(logits) of frames that live in (ideally pinned) HOST memory: the frames are copied in chunks on a side
-    stream so that the H2D copy of chunk i+1 overlaps the classifier kernels of chunk i."""
+    stream so that the H2D copy of chunk i+1 overlaps the classifier kernels of chunk i.  With ``group`` every rank uploads
+    and evaluates only its contiguous slice of the frames; one all_gather of the logits."""
+    n_all = frames_cpu.shape[0]
+    rank, world = _world(group)
+    if world > 1:
+        lo, hi = shard_bounds(n_all, rank, world)
+        local = _probs_from_host(classifier, frames_cpu[lo:hi], dev, chunk) if hi > lo else None   # softmax is row-wise
+        return gather_rows(local, n_all, group, dev)
     n = frames_cpu.shape[0]
     main = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(device=dev)
@@ -88,9 +95,10 @@ def compute_time_shap(classifier, trajectory, timesteps, target_class, group=Non
     """xai/XAI.py:1179-1234.  ``trajectory``: list of [1,3,128,128] tensors or one [T,3,128,128]."""
     dev = _dev(classifier)
     frames = trajectory if torch.is_tensor(trajectory) else torch.cat([f.to(dev).reshape(-1, 3, 128, 128) for f in trajectory])
-    if frames.device.type == "cpu" and dev.type == "cuda" and group is None and frames.shape[0] > 256:
-        # a host-resident trajectory: stream it through the classifier (copies overlap the kernels)
-        p = _probs_from_host(classifier, frames.reshape(-1, 3, 128, 128).float(), dev)[:, target_class]
+    if frames.device.type == "cpu" and dev.type == "cuda" and frames.shape[0] > 256:
+        # a host-resident trajectory: stream it through the classifier (copies overlap the kernels); with a process group
+        # every rank uploads only its slice
+        p = _probs_from_host(classifier, frames.reshape(-1, 3, 128, 128).float(), dev, group=group)[:, target_class]
     else:
         frames = frames.to(dev).reshape(-1, 3, 128, 128)
         p = _probs(classifier, frames, group)[:, target_class]
@@ -379,15 +387,16 @@ def counterfactual_intervention_advanced(image, mask, intervention_type="noise",
             aux = torch.randn(image.shape, device=dev, generator=gen)
         if intervention_type == "gaussian_noise":
             noise_std = max(noise_std, image.std().item() * 0.5)
-    elif code == 4:                                             # shuffle masked pixels per (b, c) plane
-        aux = image.clone()
-        sel = m.bool()
-        for b in range(B):
-            idx = sel[b].reshape(-1).nonzero().squeeze(1)
-            if idx.numel() > 1:
-                for c in range(Cc):
-                    perm = idx[torch.randperm(idx.numel(), device=dev, generator=gen)]
-                    aux[b, c].view(-1)[idx] = image[b, c].reshape(-1)[perm]
+    elif code == 4:
+        # shuffle the masked pixels of every (b, c) plane among themselves (XAI.py:1541-1566), all planes at once: the
+        # masked positions in natural order receive the masked values in a random order (sort of uniform keys); the
+        # unmasked tail of both index lists only moves pixels that the blend ignores (M = 0 there)
+        sel = m.bool().reshape(B, 1, H * W).expand(B, Cc, H * W)
+        keys = torch.rand((B, Cc, H * W), device=dev, generator=gen)
+        natural = torch.argsort((~sel).to(torch.uint8), dim=-1, stable=True)
+        random_ = torch.argsort(torch.where(sel, keys, torch.full_like(keys, 2.0)), dim=-1)
+        flat = image.reshape(B, Cc, H * W)
+        aux = torch.empty_like(flat).scatter_(-1, natural, flat.gather(-1, random_)).view(B, Cc, H, W)
     out = torch.empty_like(image)
     interv = torch.empty_like(image)
     # 'inpaint' is the reference's fixed 5x5 grouped box convolution (XAI.py:1529-1539); 'blur' honours blur_kernel
@@ -469,17 +478,28 @@ def compute_causal_shift_comprehensive(classifier, original_image, modified_imag
 def csi_batch(classifier, images: torch.Tensor, masks: torch.Tensor, intervention_types, target_classes,
               noise: torch.Tensor | None = None, group=None):
     """BASELINE config 5: interventions x ResNet18 inference for a whole batch.  Returns
-    cfi[type][b] = s_c(x_b) - s_c(x~_b) with s_c = log(p_c + 1e-8)."""
+    cfi[type][b] = s_c(x_b) - s_c(x~_b) with s_c = log(p_c + 1e-8).  With ``group`` the IMAGES are split contiguously over
+    the ranks (interventions and evaluations of a slice stay on one rank); one all_gather of the [n, n_types] table."""
     dev = _dev(classifier)
-    images = images.to(dev).float().contiguous()
-    tc = torch.as_tensor(target_classes, device=dev).long()
-    variants = [images]
-    for it in intervention_types:
-        kw = {"noise": noise} if it in ("noise", "gaussian_noise") and noise is not None else {}
-        variants.append(counterfactual_intervention_advanced(images, masks, it, **kw)["modified_image"])
-    probs = _probs(classifier, torch.cat(variants), group).view(len(variants), images.shape[0], -1)
-    s = torch.log(probs.gather(2, tc.view(1, -1, 1).expand(len(variants), -1, 1)).squeeze(2) + 1e-8)
-    return {it: (s[0] - s[i + 1]) for i, it in enumerate(intervention_types)}
+    n_all = images.shape[0]
+    rank, world = _world(group)
+    lo, hi = shard_bounds(n_all, rank, world) if world > 1 else (0, n_all)
+    tc_all = torch.as_tensor(target_classes).long()
+    local = None
+    if hi > lo:
+        imgs = images[lo:hi].to(dev).float().contiguous()
+        mk = masks[lo:hi] if masks.dim() == 3 and masks.shape[0] == n_all else masks
+        nz = noise[lo:hi] if noise is not None else None
+        tc = tc_all[lo:hi].to(dev)
+        variants = [imgs]
+        for it in intervention_types:
+            kw = {"noise": nz.to(dev)} if it in ("noise", "gaussian_noise") and nz is not None else {}
+            variants.append(counterfactual_intervention_advanced(imgs, mk.to(dev), it, **kw)["modified_image"])
+        probs = _probs(classifier, torch.cat(variants), None).view(len(variants), imgs.shape[0], -1)
+        sc = torch.log(probs.gather(2, tc.view(1, -1, 1).expand(len(variants), -1, 1)).squeeze(2) + 1e-8)
+        local = (sc[:1] - sc[1:]).t().contiguous()                          # [m, n_types]
+    table = gather_rows(local, n_all, group, dev) if world > 1 else local
+    return {it: table[:, i] for i, it in enumerate(intervention_types)}
 
 
 # ------------------------------------------------------------------ analyzer ------------

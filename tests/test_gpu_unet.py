@@ -228,7 +228,7 @@ def test_bulk_dataset_driver_writes_the_reference_formats(cuda_dev, tmp_path):
     from PIL import Image
     from synt_isic_b200 import bulk
     from synt_isic_b200.generator import ImageGenerator, image_seed
-    gen = ImageGenerator(device=str(cuda_dev), inference_steps=4, base_seed=7, batch_size=4)
+    gen = ImageGenerator(device=str(cuda_dev), inference_steps=4, base_seed=7, batch_size=4, allow_random_init=True)
     res = bulk.generate_dataset(gen, [("MEL", 3), ("DF", 2)], str(tmp_path), layout="flat", postprocess=False, batch_size=4)
     assert res["total"] == 5 and res["generated"] == {"MEL": 3, "DF": 2}
     folder = tmp_path / bulk.SYNTHETIC_DIR
@@ -240,3 +240,17 @@ def test_bulk_dataset_driver_writes_the_reference_formats(cuda_dev, tmp_path):
     assert rows[0] == bulk.ground_truth_header() and rows[4][0] == "ISIC_0034324.jpg" and rows[4][6] == "1.0"
     img = np.asarray(Image.open(folder / "ISIC_0034321.jpg"))
     assert img.shape == (128, 128, 3) and img.dtype == np.uint8
+    # the reference entry point with its result contract (image_generator.py:547-740), batched path and B=1 trajectory path:
+    # same file names, and (per-image noise keys) the same image for the same sidecar seed whatever the batch composition
+    res2 = gen.generate_images([("MEL", 3)], str(tmp_path / "gi"), postprocess=False)
+    assert res2["total_generated"] == 3 and res2["stopped"] is False
+    rows2 = list(csv.DictReader(open(tmp_path / "gi" / "synthetic_dataset.csv")))
+    assert [r["filename"] for r in rows2] == ["ISIC_0000001.png", "ISIC_0000002.png", "ISIC_0000003.png"]
+    gen.set_save_trajectory(True)
+    ok, traj = gen.generate_single_image("MEL", str(tmp_path / "one.png"), postprocess=False, seed=image_seed(7, "MEL", 1))
+    assert ok and len(traj) == 4
+    a = np.asarray(Image.open(tmp_path / "gi" / "MEL" / "ISIC_0000002.png")).astype(np.int32)
+    b = np.asarray(Image.open(tmp_path / "one.png")).astype(np.int32)
+    assert np.abs(a - b).mean() < 2.0                  # bf16: equal up to the batch-dependent GEMM rounding, same noise
+    gen.stop_generation()
+    assert gen.generate_images([("MEL", 2)], str(tmp_path / "gi2"))["total_generated"] == 2   # a new call resets the stop flag
