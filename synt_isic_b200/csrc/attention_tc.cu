@@ -97,9 +97,25 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// PERSISTENT kernel: the grid is two CTAs per SM and every CTA walks the work items it, it + grid, it + 2*grid, ... (item =
+// 128 queries x 4 heads of one image; all items cost the same).  Nothing is torn down between items: TMEM, the barriers
+// and all the rings (K/V stages, S buffers, P tiles) run on, the TMA producer and the V^T builder prefetch across the item
+// boundary, and only two hand-shakes are per item -- q_free / q_full around the rewrite of the query tile and o_full /
+// o_free around the read-out of the accumulators.  (The one-CTA-per-item version lost 16% of the CTA slots' time between a
+// CTA's exit and its successor's entry plus ~9% in every CTA's ramp)
+struct AtcItem { int q0, hg, b; };
+__device__ __forceinline__ AtcItem atc_item(int it, int nqt) {
+    AtcItem o;
+    o.q0 = (it % nqt) * 128;
+    const int r = it / nqt;
+    o.hg = r & 7;
+    o.b = r >> 3;
+    return o;
+}
+
 __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, int N,
-                                                                      int C, const bf16* __restrict__ qkv,
-                                                                      bf16* __restrict__ out, int exp_skip,
+                                                                      int C, int n_items, const bf16* __restrict__ qkv,
+                                                                      bf16* __restrict__ out, int* __restrict__ work_ctr,
                                                                       long long* __restrict__ tl) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();             // SWIZZLE_128B tiles need 1 KB alignment
@@ -110,36 +126,50 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
     uint64_t* s_free = s_full + ATC_NS;          // [NS]
     uint64_t* p_full = s_free + ATC_NS;          // [NS] P tiles rotate like the S buffers
     uint64_t* p_free = p_full + ATC_NS;          // [NS]
-    uint64_t* q_full = p_free + ATC_NS;          // zero-masked Q tile written by the softmax warps
-    uint64_t* o_full = q_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+    uint64_t* q_full = p_free + ATC_NS;          // zero-masked Q tile of the item written by the softmax warps
+    uint64_t* q_free = q_full + 1;               // every S MMA of the item has read the Q tile
+    uint64_t* o_full = q_free + 1;               // every P.V MMA of the item is complete
+    uint64_t* o_free = o_full + 1;               // the softmax warps have read the accumulators out
+    uint64_t* item_full = o_free + 1;            // [4] work-queue ring: item id of the CTA's k-th item published
+    int* item_ring = reinterpret_cast<int*>(item_full + 4);   // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(item_ring + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 128, hg = blockIdx.y, b = blockIdx.z;
+    const int nqt = N / 128;
     const int n_chunks = N / ATC_KEYS;
-    const int n_units = n_chunks * 4;            // unit u = chunk*4 + head
+    const int n_units = n_chunks * 4;            // unit u = chunk*4 + head; a multiple of 4, so head = global unit & 3 too
+    // DYNAMIC work queue: the TMA producer thread draws item ids from a global counter (one ahead of the item it is loading)
+    // and publishes them in a 4-deep shared-memory ring; every role reads its k-th item from slot k & 3.  The two CTAs of an
+    // SM do NOT progress at the same rate (measured with a static round-robin: 61 k vs 131 k clk per item -- the warp
+    // scheduler favours one CTA's softmax warps at the MUFU pipe), so a static split leaves the favoured CTA idle at the
+    // end; with the queue it simply takes more items.  No role can be more than two items away from the producer (the K/V
+    // stage ring is 3 chunks deep), so slot k & 3 is never overwritten while somebody still needs it.
+    auto get_item = [&](int k) -> int {
+        mbar_wait(&item_full[k & 3], ((uint32_t)k >> 2) & 1u);
+        return *reinterpret_cast<volatile int*>(&item_ring[k & 3]);
+    };
 
     pdl_launch_dependents();
-    pdl_wait();                                              // qkv / vt come from the previous kernels
-    // the softmax threads fetch their 32 bytes of the query tile first: the global latency overlaps the set-up below
+    pdl_wait();                                              // qkv comes from the previous kernel
+    // the softmax threads fetch their 32 bytes of the first item's query tile at once: the latency overlaps the set-up
     uint4 q_pre[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
-    if (warp >= 4) {
+    auto load_q = [&](const AtcItem& im) {
         const int t = threadIdx.x - 128, qrow = t >> 1, hp = t & 1;
-        const uint4* src = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + q0 + qrow) * (3 * C) + hg * 32 + hp * 16);
+        const uint4* src = reinterpret_cast<const uint4*>(qkv + ((size_t)im.b * N + im.q0 + qrow) * (3 * C) + im.hg * 32 + hp * 16);
         q_pre[0] = __ldg(src); q_pre[1] = __ldg(src + 1);
-    }
+    };
+    // (the first item of a CTA is only known after the queue is up: its query / v fetches follow the set-up barrier)
     // V^T builder (warp 3): constant rows and the first chunk's v values before the set-up barrier (latency overlap)
     uint4 nx[2][4];
-    const uint4* vsrc = reinterpret_cast<const uint4*>(qkv + ((size_t)b * N + 2 * lane) * (3 * C) + 2 * C + hg * 32);
     const size_t key_stride = (size_t)(3 * C) / 8;                            // uint4 per token row
-    auto fetch = [&](int c) {
+    auto fetch = [&](const AtcItem& im, int c) {
+        const uint4* vsrc = reinterpret_cast<const uint4*>(qkv + ((size_t)im.b * N + 2 * lane) * (3 * C) + 2 * C + im.hg * 32);
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
             for (int h = 0; h < 4; ++h) nx[kk][h] = __ldg(vsrc + ((size_t)c * ATC_KEYS + kk) * key_stride + h);
     };
     if (warp == 3) {
-        fetch(0);
         for (int i = lane; i < ATC_STAGES * 4 * 8 * 32; i += 32) {            // rows 8..15 of every head of every slot
             const int word = i & 31, row = 8 + ((i >> 5) & 7), h = (i >> 8) & 3, st = i >> 10;
             uint8_t* base = smem + ATC_OFF_STAGE + st * ATC_STAGE_BYTES + ATC_K_BYTES + h * 2048 + row * 128;
@@ -152,7 +182,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
         for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < ATC_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 128); }
         for (int g = 0; g < ATC_NS; ++g) { mbar_init(&p_full[g], 128); mbar_init(&p_free[g], 1); }
-        mbar_init(q_full, 256); mbar_init(o_full, 1);
+        mbar_init(q_full, 256); mbar_init(q_free, 1); mbar_init(o_full, 1); mbar_init(o_free, 256);
+        for (int i = 0; i < 4; ++i) mbar_init(&item_full[i], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<ATC_TMEM_COLS>(tmem_slot);
@@ -165,12 +196,24 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
         if (elect_one()) {
             // ===================== TMA producer =====================
             int stage = 0; uint32_t phase = 0;
-            for (int c = 0; c < n_chunks; ++c) {
-                mbar_wait(&empty_bar[stage], phase ^ 1u);
-                uint8_t* sk = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES;
-                mbar_arrive_expect_tx(&full_bar[stage], ATC_K_BYTES);
-                tma_load_2d(sk, &maps.k, &full_bar[stage], C + (hg >> 1) * 64, b * N + c * ATC_KEYS);
-                if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+            auto publish = [&](int k, int id) {
+                *reinterpret_cast<volatile int*>(&item_ring[k & 3]) = id;
+                mbar_arrive(&item_full[k & 3]);              // release: the id is visible to whoever sees the phase flip
+            };
+            int it = atomicAdd(work_ctr, 1);
+            publish(0, it);
+            for (int k = 0; it < n_items; ++k) {
+                const int nxt = atomicAdd(work_ctr, 1);       // one ahead: the other roles prefetch across the item boundary
+                publish(k + 1, nxt);
+                const AtcItem im = atc_item(it, nqt);
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t* sk = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], ATC_K_BYTES);
+                    tma_load_2d(sk, &maps.k, &full_bar[stage], C + (im.hg >> 1) * 64, im.b * N + c * ATC_KEYS);
+                    if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                it = nxt;
             }
         }
     } else if (warp == 3) {
@@ -179,29 +222,37 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
         // 2l, 2l+1 of the chunk: their 4 x 8 v values arrive as 2 x 64 B from global memory and leave as 32 aligned 32-bit
         // stores (two adjacent keys of one row).  Rows 8 (ones) and 9..15 (zeros) are constant: written once per slot.
         int stage = 0; uint32_t phase = 0;
-        for (int c = 0; c < n_chunks; ++c) {
-            uint4 cur[2][4];
+        int it = get_item(0);
+        if (it < n_items) fetch(atc_item(it, nqt), 0);
+        for (int k = 0; it < n_items; ++k) {
+            const AtcItem im = atc_item(it, nqt);
+            const int nxt = get_item(k + 1);
+            for (int c = 0; c < n_chunks; ++c) {
+                uint4 cur[2][4];
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
+                for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-                for (int h = 0; h < 4; ++h) cur[kk][h] = nx[kk][h];
-            if (c + 1 < n_chunks) fetch(c + 1);
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* sv = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES + ATC_K_BYTES;
+                    for (int h = 0; h < 4; ++h) cur[kk][h] = nx[kk][h];
+                if (c + 1 < n_chunks) fetch(im, c + 1);
+                else if (nxt < n_items) fetch(atc_item(nxt, nqt), 0);                    // first chunk of the next item
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                uint8_t* sv = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES + ATC_K_BYTES;
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const uint16_t* a = reinterpret_cast<const uint16_t*>(&cur[0][h]);    // key 2l:   dims 0..7 of head h
-                const uint16_t* bq = reinterpret_cast<const uint16_t*>(&cur[1][h]);   // key 2l+1
+                for (int h = 0; h < 4; ++h) {
+                    const uint16_t* a = reinterpret_cast<const uint16_t*>(&cur[0][h]);    // key 2l:   dims 0..7 of head h
+                    const uint16_t* bq = reinterpret_cast<const uint16_t*>(&cur[1][h]);   // key 2l+1
 #pragma unroll
-                for (int d = 0; d < 8; ++d) {
-                    const uint32_t pair = (uint32_t)a[d] | ((uint32_t)bq[d] << 16);
-                    *reinterpret_cast<uint32_t*>(sv + h * 2048 + d * 128 + ((((lane >> 2) ^ d) << 4) | ((lane & 3) << 2))) = pair;
+                    for (int d = 0; d < 8; ++d) {
+                        const uint32_t pair = (uint32_t)a[d] | ((uint32_t)bq[d] << 16);
+                        *reinterpret_cast<uint32_t*>(sv + h * 2048 + d * 128 + ((((lane >> 2) ^ d) << 4) | ((lane & 3) << 2))) = pair;
+                    }
                 }
+                fence_proxy_async();                                              // generic-proxy writes -> UMMA (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
             }
-            fence_proxy_async();                                              // generic-proxy writes -> UMMA (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[stage]);
-            if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+            it = nxt;
         }
     } else if (warp == 1) {
         if (elect_one()) {
@@ -209,18 +260,26 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
             constexpr uint32_t idesc_s = make_idesc_bf16(128, ATC_KEYS);
             const uint32_t q_addr = smem_u32(smem);
             int stage = 0; uint32_t phase = 0;
-            mbar_wait(q_full, 0);
-            for (int u = 0; u < n_units; ++u) {
-                const int j = u & 3, sb = u % ATC_NS;
-                if (j == 0) { mbar_wait(&full_bar[stage], phase); }
-                mbar_wait(&s_free[sb], (((uint32_t)(u / ATC_NS)) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t k_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES);
-                // A: zero-masked head j of the Q tile; B: the natural 16-column pair that holds head j of this CTA's 4 heads
-                umma_bf16(tmem + sb * ATC_KEYS, make_smem_desc_sw128(q_addr) + 2 * j,
-                          make_smem_desc_sw128(k_addr) + 4 * (hg & 1) + 2 * (j >> 1), idesc_s, 0u);
-                umma_commit(&s_full[sb]);
-                if (j == 3) { if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; } }
+            int sb = 0; uint32_t sph = 0;                    // S-buffer ring, runs across the items
+            uint32_t iph = 0;                                // item parity
+            for (int k = 0, it; (it = get_item(k)) < n_items; ++k) {
+                const int hg = atc_item(it, nqt).hg;
+                mbar_wait(q_full, iph);
+                for (int u = 0; u < n_units; ++u) {
+                    const int j = u & 3;
+                    if (j == 0) { mbar_wait(&full_bar[stage], phase); }
+                    mbar_wait(&s_free[sb], sph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t k_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES);
+                    // A: zero-masked head j of the Q tile; B: the natural 16-column pair that holds head j of this CTA's 4 heads
+                    umma_bf16(tmem + sb * ATC_KEYS, make_smem_desc_sw128(q_addr) + 2 * j,
+                              make_smem_desc_sw128(k_addr) + 4 * (hg & 1) + 2 * (j >> 1), idesc_s, 0u);
+                    umma_commit(&s_full[sb]);
+                    if (++sb == ATC_NS) { sb = 0; sph ^= 1u; }
+                    if (j == 3) { if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; } }
+                }
+                umma_commit(q_free);                         // the query tile may be rewritten for the next item
+                iph ^= 1u;
             }
         }
     } else if (warp == 2) {
@@ -229,24 +288,31 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, 16);
             const uint32_t p_addr = smem_u32(smem + ATC_OFF_P);
             int stage = 0; uint32_t phase = 0;
-            for (int u = 0; u < n_units; ++u) {
-                const int j = u & 3, c = u >> 2, pb = u % ATC_NS;
-                if (j == 0) mbar_wait(&full_bar[stage], phase);          // V of this chunk has landed
-                mbar_wait(&p_full[pb], ((uint32_t)(u / ATC_NS)) & 1u);
-                tc_fence_after();
-                const uint32_t v_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES + ATC_K_BYTES);
-                const uint64_t dp = make_smem_desc_sw128(p_addr + pb * ATC_P_BYTES);
-                const uint64_t dv = make_smem_desc_sw128(v_addr + j * 2048);
+            int pb = 0; uint32_t pph = 0;                    // P-tile ring, runs across the items
+            uint32_t iph = 0;
+            for (int k = 0; get_item(k) < n_items; ++k) {
+                if (k != 0) { mbar_wait(o_free, iph ^ 1u); tc_fence_after(); }   // previous item's accumulators were read out
+                for (int u = 0; u < n_units; ++u) {
+                    const int j = u & 3, c = u >> 2;
+                    if (j == 0) mbar_wait(&full_bar[stage], phase);          // V of this chunk has landed
+                    mbar_wait(&p_full[pb], pph);
+                    tc_fence_after();
+                    const uint32_t v_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES + ATC_K_BYTES);
+                    const uint64_t dp = make_smem_desc_sw128(p_addr + pb * ATC_P_BYTES);
+                    const uint64_t dv = make_smem_desc_sw128(v_addr + j * 2048);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(tmem + ATC_O_COL + j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv, (c | kk) != 0 ? 1u : 0u);
-                umma_commit(&p_free[pb]);
-                if (j == 3) {
-                    umma_commit(&empty_bar[stage]);                      // all S and P.V reads of this stage are done
-                    if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem + ATC_O_COL + j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv, (c | kk) != 0 ? 1u : 0u);
+                    umma_commit(&p_free[pb]);
+                    if (++pb == ATC_NS) { pb = 0; pph ^= 1u; }
+                    if (j == 3) {
+                        umma_commit(&empty_bar[stage]);                      // all S and P.V reads of this stage are done
+                        if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
                 }
+                umma_commit(o_full);
+                iph ^= 1u;
             }
-            umma_commit(o_full);
         }
     } else if (warp >= 4) {
         // ===================== softmax warpgroups =====================
@@ -254,139 +320,179 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
         const int quarter = warp & 3;                      // TMEM lane quarter of this warp
         const int r = quarter * 32 + lane;                 // query row
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-        float m[2] = {0.f, 0.f};                           // running softmax reference of heads g and g+2
-        float mnext[2] = {0.f, 0.f};                       // sampled maximum seen in the previous chunk
         const int sw = r & 7;
-        {
-            // zero-masked Q tile: thread = (query row, pair of heads); head j keeps its 8 dims in chunk 2j + (j&1) of the
-            // row (16-byte chunks, SWIZZLE_128B: physical chunk = logical ^ (row & 7)), the other chunk of the pair is 0
-            const int t = threadIdx.x - 128, qrow = t >> 1, hp = t & 1;
-            const uint4 h0 = q_pre[0], h1 = q_pre[1];                    // heads 2hp, 2hp+1 (loaded at kernel entry)
-            uint8_t* qr = smem + qrow * 128;
-            const int qs = qrow & 7;
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(qr + (((4 * hp + 0) ^ qs) << 4)) = h0;    // head 2hp   -> (q | 0)
-            *reinterpret_cast<uint4*>(qr + (((4 * hp + 1) ^ qs) << 4)) = z;
-            *reinterpret_cast<uint4*>(qr + (((4 * hp + 2) ^ qs) << 4)) = z;     // head 2hp+1 -> (0 | q)
-            *reinterpret_cast<uint4*>(qr + (((4 * hp + 3) ^ qs) << 4)) = h1;
-            fence_proxy_async();
-            mbar_arrive(q_full);
-        }
-        for (int c = 0; c < n_chunks; ++c) {
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int j = g + 2 * jj, u = c * 4 + j, sb = u % ATC_NS;
-                // tl (debug, SYNT_ATT_TIMELINE): clock64 of {unit start, S ready, P tile free, unit done} per softmax warp
+        // this warpgroup's units are g, g+2 (mod 4) of every chunk: ring position of unit (c*4 + g + 2*jj) advances by
+        // 2 per unit handled here and by 4 per chunk; kept as (index mod 3, wrap parity) of the GLOBAL unit counter
+        int sbu = g % ATC_NS; uint32_t sphu = 0;           // ring slot / parity of this warpgroup's next unit
+        auto ring_advance2 = [&]() { sbu += 2; if (sbu >= ATC_NS) { sbu -= ATC_NS; sphu ^= 1u; } };
+        uint32_t iph = 0;
 #ifdef SYNT_ATT_TIMELINE_BUILD
-                const bool rec = tl != nullptr && lane == 0 && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 1;
+        // debug build (tools/att_timeline.py): per CTA and softmax warp {smid, entry clock, then per item: end clock and the
+        // cycles spent waiting for S tiles / free P tiles / the accumulators / the query tile}; 8 + 16*6 words per warp
+        long long tw[4] = {0, 0, 0, 0}, tt0 = 0;
+        int tl_item = 0;
+        long long* trow = tl ? tl + ((size_t)blockIdx.x * 8 + (warp - 4)) * 128 : nullptr;
+        if (trow && lane == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); trow[0] = smid; trow[1] = clock64(); }
+#define ATC_T0() do { if (trow) tt0 = clock64(); } while (0)
+#define ATC_T1(i) do { if (trow) tw[i] += clock64() - tt0; } while (0)
+#define ATC_ITEM_END() do { if (trow && lane == 0 && tl_item < 20) { long long* o = trow + 8 + tl_item * 6; o[0] = clock64(); \
+        o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; o[4] = tw[3]; o[5] = it; } ++tl_item; tw[0] = tw[1] = tw[2] = tw[3] = 0; } while (0)
 #else
-                constexpr bool rec = false;                                // compile with -DSYNT_ATT_TIMELINE_BUILD for tools/att_timeline.py
+#define ATC_T0() do { } while (0)
+#define ATC_T1(i) do { } while (0)
+#define ATC_ITEM_END() do { } while (0)
 #endif
-                long long* trow = rec ? tl + ((size_t)(warp - 4) * n_units + (c * 2 + jj) * 2) * 4 : nullptr;   // [8 warps][n_units/2 per group..]
-                if (rec) trow[0] = clock64();
-                mbar_wait(&s_full[sb], ((uint32_t)(u / ATC_NS)) & 1u);
-                if (rec) trow[1] = clock64();
-                tc_fence_after();
-                // Softmax reference m of this row and head.  Any m within the bf16/fp32 exponent range of the true maximum
-                // gives the exact softmax after the final division, so only the FIRST chunk pays for an exact row maximum
-                // (a second pass over the S tile); afterwards m follows a SAMPLED maximum (every 4th key) of the previous
-                // chunk, picked up while its exponentials were computed, and moves only when that exceeds m by more than
-                // 2^8 (lazy rescale).  P may therefore exceed 2^8 for a chunk; bf16 P / fp32 accumulators have the range.
-                uint32_t v[32];
-                float alpha = 1.0f;
-                bool moved = false;
-                if (c == 0) {
-                    float cm[4];
+        int it = get_item(0);
+        if (it < n_items) load_q(atc_item(it, nqt));
+        for (int k = 0; it < n_items; ++k) {
+            const AtcItem im = atc_item(it, nqt);
+            {
+                // zero-masked Q tile: thread = (query row, pair of heads); head j keeps its 8 dims in chunk 2j + (j&1) of the
+                // row (16-byte chunks, SWIZZLE_128B: physical chunk = logical ^ (row & 7)), the other chunk of the pair is 0
+                const int t = threadIdx.x - 128, qrow = t >> 1, hp = t & 1;
+                const uint4 h0 = q_pre[0], h1 = q_pre[1];                    // heads 2hp, 2hp+1
+                ATC_T0();
+                if (k != 0) mbar_wait(q_free, iph ^ 1u);                     // the previous item's S MMAs are done with the tile
+                ATC_T1(3);
+                uint8_t* qr = smem + qrow * 128;
+                const int qs = qrow & 7;
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(qr + (((4 * hp + 0) ^ qs) << 4)) = h0;    // head 2hp   -> (q | 0)
+                *reinterpret_cast<uint4*>(qr + (((4 * hp + 1) ^ qs) << 4)) = z;
+                *reinterpret_cast<uint4*>(qr + (((4 * hp + 2) ^ qs) << 4)) = z;     // head 2hp+1 -> (0 | q)
+                *reinterpret_cast<uint4*>(qr + (((4 * hp + 3) ^ qs) << 4)) = h1;
+                fence_proxy_async();
+                mbar_arrive(q_full);
+            }
+            float m[2] = {0.f, 0.f};                           // running softmax reference of heads g and g+2
+            float mnext[2] = {0.f, 0.f};                       // sampled maximum seen in the previous chunk
+            for (int c = 0; c < n_chunks; ++c) {
 #pragma unroll
-                    for (int piece = 0; piece < ATC_KEYS / 32; ++piece) {
-                        tmem_ld_32x32b_x32(lane_addr + sb * ATC_KEYS + piece * 32, v);
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = g + 2 * jj, sb = sbu;
+                    const uint32_t sph = sphu;
+                    ring_advance2();
+                    ATC_T0();
+                    mbar_wait(&s_full[sb], sph);
+                    ATC_T1(0);
+                    tc_fence_after();
+                    // Softmax reference m of this row and head.  Any m within the bf16/fp32 exponent range of the true maximum
+                    // gives the exact softmax after the final division, so only the FIRST chunk pays for an exact row maximum
+                    // (a second pass over the S tile); afterwards m follows a SAMPLED maximum (every 4th key) of the previous
+                    // chunk, picked up while its exponentials were computed, and moves only when that exceeds m by more than
+                    // 2^8 (lazy rescale).  P may therefore exceed 2^8 for a chunk; bf16 P / fp32 accumulators have the range.
+                    uint32_t v[32];
+                    float alpha = 1.0f;
+                    bool moved = false;
+                    if (c == 0) {
+                        float cm[4];
+#pragma unroll
+                        for (int piece = 0; piece < ATC_KEYS / 32; ++piece) {
+                            tmem_ld_32x32b_x32(lane_addr + sb * ATC_KEYS + piece * 32, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float t = fmaxf(fmaxf(__uint_as_float(v[i]), __uint_as_float(v[4 + i])), __uint_as_float(v[8 + i]));
+                                t = fmaxf(fmaxf(t, __uint_as_float(v[12 + i])), __uint_as_float(v[16 + i]));
+                                t = fmaxf(fmaxf(t, __uint_as_float(v[20 + i])), __uint_as_float(v[24 + i]));
+                                t = fmaxf(t, __uint_as_float(v[28 + i]));
+                                cm[i] = piece == 0 ? t : fmaxf(cm[i], t);
+                            }
+                        }
+                        m[jj] = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
+                    } else if (mnext[jj] > m[jj] + ATC_LAZY) {
+                        alpha = ex2_approx(m[jj] - mnext[jj]); m[jj] = mnext[jj]; moved = true;
+                    }
+                    uint8_t* p_row = smem + ATC_OFF_P + sb * ATC_P_BYTES + r * 128;
+                    // P.V of the unit three before this one is complete, hence (in-order MMA pipe) so is every earlier one:
+                    // P[sb] is free and O_j (last written four units ago) has no MMA in flight
+                    ATC_T0();
+                    mbar_wait(&p_free[sb], sph ^ 1u);
+                    ATC_T1(1);
+                    if (__any_sync(0xffffffffu, moved)) {
+                        tc_fence_after();
+                        uint32_t o[16];
+                        tmem_ld_x16(lane_addr + ATC_O_COL + j * 16, o);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float t = fmaxf(fmaxf(__uint_as_float(v[i]), __uint_as_float(v[4 + i])), __uint_as_float(v[8 + i]));
-                            t = fmaxf(fmaxf(t, __uint_as_float(v[12 + i])), __uint_as_float(v[16 + i]));
-                            t = fmaxf(fmaxf(t, __uint_as_float(v[20 + i])), __uint_as_float(v[24 + i]));
-                            t = fmaxf(t, __uint_as_float(v[28 + i]));
-                            cm[i] = piece == 0 ? t : fmaxf(cm[i], t);
-                        }
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_x16(lane_addr + ATC_O_COL + j * 16, o);
                     }
-                    m[jj] = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
-                } else if (mnext[jj] > m[jj] + ATC_LAZY) {
-                    alpha = ex2_approx(m[jj] - mnext[jj]); m[jj] = mnext[jj]; moved = true;
-                }
-                uint8_t* p_row = smem + ATC_OFF_P + sb * ATC_P_BYTES + r * 128;
-                // P.V of unit u-3 is complete, hence (in-order MMA pipe) so is every earlier one: P[sb] is free and
-                // O_j (last written by unit u-4) has no MMA in flight
-                mbar_wait(&p_free[sb], (((uint32_t)(u / ATC_NS)) & 1u) ^ 1u);
-                if (rec) trow[2] = clock64();
-                if (__any_sync(0xffffffffu, moved)) {
-                    tc_fence_after();
-                    uint32_t o[16];
-                    tmem_ld_x16(lane_addr + ATC_O_COL + j * 16, o);
+                    const float mrow = m[jj];
+                    float smp = mrow;                                          // sampled maximum of this chunk (raw logits)
+                    // 16-column pieces, double-buffered in registers: the TMEM load of piece p+1 is in flight while the
+                    // exponentials of piece p are computed (tcgen05.wait::ld waits for ALL loads, so it sits after the compute)
+                    uint32_t vv[2][16];
+                    tmem_ld_x16(lane_addr + sb * ATC_KEYS, vv[0]);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st_x16(lane_addr + ATC_O_COL + j * 16, o);
-                }
-                const float mrow = m[jj];
-                float smp = mrow;                                          // sampled maximum of this chunk (raw logits)
-                // 16-column pieces, double-buffered in registers: the TMEM load of piece p+1 is in flight while the
-                // exponentials of piece p are computed (tcgen05.wait::ld waits for ALL loads, so it sits after the compute)
-                uint32_t vv[2][16];
-                tmem_ld_x16(lane_addr + sb * ATC_KEYS, vv[0]);
-                tmem_ld_wait();
+                    for (int piece = 0; piece < ATC_KEYS / 16; ++piece) {
+                        uint32_t (&cur)[16] = vv[piece & 1];
+                        if (piece + 1 < ATC_KEYS / 16) tmem_ld_x16(lane_addr + sb * ATC_KEYS + (piece + 1) * 16, vv[(piece + 1) & 1]);
+                        smp = fmaxf(fmaxf(smp, __uint_as_float(cur[0])), __uint_as_float(cur[4]));
+                        smp = fmaxf(fmaxf(smp, __uint_as_float(cur[8])), __uint_as_float(cur[12]));
 #pragma unroll
-                for (int piece = 0; piece < ATC_KEYS / 16; ++piece) {
-                    uint32_t (&cur)[16] = vv[piece & 1];
-                    if (piece + 1 < ATC_KEYS / 16) tmem_ld_x16(lane_addr + sb * ATC_KEYS + (piece + 1) * 16, vv[(piece + 1) & 1]);
-                    smp = fmaxf(fmaxf(smp, __uint_as_float(cur[0])), __uint_as_float(cur[4]));
-                    smp = fmaxf(fmaxf(smp, __uint_as_float(cur[8])), __uint_as_float(cur[12]));
+                        for (int q = 0; q < 2; ++q) {                          // 16-byte chunk = 8 keys
+                            uint32_t w[4];
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {                          // 16-byte chunk = 8 keys
-                        uint32_t w[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int e = q * 8 + i * 2;
-                            const float x0 = __uint_as_float(cur[e]) - mrow, x1 = __uint_as_float(cur[e + 1]) - mrow;
-                            // exp_skip: EXPERIMENT (SYNT_ATT_NOEXP=1, wrong results): no MUFU, to time everything else
-                            w[i] = exp_skip ? pack_bf16x2(x0 * 1e-3f, x1 * 1e-3f) : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+                            for (int i = 0; i < 4; ++i) {
+                                const int e = q * 8 + i * 2;
+                                const float x0 = __uint_as_float(cur[e]) - mrow, x1 = __uint_as_float(cur[e + 1]) - mrow;
+                                w[i] = pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+                            }
+                            *reinterpret_cast<uint4*>(p_row + (((piece * 2 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // SWIZZLE_128B
                         }
-                        *reinterpret_cast<uint4*>(p_row + (((piece * 2 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // SWIZZLE_128B
-                    }
-                    if (piece + 1 < ATC_KEYS / 16) {
-                        tmem_ld_wait();
-                        if (piece + 2 == ATC_KEYS / 16) {                  // the last load of this S buffer has completed
-                            tc_fence_before();
-                            mbar_arrive(&s_free[sb]);
+                        if (piece + 1 < ATC_KEYS / 16) {
+                            tmem_ld_wait();
+                            if (piece + 2 == ATC_KEYS / 16) {                  // the last load of this S buffer has completed
+                                tc_fence_before();
+                                mbar_arrive(&s_free[sb]);
+                            }
                         }
                     }
+                    mnext[jj] = smp;
+                    tc_fence_before();
+                    fence_proxy_async();                                       // generic-proxy writes -> async proxy (UMMA)
+                    mbar_arrive(&p_full[sb]);
                 }
-                mnext[jj] = smp;
-                tc_fence_before();
-                fence_proxy_async();                                       // generic-proxy writes -> async proxy (UMMA)
-                mbar_arrive(&p_full[sb]);
-                if (rec) trow[3] = clock64();
             }
-        }
-        // ---- epilogue: O_h / rowsum -> bf16 NHWC
-        mbar_wait(o_full, 0);
-        tc_fence_after();
+            // ---- item boundary: the next item's queries are requested before the read-out so that their latency overlaps it
+            const int nxt = get_item(k + 1);
+            if (nxt < n_items) load_q(atc_item(nxt, nqt));
+            // ---- epilogue: O_h / rowsum -> bf16 NHWC
+            ATC_T0();
+            mbar_wait(o_full, iph);
+            ATC_T1(2);
+            tc_fence_after();
+            uint32_t ov[2][16];
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            const int j = g + 2 * jj;
-            uint32_t v[16];
-            tmem_ld_x16(lane_addr + ATC_O_COL + j * 16, v);
+            for (int jj = 0; jj < 2; ++jj) tmem_ld_x16(lane_addr + ATC_O_COL + (g + 2 * jj) * 16, ov[jj]);
             tmem_ld_wait();
-            const float inv = 1.0f / __uint_as_float(v[8]);
-            float o[8];
+            tc_fence_before();
+            mbar_arrive(o_free);                               // the P.V issuer may start the next item's accumulation
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[i]) * inv;
-            store8<bf16>(out + ((size_t)b * N + q0 + r) * C + (hg * 4 + j) * 8, o);
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = g + 2 * jj;
+                const float inv = 1.0f / __uint_as_float(ov[jj][8]);
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(ov[jj][i]) * inv;
+                store8<bf16>(out + ((size_t)im.b * N + im.q0 + r) * C + (im.hg * 4 + j) * 8, o);
+            }
+            iph ^= 1u;
+            ATC_ITEM_END();
+            it = nxt;
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<ATC_TMEM_COLS>(tmem);
+    // the last CTA to leave re-arms the queue for the next launch that uses this counter pair (every draw of every CTA
+    // precedes that CTA's arrival here)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(work_ctr + 1, 1) == (int)gridDim.x - 1) { atomicExch(work_ctr, 0); atomicExch(work_ctr + 1, 0); }
+    }
 }
 
 // ---- V^T builder: vt[b*H + h][16][N] from the v part of qkv' -------------------------------
@@ -436,21 +542,36 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
         SYNT_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
         attr = true;
     }
-    static const int exp_skip = [] { const char* e = getenv("SYNT_ATT_NOEXP"); return (e && e[0] == '1') ? 1 : 0; }();
-    // debug: SYNT_ATT_TIMELINE=<file> dumps the softmax warps' clock64 samples of CTA (1,1,1) of every 1024-token launch
-    static const char* tl_path = getenv("SYNT_ATT_TIMELINE");
+    static const int num_sms = [] { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    const int n_items = (N / 128) * (C / 32) * B;            // 128 queries x 4 heads of one image each
+    const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;     // persistent: two resident CTAs per SM
+    // work-queue counters {next item, CTAs done}: a pool of pairs handed out round-robin, zero at rest (the kernel's last CTA
+    // re-arms its pair), so that launches captured into different graphs / running on different streams do not share one
+    constexpr int kCtrPairs = 1024;
+    static int* ctr_pool = nullptr;
+    static int ctr_next = 0;
+    if (!ctr_pool) {
+        SYNT_CUDA(cudaMalloc(&ctr_pool, kCtrPairs * 2 * sizeof(int)));
+        SYNT_CUDA(cudaMemset(ctr_pool, 0, kCtrPairs * 2 * sizeof(int)));
+    }
+    int* work_ctr = ctr_pool + 2 * (ctr_next++ % kCtrPairs);
     long long* tl = nullptr;
-    const size_t tl_n = (size_t)8 * (N / ATC_KEYS) * 4 * 4;
+#ifdef SYNT_ATT_TIMELINE_BUILD
+    static const char* tl_path = getenv("SYNT_ATT_TIMELINE");
+    const size_t tl_n = (size_t)grid * 8 * 128;
     if (tl_path && N == 1024 && B > 1) { SYNT_CUDA(cudaMalloc(&tl, tl_n * 8)); SYNT_CUDA(cudaMemsetAsync(tl, 0, tl_n * 8, s)); }
-    launch_pdl(attention_tc_kernel, dim3(N / 128, C / 32, B), dim3(ATC_THREADS), ATC_SMEM, s, maps, N, C, (const bf16*)qkv,
-               (bf16*)out, exp_skip, tl);
+#endif
+    launch_pdl(attention_tc_kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, s, maps, N, C, n_items, (const bf16*)qkv, (bf16*)out,
+               work_ctr, tl);
+#ifdef SYNT_ATT_TIMELINE_BUILD
     if (tl) {
         std::vector<long long> h(tl_n);
         SYNT_CUDA(cudaMemcpyAsync(h.data(), tl, tl_n * 8, cudaMemcpyDeviceToHost, s));
         SYNT_CUDA(cudaStreamSynchronize(s));
         cudaFree(tl);
-        if (FILE* f = fopen(tl_path, "ab")) { fwrite(h.data(), 8, tl_n, f); fclose(f); }
+        if (FILE* f = fopen(tl_path, "wb")) { fwrite(h.data(), 8, tl_n, f); fclose(f); }
     }
+#endif
 }
 
 }  // namespace synt

@@ -40,10 +40,13 @@ def test_attention_simt(cuda_dev, N, dt):
     assert err < (2e-6 if dt == "fp32" else 4e-3), err
 
 
-@pytest.mark.parametrize("N,B,scale", [(256, 2, 1.0), (1024, 2, 1.0), (1024, 3, 3.0)])
+@pytest.mark.parametrize("N,B,scale", [(256, 2, 1.0), (1024, 2, 1.0), (1024, 3, 3.0), (1024, 11, 1.0), (256, 43, 3.0),
+                                       (1024, 64, 2.0)])
 def test_attention_tcgen05(cuda_dev, N, B, scale):
     """Inputs as the fused q/k/v projection writes them: (q | k | v) with q pre-scaled by log2(e)/sqrt(8).
-    scale=3 gives peaky softmax rows (logits up to ~ +-60)."""
+    scale=3 gives peaky softmax rows (logits up to ~ +-60).  The kernel is persistent (two CTAs per SM walk the 128-query x
+    4-head work items): B = 11 / 43 / 64 give every CTA 2-3 / 2-3 / 13-14 items (ragged last round), i.e. they exercise the
+    item boundaries (query-tile rewrite, accumulator hand-over, rings running on)."""
     C = 256
     q, k, v = make_qkv(B, N, C, N + B, scale)
     qs = q * (math.log2(math.e) / math.sqrt(8))
@@ -55,6 +58,13 @@ def test_attention_tcgen05(cuda_dev, N, B, scale):
     qr = qkv[..., :C].float().cpu() / (math.log2(math.e) / math.sqrt(8))
     kr = qkv[..., C:2 * C].float().cpu()
     vr = qkv[..., 2 * C:].float().cpu()
-    ref = reference(qr, kr, vr)
-    err = ((out.float().cpu() - ref).norm() / ref.norm()).item()
-    assert err < 6e-3, err            # P and the output are rounded to bf16
+    if B <= 3:
+        ref = reference(qr, kr, vr)
+        err = ((out.float().cpu() - ref).norm() / ref.norm()).item()
+        assert err < 6e-3, err            # P and the output are rounded to bf16
+        return
+    worst = 0.0
+    for b in range(B):                    # large batches: reference per image on the GPU (float64)
+        ref = reference(qr[b:b + 1].to(cuda_dev), kr[b:b + 1].to(cuda_dev), vr[b:b + 1].to(cuda_dev))
+        worst = max(worst, ((out[b:b + 1].float() - ref).norm() / ref.norm()).item())
+    assert worst < 6e-3, worst

@@ -1,43 +1,39 @@
-"""Per-warp timeline of the attention kernel's softmax warps (debug build hook SYNT_ATT_TIMELINE): for CTA (1,1,1) of a
-1024-token launch, clock64 at {unit start, S tile ready, P tile free, unit done} for every unit of every softmax warp.
+"""Per-CTA timeline of the persistent attention kernel (debug build).  On the GPU box:
 
-    SYNT_EXTRA_NVCC_FLAGS=-DSYNT_ATT_TIMELINE_BUILD python -m synt_isic_b200.build --force   # instrumented build
-    SYNT_ATT_TIMELINE=/tmp/att_tl.bin python tools/att_timeline.py
-"""
-import os
+    SYNT_EXTRA_NVCC_FLAGS=-DSYNT_ATT_TIMELINE_BUILD python -m synt_isic_b200.build --force
+    SYNT_ATT_TIMELINE=gpurun_out/att_tl.bin python tools/att_bench.py; python tools/att_timeline.py gpurun_out/att_tl.bin
+    python -m synt_isic_b200.build --force          # back to the product build
+
+Record per CTA and softmax warp: smid, entry clock, then per item {end clock, cycles waiting for S tiles, for free P tiles,
+for the accumulators (o_full), for the query tile (q_free), item id}."""
 import sys
+import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np  # noqa: E402
-import torch  # noqa: E402
-
-from synt_isic_b200 import _lib  # noqa: E402
-
-path = os.environ.setdefault("SYNT_ATT_TIMELINE", "/tmp/att_tl.bin")
-if os.path.exists(path):
-    os.unlink(path)
-dev = torch.device("cuda:0")
-B, N, C = 64, 1024, 256
-g = torch.Generator().manual_seed(0)
-qkv = (torch.randn(B, N, 3 * C, generator=g) * 0.7).to(torch.bfloat16).to(dev)
-out = torch.empty(B, N, C, dtype=torch.bfloat16, device=dev)
-for _ in range(3):
-    _lib.check(_lib.lib().synt_debug_attention(1, 1, qkv.data_ptr(), B, N, C, out.data_ptr(), _lib.current_stream_ptr()))
-torch.cuda.synchronize()
-raw = np.fromfile(path, dtype=np.int64)
-rec = raw.reshape(-1, 8, 64, 4)[-1]                  # last launch: [warp][slot][4]; slots 0,2,4,.. used
-rec = rec[:, 0::2, :]                                # [8 warps][32 units][4]
-t0 = rec[:, :, 0].min()
-print("units per warp:", rec.shape[1], " CTA lifetime (clk):", int(rec[:, :, 3].max() - t0))
-for w in range(8):
-    r = rec[w] - t0
-    wait_s = (r[:, 1] - r[:, 0])
-    wait_p = (r[:, 2] - r[:, 1])
-    work = (r[:, 3] - r[:, 2])
-    gap = np.concatenate([[0], r[1:, 0] - r[:-1, 3]])
-    print(f"warp {w + 4}: start {int(r[0, 0]):6d}  s_full wait avg {wait_s[1:].mean():7.1f} (first {int(wait_s[0])})  "
-          f"max+p_free avg {wait_p[2:].mean():7.1f} (first chunk {wait_p[:2].mean():7.1f})  exp+store avg {work.mean():7.1f}  "
-          f"unit period avg {np.diff(r[:, 0]).mean():7.1f}")
-w0 = rec[0] - t0
-print("warp 4 first units [start, S ready, P free, done]:")
-print(w0[:8])
+a = np.fromfile(sys.argv[1], dtype=np.int64).reshape(-1, 8, 128)
+ncta = a.shape[0]
+smid = a[:, 0, 0]
+entry = a[:, :, 1]
+items = a[:, :, 8:8 + 20 * 6].reshape(ncta, 8, 20, 6)
+n_items = (items[:, 0, :, 0] > 0).sum(1)
+print(f"CTAs {ncta}, SMs used {len(set(smid.tolist()))}, CTAs per SM: {np.bincount(np.bincount(smid))[1:]} (index = count)")
+print(f"items per CTA: min {n_items.min()} max {n_items.max()}")
+t0 = entry.min()
+end_all = items[:, :, :, 0].max()
+print(f"kernel span {end_all - t0} clk; entry spread {entry.max() - t0}")
+w = 0                                                     # warp 0 of warpgroup 0
+first_end = items[:, w, 0, 0] - entry[:, w]
+print(f"first item: entry -> end  mean {first_end.mean():.0f} clk")
+dur = np.diff(items[:, w, :, 0], axis=1)
+valid = items[:, w, 1:, 0] > 0
+print(f"later items: duration mean {dur[valid].mean():.0f} min {dur[valid].min()} max {dur[valid].max()} clk")
+for k, name in enumerate(["wait S tile", "wait free P tile", "wait accumulators (o_full)", "wait query tile (q_free)"]):
+    v = items[:, w, 1:, 1 + k][valid]
+    print(f"  {name:32s} mean {v.mean():8.0f} clk per item ({100 * v.mean() / dur[valid].mean():.1f}%)")
+for wg, ww in (("wg0", 0), ("wg1", 4)):
+    v = items[:, ww, 1:, 1:5][items[:, ww, 1:, 0] > 0]
+    print(f"{wg}: waits per item  S {v[:, 0].mean():.0f}  P {v[:, 1].mean():.0f}  O {v[:, 2].mean():.0f}  Q {v[:, 3].mean():.0f}")
+# are the two CTAs of an SM in phase?  item-end clocks modulo the mean item duration
+sm0 = np.where(smid == smid[0])[0]
+print("CTAs on SM", smid[0], ":", sm0.tolist())
+for c in sm0:
+    print("  cta", c, "entry", entry[c, 0] - t0, "item ends", (items[c, 0, :6, 0] - t0).tolist())
