@@ -32,6 +32,7 @@
 #include "ptx.cuh"
 #include "tmap.cuh"
 #include <cstdio>
+#include <type_traits>
 #include <vector>
 
 namespace synt {
@@ -53,6 +54,7 @@ constexpr int ATC_OFF_BAR = ATC_OFF_P + ATC_NS * ATC_P_BYTES;   // P tiles rotat
 constexpr int ATC_SMEM = ATC_OFF_BAR + 256;            // the dynamic window starts 1 KB aligned (checked in the kernel)
 constexpr uint32_t ATC_TMEM_COLS = 256;                // S buffers [0,192), O_h [192+16h, +16)
 constexpr uint32_t ATC_O_COL = 192;
+constexpr int ATC_POLY_DEFAULT = 1;                    // exponentials per 4 pairs on the FMA pipe (SYNT_ATT_POLY overrides)
 constexpr float ATC_LAZY = 8.0f;                       // rescale only when the max grows by more than 2^8
 static_assert(2 * (ATC_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit in shared memory");
 
@@ -63,7 +65,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// NOTE (measured, B200): moving 3 of every 8 exponentials to an FMA-pipe polynomial (Cody-Waite + degree-3
+// exp2 on the FMA pipe (Cody-Waite split + cubic minimax, relative error 7.6e-5, far below the bf16 rounding of P): x is split
+// into its nearest integer n (low mantissa bits of x + 1.5*2^23) and f = x - n in [-0.5, 0.5]; 2^f by Horner; n is added to
+// the exponent field with one integer multiply-add.  7 FMA-pipe instructions + 1 FMNMX against one 8-clk MUFU slot.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);                                   // below, the exponent arithmetic would wrap (P is ~0 there anyway)
+    const float t = x + 12582912.0f;
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(f, 0.05520550534129143f, 0.24261397123336792f);
+    p = fmaf(p, f, 0.6932547688484192f);
+    p = fmaf(p, f, 0.9999276995658875f);
+    return __int_as_float(__float_as_int(t) * 8388608 + __float_as_int(p));
+}
+// Measured (B200, round 2, persistent kernel, B=64 N=1024): POLY 0 / 1 / 2 / 3 -> 672 / 653 / 727 / 942 us per launch: the
+// softmax warps are balanced between the MUFU pipe and their issue slots, so one pair in four is the optimum.  A zero-reference
+// fast path (P = 2^S without the subtraction while the row maximum stays within 2^+-40) measured SLOWER (714 us): the second
+// copy of the unrolled loop costs more in registers / spills than the 64 FADDs per unit it removes.
+// NOTE (measured, B200, round 1): moving 3 of every 8 exponentials to an FMA-pipe polynomial (Cody-Waite + degree-3
 // minimax) made the kernel 10% SLOWER (4.09 -> 4.50 ms/step): the softmax warps are issue/FMA-pipe limited
 // next to the MUFU pipe, and packed ex2.approx.{f16,bf16}x2 lowers to two MUFU ops on sm_100a.  All
 // exponentials therefore stay on MUFU.EX2.
@@ -113,6 +131,8 @@ __device__ __forceinline__ AtcItem atc_item(int it, int nqt) {
     return o;
 }
 
+// POLY: of every four bf16 pairs of P, POLY are computed with ex2_poly on the FMA pipe instead of MUFU.EX2
+template <int POLY>
 __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, int N,
                                                                       int C, int n_items, const bf16* __restrict__ qkv,
                                                                       bf16* __restrict__ out, int* __restrict__ work_ctr,
@@ -421,32 +441,35 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                     const float mrow = m[jj];
                     float smp = mrow;                                          // sampled maximum of this chunk (raw logits)
                     // 16-column pieces, double-buffered in registers: the TMEM load of piece p+1 is in flight while the
-                    // exponentials of piece p are computed (tcgen05.wait::ld waits for ALL loads, so it sits after the compute)
-                    uint32_t vv[2][16];
-                    tmem_ld_x16(lane_addr + sb * ATC_KEYS, vv[0]);
-                    tmem_ld_wait();
+                    // exponentials of piece p are computed (tcgen05.wait::ld waits for ALL loads, so it sits after the compute).
+                    {
+                        uint32_t vv[2][16];
+                        tmem_ld_x16(lane_addr + sb * ATC_KEYS, vv[0]);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int piece = 0; piece < ATC_KEYS / 16; ++piece) {
-                        uint32_t (&cur)[16] = vv[piece & 1];
-                        if (piece + 1 < ATC_KEYS / 16) tmem_ld_x16(lane_addr + sb * ATC_KEYS + (piece + 1) * 16, vv[(piece + 1) & 1]);
-                        smp = fmaxf(fmaxf(smp, __uint_as_float(cur[0])), __uint_as_float(cur[4]));
-                        smp = fmaxf(fmaxf(smp, __uint_as_float(cur[8])), __uint_as_float(cur[12]));
+                        for (int piece = 0; piece < ATC_KEYS / 16; ++piece) {
+                            uint32_t (&cur)[16] = vv[piece & 1];
+                            if (piece + 1 < ATC_KEYS / 16) tmem_ld_x16(lane_addr + sb * ATC_KEYS + (piece + 1) * 16, vv[(piece + 1) & 1]);
+                            smp = fmaxf(fmaxf(smp, __uint_as_float(cur[0])), __uint_as_float(cur[4]));
+                            smp = fmaxf(fmaxf(smp, __uint_as_float(cur[8])), __uint_as_float(cur[12]));
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {                          // 16-byte chunk = 8 keys
-                            uint32_t w[4];
+                            for (int q = 0; q < 2; ++q) {                          // 16-byte chunk = 8 keys
+                                uint32_t w[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int e = q * 8 + i * 2;
-                                const float x0 = __uint_as_float(cur[e]) - mrow, x1 = __uint_as_float(cur[e + 1]) - mrow;
-                                w[i] = pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+                                for (int i = 0; i < 4; ++i) {
+                                    const int e = q * 8 + i * 2;
+                                    const float x0 = __uint_as_float(cur[e]) - mrow, x1 = __uint_as_float(cur[e + 1]) - mrow;
+                                    w[i] = (POLY > 0 && i >= 4 - POLY) ? pack_bf16x2(ex2_poly(x0), ex2_poly(x1))
+                                                                        : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+                                }
+                                *reinterpret_cast<uint4*>(p_row + (((piece * 2 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // SWIZZLE_128B
                             }
-                            *reinterpret_cast<uint4*>(p_row + (((piece * 2 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // SWIZZLE_128B
-                        }
-                        if (piece + 1 < ATC_KEYS / 16) {
-                            tmem_ld_wait();
-                            if (piece + 2 == ATC_KEYS / 16) {                  // the last load of this S buffer has completed
-                                tc_fence_before();
-                                mbar_arrive(&s_free[sb]);
+                            if (piece + 1 < ATC_KEYS / 16) {
+                                tmem_ld_wait();
+                                if (piece + 2 == ATC_KEYS / 16) {                  // the last load of this S buffer has completed
+                                    tc_fence_before();
+                                    mbar_arrive(&s_free[sb]);
+                                }
                             }
                         }
                     }
@@ -537,9 +560,11 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
         cuuint32_t boxk[2] = {64, ATC_KEYS};
         encode_bf16_sw128(&maps.k, qkv, 2, dims, strides, boxk, "attention k");
     }
+    static const int poly = [] { const char* e = getenv("SYNT_ATT_POLY"); const int v = e ? atoi(e) : ATC_POLY_DEFAULT; return v < 0 ? 0 : (v > 3 ? 3 : v); }();
+    auto kern = poly == 0 ? attention_tc_kernel<0> : poly == 1 ? attention_tc_kernel<1> : poly == 2 ? attention_tc_kernel<2> : attention_tc_kernel<3>;
     static bool attr = false;
     if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+        SYNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
         attr = true;
     }
     static const int num_sms = [] { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
@@ -561,7 +586,7 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
     const size_t tl_n = (size_t)grid * 8 * 128;
     if (tl_path && N == 1024 && B > 1) { SYNT_CUDA(cudaMalloc(&tl, tl_n * 8)); SYNT_CUDA(cudaMemsetAsync(tl, 0, tl_n * 8, s)); }
 #endif
-    launch_pdl(attention_tc_kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, s, maps, N, C, n_items, (const bf16*)qkv, (bf16*)out,
+    launch_pdl(kern, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, s, maps, N, C, n_items, (const bf16*)qkv, (bf16*)out,
                work_ctr, tl);
 #ifdef SYNT_ATT_TIMELINE_BUILD
     if (tl) {

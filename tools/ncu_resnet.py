@@ -1,4 +1,4 @@
-"""Small fixed workload for ncu: ResNet18 logits of 256 images (bf16 path)."""
+"""Small fixed workload for ncu: ResNet18 logits of 512 images (argv[1] overrides) (bf16 path)."""
 import os
 import sys
 
@@ -9,7 +9,7 @@ from synt_isic_b200 import MelanomaClassifierAdaptive  # noqa: E402
 
 dev = torch.device("cuda:0")
 clf = MelanomaClassifierAdaptive(num_classes=7, pretrained=False, precision="bf16").to(dev).eval()
-x = torch.tanh(torch.randn(256, 3, 128, 128, device=dev))
+x = torch.tanh(torch.randn(int(sys.argv[1]) if len(sys.argv) > 1 else 512, 3, 128, 128, device=dev))
 for _ in range(2):
     y = clf(x)
 torch.cuda.synchronize()
