@@ -8,6 +8,7 @@
 //                ReLU / residual / 1x1-stride-2 downsample fused into the conv epilogue
 //   head         global average pool + Linear(512, num_classes)
 #include "kernels.cuh"
+#include "preprocess.cuh"
 #include "pool.h"
 #include "../../include/synt_isic.h"
 #include <cmath>
@@ -19,32 +20,6 @@
 namespace synt {
 
 extern thread_local std::string g_last_error;
-
-// =============================================================== kernels ============
-// classifier preprocess of one output pixel (xai/XAI.py:399-431): clamp((x+1)/2, 0, 1) -> bilinear Hin x Win -> Hout x Wout
-// (align_corners=False; antialias is a no-op when upsampling) -> ImageNet normalise.  One definition, used by the
-// stand-alone kernel and by the fused stem, so both produce bit-identical values.
-__device__ __forceinline__ void preprocess_pixel(const float* __restrict__ img /* [3][Hin][Win] */, int Hin, int Win, float sy, float sx,
-                                                 int oy, int ox, float (&v3)[3]) {
-    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
-    float fy = ((float)oy + 0.5f) * sy - 0.5f; if (fy < 0.f) fy = 0.f;
-    float fx = ((float)ox + 0.5f) * sx - 0.5f; if (fx < 0.f) fx = 0.f;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
-    const float ly = fy - (float)y0, lx = fx - (float)x0;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float* pl = img + (long long)c * Hin * Win;
-        auto px = [&](int yy, int xx) {
-            float v = (pl[yy * Win + xx] + 1.0f) / 2.0f;
-            return fminf(fmaxf(v, 0.f), 1.f);
-        };
-        const float top = px(y0, x0) * (1.f - lx) + px(y0, x1) * lx;
-        const float bot = px(y1, x0) * (1.f - lx) + px(y1, x1) * lx;
-        const float v = top * (1.f - ly) + bot * ly;
-        v3[c] = (v - mean[c]) / stdv[c];
-    }
-}
 
 template <typename T>
 __global__ void preprocess_kernel(const float* __restrict__ x, int Hin, int Win, int Hout, int Wout, long long npix,
@@ -559,7 +534,8 @@ struct synt_resnet18 {
     bool fuse_front = true;                  // preprocess + stem + maxpool in one kernel (SYNT_RESNET_FUSE_FRONT=0: three kernels)
     RConv stem;                              // 7x7 s2 on the fp32-FMA kernel (fp32 mode)
     RConv stem_tc;                           // the same stem as a 1x1 conv over the im2col'd input (K 147 -> 192), bf16 tcgen05
-    RPtr stem_frag;                          // stem weights as mma.sync B fragments (fused stem kernel, default in bf16 mode)
+    RPtr stem_frag;                          // stem weights as mma.sync B fragments (mma.sync stem kernels)
+    RPtr stem_taps;                          // stem weights as 16 space-to-depth tap tiles (tcgen05 front end, default in bf16 mode)
     RConv c1[4][2], c2[4][2];
     // data-gradient convolutions of the same layers (built on first use by ensure_bwd): d2 = dgrad of conv2 (c -> c),
     // d1 = dgrad of conv1 (c -> block input channels; the stride-2 blocks carry the 1x1 downsample dgrad as shortcut segment)
@@ -576,6 +552,10 @@ namespace synt {
 void stem_im2col(const void* pre, int B, void* out, cudaStream_t s);
 void stem_mma(const void* pre, int B, const void* bfrag, const float* bias, void* out, cudaStream_t s);
 void stem_fused(const float* x_nchw, int B, const void* bfrag, const float* bias, void* out, cudaStream_t s);
+// tcgen05 front end (stem_tc.cu)
+void stem_tc(const float* x_nchw, int B, const void* w_taps, const float* bias, void* out, cudaStream_t s);
+void stem_tc_pack_weights(const uint16_t* w_k192, uint16_t* out);
+int stem_tc_weight_bytes();
 
 struct RFwd {
     synt_resnet18* r; cudaStream_t s; int B;
@@ -608,7 +588,8 @@ struct RFwd {
         if (r->use_tc && r->stem_frag && r->fuse_front && !r->tap_out) {
             // preprocess + stem + maxpool in one kernel (the debug taps "preprocess" / "relu" / "maxpool" use the unfused path)
             cur = make(56, 56, 64);
-            stem_fused(x_nchw, B, r->stem_frag->p, (const float*)r->stem_tc.b->p, cur, s);
+            if (r->stem_taps) stem_tc(x_nchw, B, r->stem_taps->p, (const float*)r->stem_tc.b->p, cur, s);
+            else stem_fused(x_nchw, B, r->stem_frag->p, (const float*)r->stem_tc.b->p, cur, s);
             ++r->launches;
         } else {
             void* pre = make(224, 224, 3);
@@ -869,6 +850,12 @@ int synt_resnet18_create(const float* P, long long n_params, int num_classes, in
                         o[1] = wv(k0 + 8, n) | (wv(k0 + 9, n) << 16);
                     }
             r->stem_frag = r_upload(fr.data(), fr.size() * 4);
+            const char* st = getenv("SYNT_STEM_TC");         // =0: the mma.sync fused front end instead of the tcgen05 one
+            if (!(st && st[0] == '0')) {
+                std::vector<uint16_t> taps((size_t)stem_tc_weight_bytes() / 2);
+                stem_tc_pack_weights(pk.data(), taps.data());
+                r->stem_taps = r_upload(taps.data(), taps.size() * 2);
+            }
         }
     }
     int cin = 64;

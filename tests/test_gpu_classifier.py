@@ -173,7 +173,7 @@ def test_integrated_analyzer_runs(cuda_dev, frames):
 
 
 def test_fused_front_end_is_bit_identical_to_the_three_kernels(oc, cuda_dev, frames, monkeypatch):
-    """bf16 mode: preprocess + 7x7/s2 stem + maxpool in ONE kernel (default) against the unfused chain
+    """bf16 mode: preprocess + 7x7/s2 stem + maxpool in ONE kernel (tcgen05 by default, mma.sync with SYNT_STEM_TC=0) against the unfused chain
     (SYNT_RESNET_FUSE_FRONT=0) and against the im2col + tcgen05 stem (SYNT_STEM_IM2COL=1): same arithmetic per output
     element, hence identical logits for the first two and bf16-level agreement with the third
     (classifier of xai/XAI.py:357-471)."""
@@ -187,11 +187,13 @@ def test_fused_front_end_is_bit_identical_to_the_three_kernels(oc, cuda_dev, fra
         for k in env:
             monkeypatch.delenv(k)
         return y
-    fused = build({})
+    tc = build({})                                            # default: the tcgen05 front end (space-to-depth taps)
+    fused = build({"SYNT_STEM_TC": "0"})                      # the mma.sync fused front end
     chain = build({"SYNT_RESNET_FUSE_FRONT": "0"})
     im2col = build({"SYNT_RESNET_FUSE_FRONT": "0", "SYNT_STEM_IM2COL": "1"})
     assert torch.equal(fused, chain)
     assert rel(im2col, fused) < 5e-3
+    assert rel(tc, fused) < 5e-3                              # same bf16 operands, another fp32 summation order
 
 
 def test_time_shap_streams_a_host_trajectory(clfs, cuda_dev):
