@@ -160,6 +160,18 @@ int synt_patch_mask_apply(const float* x_dev, const unsigned char* patch_masks_d
 int synt_select_regions(const float* attr_dev, int n_maps, int C, int H, int W, int use_abs, double k_percent, int bottom,
                         int morphology_cleanup, int connectivity, unsigned char* mask_dev, double* stats_dev, void* stream);
 
+/* replaces the resampling loops of statistical_validation_comprehensive (XAI.py:1708-2005), one thread per replicate, float64
+ * means in numpy's pairwise summation order:
+ *   bootstrap   (XAI.py:1852-1878): out[b] = mean(top[idx_top[b][0..n1)]) - mean(bottom[idx_bottom[b][0..n2)])
+ *   permutation (XAI.py:1882-1913): out[b] = mean(combined[perm[b][0..n1)]) - mean(combined[perm[b][n1..n)])
+ * idx / perms (int32, device) inject the reference's numpy draws (bit-identical replicates); NULL = in-kernel Philox(seed)
+ * draws (bootstrap: uniform indices; permutation: Fisher-Yates, n <= 1024). */
+int synt_stat_bootstrap_mean_diff(const double* top_dev, int n1, const double* bottom_dev, int n2, const int* idx_top_dev,
+                                  const int* idx_bottom_dev, unsigned long long seed, int n_bootstrap, double* out_dev,
+                                  void* stream);
+int synt_stat_permutation_mean_diff(const double* combined_dev, int n, int n1, const int* perms_dev, unsigned long long seed,
+                                    int n_permutations, double* out_dev, void* stream);
+
 /* ---------------- test hook (kernel-level parity tests; not a reference entry point) ------ */
 /* one convolution on caller-provided NHWC tensors: use_tc=1 tcgen05 (bf16), 0 fp32-FMA carrier.
  * weight is K-major [Cout][K*K*Cin + sc0_C + sc1_C], bf16 for use_tc else fp32. */

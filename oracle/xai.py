@@ -268,3 +268,52 @@ def select_regions(attribution_map, k_percent=10, region_type="top", morphology_
     return {"mask": mask, "threshold": thr, "statistics": stats,
             "metadata": {"region_type": region_type, "morphology_cleanup": morphology_cleanup, "connectivity": connectivity,
                          "original_shape": shape}}
+
+
+# ---------------------------------------------------------------- statistics (XAI.py:1708-2005) ----
+def bootstrap_and_permutation(top_k, bottom_k, n_bootstrap=1000, n_permutations=10000):
+    """The two resampling loops of ``statistical_validation_comprehensive`` exactly as the reference runs them, drawing from
+    the GLOBAL numpy RNG in the reference's call order (bootstrap :1852-1865, then the permutation test :1882-1900).
+    Returns (bootstrap_diffs, permuted_diffs) as float64 arrays."""
+    top_k = np.array(top_k, dtype=np.float64)
+    bottom_k = np.array(bottom_k, dtype=np.float64)
+    boot = []
+    for _ in range(n_bootstrap):
+        top_sample = np.random.choice(top_k, len(top_k), replace=True)
+        bottom_sample = np.random.choice(bottom_k, len(bottom_k), replace=True)
+        boot.append(np.mean(top_sample) - np.mean(bottom_sample))
+    combined = np.concatenate([top_k, bottom_k])
+    observed = np.mean(top_k) - np.mean(bottom_k)
+    perm = []
+    if len(top_k) >= 2 and len(bottom_k) >= 2:
+        for _ in range(n_permutations):
+            np.random.shuffle(combined)
+            perm.append(np.mean(combined[:len(top_k)]) - np.mean(combined[len(top_k):]))
+    else:
+        perm = [observed]
+    return np.array(boot), np.array(perm)
+
+
+def numpy_pairwise_sum(a):
+    """numpy's float64 summation order (DOUBLE_pairwise_sum), restated: what the CUDA replicate means must reproduce."""
+    n = len(a)
+    if n < 8:
+        r = 0.0
+        for v in a:
+            r += float(v)
+        return r
+    if n <= 128:
+        r = [float(a[j]) for j in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] += float(a[i + j])
+            i += 8
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+        while i < n:
+            res += float(a[i])
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return numpy_pairwise_sum(a[:n2]) + numpy_pairwise_sum(a[n2:])

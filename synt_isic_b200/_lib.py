@@ -55,6 +55,8 @@ SIGNATURES = {
     "synt_ig_reduce": (C.c_int, [vp, vp, vp, C.c_int, C.c_longlong, vp, vp]),
     "synt_intervene_blend": (C.c_int, [vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "synt_intervene_blend_ex": (C.c_int, [vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "synt_stat_bootstrap_mean_diff": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, C.c_ulonglong, C.c_int, vp, vp]),
+    "synt_stat_permutation_mean_diff": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_ulonglong, C.c_int, vp, vp]),
     "synt_debug_conv": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, vp]),
     "synt_debug_conv_gn": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int,

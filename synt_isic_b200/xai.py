@@ -15,9 +15,10 @@ of the CUDA classifier and (optionally) sharded across ranks with a single all_g
   compute_gradient_attribution          xai/XAI.py:1087-1109
   compute_combined_attribution          xai/XAI.py:1236-1291
   select_regions_advanced               xai/XAI.py:1340-1451   (numpy percentile + scipy.ndimage -> one CTA per map)
+  statistical_validation_comprehensive  xai/XAI.py:1708-2005   (bootstrap / permutation loops -> one thread per replicate)
   IntegratedXAIAnalyzer                 xai/xai_integration.py:75-132
 
-Out of scope: Grad-CAM, statistics and plots.
+Out of scope: Grad-CAM and plots.
 """
 from __future__ import annotations
 
@@ -502,6 +503,159 @@ def csi_batch(classifier, images: torch.Tensor, masks: torch.Tensor, interventio
     return {it: table[:, i] for i, it in enumerate(intervention_types)}
 
 
+# ------------------------------------------------------------------ statistics ----------
+ALPHA_LEVEL = 0.1          # xai/XAI.py:270
+N_BOOTSTRAP = 1000         # xai/XAI.py:271
+N_PERMUTATIONS = 10000     # xai/XAI.py:272
+
+
+def draw_bootstrap_indices(n1: int, n2: int, n_bootstrap: int):
+    """The resampling indices exactly as the reference's loop draws them from the GLOBAL numpy RNG (XAI.py:1856-1860:
+    ``np.random.choice(top_k, n1, replace=True)`` then ``np.random.choice(bottom_k, n2, replace=True)`` per replicate --
+    ``choice`` on an array draws ``randint(0, n, size=n)`` indices).  int32 [n_bootstrap, n1], [n_bootstrap, n2]."""
+    it = np.empty((n_bootstrap, n1), np.int32)
+    ib = np.empty((n_bootstrap, n2), np.int32)
+    for b in range(n_bootstrap):
+        it[b] = np.random.choice(n1, n1, replace=True)
+        ib[b] = np.random.choice(n2, n2, replace=True)
+    return it, ib
+
+
+def draw_permutations(n: int, n_permutations: int) -> np.ndarray:
+    """The reference shuffles the SAME pooled array in place again and again (XAI.py:1892-1893), i.e. replicate k sees the
+    composition of the first k+1 shuffles: an index array shuffled in place with the same calls reproduces it.  int32 [n_perm, n]."""
+    idx = np.arange(n)
+    out = np.empty((n_permutations, n), np.int32)
+    for k in range(n_permutations):
+        np.random.shuffle(idx)
+        out[k] = idx
+    return out
+
+
+def resampled_mean_differences(top_k, bottom_k, n_bootstrap=N_BOOTSTRAP, n_permutations=N_PERMUTATIONS, device="cuda",
+                               bootstrap_indices=None, permutations=None, seed: int = 0):
+    """The two resampling loops of the reference's statistical validation on the GPU (one thread per replicate, float64 means
+    in numpy's summation order): returns (bootstrap_diffs [n_bootstrap], permuted_diffs [n_permutations]) as numpy float64.
+    ``bootstrap_indices`` = (idx_top, idx_bottom) and ``permutations`` inject the draws (``draw_bootstrap_indices`` /
+    ``draw_permutations`` replay the reference's numpy stream); otherwise they come from an in-kernel Philox stream."""
+    dev = torch.device(device)
+    t = torch.as_tensor(np.asarray(top_k, np.float64), device=dev).contiguous()
+    b = torch.as_tensor(np.asarray(bottom_k, np.float64), device=dev).contiguous()
+    n1, n2 = t.numel(), b.numel()
+    L = _lib.lib()
+    boot = torch.empty(n_bootstrap, dtype=torch.float64, device=dev)
+    perm = torch.empty(max(n_permutations, 1), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.current_stream_ptr()
+        it = ib = None
+        if bootstrap_indices is not None:
+            it = torch.as_tensor(np.ascontiguousarray(bootstrap_indices[0], np.int32), device=dev)
+            ib = torch.as_tensor(np.ascontiguousarray(bootstrap_indices[1], np.int32), device=dev)
+        _lib.check(L.synt_stat_bootstrap_mean_diff(t.data_ptr(), n1, b.data_ptr(), n2, it.data_ptr() if it is not None else None,
+                                                   ib.data_ptr() if ib is not None else None, int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                   n_bootstrap, boot.data_ptr(), st), "stat_bootstrap")
+        if n1 >= 2 and n2 >= 2 and n_permutations > 0:
+            comb = torch.cat([t, b]).contiguous()
+            pm = torch.as_tensor(np.ascontiguousarray(permutations, np.int32), device=dev) if permutations is not None else None
+            _lib.check(L.synt_stat_permutation_mean_diff(comb.data_ptr(), n1 + n2, n1, pm.data_ptr() if pm is not None else None,
+                                                         (int(seed) + 1) & 0xFFFFFFFFFFFFFFFF, n_permutations, perm.data_ptr(), st),
+                       "stat_permutation")
+            permuted = perm[:n_permutations].cpu().numpy()
+        else:                                                       # XAI.py:1898-1900: too few values for a permutation test
+            permuted = np.array([np.mean(np.asarray(top_k, np.float64)) - np.mean(np.asarray(bottom_k, np.float64))])
+    return boot.cpu().numpy(), permuted
+
+
+def statistical_validation_comprehensive(top_k_shifts, bottom_k_shifts, alpha=ALPHA_LEVEL, n_bootstrap=N_BOOTSTRAP,
+                                         n_permutations=N_PERMUTATIONS, device="cuda", bootstrap_indices=None,
+                                         permutations=None, seed: int = 0):
+    """xai/XAI.py:1708-2005 with the reference's result dictionary.  The bootstrap (1000 resamples) and the permutation test
+    (10000 shuffles) -- the Python loops of the reference -- run on the GPU (``resampled_mean_differences``); the closed-form
+    tests on the few dozen CFI scalars are the reference's own scipy / numpy calls."""
+    from datetime import datetime
+    from scipy import stats
+    top_k = np.array(top_k_shifts, dtype=np.float64)
+    bottom_k = np.array(bottom_k_shifts, dtype=np.float64)
+
+    def describe(data, name):
+        return {"name": name, "n": len(data), "mean": np.mean(data), "median": np.median(data), "std": np.std(data, ddof=1),
+                "var": np.var(data, ddof=1), "min": np.min(data), "max": np.max(data), "q25": np.percentile(data, 25),
+                "q75": np.percentile(data, 75), "iqr": np.percentile(data, 75) - np.percentile(data, 25),
+                "skewness": stats.skew(data), "kurtosis": stats.kurtosis(data)}
+
+    descriptive = {"top_k": describe(top_k, "Top-k"), "bottom_k": describe(bottom_k, "Bottom-k")}
+    parametric, nonparametric = {}, {}
+    t_stat, t_p = stats.ttest_ind(top_k, bottom_k)
+    parametric["t_test"] = {"statistic": t_stat, "p_value": t_p, "significant": t_p < alpha, "description": "Independent samples t-test"}
+    w_stat, w_p = stats.ttest_ind(top_k, bottom_k, equal_var=False)
+    parametric["welch_t_test"] = {"statistic": w_stat, "p_value": w_p, "significant": w_p < alpha,
+                                  "description": "Welch's t-test (unequal variances)"}
+    u_stat, u_p = stats.mannwhitneyu(top_k, bottom_k, alternative="two-sided")
+    nonparametric["mann_whitney_u"] = {"statistic": u_stat, "p_value": u_p, "significant": u_p < alpha, "description": "Mann-Whitney U test"}
+    try:
+        r_stat, r_p = stats.ranksums(top_k, bottom_k)
+        nonparametric["wilcoxon_rank_sum"] = {"statistic": r_stat, "p_value": r_p, "significant": r_p < alpha,
+                                              "description": "Wilcoxon rank-sum test"}
+    except Exception:                                              # noqa: BLE001  (XAI.py:1806-1807)
+        pass
+    n1, n2 = len(top_k), len(bottom_k)
+    pooled = np.sqrt(((n1 - 1) * np.var(top_k, ddof=1) + (n2 - 1) * np.var(bottom_k, ddof=1)) / (n1 + n2 - 2))
+    d = (np.mean(top_k) - np.mean(bottom_k)) / pooled if pooled > 0 else 0
+    interp = "negligible" if abs(d) < 0.2 else "small" if abs(d) < 0.5 else "medium" if abs(d) < 0.8 else "large"
+    effect = {"cohens_d": {"value": d, "interpretation": interp, "description": "Cohen's d (standardized mean difference)"},
+              "glass_delta": {"value": (np.mean(top_k) - np.mean(bottom_k)) / np.std(bottom_k, ddof=1),
+                              "description": "Glass's delta (using control group std)"}}
+    boot, permuted = resampled_mean_differences(top_k, bottom_k, n_bootstrap, n_permutations, device, bootstrap_indices,
+                                                permutations, seed)
+    level = 1 - alpha
+    ci_lo, ci_hi = np.percentile(boot, (1 - level) / 2 * 100), np.percentile(boot, (1 + level) / 2 * 100)
+    bootstrap = {"bootstrap_diffs": boot, "mean_diff": np.mean(boot), "ci_lower": ci_lo, "ci_upper": ci_hi,
+                 "ci_contains_zero": ci_lo <= 0 <= ci_hi, "confidence_level": level}
+    observed = np.mean(top_k) - np.mean(bottom_k)
+    p_perm = np.mean(np.abs(permuted) >= np.abs(observed)) if permuted.size > 1 else 1.0
+    permutation = {"observed_difference": observed, "permuted_differences": permuted, "p_value": p_perm,
+                   "significant": p_perm < alpha, "n_permutations": n_permutations}
+    normality = {}
+    try:
+        if 3 <= n1 <= 5000 and 3 <= n2 <= 5000:
+            st, sb = stats.shapiro(top_k), stats.shapiro(bottom_k)
+            normality["shapiro_wilk"] = {"top_k": {"statistic": st[0], "p_value": st[1], "normal": st[1] > alpha},
+                                         "bottom_k": {"statistic": sb[0], "p_value": sb[1], "normal": sb[1] > alpha}}
+        else:
+            normality["shapiro_wilk"] = {"top_k": {"skipped": True, "reason": "sample_size < 3 or > 5000"},
+                                         "bottom_k": {"skipped": True, "reason": "sample_size < 3 or > 5000"}}
+    except Exception as e:                                         # noqa: BLE001
+        normality["shapiro_wilk"] = {"error": str(e)}
+    # XAI.py:1934-1935 calls kstest(x, 'norm', args=(mean, std)); scipy >= 1.15 rejects that form for the fast normal CDF, the
+    # frozen distribution's cdf is the same test
+    kt = stats.kstest(top_k, stats.norm(loc=np.mean(top_k), scale=np.std(top_k)).cdf)
+    kb = stats.kstest(bottom_k, stats.norm(loc=np.mean(bottom_k), scale=np.std(bottom_k)).cdf)
+    normality["kolmogorov_smirnov"] = {"top_k": {"statistic": kt[0], "p_value": kt[1], "normal": kt[1] > alpha},
+                                       "bottom_k": {"statistic": kb[0], "p_value": kb[1], "normal": kb[1] > alpha}}
+    lev_stat, lev_p = stats.levene(top_k, bottom_k)
+    f_stat = np.var(top_k, ddof=1) / np.var(bottom_k, ddof=1)
+    f_p = 2 * min(stats.f.cdf(f_stat, n1 - 1, n2 - 1), 1 - stats.f.cdf(f_stat, n1 - 1, n2 - 1))
+    variance = {"levene": {"statistic": lev_stat, "p_value": lev_p, "equal_variances": lev_p > alpha,
+                           "description": "Levene's test for equal variances"},
+                "f_test": {"statistic": f_stat, "p_value": f_p, "equal_variances": f_p > alpha,
+                           "description": "F-test for equal variances"}}
+    consensus = {"parametric_significant": any(t["significant"] for t in parametric.values()),
+                 "nonparametric_significant": any(t["significant"] for t in nonparametric.values()),
+                 "bootstrap_significant": not bootstrap["ci_contains_zero"],
+                 "permutation_significant": permutation["significant"]}
+    n_sig = sum(consensus.values())
+    overall = n_sig >= len(consensus) // 2 + 1
+    return {
+        "descriptive_statistics": descriptive, "parametric_tests": parametric, "nonparametric_tests": nonparametric,
+        "effect_sizes": effect, "bootstrap_analysis": bootstrap, "permutation_analysis": permutation,
+        "normality_tests": normality, "variance_tests": variance, "significance_consensus": consensus,
+        "overall_conclusion": {"significant": overall, "significant_tests_count": n_sig, "total_tests_count": len(consensus),
+                               "alpha_level": alpha, "recommendation": "significant" if overall else "not_significant"},
+        "metadata": {"analysis_timestamp": datetime.now().isoformat(), "n_bootstrap_samples": n_bootstrap,
+                     "n_permutations": n_permutations, "alpha_level": alpha},
+    }
+
+
 # ------------------------------------------------------------------ analyzer ------------
 def select_regions_batch(attributions: torch.Tensor, k_percent=TOP_K_PERCENT, region_type: str = "top",
                          morphology_cleanup: bool = True, connectivity: int = 8):
@@ -550,6 +704,23 @@ def select_regions_advanced(attribution_map, k_percent=TOP_K_PERCENT, region_typ
         "metadata": {"region_type": region_type, "morphology_cleanup": morphology_cleanup, "connectivity": connectivity,
                      "original_shape": shape},
     }
+
+
+def _jsonable(o):
+    """Result dictionaries for the JSON side-cars: numpy scalars -> Python scalars, replicate arrays -> their length."""
+    if isinstance(o, dict):
+        return {k: _jsonable(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_jsonable(v) for v in o]
+    if isinstance(o, np.ndarray):
+        return {"n": int(o.size), "mean": float(o.mean()) if o.size else 0.0}
+    if isinstance(o, (np.bool_, bool)):
+        return bool(o)
+    if isinstance(o, np.integer):
+        return int(o)
+    if isinstance(o, np.floating):
+        return float(o)
+    return o
 
 
 class IntegratedXAIAnalyzer:
@@ -624,6 +795,16 @@ class IntegratedXAIAnalyzer:
                     mod = counterfactual_intervention_advanced(frame, mask, it)["modified_image"]
                     r = compute_causal_shift_comprehensive(self.classifier, frame, mod, target, group=self.group)
                     cfi[f"t_{k}/{rname}/{it}"] = r["target_class_analysis"]
+        # stages 4 / 5 of the reference pipeline (XAI.py:3174-3203): top-k against bottom-k CFI shifts over the key frames
+        top_shifts = [v["cfi"] for k, v in cfi.items() if "/top_k/" in k]
+        bot_shifts = [v["cfi"] for k, v in cfi.items() if "/bottom_k/" in k]
+        statistical = None
+        if len(top_shifts) >= 2 and len(bot_shifts) >= 2:
+            try:
+                statistical = _jsonable(statistical_validation_comprehensive(top_shifts, bot_shifts, device=str(self.device),
+                                                                             seed=int(seed) if seed is not None else 0))
+            except Exception as e:                                # noqa: BLE001  (the reference logs and goes on, XAI.py:3217-3219)
+                statistical = {"error": str(e)}
         return {
             "filename": filename, "file_path": str(file_path), "class_name": class_name, "seed": seed,
             "inference_steps": inference_steps, "n_frames": T,
@@ -633,9 +814,10 @@ class IntegratedXAIAnalyzer:
                           "timesteps": [int(t) for t in timesteps]},
             "region_analysis": regions,
             "cfi": cfi,
+            "statistical_validation": statistical,
             "attribution_methods": list(methods),
             "stage1_frames": len(stage1),
-            "skipped_stages": ["grad_cam", "statistics", "plots"],
+            "skipped_stages": ["grad_cam", "plots"],
         }
 
 
