@@ -95,15 +95,18 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
 
-bool pdl_enabled();                                  // SYNT_PDL=1 switches the attribute on (default: plain stream order, which measured faster)
+// SYNT_PDL: 0 = plain stream order, 1 = every kernel of the chain may launch early, 2 = only the GEMM kernels (their prologue --
+// barrier init, TMEM allocation, tensor-map prefetch -- then overlaps the small GroupNorm-finalize kernel in front of them)
+int pdl_mode();
+inline bool pdl_enabled(bool gemm_kernel = false) { const int m = pdl_mode(); return m == 1 || (m == 2 && gemm_kernel); }
 
-template <typename... KArgs, typename... Args>
+template <bool GEMM = false, typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled(GEMM) ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 1;
     SYNT_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
 }

@@ -260,7 +260,7 @@ static void launch_tc(const ConvTcMaps& maps, const ConvTcParams& p, dim3 grid, 
         SYNT_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr = true;
     }
-    launch_pdl(conv_tc_kernel<BN, STAGES>, grid, dim3(TC_THREADS), L::TOTAL, s, maps, p);
+    launch_pdl<true>(conv_tc_kernel<BN, STAGES>, grid, dim3(TC_THREADS), L::TOTAL, s, maps, p);
     SYNT_LAUNCH_CHECK();
 }
 

@@ -659,7 +659,7 @@ static void launch_v2(const V2Maps& maps, const V2Params& p, int grid, bf16* out
         SYNT_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr = true;
     }
-    launch_pdl(conv_tc2_kernel<BN, RES, false>, dim3(grid), dim3(V2_THREADS), L::TOTAL, s, maps, p, out);
+    launch_pdl<true>(conv_tc2_kernel<BN, RES, false>, dim3(grid), dim3(V2_THREADS), L::TOTAL, s, maps, p, out);
 }
 
 static void make_halo_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_h, int box_n) {
