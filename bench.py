@@ -508,7 +508,7 @@ def run_ours(args):
                 "algorithmic": note}
     px = B * 128 * 128
     roofline_hbm = [
-        hbm_entry("conv_in3_tiled_kernel", prof["conv_in"]["ms"], prof["conv_in"]["launches"], px * (3 * 4 + 64 * 2),
+        hbm_entry("conv_in_tc_kernel (tcgen05, hi/lo split operands)", prof["conv_in"]["ms"], prof["conv_in"]["launches"], px * (3 * 4 + 64 * 2),
                   "read x fp32 NCHW (12 B/pixel) + write the 64-channel bf16 NHWC activation (128 B/pixel)"),
         hbm_entry("conv_out3_mma_kernel + DDPMScheduler.step epilogue", prof["conv_out_sched"]["ms"],
                   prof["conv_out_sched"]["launches"], px * (64 * 2 + 3 * 4 + 3 * 4),

@@ -62,6 +62,12 @@ int conv_in3_stats_slots(int H, int W, int dt);
 void conv_in3(const float* x_nchw, const ConvInW& w, int B, int H, int W, void* out, int dt, float2* stats_out,
               cudaStream_t s);
 
+// tcgen05 version (conv_in_tc.cu, bf16 mode, 128x128 images): w_taps from conv_in_tc_pack_weights (device copy), same
+// statistics layout as conv_in3 ([B][16][64] partial rows, one per 8-row band)
+void conv_in_tc(const float* x_nchw, int B, const void* w_taps, const float* bias, void* out, float2* stats, cudaStream_t s);
+void conv_in_tc_pack_weights(const ConvInW& w, uint16_t* out);
+int conv_in_tc_weight_bytes();
+
 // UNet tail: eps = conv_out(SiLU(GN(h))) fused with DDPMScheduler.step.
 struct ConvOutW { float w[9][64][3]; float b[3]; };
 struct SchedArgs {

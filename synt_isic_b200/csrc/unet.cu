@@ -200,6 +200,7 @@ struct synt_unet {
     bool fuse_gn = true;                          // GroupNorm(+SiLU) applied inside conv_tc2 (no normalised tensor in HBM)
     bool fuse_up = true;                          // Upsample2D folded into its conv (sub-pixel phases)
     ConvInW conv_in_w;
+    DevPtr conv_in_taps, conv_in_bias;            // conv_in as nine tcgen05 tap tiles (bf16 mode; SYNT_CONV_IN_TC=0: the FMA kernel)
     ConvOutW conv_out_w;
     DevPtr norm_out_g, norm_out_b;
     DevPtr conv_out_frag;                         // conv_out weights as mma.sync B fragments (bf16 mode)
@@ -326,6 +327,13 @@ static void build_unet(synt_unet* u, const float* P) {
             for (int c = 0; c < 64; ++c)
                 for (int t = 0; t < 9; ++t) u->conv_out_w.w[t][c][n] = wo[((size_t)n * 64 + c) * 9 + t];
         memcpy(u->conv_out_w.b, P + m.find("conv_out.bias"), 3 * 4);
+        const char* cit = getenv("SYNT_CONV_IN_TC");
+        if (b16 && !(cit && cit[0] == '0')) {
+            std::vector<uint16_t> taps((size_t)conv_in_tc_weight_bytes() / 2);
+            conv_in_tc_pack_weights(u->conv_in_w, taps.data());
+            u->conv_in_taps = dev_upload(taps.data(), taps.size() * 2);
+            u->conv_in_bias = dev_upload(u->conv_in_w.b, 64 * 4);
+        }
         if (b16) {                                          // B fragments of mma.sync.m16n8k16 (see kernels.cuh)
             std::vector<uint32_t> fr((size_t)36 * 32 * 2);
             auto wv = [&](int tap, int c, int n) -> uint32_t { return n < 3 ? f2bf(wo[((size_t)n * 64 + c) * 9 + tap]) : 0u; };
@@ -611,7 +619,13 @@ struct Fwd {
             h.stats_slots = in_slots;
             h.stats = (float2*)pool->alloc((size_t)B * in_slots * 64 * sizeof(float2));
         }
-        { ProfScope ps(u, s, PC_CONV_IN, 2.0 * B * kImg * kImg * 64.0 * 27); conv_in3(x_nchw, u->conv_in_w, B, kImg, kImg, h.p, u->dt, h.stats, s); }
+        {
+            ProfScope ps(u, s, PC_CONV_IN, 2.0 * B * kImg * kImg * 64.0 * 27);
+            if (u->conv_in_taps && in_slots == 16)
+                conv_in_tc(x_nchw, B, u->conv_in_taps->p, (const float*)u->conv_in_bias->p, h.p, h.stats, s);
+            else
+                conv_in3(x_nchw, u->conv_in_w, B, kImg, kImg, h.p, u->dt, h.stats, s);
+        }
         ++u->launches;
         if (in_slots == 0) standalone_stats(h);
         tap("conv_in", h);

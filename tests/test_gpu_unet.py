@@ -103,6 +103,28 @@ def test_intermediate_modules(oracle, models, cuda_dev, prec):
         assert rel(got, cap[t]) < 1e-5, t
 
 
+def test_conv_in_on_the_tensor_path(oracle, models, cuda_dev, monkeypatch):
+    """conv_in of the bf16 mode runs on tcgen05 with a hi/lo split of x and of the weights (conv_in_tc.cu): its output equals
+    the oracle's fp32 conv up to the bf16 rounding of the stored activation (<= 2^-9 per element), ragged batch, x_t-like and
+    image-like value ranges, and agrees with the FMA kernel it replaces (SYNT_CONV_IN_TC=0) to the same rounding."""
+    g = torch.Generator().manual_seed(21)
+    x = torch.cat([torch.randn(3, 3, 128, 128, generator=g) * 1.7, torch.tanh(torch.randn(2, 3, 128, 128, generator=g))])
+    with torch.no_grad():
+        ref = oracle.conv_in(x)
+    got = models["bf16"].debug_tap(x.to(cuda_dev), 10, "conv_in").cpu()
+    assert got.shape == ref.shape
+    assert rel(got, ref) < 3e-3
+    # every element within one bf16 rounding of the stored value + the dropped xl*wl products (2^-16 of sum |x||w| ~ 4)
+    assert ((got - ref).abs() <= 2.0 ** -8 * ref.abs() + 2e-4).all()
+    monkeypatch.setenv("SYNT_CONV_IN_TC", "0")
+    fma = UNet2DModel(precision="bf16", **SUPPORTED_CONFIG)
+    fma.load_state_dict(oracle.state_dict(), strict=True)
+    old = fma.to(cuda_dev).debug_tap(x.to(cuda_dev), 10, "conv_in").cpu()
+    monkeypatch.delenv("SYNT_CONV_IN_TC")
+    assert (old != got).float().mean().item() < 0.02                        # rare one-ulp bf16 flips only
+    assert rel(old, got) < 1e-3
+
+
 def test_scheduler_step_matches_oracle(cuda_dev):
     s, o = DDPMScheduler(beta_schedule="squaredcos_cap_v2"), DDPMSchedulerOracle()
     s.set_timesteps(50)
