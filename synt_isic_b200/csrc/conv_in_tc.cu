@@ -40,7 +40,8 @@ constexpr int CIT_OFF_W = CIT_PATCH_BYTES;
 constexpr int CIT_OFF_STAGE = CIT_OFF_W + CIT_W_BYTES;
 constexpr int CIT_OFF_BIAS = CIT_OFF_STAGE + CIT_ROUND * CIT_STAGE_BYTES;
 constexpr int CIT_OFF_RED = CIT_OFF_BIAS + 256;            // [12 warps... 4 pixel quarters x 3 tiles][64] float2 statistics scratch
-constexpr int CIT_OFF_BAR = CIT_OFF_RED + 12 * 64 * 8;
+constexpr int CIT_OFF_ROWPIX = CIT_OFF_RED + 12 * 64 * 8;  // [3 tiles][128 rows] output pixel of a staged row (or -1)
+constexpr int CIT_OFF_BAR = CIT_OFF_ROWPIX + CIT_ROUND * 128 * 4;
 constexpr int CIT_SMEM = CIT_OFF_BAR + 64;
 constexpr int CIT_IN_PER_THREAD = (3 * CIT_PH * CIT_PW + CIT_THREADS - 1) / CIT_THREADS;   // 11 raw input values per thread
 static_assert(CIT_TILES == 9 && CIT_TILES % CIT_ROUND == 0, "tile rounds");
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(CIT_THREADS, 2) conv_in_tc_kernel(const float*
     uint8_t* stage = cit_smem + CIT_OFF_STAGE;
     float* bias_s = reinterpret_cast<float*>(cit_smem + CIT_OFF_BIAS);
     float2* red = reinterpret_cast<float2*>(cit_smem + CIT_OFF_RED);
+    int* row_pix = reinterpret_cast<int*>(cit_smem + CIT_OFF_ROWPIX);
     uint64_t* mma_bar = reinterpret_cast<uint64_t*>(cit_smem + CIT_OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,6 +153,11 @@ __global__ void __launch_bounds__(CIT_THREADS, 2) conv_in_tc_kernel(const float*
             {
                 const int t = warp >> 2, quarter = warp & 3, r = quarter * 32 + lane;
                 uint8_t* dst = stage + t * CIT_STAGE_BYTES + r * CIT_STAGE_PITCH;
+                // rows that are no output pixel (the two wrap-around columns of a patch row, the tail of the last tile) are
+                // staged as zeros -- they drop out of the statistics -- and marked -1 in the row table of the copy-out
+                const int i = (rd * CIT_ROUND + t) * 128 + r, orow = i / CIT_PW, ocol = i - orow * CIT_PW;
+                const bool valid = orow < CIT_ROWS && ocol < CIT_W;
+                row_pix[t * 128 + r] = valid ? orow * 128 + ocol : -1;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v[32];
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(CIT_THREADS, 2) conv_in_tc_kernel(const float*
                             h2[j] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * j]) + bias_s[ch],
                                                           __uint_as_float(v[g * 8 + 2 * j + 1]) + bias_s[ch + 1]);
                         }
-                        *reinterpret_cast<uint4*>(dst + half * 64 + g * 16) = pk;
+                        *reinterpret_cast<uint4*>(dst + half * 64 + g * 16) = valid ? pk : make_uint4(0u, 0u, 0u, 0u);
                     }
                 }
             }
@@ -175,24 +182,20 @@ __global__ void __launch_bounds__(CIT_THREADS, 2) conv_in_tc_kernel(const float*
             // ---- D: statistics of the staged bf16 values (valid pixels only) and coalesced stores
             {
                 const uint8_t* src = stage + st_tile * CIT_STAGE_BYTES;
-                const int base = (rd * CIT_ROUND + st_tile) * 128;        // patch-linear index of the tile's row 0
-#pragma unroll 4
+#pragma unroll 8
                 for (int k = 0; k < 32; ++k) {
-                    const int r = st_q * 32 + k, i = base + r;
-                    const int orow = i / CIT_PW, ocol = i - orow * CIT_PW;
-                    if (orow < CIT_ROWS && ocol < CIT_W) {
-                        const uint32_t u = *reinterpret_cast<const uint32_t*>(src + r * CIT_STAGE_PITCH + lane * 4);
-                        const float v0 = __uint_as_float(u << 16), v1 = __uint_as_float(u & 0xffff0000u);
-                        acc[0] += v0; acc[1] = fmaf(v0, v0, acc[1]); acc[2] += v1; acc[3] = fmaf(v1, v1, acc[3]);
-                    }
+                    const uint32_t u = *reinterpret_cast<const uint32_t*>(src + (st_q * 32 + k) * CIT_STAGE_PITCH + lane * 4);
+                    const float v0 = __uint_as_float(u << 16), v1 = __uint_as_float(u & 0xffff0000u);
+                    acc[0] += v0; acc[1] = fmaf(v0, v0, acc[1]); acc[2] += v1; acc[3] = fmaf(v1, v1, acc[3]);
                 }
                 const int tt = threadIdx.x & 127;                         // copy-out: 4 warps per tile, 8 chunks of 16 B per pixel
+                bf16* band_out = out + ((size_t)b * 128 + oy0) * 128 * 64;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const int q = k * 128 + tt, r = q >> 3, chunk = q & 7, i = base + r;
-                    const int orow = i / CIT_PW, ocol = i - orow * CIT_PW;
-                    if (orow < CIT_ROWS && ocol < CIT_W)
-                        *reinterpret_cast<uint4*>(out + ((((size_t)b * 128 + oy0 + orow) * 128 + ocol) * 64 + chunk * 8)) =
+                    const int q = k * 128 + tt, r = q >> 3, chunk = q & 7;
+                    const int pix = row_pix[st_tile * 128 + r];
+                    if (pix >= 0)
+                        *reinterpret_cast<uint4*>(band_out + (size_t)pix * 64 + chunk * 8) =
                             *reinterpret_cast<const uint4*>(src + r * CIT_STAGE_PITCH + chunk * 16);
                 }
             }
