@@ -23,10 +23,16 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 CFLAGS += os.environ.get("SYNT_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DSYNT_ATT_TIMELINE_BUILD for tools/att_timeline.py
+# SYNT_EXPERIMENTS=1: the measurement scaffolding (role knock-outs of conv_tc2, the halo-descriptor experiment kernel) is
+# compiled in; the product build carries none of it
+EXPERIMENTS = os.environ.get("SYNT_EXPERIMENTS", "0") == "1"
+if EXPERIMENTS:
+    CFLAGS.append("-DSYNT_EXPERIMENTS")
+EXPERIMENT_SOURCES = {"conv_tc_halo.cu"}
 
 
 def _sources():
-    return sorted(CSRC.glob("*.cu"))
+    return sorted(p for p in CSRC.glob("*.cu") if EXPERIMENTS or p.name not in EXPERIMENT_SOURCES)
 
 
 def _fingerprint() -> str:

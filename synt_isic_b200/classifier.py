@@ -91,6 +91,14 @@ class MelanomaClassifierAdaptive(nn.Module):
         self._handles[self.precision] = (h, key)
         return h
 
+    def refresh_weights(self):
+        """Rebuilds the folded native weights on the next call.  In-place edits through ``param.data`` bump neither
+        ``data_ptr`` nor ``_version`` and are NOT detected automatically (edits through the parameter or buffer itself are:
+        the reference's sanity check, XAI.py:2055-2059, mutates ``param`` under ``no_grad``)."""
+        for h, _ in self._handles.values():
+            _lib.lib().synt_resnet18_destroy(h)
+        self._handles = {}
+
     def __del__(self):
         try:
             for h, _ in self._handles.values():

@@ -562,11 +562,7 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
     }
     static const int poly = [] { const char* e = getenv("SYNT_ATT_POLY"); const int v = e ? atoi(e) : ATC_POLY_DEFAULT; return v < 0 ? 0 : (v > 3 ? 3 : v); }();
     auto kern = poly == 0 ? attention_tc_kernel<0> : poly == 1 ? attention_tc_kernel<1> : poly == 2 ? attention_tc_kernel<2> : attention_tc_kernel<3>;
-    static bool attr = false;
-    if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
-        attr = true;
-    }
+    ensure_dynamic_smem((const void*)(kern), ATC_SMEM);
     static const int num_sms = [] { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
     const int n_items = (N / 128) * (C / 32) * B;            // 128 queries x 4 heads of one image each
     const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;     // persistent: two resident CTAs per SM

@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <string>
 #include <stdexcept>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace synt {
 
@@ -83,6 +86,19 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: set it once per (kernel, device), so that
+// a second GPU used from the same process gets it too
+inline void ensure_dynamic_smem(const void* kern, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    SYNT_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({kern, dev})) return;
+    SYNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert({kern, dev});
+}
 
 // ---- programmatic dependent launch (PDL) ----------------------------------------------
 // The ~140 kernels of one sampling step form a chain.  Launched with the programmatic-stream-serialization attribute,

@@ -239,11 +239,7 @@ void conv_in_tc_pack_weights(const ConvInW& w, uint16_t* out /* CIT_W_BYTES / 2 
 int conv_in_tc_weight_bytes() { return CIT_W_BYTES; }
 
 void conv_in_tc(const float* x_nchw, int B, const void* w_taps, const float* bias, void* out, float2* stats, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CIT_SMEM));
-        attr = true;
-    }
+    ensure_dynamic_smem((const void*)(conv_in_tc_kernel), CIT_SMEM);
     static const int num_sms = [] { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
     const int n_items = B * 16;
     const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;

@@ -255,11 +255,7 @@ static void pick_tile(int Ho, int Wo, int& TW, int& TH, int& TN) {
 template <int BN, int STAGES>
 static void launch_tc(const ConvTcMaps& maps, const ConvTcParams& p, dim3 grid, cudaStream_t s) {
     using L = TcSmem<BN, STAGES>;
-    static bool attr = false;
-    if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr = true;
-    }
+    ensure_dynamic_smem((const void*)(conv_tc_kernel<BN, STAGES>), L::TOTAL);
     launch_pdl<true>(conv_tc_kernel<BN, STAGES>, grid, dim3(TC_THREADS), L::TOTAL, s, maps, p);
     SYNT_LAUNCH_CHECK();
 }

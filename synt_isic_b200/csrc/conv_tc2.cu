@@ -67,6 +67,14 @@ struct V2Smem {
     static_assert(NBUF * V2_MT * BN <= 512, "TMEM columns");
 };
 
+// Role knock-outs (profiles/r01c_experiments.md): compiled only with -DSYNT_EXPERIMENTS (SYNT_EXPERIMENTS=1 python -m
+// synt_isic_b200.build); the product kernel carries no run-time experiment tests.
+#ifdef SYNT_EXPERIMENTS
+#define V2_EXP(mask) ((p.exp_nob & (mask)) != 0)
+#else
+#define V2_EXP(mask) (false)
+#endif
+
 struct V2Maps { CUtensorMap a[4]; CUtensorMap b; CUtensorMap out[4]; CUtensorMap res; };   // a[i]: source of segment i; out[phase]
 // A K segment = one source tensor: `chunks` 64-channel blocks x `taps` (9 = 3x3 window, 1 = centre tap);
 // weight K block of (tap, chunk) = kb_base + tap*kb_stride + chunk; xform: 0 raw, 1 GroupNorm affine,
@@ -187,20 +195,20 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         if (elect_one()) {
             // ===================== TMA producer =====================
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
-            if (RES && !(p.exp_nob & 64)) {                           // whole weight matrix, once (n_ntiles == 1)
+            if (RES && !V2_EXP(64)) {                           // whole weight matrix, once (n_ntiles == 1)
                 int nkb = 0;
                 for (int sg = 0; sg < p.n_seg; ++sg) nkb += p.seg[sg].chunks * p.seg[sg].taps;
                 mbar_arrive_expect_tx(&b_full[0], nkb * L::B_TILE);
                 for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d(smem + L::OFF_B + kb * L::B_TILE, &maps.b, &b_full[0], kb * 64, 0);
             }
-            for (int it = 0, w; (w = v2_item(p, it)) >= 0 && !(p.exp_nob & 64); ++it) {
+            for (int it = 0, w; (w = v2_item(p, it)) >= 0 && !V2_EXP(64); ++it) {
                 const V2Work wk = v2_decode(p, w);
                 for (int sg = 0; sg < p.n_seg; ++sg) {
                     const V2Seg sp = p.seg[sg];
                     for (int ch = 0; ch < sp.chunks; ++ch) {
                         mbar_wait(&a_empty[as], aph ^ 1u);
-                        if ((p.exp_nob & 16) && (it > 0 || aph)) { mbar_arrive(&a_full[as]); }
+                        if (V2_EXP(16) && (it > 0 || aph)) { mbar_arrive(&a_full[as]); }
                         else {
                             mbar_arrive_expect_tx(&a_full[as], a_bytes);
                             tma_load_4d(smem + as * L::A_SLOT, &maps.a[sg], &a_full[as], ch * 64, wk.x0 - 1, wk.y0 - 1, wk.n0);
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         for (int tap = 0; tap < sp.taps && !RES; ++tap) {
                             const int kb = sp.kb_base + tap * sp.kb_stride + ch;
                             mbar_wait(&b_empty[bs], bph ^ 1u);
-                            if ((p.exp_nob & 1) && (it > 0 || bph)) { mbar_arrive(&b_full[bs]); }
+                            if (V2_EXP(1) && (it > 0 || bph)) { mbar_arrive(&b_full[bs]); }
                             else if (PAIR) {                             // this CTA's half of the weight tile (maps.b box: BN/2 rows)
                                 mbar_arrive_expect_tx(&b_full[bs], L::B_TILE / 2);
                                 tma_load_2d(smem + L::OFF_B + bs * L::B_TILE, &maps.b, &b_full[bs], kb * 64,
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
                     mbar_wait(&t_empty[tb], tph ^ 1u);
                     mbar_arrive_remote(&pt_empty[tb], 0);
-                    for (int sg = 0; sg < p.n_seg && !(p.exp_nob & 64); ++sg) {
+                    for (int sg = 0; sg < p.n_seg && !V2_EXP(64); ++sg) {
                         const V2Seg sp = p.seg[sg];
                         for (int ch = 0; ch < sp.chunks; ++ch) {
                             mbar_wait(&a_ready[as], aph);
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             };
             auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int tb = 0; uint32_t tph = 0;
-            if (RES && !(p.exp_nob & 64)) mbar_wait(&b_full[0], 0);
+            if (RES && !V2_EXP(64)) mbar_wait(&b_full[0], 0);
             for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
                 const V2Work wk = v2_decode(p, w);
                 mbar_wait(&t_empty[tb], tph ^ 1u);                    // epilogue drained this accumulator pair
@@ -266,8 +274,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 for (int sg = 0; sg < p.n_seg; ++sg) {
                     const V2Seg sp = p.seg[sg];
                     for (int ch = 0; ch < sp.chunks; ++ch) {
-                        if (!(p.exp_nob & 64)) mbar_wait(&a_ready[as], aph);   // landed AND transformed
-                        if (PAIR && !(p.exp_nob & 64)) mbar_wait_cluster(&pa_ready[as], aph);
+                        if (!V2_EXP(64)) mbar_wait(&a_ready[as], aph);   // landed AND transformed
+                        if (PAIR && !V2_EXP(64)) mbar_wait_cluster(&pa_ready[as], aph);
                         tc_fence_after();
                         const uint32_t a_base = smem_u32(smem + as * L::A_SLOT);
                         for (int tap = 0; tap < sp.taps; ++tap) {
@@ -276,7 +284,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                             const int dy = sp.taps == 9 ? tap / 3 : (sp.taps == 4 ? (wk.phase >> 1) + (tap >> 1) : 1);
                             const int dx = sp.taps == 9 ? tap % 3 : (sp.taps == 4 ? (wk.phase & 1) + (tap & 1) : 1);
                             if (RES) bs = sp.kb_base + tap * sp.kb_stride + ch;
-                            else if (!(p.exp_nob & 64)) {
+                            else if (!V2_EXP(64)) {
                                 mbar_wait(&b_full[bs], bph);
                                 if (PAIR) mbar_wait_cluster(&pb_full[bs], bph);   // (skipped with the b_full wait under mask 64)
                                 tc_fence_after();
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         const int hy0 = r0 / 10, hx0 = r0 - hy0 * 10;                    // halo coordinates of the first row (10 pixels per halo row)
         constexpr int RSTEP = V2_XF_THREADS / 8;                         // rows advance by 32 = 3 halo rows + 2 pixels
         int as = 0; uint32_t aph = 0;
-        for (int it = 0, w; (w = v2_item(p, it)) >= 0 && !(p.exp_nob & 64); ++it) {
+        for (int it = 0, w; (w = v2_item(p, it)) >= 0 && !V2_EXP(64); ++it) {
             const V2Work wk = v2_decode(p, w);
             for (int sg = 0; sg < p.n_seg; ++sg) {
                 const V2Seg sp = p.seg[sg];
@@ -332,7 +340,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                     };
                     if (sp.xform) load_ss(0);
                     mbar_wait(&a_full[as], aph);
-                    if (sp.xform && !(p.exp_nob & 2)) {
+                    if (sp.xform && !V2_EXP(2)) {
                         uint8_t* slot = smem + as * L::A_SLOT;
                         auto run = [&](auto silu_tag) {
                             constexpr bool SILU = decltype(silu_tag)::value;
@@ -437,7 +445,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 wg_sync();                                           // staging free (leader waited for the previous store), bias visible
 #pragma unroll
                 for (int c0 = 0; c0 < EC; c0 += 32) {
-                    if (p.exp_nob & 32) break;
+                    if (V2_EXP(32)) break;
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tb * V2_MT + e) * BN + cb + c0), v);
                     tmem_ld_wait();
@@ -478,7 +486,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 }
                 fence_proxy_async();
                 wg_sync();
-                if (lead_warp && valid && !(p.exp_nob & 8)) {
+                if (lead_warp && valid && !V2_EXP(8)) {
                     if (elect_one()) {
 #pragma unroll
                         for (int j = 0; j < EC / 64; ++j)
@@ -486,7 +494,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         tma_store_commit();
                     }
                 }
-                if (p.stats && !(p.exp_nob & 4)) {
+                if (p.stats && !V2_EXP(4)) {
                     // fused GroupNorm statistics: per-channel (sum, sumsq) of the bf16 values just staged.  Warp q of the
                     // warpgroup owns EC/4 columns; lane = (column quad cq, row part rp): 8-byte loads of 4 columns, the row
                     // parts interleaved so that the lanes of one load phase hit distinct banks of the swizzled tile; the
@@ -637,11 +645,7 @@ int conv_tc2_stats_slots(const ConvArgs& a) {
 static void launch_v2_pair(const V2Maps& maps, const V2Params& p, int grid, bf16* out, cudaStream_t s) {
     using L = V2Smem<128, false>;
     auto kern = conv_tc2_kernel<128, false, true>;
-    static bool attr = false;
-    if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr = true;
-    }
+    ensure_dynamic_smem((const void*)(kern), L::TOTAL);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -654,11 +658,7 @@ static void launch_v2_pair(const V2Maps& maps, const V2Params& p, int grid, bf16
 template <int BN, bool RES>
 static void launch_v2(const V2Maps& maps, const V2Params& p, int grid, bf16* out, cudaStream_t s) {
     using L = V2Smem<BN, RES>;
-    static bool attr = false;
-    if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr = true;
-    }
+    ensure_dynamic_smem((const void*)(conv_tc2_kernel<BN, RES>), L::TOTAL);
     launch_pdl<true>(conv_tc2_kernel<BN, RES, false>, dim3(grid), dim3(V2_THREADS), L::TOTAL, s, maps, p, out);
 }
 
@@ -709,7 +709,9 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     p.bias = a.bias; p.bias2 = a.bias2; p.has_res = a.residual != nullptr; p.relu = a.relu;
     p.stats = a.stats_out; p.stats_slots = conv_tc2_stats_slots(a);
     p.chunk = v2_chunk(a, BN);
+#ifdef SYNT_EXPERIMENTS
     { static const char* e = getenv("SYNT_EXP_NOB"); p.exp_nob = e ? atoi(e) : 0; }
+#endif
     V2Maps maps;
     const int bh = v2_two_img(a) ? 18 : 34, bn = v2_two_img(a) ? 2 : 1;
     for (int i = 0; i < 4; ++i) {

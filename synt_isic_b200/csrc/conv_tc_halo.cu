@@ -180,11 +180,7 @@ void conv_tc_halo(const ConvArgs& a, int variant, cudaStream_t s) {
         cuuint32_t box[2] = {64, HL_BN};
         encode_bf16_sw128(&maps.b, a.weight, 2, dims, strides, box, "halo weight");
     }
-    static bool attr = false;
-    if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM));
-        attr = true;
-    }
+    ensure_dynamic_smem((const void*)(conv_halo_kernel), HL_SMEM);
     dim3 grid(a.B * p.tiles_x * p.tiles_y, a.Cout / HL_BN);
     conv_halo_kernel<<<grid, HL_THREADS, HL_SMEM, s>>>(maps, p);
     SYNT_LAUNCH_CHECK();

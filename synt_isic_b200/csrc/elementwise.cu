@@ -743,13 +743,9 @@ __global__ void __launch_bounds__(256) conv_out3_mma_kernel(const bf16* __restri
 void conv_out3(const void* h, int dt, const float2* scale_shift, const ConvOutW& w, const void* bfrag, int B, int H, int W,
                float* eps_nchw, const SchedArgs& sch, cudaStream_t s) {
     dim3 grid(ceil_div(W, CO_TILE), ceil_div(H, CO_TILE), B);
-    static bool attr_set = false;
-    if (!attr_set) {
-        SYNT_CUDA(cudaFuncSetAttribute(conv_out3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, CO_SMEM_BYTES));
-        SYNT_CUDA(cudaFuncSetAttribute(conv_out3_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CO_SMEM_BYTES));
-        SYNT_CUDA(cudaFuncSetAttribute(conv_out3_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COT_SMEM_BYTES));
-        attr_set = true;
-    }
+    ensure_dynamic_smem((const void*)(conv_out3_kernel<float>), CO_SMEM_BYTES);
+    ensure_dynamic_smem((const void*)(conv_out3_kernel<bf16>), CO_SMEM_BYTES);
+    ensure_dynamic_smem((const void*)(conv_out3_mma_kernel), COT_SMEM_BYTES);
     if (dt == DT_F32)
         conv_out3_kernel<float><<<grid, 256, CO_SMEM_BYTES, s>>>((const float*)h, scale_shift, w, B, H, W, eps_nchw, sch);
     else if (bfrag)

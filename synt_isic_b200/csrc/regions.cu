@@ -194,11 +194,7 @@ void select_regions(const float* attr, int n_maps, int C, int H, int W, int use_
     SYNT_CHECK(C >= 1, "select_regions: C >= 1");
     SYNT_CHECK(connectivity == 4 || connectivity == 8, "select_regions: connectivity 4 or 8");
     SYNT_CHECK(q_percent >= 0.0 && q_percent <= 100.0, "select_regions: percentile outside [0, 100]");
-    static bool attr_set = false;
-    if (!attr_set) {
-        SYNT_CUDA(cudaFuncSetAttribute(select_regions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_SMEM));
-        attr_set = true;
-    }
+    ensure_dynamic_smem((const void*)(select_regions_kernel), RG_SMEM);
     select_regions_kernel<<<n_maps, RG_THREADS, RG_SMEM, s>>>(attr, C, H, W, use_abs, q_percent, bottom, morphology,
                                                               connectivity == 4, mask, stats);
     SYNT_LAUNCH_CHECK();

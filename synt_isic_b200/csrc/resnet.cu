@@ -169,11 +169,7 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const bf16* __restrict__ 
     }
 }
 void stem_mma(const void* pre, int B, const void* bfrag, const float* bias, void* out, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(stem_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-        attr = true;
-    }
+    ensure_dynamic_smem((const void*)(stem_mma_kernel), ST_SMEM);
     stem_mma_kernel<<<dim3(112 / ST_TILE, 112 / ST_TILE, B), 256, ST_SMEM, s>>>((const bf16*)pre, (const uint2*)bfrag, bias, (bf16*)out);
     SYNT_LAUNCH_CHECK();
 }
@@ -290,11 +286,7 @@ __global__ void __launch_bounds__(320, 2) stem_fused_kernel(const float* __restr
     }
 }
 void stem_fused(const float* x_nchw, int B, const void* bfrag, const float* bias, void* out, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
-        attr = true;
-    }
+    ensure_dynamic_smem((const void*)(stem_fused_kernel), SF_SMEM);
     stem_fused_kernel<<<dim3(56 / SF_POOL, 56 / SF_POOL, B), 320, SF_SMEM, s>>>(x_nchw, (const uint2*)bfrag, bias, (bf16*)out);
     SYNT_LAUNCH_CHECK();
 }

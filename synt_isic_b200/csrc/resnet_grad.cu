@@ -379,11 +379,7 @@ __global__ void __launch_bounds__(256, 2) stem_dgrad_tiled_kernel(const bf16* __
 void stem_dgrad(const void* g, int dt, int B, const float* w, float* dpre, cudaStream_t s) {
     static const bool tiled = [] { const char* e = getenv("SYNT_STEM_DGRAD_TILED"); return !(e && e[0] == '0'); }();
     if (dt == DT_BF16 && tiled) {
-        static bool attr = false;
-        if (!attr) {
-            SYNT_CUDA(cudaFuncSetAttribute(stem_dgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDT_SMEM));
-            attr = true;
-        }
+        ensure_dynamic_smem((const void*)(stem_dgrad_tiled_kernel), SDT_SMEM);
         stem_dgrad_tiled_kernel<<<dim3(49, B), 256, SDT_SMEM, s>>>((const bf16*)g, w, dpre);
         SYNT_LAUNCH_CHECK();
         return;

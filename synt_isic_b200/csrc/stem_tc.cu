@@ -275,11 +275,7 @@ void stem_tc_pack_weights(const uint16_t* w_k192 /* [64][192] */, uint16_t* out 
 int stem_tc_weight_bytes() { return STC_W_BYTES; }
 
 void stem_tc(const float* x_nchw, int B, const void* w_taps, const float* bias, void* out, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        SYNT_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STC_SMEM));
-        attr = true;
-    }
+    ensure_dynamic_smem((const void*)(stem_tc_kernel), STC_SMEM);
     static const int num_sms = [] { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
     const int n_items = B * 49;
     const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;

@@ -1040,8 +1040,12 @@ extern "C" int synt_debug_conv(int use_tc, int act_dtype, const void* in, int B,
         SYNT_CHECK(act_dtype == DT_BF16 && conv_tc2_supported(a), "conv_tc2: unsupported");
         conv_tc2(a, (cudaStream_t)stream);
     } else if (use_tc >= 2) {
+#ifdef SYNT_EXPERIMENTS
         SYNT_CHECK(act_dtype == DT_BF16, "tcgen05 conv needs bf16 activations");
         conv_tc_halo(a, use_tc - 2, (cudaStream_t)stream);
+#else
+        throw Error(-3, "the halo-descriptor experiments (tools/exp_halo.py) need a build with SYNT_EXPERIMENTS=1");
+#endif
     } else if (use_tc) {
         SYNT_CHECK(act_dtype == DT_BF16, "tcgen05 conv needs bf16 activations");
         conv_tc(a, (cudaStream_t)stream);

@@ -136,9 +136,10 @@ class DDPMScheduler:
                                                             dtype=eps.dtype)
             z = z.contiguous().float()
         out = torch.empty_like(x)
-        _lib.check(_lib.lib().synt_ddpm_step(eps.data_ptr(), x.data_ptr(), z.data_ptr() if z is not None else None,
-                                             out.data_ptr(), x.numel(), c.ctypes.data_as(_lib.c_f32p),
-                                             _lib.current_stream_ptr()), "ddpm_step")
+        with torch.cuda.device(x.device):                       # the tensor's device, not whichever happens to be current
+            _lib.check(_lib.lib().synt_ddpm_step(eps.data_ptr(), x.data_ptr(), z.data_ptr() if z is not None else None,
+                                                 out.data_ptr(), x.numel(), c.ctypes.data_as(_lib.c_f32p),
+                                                 _lib.current_stream_ptr()), "ddpm_step")
         if not return_dict:
             return (out,)
         return DDPMSchedulerOutput(prev_sample=out)

@@ -120,6 +120,15 @@ class UNet2DModel(nn.Module):
     def _version_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
+    def refresh_weights(self):
+        """Rebuilds the native weights on the next call.  In-place edits through ``param.data`` (``.data.mul_()``,
+        ``.data.copy_()``) bump neither ``data_ptr`` nor ``_version`` and are therefore NOT detected automatically; edits
+        through the parameter itself (``load_state_dict``, ``param.mul_()`` under ``no_grad``) are."""
+        for h, _ in self._handles.values():
+            _lib.lib().synt_unet_destroy(h)
+        self._handles = {}
+        self._schedule_key = None
+
     def _packed_params(self) -> np.ndarray:
         sd = self.state_dict()
         total = self._manifest[-1][2] + self._manifest[-1][1]
