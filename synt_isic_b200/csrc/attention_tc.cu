@@ -57,6 +57,27 @@ constexpr uint32_t ATC_O_COL = 192;
 constexpr int ATC_POLY_DEFAULT = 1;                    // exponentials per 4 pairs on the FMA pipe (SYNT_ATT_POLY overrides)
 constexpr float ATC_LAZY = 8.0f;                       // rescale only when the max grows by more than 2^8
 static_assert(2 * (ATC_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit in shared memory");
+// Measurement knock-outs (tools/ubench/att_knock.cu compiles this file with -DATC_KNOCK=<mask>; wrong results, timing only):
+// 1 exponentials -> one multiply, 2 no P-tile stores, 4 no P.V MMAs, 8 no S MMAs, 16 no V^T builder stores, 32 no exact
+// first-chunk maximum, 64 softmax warps do not wait for S tiles (and never rescale), 128 nor for free P tiles.  The product build has ATC_KNOCK == 0 and carries none of it.
+#ifndef ATC_KNOCK
+#define ATC_KNOCK 0
+#endif
+// nanosleep per retry in the waits of the roles that have ring slack (ns): A = TMA producer / V^T builder waiting for a free
+// K/V stage (3 chunks = 12 units of slack), B = P.V issuer waiting for a P tile, C = S issuer waiting for a free S buffer
+#ifndef ATC_REGS_ROLE
+#define ATC_REGS_ROLE 56
+#define ATC_REGS_SOFTMAX 88
+#endif
+#ifndef ATC_SLEEP_A
+#define ATC_SLEEP_A 0
+#endif
+#ifndef ATC_SLEEP_B
+#define ATC_SLEEP_B 0
+#endif
+#ifndef ATC_SLEEP_C
+#define ATC_SLEEP_C 0
+#endif
 
 struct AttnTcMaps { CUtensorMap k; };
 
@@ -85,6 +106,39 @@ __device__ __forceinline__ float ex2_poly(float x) {
 // minimax) made the kernel 10% SLOWER (4.09 -> 4.50 ms/step): the softmax warps are issue/FMA-pipe limited
 // next to the MUFU pipe, and packed ex2.approx.{f16,bf16}x2 lowers to two MUFU ops on sm_100a.  All
 // exponentials therefore stay on MUFU.EX2.
+// Packed fp32x2 arithmetic (sm_100: add / mul / fma .f32x2 on 64-bit register pairs): one issue slot for two elements.  The
+// softmax warps are bound by instruction issue next to the MUFU pipe (ncu: issue active 72%, XU 59%), so the subtraction of
+// the reference and the whole polynomial run on pairs.
+#ifndef ATC_PACKED
+#define ATC_PACKED 1
+#endif
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.ftz.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.ftz.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+// ex2_poly on a pair (same arithmetic per element as ex2_poly)
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    x.x = fmaxf(x.x, -126.0f); x.y = fmaxf(x.y, -126.0f);
+    const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+    const float2 t = add2(x, magic);
+    const float2 n = add2(t, nmagic);
+    const float2 f = add2(x, make_float2(-n.x, -n.y));
+    float2 p = fma2(f, make_float2(0.05520550534129143f, 0.05520550534129143f), make_float2(0.24261397123336792f, 0.24261397123336792f));
+    p = fma2(p, f, make_float2(0.6932547688484192f, 0.6932547688484192f));
+    p = fma2(p, f, make_float2(0.9999276995658875f, 0.9999276995658875f));
+    return make_float2(__int_as_float(__float_as_int(t.x) * 8388608 + __float_as_int(p.x)),
+                       __int_as_float(__float_as_int(t.y) * 8388608 + __float_as_int(p.y)));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -211,7 +265,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-
+    // register re-allocation: the role warpgroup (warps 0..3) hands registers to the two softmax warpgroups, whose unrolled
+    // unit body otherwise spills inside the hot loop (ncu: long-scoreboard stalls on the reloads)
+    if (warp < 4) {
+#if ATC_REGS_ROLE > 0
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATC_REGS_ROLE));
+#endif
     if (warp == 0) {
         if (elect_one()) {
             // ===================== TMA producer =====================
@@ -227,7 +286,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 publish(k + 1, nxt);
                 const AtcItem im = atc_item(it, nqt);
                 for (int c = 0; c < n_chunks; ++c) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_wait<ATC_SLEEP_A>(&empty_bar[stage], phase ^ 1u);
                     uint8_t* sk = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], ATC_K_BYTES);
                     tma_load_2d(sk, &maps.k, &full_bar[stage], C + (im.hg >> 1) * 64, im.b * N + c * ATC_KEYS);
@@ -248,25 +307,23 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
             const AtcItem im = atc_item(it, nqt);
             const int nxt = get_item(k + 1);
             for (int c = 0; c < n_chunks; ++c) {
-                uint4 cur[2][4];
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) cur[kk][h] = nx[kk][h];
-                if (c + 1 < n_chunks) fetch(im, c + 1);
-                else if (nxt < n_items) fetch(atc_item(nxt, nqt), 0);                    // first chunk of the next item
-                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                mbar_wait<ATC_SLEEP_A>(&empty_bar[stage], phase ^ 1u);
                 uint8_t* sv = smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES + ATC_K_BYTES;
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
-                    const uint16_t* a = reinterpret_cast<const uint16_t*>(&cur[0][h]);    // key 2l:   dims 0..7 of head h
-                    const uint16_t* bq = reinterpret_cast<const uint16_t*>(&cur[1][h]);   // key 2l+1
+                    const uint16_t* a = reinterpret_cast<const uint16_t*>(&nx[0][h]);     // key 2l:   dims 0..7 of head h
+                    const uint16_t* bq = reinterpret_cast<const uint16_t*>(&nx[1][h]);    // key 2l+1
 #pragma unroll
                     for (int d = 0; d < 8; ++d) {
                         const uint32_t pair = (uint32_t)a[d] | ((uint32_t)bq[d] << 16);
+                        if (!(ATC_KNOCK & 16) || pair == 0x12345678u)
                         *reinterpret_cast<uint32_t*>(sv + h * 2048 + d * 128 + ((((lane >> 2) ^ d) << 4) | ((lane & 3) << 2))) = pair;
                     }
                 }
+                // the next chunk's values are requested after the stores (one register set; the ring keeps the builder up to
+                // three chunks ahead of the MMAs, so the load latency hides behind the wait for the next free stage)
+                if (c + 1 < n_chunks) fetch(im, c + 1);
+                else if (nxt < n_items) fetch(atc_item(nxt, nqt), 0);                    // first chunk of the next item
                 fence_proxy_async();                                              // generic-proxy writes -> UMMA (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[stage]);
@@ -288,10 +345,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 for (int u = 0; u < n_units; ++u) {
                     const int j = u & 3;
                     if (j == 0) { mbar_wait(&full_bar[stage], phase); }
-                    mbar_wait(&s_free[sb], sph ^ 1u);
+                    mbar_wait<ATC_SLEEP_C>(&s_free[sb], sph ^ 1u);
                     tc_fence_after();
                     const uint32_t k_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES);
                     // A: zero-masked head j of the Q tile; B: the natural 16-column pair that holds head j of this CTA's 4 heads
+                    if (!(ATC_KNOCK & 8))
                     umma_bf16(tmem + sb * ATC_KEYS, make_smem_desc_sw128(q_addr) + 2 * j,
                               make_smem_desc_sw128(k_addr) + 4 * (hg & 1) + 2 * (j >> 1), idesc_s, 0u);
                     umma_commit(&s_full[sb]);
@@ -315,13 +373,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 for (int u = 0; u < n_units; ++u) {
                     const int j = u & 3, c = u >> 2;
                     if (j == 0) mbar_wait(&full_bar[stage], phase);          // V of this chunk has landed
-                    mbar_wait(&p_full[pb], pph);
+                    mbar_wait<ATC_SLEEP_B>(&p_full[pb], pph);
                     tc_fence_after();
                     const uint32_t v_addr = smem_u32(smem + ATC_OFF_STAGE + stage * ATC_STAGE_BYTES + ATC_K_BYTES);
                     const uint64_t dp = make_smem_desc_sw128(p_addr + pb * ATC_P_BYTES);
                     const uint64_t dv = make_smem_desc_sw128(v_addr + j * 2048);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
+                        if (!(ATC_KNOCK & 4))
                         umma_bf16(tmem + ATC_O_COL + j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv, (c | kk) != 0 ? 1u : 0u);
                     umma_commit(&p_free[pb]);
                     if (++pb == ATC_NS) { pb = 0; pph ^= 1u; }
@@ -334,7 +393,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                 iph ^= 1u;
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+#if ATC_REGS_ROLE > 0
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ATC_REGS_SOFTMAX));
+#endif
         // ===================== softmax warpgroups =====================
         const int g = (warp - 4) >> 2;                     // warpgroup 0 / 1
         const int quarter = warp & 3;                      // TMEM lane quarter of this warp
@@ -393,41 +456,24 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                     const uint32_t sph = sphu;
                     ring_advance2();
                     ATC_T0();
-                    mbar_wait(&s_full[sb], sph);
+                    if (!(ATC_KNOCK & 64)) mbar_wait(&s_full[sb], sph);
                     ATC_T1(0);
                     tc_fence_after();
                     // Softmax reference m of this row and head.  Any m within the bf16/fp32 exponent range of the true maximum
-                    // gives the exact softmax after the final division, so only the FIRST chunk pays for an exact row maximum
-                    // (a second pass over the S tile); afterwards m follows a SAMPLED maximum (every 4th key) of the previous
-                    // chunk, picked up while its exponentials were computed, and moves only when that exceeds m by more than
-                    // 2^8 (lazy rescale).  P may therefore exceed 2^8 for a chunk; bf16 P / fp32 accumulators have the range.
-                    uint32_t v[32];
+                    // gives the exact softmax after the final division: m starts at the maximum of the item's first 16 keys
+                    // (below) and then follows a SAMPLED maximum (every 4th key) of the previous chunk, picked up while its
+                    // exponentials were computed; it moves only when that exceeds m by more than 2^8 (lazy rescale).  P may
+                    // therefore exceed 2^8 for a chunk; bf16 P / fp32 accumulators have the range.
                     float alpha = 1.0f;
                     bool moved = false;
-                    if (c == 0) {
-                        float cm[4];
-#pragma unroll
-                        for (int piece = 0; piece < ATC_KEYS / 32; ++piece) {
-                            tmem_ld_32x32b_x32(lane_addr + sb * ATC_KEYS + piece * 32, v);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                float t = fmaxf(fmaxf(__uint_as_float(v[i]), __uint_as_float(v[4 + i])), __uint_as_float(v[8 + i]));
-                                t = fmaxf(fmaxf(t, __uint_as_float(v[12 + i])), __uint_as_float(v[16 + i]));
-                                t = fmaxf(fmaxf(t, __uint_as_float(v[20 + i])), __uint_as_float(v[24 + i]));
-                                t = fmaxf(t, __uint_as_float(v[28 + i]));
-                                cm[i] = piece == 0 ? t : fmaxf(cm[i], t);
-                            }
-                        }
-                        m[jj] = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
-                    } else if (mnext[jj] > m[jj] + ATC_LAZY) {
+                    if (c != 0 && !(ATC_KNOCK & 64) && mnext[jj] > m[jj] + ATC_LAZY) {
                         alpha = ex2_approx(m[jj] - mnext[jj]); m[jj] = mnext[jj]; moved = true;
                     }
                     uint8_t* p_row = smem + ATC_OFF_P + sb * ATC_P_BYTES + r * 128;
                     // P.V of the unit three before this one is complete, hence (in-order MMA pipe) so is every earlier one:
                     // P[sb] is free and O_j (last written four units ago) has no MMA in flight
                     ATC_T0();
-                    mbar_wait(&p_free[sb], sph ^ 1u);
+                    if (!(ATC_KNOCK & 128)) mbar_wait(&p_free[sb], sph ^ 1u);
                     ATC_T1(1);
                     if (__any_sync(0xffffffffu, moved)) {
                         tc_fence_after();
@@ -438,14 +484,27 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                         for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                         tmem_st_x16(lane_addr + ATC_O_COL + j * 16, o);
                     }
-                    const float mrow = m[jj];
-                    float smp = mrow;                                          // sampled maximum of this chunk (raw logits)
                     // 16-column pieces, double-buffered in registers: the TMEM load of piece p+1 is in flight while the
                     // exponentials of piece p are computed (tcgen05.wait::ld waits for ALL loads, so it sits after the compute).
+                    float smp;
                     {
                         uint32_t vv[2][16];
                         tmem_ld_x16(lane_addr + sb * ATC_KEYS, vv[0]);
                         tmem_ld_wait();
+                        if (c == 0 && !(ATC_KNOCK & 32)) {
+                            // first chunk of the item: the reference starts at the exact maximum of the chunk's first 16 keys
+                            // (no second pass over the S tile -- a full-chunk maximum cost 5% of the kernel); from here on it
+                            // follows the sampled maxima like in every later chunk
+                            float t0 = fmaxf(fmaxf(__uint_as_float(vv[0][0]), __uint_as_float(vv[0][1])), __uint_as_float(vv[0][2]));
+                            float t1 = fmaxf(fmaxf(__uint_as_float(vv[0][3]), __uint_as_float(vv[0][4])), __uint_as_float(vv[0][5]));
+                            float t2 = fmaxf(fmaxf(__uint_as_float(vv[0][6]), __uint_as_float(vv[0][7])), __uint_as_float(vv[0][8]));
+                            float t3 = fmaxf(fmaxf(__uint_as_float(vv[0][9]), __uint_as_float(vv[0][10])), __uint_as_float(vv[0][11]));
+                            t0 = fmaxf(fmaxf(t0, __uint_as_float(vv[0][12])), __uint_as_float(vv[0][13]));
+                            t1 = fmaxf(fmaxf(t1, __uint_as_float(vv[0][14])), __uint_as_float(vv[0][15]));
+                            m[jj] = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+                        }
+                        const float mrow = m[jj];
+                        smp = mrow;                                            // sampled maximum of this chunk (raw logits)
 #pragma unroll
                         for (int piece = 0; piece < ATC_KEYS / 16; ++piece) {
                             uint32_t (&cur)[16] = vv[piece & 1];
@@ -458,10 +517,19 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     const int e = q * 8 + i * 2;
+#if ATC_PACKED
+                                    const float2 xx = add2(make_float2(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])), make_float2(-mrow, -mrow));
+                                    const float x0 = xx.x, x1 = xx.y;
+                                    if (!(ATC_KNOCK & 1) && POLY > 0 && i >= 4 - POLY) { const float2 y = ex2_poly2(xx); w[i] = pack_bf16x2(y.x, y.y); continue; }
+#else
                                     const float x0 = __uint_as_float(cur[e]) - mrow, x1 = __uint_as_float(cur[e + 1]) - mrow;
+#endif
+                                    if (ATC_KNOCK & 1) w[i] = pack_bf16x2(x0 * 0.5f, x1 * 0.5f);
+                                    else
                                     w[i] = (POLY > 0 && i >= 4 - POLY) ? pack_bf16x2(ex2_poly(x0), ex2_poly(x1))
                                                                         : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
                                 }
+                                if (!(ATC_KNOCK & 2) || w[0] == 0x12345678u)
                                 *reinterpret_cast<uint4*>(p_row + (((piece * 2 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // SWIZZLE_128B
                             }
                             if (piece + 1 < ATC_KEYS / 16) {
