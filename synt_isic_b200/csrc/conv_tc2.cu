@@ -20,8 +20,8 @@
 //     -- the normalised activation tensor is never materialised in HBM.
 // L2 -> smem bytes per MMA clock: (43.5 KB + 9*BN*128 B) / (36*BN clk) = 42 B/clk for BN = 128.
 //
-// Warp roles (640 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (both one elected
-// lane), warps 4..7 / 8..11 two epilogue warpgroups (warpgroup e owns M tile e of every super-tile, its own
+// Warp roles (640 threads): warp 0 TMA producer of the activation tiles, warp 2 TMA producer of the weight tiles, warp 1 TMEM
+// allocator + MMA issuer (one elected lane each), warps 4..7 / 8..11 two epilogue warpgroups (warpgroup e owns M tile e of every super-tile, its own
 // staging tile and TMA stores; the residual tile is TMA-loaded INTO the staging tile and updated in place),
 // warps 12..19 input transform.  The roles are latency-bound (one warp per SM sub-partition each would
 // leave the tensor pipe waiting), hence two warps per sub-partition for epilogue and transform.
@@ -29,6 +29,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include <type_traits>
+#include <vector>
 #include "tmap.cuh"
 
 namespace synt {
@@ -71,8 +72,16 @@ struct V2Smem {
 // synt_isic_b200.build); the product kernel carries no run-time experiment tests.
 #ifdef SYNT_EXPERIMENTS
 #define V2_EXP(mask) ((p.exp_nob & (mask)) != 0)
+// wait-time accounting of one thread per role: V2_TW(i, wait) adds the cycles spent in `wait` to record i of this CTA
+#define V2_TW(i, stmt) do { if (p.tl) { const long long _t = clock64(); stmt; tlacc[i] += clock64() - _t; } else { stmt; } } while (0)
+#define V2_TL_DECL long long tlacc[4] = {0, 0, 0, 0}; const long long tl_t0 = clock64()
+#define V2_TL_FLUSH(base, n) do { if (p.tl) { for (int _i = 0; _i < (n); ++_i) p.tl[blockIdx.x * 16 + (base) + _i] = tlacc[_i]; \
+        p.tl[blockIdx.x * 16 + (base) + (n)] = clock64() - tl_t0; } } while (0)
 #else
 #define V2_EXP(mask) (false)
+#define V2_TW(i, stmt) do { stmt; } while (0)
+#define V2_TL_DECL do { } while (0)
+#define V2_TL_FLUSH(base, n) do { } while (0)
 #endif
 
 struct V2Maps { CUtensorMap a[4]; CUtensorMap b; CUtensorMap out[4]; CUtensorMap res; };   // a[i]: source of segment i; out[phase]
@@ -90,9 +99,11 @@ struct V2Params {
     const float* bias; const float* bias2; int has_res; int relu;   // residual tile arrives through maps.res
     float2* stats; int stats_slots;   // optional fused GroupNorm partials [B][stats_slots][Cout]
     int chunk;                         // consecutive work items per CTA turn (divides the super-tiles per image)
+    long long* tl;                     // EXPERIMENTS: per-CTA wait-time records [grid][16] (SYNT_CONV_TL=1, tools/conv_timeline.py)
     int exp_nob;                       // EXPERIMENTS (SYNT_EXP_NOB bit mask, wrong results): 1 skip the weight-tile TMA loads after the
                                        // first ring fill, 2 skip the input transform, 4 skip the statistics pass, 8 TMA stores, 16 A-tile loads, 32 epilogue
-                                       // body, 64 no producer/transform at all and no operand waits in the MMA issuer (pure MMA issue rate)
+                                       // body, 64 no producer/transform at all and no operand waits in the MMA issuer (pure MMA issue rate),
+                                       // 128 transform copies without arithmetic, 256 transform without the store-back, 512 transform without SiLU
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
@@ -193,8 +204,34 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
 
     if (warp == 0) {
         if (elect_one()) {
-            // ===================== TMA producer =====================
-            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+            // ===================== TMA producer, activations =====================
+            // (the weight tiles have their own producer thread, warp 2: one thread issuing both streams in program order would
+            // reach the halo load of chunk i+1 only after the last four weight taps of chunk i have found a free slot, i.e. at
+            // 5/9 of chunk i's MMAs -- measured: the MMA issuer then waits 38% of its time for a_ready on the N = 128 layers)
+            int as = 0; uint32_t aph = 0;
+            V2_TL_DECL;
+            for (int it = 0, w; (w = v2_item(p, it)) >= 0 && !V2_EXP(64); ++it) {
+                const V2Work wk = v2_decode(p, w);
+                for (int sg = 0; sg < p.n_seg; ++sg) {
+                    const V2Seg sp = p.seg[sg];
+                    for (int ch = 0; ch < sp.chunks; ++ch) {
+                        V2_TW(0, mbar_wait(&a_empty[as], aph ^ 1u));
+                        if (V2_EXP(16) && (it > 0 || aph)) { mbar_arrive(&a_full[as]); }
+                        else {
+                            mbar_arrive_expect_tx(&a_full[as], a_bytes);
+                            tma_load_4d(smem + as * L::A_SLOT, &maps.a[sg], &a_full[as], ch * 64, wk.x0 - 1, wk.y0 - 1, wk.n0);
+                        }
+                        if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
+                    }
+                }
+            }
+            V2_TL_FLUSH(0, 2);
+        }
+    } else if (warp == 2) {
+        if (elect_one()) {
+            // ===================== TMA producer, weights =====================
+            int bs = 0; uint32_t bph = 0;
+            V2_TL_DECL;
             if (RES && !V2_EXP(64)) {                           // whole weight matrix, once (n_ntiles == 1)
                 int nkb = 0;
                 for (int sg = 0; sg < p.n_seg; ++sg) nkb += p.seg[sg].chunks * p.seg[sg].taps;
@@ -202,21 +239,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d(smem + L::OFF_B + kb * L::B_TILE, &maps.b, &b_full[0], kb * 64, 0);
             }
-            for (int it = 0, w; (w = v2_item(p, it)) >= 0 && !V2_EXP(64); ++it) {
+            for (int it = 0, w; !RES && (w = v2_item(p, it)) >= 0 && !V2_EXP(64); ++it) {
                 const V2Work wk = v2_decode(p, w);
                 for (int sg = 0; sg < p.n_seg; ++sg) {
                     const V2Seg sp = p.seg[sg];
                     for (int ch = 0; ch < sp.chunks; ++ch) {
-                        mbar_wait(&a_empty[as], aph ^ 1u);
-                        if (V2_EXP(16) && (it > 0 || aph)) { mbar_arrive(&a_full[as]); }
-                        else {
-                            mbar_arrive_expect_tx(&a_full[as], a_bytes);
-                            tma_load_4d(smem + as * L::A_SLOT, &maps.a[sg], &a_full[as], ch * 64, wk.x0 - 1, wk.y0 - 1, wk.n0);
-                        }
-                        if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
-                        for (int tap = 0; tap < sp.taps && !RES; ++tap) {
+                        for (int tap = 0; tap < sp.taps; ++tap) {
                             const int kb = sp.kb_base + tap * sp.kb_stride + ch;
-                            mbar_wait(&b_empty[bs], bph ^ 1u);
+                            V2_TW(1, mbar_wait(&b_empty[bs], bph ^ 1u));
                             if (V2_EXP(1) && (it > 0 || bph)) { mbar_arrive(&b_full[bs]); }
                             else if (PAIR) {                             // this CTA's half of the weight tile (maps.b box: BN/2 rows)
                                 mbar_arrive_expect_tx(&b_full[bs], L::B_TILE / 2);
@@ -231,6 +261,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                     }
                 }
             }
+            V2_TL_FLUSH(13, 2);
         }
     } else if (warp == 1) {
         if (PAIR && rank == 1) {
@@ -264,17 +295,18 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             };
             auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int tb = 0; uint32_t tph = 0;
+            V2_TL_DECL;
             if (RES && !V2_EXP(64)) mbar_wait(&b_full[0], 0);
             for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
                 const V2Work wk = v2_decode(p, w);
-                mbar_wait(&t_empty[tb], tph ^ 1u);                    // epilogue drained this accumulator pair
+                V2_TW(0, mbar_wait(&t_empty[tb], tph ^ 1u));          // epilogue drained this accumulator pair
                 if (PAIR) mbar_wait_cluster(&pt_empty[tb], tph);      // ... and so did the peer's
                 tc_fence_after();
                 uint32_t first = 1;
                 for (int sg = 0; sg < p.n_seg; ++sg) {
                     const V2Seg sp = p.seg[sg];
                     for (int ch = 0; ch < sp.chunks; ++ch) {
-                        if (!V2_EXP(64)) mbar_wait(&a_ready[as], aph);   // landed AND transformed
+                        if (!V2_EXP(64)) V2_TW(1, mbar_wait(&a_ready[as], aph));   // landed AND transformed
                         if (PAIR && !V2_EXP(64)) mbar_wait_cluster(&pa_ready[as], aph);
                         tc_fence_after();
                         const uint32_t a_base = smem_u32(smem + as * L::A_SLOT);
@@ -285,7 +317,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                             const int dx = sp.taps == 9 ? tap % 3 : (sp.taps == 4 ? (wk.phase & 1) + (tap & 1) : 1);
                             if (RES) bs = sp.kb_base + tap * sp.kb_stride + ch;
                             else if (!V2_EXP(64)) {
-                                mbar_wait(&b_full[bs], bph);
+                                V2_TW(2, mbar_wait(&b_full[bs], bph));
                                 if (PAIR) mbar_wait_cluster(&pb_full[bs], bph);   // (skipped with the b_full wait under mask 64)
                                 tc_fence_after();
                             }
@@ -314,6 +346,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 commit(&t_full[tb]);
                 if (++tb == L::NBUF) { tb = 0; tph ^= 1u; }
             }
+            V2_TL_FLUSH(3, 3);
         }
     } else if (warp >= V2_XF_BASE / 32) {
         // ===================== input transform (warps 12..19): GroupNorm affine (+SiLU) in place =====================
@@ -322,6 +355,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         const int hy0 = r0 / 10, hx0 = r0 - hy0 * 10;                    // halo coordinates of the first row (10 pixels per halo row)
         constexpr int RSTEP = V2_XF_THREADS / 8;                         // rows advance by 32 = 3 halo rows + 2 pixels
         int as = 0; uint32_t aph = 0;
+        V2_TL_DECL;
         for (int it = 0, w; (w = v2_item(p, it)) >= 0 && !V2_EXP(64); ++it) {
             const V2Work wk = v2_decode(p, w);
             for (int sg = 0; sg < p.n_seg; ++sg) {
@@ -339,7 +373,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         }
                     };
                     if (sp.xform) load_ss(0);
-                    mbar_wait(&a_full[as], aph);
+                    V2_TW(0, mbar_wait(&a_full[as], aph));
+#ifdef SYNT_EXPERIMENTS
+                    const long long tx0 = clock64();
+#endif
                     if (sp.xform && !V2_EXP(2)) {
                         uint8_t* slot = smem + as * L::A_SLOT;
                         auto run = [&](auto silu_tag) {
@@ -368,10 +405,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                                         __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v[uu]);
 #pragma unroll
                                         for (int j = 0; j < 4; ++j) {
+                                            if (V2_EXP(128)) continue;                 // experiment: copy only
                                             float2 f = __bfloat1622float2(h2[j]);
                                             f.x = fmaf(f.x, sc[2 * j], sh[2 * j]);
                                             f.y = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
-                                            if (SILU) {
+                                            if (SILU && !V2_EXP(512)) {
                                                 float t0, t1;
                                                 asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(f.x));
                                                 asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(f.y));
@@ -379,7 +417,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                                             }
                                             h2[j] = __floats2bfloat162_rn(f.x, f.y);
                                         }
-                                        *ptr[uu] = v[uu];
+                                        if (!V2_EXP(256) || v[uu].x == 0x12345678u) *ptr[uu] = v[uu];
                                     }
                                 }
                             }
@@ -388,10 +426,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         fence_proxy_async();                               // generic-proxy writes -> UMMA (async proxy)
                     }
                     mbar_arrive(&a_ready[as]);
+#ifdef SYNT_EXPERIMENTS
+                    tlacc[1] += clock64() - tx0; tlacc[2] += 1;
+#endif
                     if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
                 }
             }
         }
+        if (tt == 0) V2_TL_FLUSH(7, 3);
     } else if (warp >= V2_EPI_BASE / 32) {
         // ===================== epilogue: warpgroup e (warps 4..7 / 8..11) owns M tile e of every super-tile ==========
         const int e = (warp - V2_EPI_BASE / 32) >> 2;                // warpgroup = M tile index
@@ -426,6 +468,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             const int w0 = v2_item(p, 0);
             if (w0 >= 0) { if (elect_one()) load_residual(v2_decode(p, w0), 0); }
         }
+        V2_TL_DECL;
         for (int it = 0, w; (w = v2_item(p, it)) >= 0; ++it) {
             const V2Work wk = v2_decode(p, w);
             int n_img, ty0;
@@ -435,7 +478,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 for (int i = et; i < BN; i += 128) bias_s[i] = p.bias[wk.ntr * BN + i] + (p.bias2 ? p.bias2[wk.ntr * BN + i] : 0.f);
                 last_nt = wk.ntr;
             }
-            mbar_wait(&t_full[tb], tph);
+            V2_TW(0, mbar_wait(&t_full[tb], tph));
             tc_fence_after();
             const bool has_res = p.has_res && valid;
 #pragma unroll 1
@@ -559,6 +602,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
             }
             if (++tb == L::NBUF) { tb = 0; tph ^= 1u; }
         }
+        if (et == 0 && e == 0) V2_TL_FLUSH(11, 1);
         if (lead_warp) { if (elect_one()) tma_store_wait_all(); }
     }
     tc_fence_before();
@@ -711,6 +755,13 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     p.chunk = v2_chunk(a, BN);
 #ifdef SYNT_EXPERIMENTS
     { static const char* e = getenv("SYNT_EXP_NOB"); p.exp_nob = e ? atoi(e) : 0; }
+    p.tl = nullptr;
+#ifdef SYNT_EXPERIMENTS
+    static const char* tl_env = getenv("SYNT_CONV_TL");     // file prefix: one record file per launch (debug tools only)
+    static int tl_launch = 0;
+    long long* tl_dev = nullptr;
+    if (tl_env) { SYNT_CUDA(cudaMalloc(&tl_dev, 148 * 16 * 8)); SYNT_CUDA(cudaMemsetAsync(tl_dev, 0, 148 * 16 * 8, s)); p.tl = tl_dev; }
+#endif
 #endif
     V2Maps maps;
     const int bh = v2_two_img(a) ? 18 : 34, bn = v2_two_img(a) ? 2 : 1;
@@ -757,6 +808,20 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     else if (BN == 128) launch_v2<128, false>(maps, p, grid, (bf16*)a.out, s);
     else if (resident) launch_v2<64, true>(maps, p, grid, (bf16*)a.out, s);
     else               launch_v2<64, false>(maps, p, grid, (bf16*)a.out, s);
+#ifdef SYNT_EXPERIMENTS
+    if (tl_dev) {                                          // averages over the CTAs of this launch, cycles
+        std::vector<long long> h(148 * 16);
+        SYNT_CUDA(cudaStreamSynchronize(s));
+        SYNT_CUDA(cudaMemcpy(h.data(), tl_dev, h.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(tl_dev);
+        double avg[16] = {0};
+        for (int c = 0; c < grid; ++c) for (int i = 0; i < 16; ++i) avg[i] += (double)h[c * 16 + i] / grid;
+        fprintf(stderr, "[conv_tl %d] M=%d N=%d(BN %d) K=%d gn=%d | producer: wait a_empty %.0f b_empty %.0f total %.0f | mma: wait t_empty %.0f "
+                "a_ready %.0f b_full %.0f total %.0f | xform: wait a_full %.0f busy %.0f chunks %.0f total %.0f | epi: wait t_full %.0f total %.0f\n",
+                tl_launch++, a.B * a.H * a.W, a.Cout, BN, a.ktot(), a.gn_mode, avg[0], avg[14], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7],
+                avg[8], avg[9], avg[10], avg[11], avg[12]);
+    }
+#endif
 }
 
 }  // namespace synt

@@ -37,7 +37,9 @@ def run(B, H, W, Cin, Cout, gn, res, stats, K=3, iters=10):
     return ms * 1e3, fl / ms / 1e9
 
 
-for shape in ((64, 128, 128, 64, 64), (64, 128, 128, 128, 64), (64, 64, 64, 128, 128), (64, 32, 32, 256, 256), (64, 16, 16, 256, 256)):
+SHAPES = ((64, 128, 128, 64, 64), (64, 128, 128, 128, 64), (64, 64, 64, 128, 128), (64, 32, 32, 256, 256), (64, 16, 16, 256, 256))
+ITERS = int(os.environ.get("EXP_ITERS", "10"))
+for shape in SHAPES:
     for gn, res, stats in ((0, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 0), (1, 1, 1)):
-        us, tf = run(*shape, gn, res, stats)
+        us, tf = run(*shape, gn, res, stats, iters=ITERS)
         print(f"{shape}  gn={gn} res={res} stats={stats}: {us:8.1f} us  {tf:7.1f} TFLOP/s", flush=True)
