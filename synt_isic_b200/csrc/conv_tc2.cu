@@ -45,21 +45,27 @@ constexpr int V2_A_STAGES = 2;
 
 // RES = true: the whole weight matrix of the layer (<= 12 K blocks of 64 x BN) stays resident in shared
 // memory for the life of the persistent CTA (Cout = 64 layers with Ktot <= 768: L2 traffic is A only).
-template <int BN, bool RES>
+// K1 = true: 1x1 projections (qkv, attention out-projection; BN = 128): no halo -- an A slot is exactly the 256 pixels of the
+// super-tile (32 KB) -- and FOUR slots.  A chunk of a 1x1 conv feeds only 8 MMAs (~700 clk) while its load takes ~2500 clk, so
+// the 2-deep ring of the 3x3 geometry ran these layers at the load latency (measured: the MMA issuer waits 35% of its time for
+// a_ready and the qkv projection takes 59 us against ~20 us of HBM time); the staging tiles shrink to 64-column passes to pay
+// for the two extra slots.
+template <int BN, bool RES, bool K1 = false>
 struct V2Smem {
-    static constexpr int A_SLOT = 46080;                   // max(34*10, 2*18*10) * 128, already 1 KB aligned
+    static constexpr int A_STAGES = K1 ? 4 : V2_A_STAGES;
+    static constexpr int A_SLOT = K1 ? 32768 : 46080;      // 46080 = max(34*10, 2*18*10) * 128, already 1 KB aligned
     static constexpr int B_TILE = BN * 128;
     // BN = 256 (Cout = 256, large K): one UMMA of N = 256 per M tile -- per MMA the tensor core reads 4 KB of A and
     // BN*32 B of B from shared memory, and that operand traffic (measured ~90 B/clk) is what paces N <= 128 tiles
     // (98 clk per N = 128 UMMA against a 64 clk floor); N = 256 runs at its 128 clk floor.  The price: the two
     // accumulators of a super-tile fill all 512 TMEM columns (NBUF = 1, the epilogue does not overlap the next
     // mainloop) and the epilogue walks the tile in EC = 64-column passes so that the staging tiles stay small.
-    static constexpr int EC = BN == 256 ? 64 : BN;         // columns per epilogue pass
+    static constexpr int EC = (BN == 256 || K1) ? 64 : BN; // columns per epilogue pass
     static constexpr int NPASS = BN / EC;
     static constexpr int NBUF = BN == 256 ? 1 : 2;         // TMEM accumulator buffers (each V2_MT x BN columns)
     static constexpr int STAGING = 128 * EC * 2;           // one pass of one M tile of bf16 output (one per epilogue warpgroup)
     static constexpr int NB = RES ? 12 : (BN == 256 ? 3 : (BN == 128 ? 4 : 8));
-    static constexpr int OFF_B = V2_A_STAGES * A_SLOT;
+    static constexpr int OFF_B = A_STAGES * A_SLOT;
     static constexpr int OFF_STAGING = OFF_B + NB * B_TILE;
     static constexpr int OFF_BIAS = OFF_STAGING + V2_MT * STAGING;
     static constexpr int OFF_BAR = OFF_BIAS + V2_MT * BN * 4;
@@ -152,11 +158,12 @@ __device__ __forceinline__ int v2_item(const V2Params& p, int i) {
 // so per MMA an SM fetches 4 KB of A and only BN*16 B of B from shared memory.  The peer's MMA warp is a relay: it
 // forwards "my A tile is transformed / my half of B has landed / my epilogue drained the accumulators" to the leader
 // with remote mbarrier arrives; the leader's commits are multicast to both CTAs' empty / full barriers.
-template <int BN, bool RES, bool PAIR = false>
+template <int BN, bool RES, bool PAIR = false, bool K1 = false>
 __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ V2Maps maps,
                                                                  const __grid_constant__ V2Params p, bf16* __restrict__ out) {
-    using L = V2Smem<BN, RES>;
-    static_assert(!PAIR || (!RES && L::NBUF == 2), "pair mode: streamed weights, double-buffered accumulators");
+    using L = V2Smem<BN, RES, K1>;
+    constexpr int A_STAGES = L::A_STAGES;
+    static_assert(!PAIR || (!RES && L::NBUF == 2 && !K1), "pair mode: streamed weights, double-buffered accumulators");
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     // iteration i of this CTA -> work item (or -1 when exhausted); pair mode: cluster c takes pair-items c, c + #clusters, ...
     auto v2_item = [&](const V2Params& pp, int i) -> int {
@@ -169,28 +176,28 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* a_full = bars;                        // [2]
-    uint64_t* a_empty = a_full + V2_A_STAGES;       // [2]
-    uint64_t* a_ready = a_empty + V2_A_STAGES;      // [2] halo tile transformed (or passed through)
-    uint64_t* b_full = a_ready + V2_A_STAGES;       // [NB]
+    uint64_t* a_empty = a_full + A_STAGES;       // [2]
+    uint64_t* a_ready = a_empty + A_STAGES;      // [2] halo tile transformed (or passed through)
+    uint64_t* b_full = a_ready + A_STAGES;       // [NB]
     uint64_t* b_empty = b_full + L::NB;             // [NB]
     uint64_t* t_full = b_empty + L::NB;             // [2]
     uint64_t* t_empty = t_full + 2;                 // [2]
     uint64_t* r_full = t_empty + 2;                 // [2] residual tile of epilogue warpgroup e has landed in its staging
     uint64_t* pa_ready = r_full + 2;                // [2]  pair mode, leader: the peer's a_ready / b_full / t_empty, relayed
-    uint64_t* pb_full = pa_ready + V2_A_STAGES;     // [NB]
+    uint64_t* pb_full = pa_ready + A_STAGES;     // [NB]
     uint64_t* pt_empty = pb_full + L::NB;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pt_empty + 2);
-    static_assert((3 * V2_A_STAGES + 3 * L::NB + 8) * 8 + 4 <= 512, "barrier region");
+    static_assert((3 * A_STAGES + 3 * L::NB + 8) * 8 + 4 <= 512, "barrier region");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_bytes = p.imgs_per_super == 1 ? 34 * 10 * 128 : 2 * 18 * 10 * 128;
+    const int a_bytes = K1 ? 256 * 128 : (p.imgs_per_super == 1 ? 34 * 10 * 128 : 2 * 18 * 10 * 128);
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.b); prefetch_tmap(&maps.out[0]);
-        for (int s = 0; s < V2_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_ready[s], V2_XF_THREADS); }
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_ready[s], V2_XF_THREADS); }
         for (int s = 0; s < L::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 256); mbar_init(&r_full[s], 1); }
-        for (int s = 0; s < V2_A_STAGES; ++s) mbar_init(&pa_ready[s], 1);
+        for (int s = 0; s < A_STAGES; ++s) mbar_init(&pa_ready[s], 1);
         for (int s = 0; s < L::NB; ++s) mbar_init(&pb_full[s], 1);
         for (int s = 0; s < 2; ++s) mbar_init(&pt_empty[s], 1);
         fence_barrier_init();
@@ -219,9 +226,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         if (V2_EXP(16) && (it > 0 || aph)) { mbar_arrive(&a_full[as]); }
                         else {
                             mbar_arrive_expect_tx(&a_full[as], a_bytes);
-                            tma_load_4d(smem + as * L::A_SLOT, &maps.a[sg], &a_full[as], ch * 64, wk.x0 - 1, wk.y0 - 1, wk.n0);
+                            tma_load_4d(smem + as * L::A_SLOT, &maps.a[sg], &a_full[as], ch * 64, wk.x0 - (K1 ? 0 : 1), wk.y0 - (K1 ? 0 : 1), wk.n0);
                         }
-                        if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
+                        if (++as == A_STAGES) { as = 0; aph ^= 1u; }
                     }
                 }
             }
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                                 mbar_arrive_remote(&pb_full[bs], 0);
                                 if (++bs == L::NB) { bs = 0; bph ^= 1u; }
                             }
-                            if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
+                            if (++as == A_STAGES) { as = 0; aph ^= 1u; }
                         }
                     }
                     if (++tb == L::NBUF) { tb = 0; tph ^= 1u; }
@@ -326,7 +333,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                             uint64_t da[V2_MT];
 #pragma unroll
                             for (int mt = 0; mt < V2_MT; ++mt)
-                                da[mt] = make_smem_desc_sw128(a_base + ((mt * p.row_off + dy) * 10 + dx) * 128, 1280);
+                                da[mt] = K1 ? make_smem_desc_sw128(a_base + mt * 16384, 1024)      // rows mt*128 .. +127 of the box
+                                            : make_smem_desc_sw128(a_base + ((mt * p.row_off + dy) * 10 + dx) * 128, 1280);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                             }
                         }
                         commit(&a_empty[as]);
-                        if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
+                        if (++as == A_STAGES) { as = 0; aph ^= 1u; }
                     }
                 }
                 commit(&t_full[tb]);
@@ -381,11 +389,43 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         uint8_t* slot = smem + as * L::A_SLOT;
                         auto run = [&](auto silu_tag) {
                             constexpr bool SILU = decltype(silu_tag)::value;
+                            auto apply = [&](uint4& v) {                  // 8 channels of one pixel: affine (+SiLU) in fp32
+                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    if (V2_EXP(128)) continue;             // experiment: copy only
+                                    float2 f = __bfloat1622float2(h2[j]);
+                                    f.x = fmaf(f.x, sc[2 * j], sh[2 * j]);
+                                    f.y = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+                                    if (SILU && !V2_EXP(512)) {
+                                        float t0, t1;
+                                        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(f.x));
+                                        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(f.y));
+                                        f.x = fmaf(f.x, t0, f.x); f.y = fmaf(f.y, t1, f.y);
+                                    }
+                                    h2[j] = __floats2bfloat162_rn(f.x, f.y);
+                                }
+                            };
 #pragma unroll
                             for (int im = 0; im < 2; ++im) {
                                 if (im >= p.imgs_per_super || wk.n0 + im >= p.B) continue;
                                 if (im == 1) load_ss(1);                   // 16x16 layers: second image of the super-tile
                                 constexpr int UR = 4;                      // rows in flight per thread (hides LDS/MUFU latency)
+                                if (K1) {                                  // no halo: rows r0, r0 + 32, ... of this image's pixels
+                                    const int rpi = p.imgs_per_super == 1 ? 256 : 128;
+                                    for (int k0 = 0; k0 < rpi / RSTEP; k0 += UR) {
+                                        uint4 v[UR]; uint4* ptr[UR];
+#pragma unroll
+                                        for (int uu = 0; uu < UR; ++uu) {
+                                            const int r = im * rpi + r0 + (k0 + uu) * RSTEP;
+                                            ptr[uu] = reinterpret_cast<uint4*>(slot + r * 128 + ((lv ^ (r & 7)) << 4));
+                                            v[uu] = *ptr[uu];
+                                        }
+#pragma unroll
+                                        for (int uu = 0; uu < UR; ++uu) { apply(v[uu]); *ptr[uu] = v[uu]; }
+                                    }
+                                    continue;
+                                }
                                 int hy = wk.y0 - 1 + hy0, hx = wk.x0 - 1 + hx0;     // image coordinates of the current row
                                 for (int rr = r0; rr < rows_per_img;) {
                                     uint4 v[UR]; uint4* ptr[UR]; bool ok[UR];
@@ -402,21 +442,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
 #pragma unroll
                                     for (int uu = 0; uu < UR; ++uu) {
                                         if (!ok[uu]) continue;
-                                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v[uu]);
-#pragma unroll
-                                        for (int j = 0; j < 4; ++j) {
-                                            if (V2_EXP(128)) continue;                 // experiment: copy only
-                                            float2 f = __bfloat1622float2(h2[j]);
-                                            f.x = fmaf(f.x, sc[2 * j], sh[2 * j]);
-                                            f.y = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
-                                            if (SILU && !V2_EXP(512)) {
-                                                float t0, t1;
-                                                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(f.x));
-                                                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(f.y));
-                                                f.x = fmaf(f.x, t0, f.x); f.y = fmaf(f.y, t1, f.y);
-                                            }
-                                            h2[j] = __floats2bfloat162_rn(f.x, f.y);
-                                        }
+                                        apply(v[uu]);
                                         if (!V2_EXP(256) || v[uu].x == 0x12345678u) *ptr[uu] = v[uu];
                                     }
                                 }
@@ -429,7 +455,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
 #ifdef SYNT_EXPERIMENTS
                     tlacc[1] += clock64() - tx0; tlacc[2] += 1;
 #endif
-                    if (++as == V2_A_STAGES) { as = 0; aph ^= 1u; }
+                    if (++as == A_STAGES) { as = 0; aph ^= 1u; }
                 }
             }
         }
@@ -654,6 +680,17 @@ static bool v2_pair(const ConvArgs& a) {
     return per_img % 2 == 0;
 }
 
+// 1x1 projections on full tile grids take the no-halo, four-slot variant (V2Smem<128, false, true>)
+static bool v2_k1(const ConvArgs& a) {
+    if (!(a.KH == 1 && v2_bn(a) == 128 && !a.up2x)) return false;
+    if (a.residual || a.stats_out) return false;      // the out-projection (residual + statistics) measured 2 us slower with 64-column passes
+    if (!(a.W % 8 == 0 && (a.H % 32 == 0 || a.H == 16))) return false;     // ragged planes keep the halo geometry (zero fill)
+    static const char* e = getenv("SYNT_CONV_K1");
+    return !(e && e[0] == '0');
+}
+
+bool conv_tc2_is_k1(const ConvArgs& a) { return conv_tc2_supported(a) && v2_k1(a) && !v2_pair(a); }
+
 static int v2_num_sms() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
@@ -681,7 +718,7 @@ int conv_tc2_stats_slots(const ConvArgs& a) {
     const int phases = a.up2x ? 4 : 1;
     if (v2_two_img(a)) return phases * v2_tiles_x(a);                      // one row per tile
     const int per_img = v2_tiles_x(a) * v2_supers(a);
-    if (BN == 256 || v2_pair(a)) return phases * per_img * V2_MT;          // multi-pass tiles / pair mode: one row per tile
+    if (BN == 256 || v2_pair(a) || v2_k1(a)) return phases * per_img * V2_MT;   // multi-pass tiles / pair mode: one row per tile
     return phases * (per_img / v2_chunk(a, BN)) * V2_MT;                   // one row per chunk and epilogue warpgroup
 }
 
@@ -699,17 +736,17 @@ static void launch_v2_pair(const V2Maps& maps, const V2Params& p, int grid, bf16
     SYNT_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p, out));
 }
 
-template <int BN, bool RES>
+template <int BN, bool RES, bool K1 = false>
 static void launch_v2(const V2Maps& maps, const V2Params& p, int grid, bf16* out, cudaStream_t s) {
-    using L = V2Smem<BN, RES>;
-    ensure_dynamic_smem((const void*)(conv_tc2_kernel<BN, RES>), L::TOTAL);
-    launch_pdl<true>(conv_tc2_kernel<BN, RES, false>, dim3(grid), dim3(V2_THREADS), L::TOTAL, s, maps, p, out);
+    using L = V2Smem<BN, RES, K1>;
+    ensure_dynamic_smem((const void*)(conv_tc2_kernel<BN, RES, false, K1>), L::TOTAL);
+    launch_pdl<true>(conv_tc2_kernel<BN, RES, false, K1>, dim3(grid), dim3(V2_THREADS), L::TOTAL, s, maps, p, out);
 }
 
-static void make_halo_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_h, int box_n) {
+static void make_halo_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_h, int box_n, int box_w = 10) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, 10, (cuuint32_t)box_h, (cuuint32_t)box_n};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
     encode_bf16_sw128(m, base, 4, dims, strides, box, "halo activation");
 }
 
@@ -753,20 +790,19 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     p.bias = a.bias; p.bias2 = a.bias2; p.has_res = a.residual != nullptr; p.relu = a.relu;
     p.stats = a.stats_out; p.stats_slots = conv_tc2_stats_slots(a);
     p.chunk = v2_chunk(a, BN);
+    p.exp_nob = 0; p.tl = nullptr;
 #ifdef SYNT_EXPERIMENTS
     { static const char* e = getenv("SYNT_EXP_NOB"); p.exp_nob = e ? atoi(e) : 0; }
-    p.tl = nullptr;
-#ifdef SYNT_EXPERIMENTS
     static const char* tl_env = getenv("SYNT_CONV_TL");     // file prefix: one record file per launch (debug tools only)
     static int tl_launch = 0;
     long long* tl_dev = nullptr;
     if (tl_env) { SYNT_CUDA(cudaMalloc(&tl_dev, 148 * 16 * 8)); SYNT_CUDA(cudaMemsetAsync(tl_dev, 0, 148 * 16 * 8, s)); p.tl = tl_dev; }
 #endif
-#endif
     V2Maps maps;
-    const int bh = v2_two_img(a) ? 18 : 34, bn = v2_two_img(a) ? 2 : 1;
+    const bool k1v = !pair && v2_k1(a);
+    const int bh = k1v ? (v2_two_img(a) ? 16 : 32) : (v2_two_img(a) ? 18 : 34), bn = v2_two_img(a) ? 2 : 1;
     for (int i = 0; i < 4; ++i) {
-        if (i < p.n_seg) make_halo_map(&maps.a[i], srcs[i], a.B, a.H, a.W, src_C[i], bh, bn);
+        if (i < p.n_seg) make_halo_map(&maps.a[i], srcs[i], a.B, a.H, a.W, src_C[i], bh, bn, k1v ? 8 : 10);
         else maps.a[i] = maps.a[0];
     }
     {
@@ -805,6 +841,7 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
 
     const bool resident = BN == 64 && p.n_ntiles == 1 && !a.up2x && a.ktot() / 64 <= 12;
     if (BN == 256)     launch_v2<256, false>(maps, p, grid, (bf16*)a.out, s);
+    else if (BN == 128 && k1v) launch_v2<128, false, true>(maps, p, grid, (bf16*)a.out, s);
     else if (BN == 128) launch_v2<128, false>(maps, p, grid, (bf16*)a.out, s);
     else if (resident) launch_v2<64, true>(maps, p, grid, (bf16*)a.out, s);
     else               launch_v2<64, false>(maps, p, grid, (bf16*)a.out, s);

@@ -48,6 +48,7 @@ bool conv_tc_supported(const ConvArgs& a);
 void conv_tc(const ConvArgs& a, cudaStream_t s);
 // persistent halo-tile kernel for 3x3 stride-1 convs (+ fused 1x1 shortcut segments), see conv_tc2.cu
 bool conv_tc2_supported(const ConvArgs& a);
+bool conv_tc2_is_k1(const ConvArgs& a);   // 1x1 projection on the no-halo four-slot variant (input transform once per load)
 void conv_tc2(const ConvArgs& a, cudaStream_t s);
 int conv_tc2_stats_slots(const ConvArgs& a);     // partial rows per image written when stats_out != null
 void conv_tc2_set_pair(int on);                  // experimental CTA-pair (cta_group::2) variant of the N = 128 kernel

@@ -545,7 +545,8 @@ struct Fwd {
         {
             ConvArgs c; c.B = B; c.H = H; c.W = W; c.Cin = C; c.KH = c.KW = 1; c.pad = 0; c.Ho = H; c.Wo = W;
             c.Cout = qkv.C; c.bias = (const float*)(tc ? w.bqkv_tc : w.bqkv)->p; c.out = qkv.p;
-            if (u->fuse_gn && fused_ok(c) && c.Cout <= 256) {     // many N tiles would re-transform the tile per N tile
+            // (the halo geometry would re-transform a 46 KB tile per N tile; the 1x1 variant's affine-only pass over 32 KB is cheap)
+            if (u->fuse_gn && fused_ok(c) && (c.Cout <= 256 || conv_tc2_is_k1(c))) {
                 float2* ss = gn_scale_shift(x, nullptr, w.g, w.b);
                 c.in = x.p; c.gn_ss = ss; c.gn_mode = 1;
                 conv(c, tc ? w.wqkv_tc : w.wqkv);

@@ -39,6 +39,12 @@ def run(B, H, W, Cin, Cout, gn, res, stats, K=3, iters=10):
 
 SHAPES = ((64, 128, 128, 64, 64), (64, 128, 128, 128, 64), (64, 64, 64, 128, 128), (64, 32, 32, 256, 256), (64, 16, 16, 256, 256))
 ITERS = int(os.environ.get("EXP_ITERS", "10"))
+if os.environ.get("EXP_K1"):                 # the 1x1 projections of the attention blocks (qkv, out-projection)
+    for shape, cfgs in (((64, 32, 32, 256, 768), ((0, 0, 0), (1, 0, 0))), ((64, 32, 32, 256, 256), ((0, 0, 0), (0, 1, 1)))):
+        for gn, res, stats in cfgs:
+            us, tf = run(*shape, gn, res, stats, K=1, iters=ITERS)
+            print(f"1x1 {shape}  gn={gn} res={res} stats={stats}: {us:8.1f} us  {tf:7.1f} TFLOP/s", flush=True)
+    sys.exit(0)
 for shape in SHAPES:
     for gn, res, stats in ((0, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 0), (1, 1, 1)):
         us, tf = run(*shape, gn, res, stats, iters=ITERS)
