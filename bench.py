@@ -513,10 +513,23 @@ def run_ours(args):
         hbm_entry("conv_out3_mma_kernel + DDPMScheduler.step epilogue", prof["conv_out_sched"]["ms"],
                   prof["conv_out_sched"]["launches"], px * (64 * 2 + 3 * 4 + 3 * 4),
                   "read the 64-channel bf16 activation (128 B/pixel) + read x_t and write x_{t-1} fp32 (24 B/pixel); Philox noise in-kernel"),
-        hbm_entry("gn_apply_kernel (GroupNorm in front of the qkv projections)", prof["groupnorm_apply"]["ms"],
-                  prof["groupnorm_apply"]["launches"], B * (5 * 1024 + 256) * 256 * 2 * 2,
-                  "read + write bf16 [B,HW,256] at the 5 attention sites of 32x32 and the one of 16x16"),
     ]
+    if prof["groupnorm_apply"]["launches"]:          # (round 2: fused into the qkv projection's input transform -- no launches left)
+        roofline_hbm.append(hbm_entry("gn_apply_kernel (GroupNorm in front of the qkv projections)", prof["groupnorm_apply"]["ms"],
+                                      prof["groupnorm_apply"]["launches"], B * (5 * 1024 + 256) * 256 * 2 * 2,
+                                      "read + write bf16 [B,HW,256] at the 5 attention sites of 32x32 and the one of 16x16"))
+    # attention is bound by the exponentials (d = 8: N^2 ex2 per head against 16 MUFU results/clk/SM), not by the tensor pipe
+    att_ms = prof["attention"]["ms"]
+    att_exps = B * 32 * (5 * 1024 ** 2 + 256 ** 2)
+    mufu_peak = 16.0 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6
+    roofline_mufu = {"kernel": "attention_tc_kernel (5 launches at N=1024, 1 at N=256)", "bound": "mufu (ex2)",
+                     "ms_per_step": att_ms, "exponentials_per_step": att_exps,
+                     "achieved": att_exps / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0,
+                     "peak": mufu_peak / 1e12, "unit": "T exponentials/s",
+                     "frac": att_exps / (att_ms * 1e-3) / mufu_peak if att_ms > 0 else 0.0,
+                     "peak_source": "16 results/clk/SM measured (tools/ubench/mufu.cu) x 148 SMs x SM clock under load",
+                     "note": "one pair in four of the exponentials is evaluated on the FMA pipe (packed f32x2 Cody-Waite polynomial), "
+                             "so frac counts every exponential against the MUFU-only peak"}
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -545,6 +558,7 @@ def run_ours(args):
                      "whole_step_tflops": B * GFLOP_PER_IMAGE_STEP * 1e9 / sec_step / 1e12,
                      "whole_step_frac": B * GFLOP_PER_IMAGE_STEP * 1e9 / sec_step / 1e12 / peak},
         "roofline_hbm": roofline_hbm,
+        "roofline_mufu": roofline_mufu,
         "exchange": exchange,
         "step_breakdown_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
         "step_breakdown_launches": {k: v["launches"] for k, v in prof.items()},
