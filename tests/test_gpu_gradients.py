@@ -66,7 +66,7 @@ def _log(line):
         f.write(line + "\n")
 
 
-@pytest.mark.parametrize("prec,tol_rel,tol_cos", [("fp32", 1e-2, 0.9999), ("bf16", 0.3, 0.96)])
+@pytest.mark.parametrize("prec,tol_rel,tol_cos", [("fp32", 1e-2, 0.9999), ("bf16", 0.25, 0.975)])   # bf16 measured: 0.205 / 0.9789 (ReLU-mask flips)
 def test_input_gradient_chain_matches_autograd(oc, clfs, images, cuda_dev, prec, tol_rel, tol_cos):
     taps, score = oxai.classifier_gradient_taps(oc, images, TARGET)
     x = images.to(cuda_dev)
@@ -93,7 +93,7 @@ def test_input_gradient_chain_matches_autograd(oc, clfs, images, cuda_dev, prec,
     assert rel(one.cpu(), g[:1].cpu()) < (1e-5 if prec == "fp32" else 0.1)     # bf16: tile pairing differs with B -> mask flips
 
 
-@pytest.mark.parametrize("prec,tol_rel,tol_cos", [("fp32", 2e-3, 0.99999), ("bf16", 0.2, 0.98)])
+@pytest.mark.parametrize("prec,tol_rel,tol_cos", [("fp32", 2e-3, 0.99999), ("bf16", 8e-2, 0.997)])   # bf16 measured: 5.5e-2 / 0.9985
 def test_integrated_gradients_matches_the_oracle(oc, clfs, images, cuda_dev, prec, tol_rel, tol_cos):
     """captum riemann_right with 50 steps and an injected baseline: attribution map and completeness."""
     g = torch.Generator().manual_seed(9)
@@ -107,8 +107,8 @@ def test_integrated_gradients_matches_the_oracle(oc, clfs, images, cuda_dev, pre
     _log(f"[{prec}] IG rel {r:.3e} cos {c:.6f}  sum {got.sum().item():.5f} vs {want.sum().item():.5f}  "
          f"delta {delta:.4e} vs {want_delta:.4e}")
     assert r <= tol_rel and c >= tol_cos
-    assert abs(got.sum().item() - want.sum().item()) < (2e-3 if prec == "fp32" else 0.1)
-    assert abs(delta - want_delta) < (2e-3 if prec == "fp32" else 0.1)
+    assert abs(got.sum().item() - want.sum().item()) < (2e-3 if prec == "fp32" else 5e-2)      # bf16 measured: 2.2e-2
+    assert abs(delta - want_delta) < (2e-3 if prec == "fp32" else 3e-2)                          # completeness delta, bf16: 1.5e-2
 
 
 def test_path_points_and_reduction_kernels(clfs, images, cuda_dev):
