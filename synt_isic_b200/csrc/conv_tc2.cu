@@ -105,6 +105,7 @@ struct V2Params {
     const float* bias; const float* bias2; int has_res; int relu;   // residual tile arrives through maps.res
     float2* stats; int stats_slots;   // optional fused GroupNorm partials [B][stats_slots][Cout]
     int chunk;                         // consecutive work items per CTA turn (divides the super-tiles per image)
+    uint32_t mg_per_img, mg_ntiles, mg_nt_real, mg_tiles_x, mg_chunk;   // v2_div magic numbers of the decode's divisors
     long long* tl;                     // EXPERIMENTS: per-CTA wait-time records [grid][16] (SYNT_CONV_TL=1, tools/conv_timeline.py)
     int exp_nob;                       // EXPERIMENTS (SYNT_EXP_NOB bit mask, wrong results): 1 skip the weight-tile TMA loads after the
                                        // first ring fill, 2 skip the input transform, 4 skip the statistics pass, 8 TMA stores, 16 A-tile loads, 32 epilogue
@@ -133,23 +134,29 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // (L2/DRAM locality) while each chunk stays inside one (image, N tile), so GroupNorm partial sums are
 // carried in registers across the chunk and written once -- slot = chunk index within the image.
 struct V2Work { int n0, y0, x0, nt, grp, phase, ntr; };   // nt: virtual N tile (weights), ntr: real N tile (channels)
+// Division by a launch-invariant divisor d: q = umulhi(n, 2^32 / d + 1), exact while n * d < 2^32 (work-item indices are
+// < 2^20, divisors < 2^12).  Every thread of every role decodes its work items: with emulated integer division that was
+// ~400 instructions per thread and item, i.e. ~2000 issue slots per sub-partition and item for the 20 warps of the CTA.
+__device__ __forceinline__ int v2_div(int n, uint32_t magic, int d) { return d == 1 ? n : (int)__umulhi((uint32_t)n, magic); }
 __device__ __forceinline__ V2Work v2_decode(const V2Params& p, int w) {
     V2Work o;
     const int per_img = p.tiles_x * p.supers_per_img;
-    const int rem = w % per_img, key = w / per_img;
-    o.nt = key % p.n_ntiles;
-    o.grp = key / p.n_ntiles;
-    o.phase = o.nt / p.nt_real;
-    o.ntr = o.nt % p.nt_real;
+    const int key = v2_div(w, p.mg_per_img, per_img), rem = w - key * per_img;
+    o.grp = v2_div(key, p.mg_ntiles, p.n_ntiles);
+    o.nt = key - o.grp * p.n_ntiles;
+    o.phase = v2_div(o.nt, p.mg_nt_real, p.nt_real);
+    o.ntr = o.nt - o.phase * p.nt_real;
     o.n0 = o.grp * p.imgs_per_super;
-    o.y0 = (rem / p.tiles_x) * (p.imgs_per_super == 1 ? 32 : 0);
-    o.x0 = (rem % p.tiles_x) * 8;
+    const int ty = v2_div(rem, p.mg_tiles_x, p.tiles_x);
+    o.y0 = ty * (p.imgs_per_super == 1 ? 32 : 0);
+    o.x0 = (rem - ty * p.tiles_x) * 8;
     return o;
 }
 // iteration i of this CTA -> work item (or -1 when exhausted)
 __device__ __forceinline__ int v2_item(const V2Params& p, int i) {
-    const int chunk = (i / p.chunk) * (int)gridDim.x + (int)blockIdx.x;
-    const int w = chunk * p.chunk + i % p.chunk;
+    const int turn = v2_div(i, p.mg_chunk, p.chunk);
+    const int chunk = turn * (int)gridDim.x + (int)blockIdx.x;
+    const int w = chunk * p.chunk + (i - turn * p.chunk);
     return w < p.n_work ? w : -1;
 }
 
@@ -790,6 +797,12 @@ void conv_tc2(const ConvArgs& a, cudaStream_t s) {
     p.bias = a.bias; p.bias2 = a.bias2; p.has_res = a.residual != nullptr; p.relu = a.relu;
     p.stats = a.stats_out; p.stats_slots = conv_tc2_stats_slots(a);
     p.chunk = v2_chunk(a, BN);
+    {
+        auto magic = [](int d) { return (uint32_t)((1ull << 32) / (unsigned long long)d + 1ull); };
+        p.mg_per_img = magic(p.tiles_x * p.supers_per_img); p.mg_ntiles = magic(p.n_ntiles); p.mg_nt_real = magic(p.nt_real);
+        p.mg_tiles_x = magic(p.tiles_x); p.mg_chunk = magic(p.chunk);
+        SYNT_CHECK((long long)p.n_work * (p.tiles_x * p.supers_per_img) < (1ll << 32), "conv_tc2: work-item index range");
+    }
     p.exp_nob = 0; p.tl = nullptr;
 #ifdef SYNT_EXPERIMENTS
     { static const char* e = getenv("SYNT_EXP_NOB"); p.exp_nob = e ? atoi(e) : 0; }
