@@ -40,14 +40,26 @@ namespace synt {
 using namespace ptx;
 
 constexpr int ATC_THREADS = 384;
-constexpr int ATC_STAGES = 3;
+#ifndef ATC_STAGES_N
+#define ATC_STAGES_N 3
+#endif
+constexpr int ATC_STAGES = ATC_STAGES_N;
 constexpr int ATC_KEYS = 64;                           // keys per chunk
 constexpr int ATC_NS = 3;                              // S buffers (64 TMEM columns each) and P tiles
 constexpr int ATC_Q_BYTES = 128 * 128;                 // 128 queries x (4 heads x 16) bf16, zero-masked
 constexpr int ATC_K_BYTES = ATC_KEYS * 128;            // 64 keys x 8 heads x 8 dims bf16 (natural layout, this CTA uses 4 heads)
 constexpr int ATC_V_BYTES = 4 * 16 * 128;              // 4 heads x 16 rows x 64 keys
 constexpr int ATC_STAGE_BYTES = ATC_K_BYTES + ATC_V_BYTES;
-constexpr int ATC_P_BYTES = 128 * 128;                 // 128 queries x 64 keys bf16
+// P through TENSOR MEMORY (round 2): the softmax warps write the bf16 probabilities with tcgen05.st over the S columns they
+// have just consumed (unit u: P in columns [64 u', 64 u' + 32) of its S buffer, two keys per 32-bit column) and the P.V MMAs
+// take their A operand from there (tcgen05.mma [d], [a_tmem], b_desc; layout checked by tools/ubench/mma_ts.cu).  No P tile
+// in shared memory: -32 KB of shared-memory traffic per unit (16 KB of stores + 16 KB of operand fetch), no swizzled store
+// addresses, no generic->async proxy fence in the unit body.  The S buffer is released by the P.V issuer's commit instead of
+// by the softmax warps' last load.  ATC_P_TMEM=0 keeps the shared-memory path (three rotating P tiles).
+#ifndef ATC_P_TMEM
+#define ATC_P_TMEM 1
+#endif
+constexpr int ATC_P_BYTES = ATC_P_TMEM ? 0 : 128 * 128; // 128 queries x 64 keys bf16
 constexpr int ATC_OFF_STAGE = ATC_Q_BYTES;
 constexpr int ATC_OFF_P = ATC_OFF_STAGE + ATC_STAGES * ATC_STAGE_BYTES;
 constexpr int ATC_OFF_BAR = ATC_OFF_P + ATC_NS * ATC_P_BYTES;   // P tiles rotate with the S buffers (unit u -> u % 3)
@@ -155,6 +167,21 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st_x8_nowait(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: M = 128 rows in the 128 lanes, K = 16 bf16 in 8 columns from tmem_a
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // PERSISTENT kernel: the grid is two CTAs per SM and every CTA walks the work items it, it + grid, it + 2*grid, ... (item =
 // 128 queries x 4 heads of one image; all items cost the same).  Nothing is torn down between items: TMEM, the barriers
 // and all the rings (K/V stages, S buffers, P tiles) run on, the TMA producer and the V^T builder prefetch across the item
@@ -240,7 +267,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
         prefetch_tmap(&maps.k);
         // full: the TMA producer's arrive.expect_tx (K tile) + the V^T builder's arrive
         for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < ATC_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 128); }
+        for (int s = 0; s < ATC_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], ATC_P_TMEM ? 1 : 128); }
         for (int g = 0; g < ATC_NS; ++g) { mbar_init(&p_full[g], 128); mbar_init(&p_free[g], 1); }
         mbar_init(q_full, 256); mbar_init(q_free, 1); mbar_init(o_full, 1); mbar_init(o_free, 256);
         for (int i = 0; i < 4; ++i) mbar_init(&item_full[i], 1);
@@ -365,10 +392,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                     const uint64_t dp = make_smem_desc_sw128(p_addr + pb * ATC_P_BYTES);
                     const uint64_t dv = make_smem_desc_sw128(v_addr + j * 2048);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        if (!(ATC_KNOCK & 4))
-                        umma_bf16(tmem + ATC_O_COL + j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv, (c | kk) != 0 ? 1u : 0u);
-                    umma_commit(&p_free[pb]);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (ATC_KNOCK & 4) continue;
+                        if (ATC_P_TMEM) umma_bf16_ts(tmem + ATC_O_COL + j * 16, tmem + pb * ATC_KEYS + 8 * kk, dv + 2 * kk, idesc_pv, (c | kk) != 0 ? 1u : 0u);
+                        else umma_bf16(tmem + ATC_O_COL + j * 16, dp + 2 * kk, dv + 2 * kk, idesc_pv, (c | kk) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(ATC_P_TMEM ? &s_free[pb] : &p_free[pb]);     // P in TMEM: this also frees the S buffer it lives in
                     if (++pb == ATC_NS) { pb = 0; pph ^= 1u; }
                     if (j == 3) {
                         umma_commit(&empty_bar[stage]);                      // all S and P.V reads of this stage are done
@@ -459,7 +488,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                     // P.V of the unit three before this one is complete, hence (in-order MMA pipe) so is every earlier one:
                     // P[sb] is free and O_j (last written four units ago) has no MMA in flight
                     ATC_T0();
-                    if (!(ATC_KNOCK & 128)) mbar_wait(&p_free[sb], sph ^ 1u);
+                    // (P in TMEM: s_full of this unit already implies it -- the S MMA was issued behind the P.V commit that
+                    // freed this buffer)
+                    if (!ATC_P_TMEM && !(ATC_KNOCK & 128)) mbar_wait(&p_free[sb], sph ^ 1u);
                     ATC_T1(1);
                     if (__any_sync(0xffffffffu, moved)) {
                         tc_fence_after();
@@ -498,8 +529,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                             smp = fmaxf(fmaxf(smp, __uint_as_float(cur[0])), __uint_as_float(cur[4]));
                             smp = fmaxf(fmaxf(smp, __uint_as_float(cur[8])), __uint_as_float(cur[12]));
 #pragma unroll
+                            uint32_t pw[8];                                        // the piece's 16 probabilities, packed
+#pragma unroll
                             for (int q = 0; q < 2; ++q) {                          // 16-byte chunk = 8 keys
-                                uint32_t w[4];
+                                uint32_t (&w)[4] = *reinterpret_cast<uint32_t (*)[4]>(&pw[q * 4]);
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     const int e = q * 8 + i * 2;
@@ -515,12 +548,15 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                                     w[i] = (POLY > 0 && i >= 4 - POLY) ? pack_bf16x2(ex2_poly(x0), ex2_poly(x1))
                                                                         : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
                                 }
-                                if (!(ATC_KNOCK & 2) || w[0] == 0x12345678u)
+                                if (!ATC_P_TMEM && (!(ATC_KNOCK & 2) || w[0] == 0x12345678u))
                                 *reinterpret_cast<uint4*>(p_row + (((piece * 2 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // SWIZZLE_128B
                             }
+                            // P in TMEM: the 16 keys of this piece -> columns 8 piece .. 8 piece + 7 of the S buffer; they were S
+                            // columns of a piece <= this one, i.e. already in registers (the load in flight reads piece + 1)
+                            if (ATC_P_TMEM && !(ATC_KNOCK & 2)) tmem_st_x8_nowait(lane_addr + sb * ATC_KEYS + piece * 8, pw);
                             if (piece + 1 < ATC_KEYS / 16) {
                                 tmem_ld_wait();
-                                if (piece + 2 == ATC_KEYS / 16) {                  // the last load of this S buffer has completed
+                                if (!ATC_P_TMEM && piece + 2 == ATC_KEYS / 16) {   // the last load of this S buffer has completed
                                     tc_fence_before();
                                     mbar_arrive(&s_free[sb]);
                                 }
@@ -528,8 +564,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
                         }
                     }
                     mnext[jj] = smp;
+                    if (ATC_P_TMEM) tmem_st_wait();
                     tc_fence_before();
-                    fence_proxy_async();                                       // generic-proxy writes -> async proxy (UMMA)
+                    if (!ATC_P_TMEM) fence_proxy_async();                      // generic-proxy writes -> async proxy (UMMA)
                     mbar_arrive(&p_full[sb]);
                 }
             }
