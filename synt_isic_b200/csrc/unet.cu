@@ -614,6 +614,7 @@ struct Fwd {
 
     // eps = UNet(x, t) for one micro-batch; temb_cur must already hold the row of t.
     void run(const float* x_nchw, float* eps_nchw, const SchedArgs& sch) {
+        Pool::Scope scope(*pool);                                   // an exception below returns every block still out
         Act h = make(kImg, kImg, 64);
         const int in_slots = conv_in3_stats_slots(kImg, kImg, u->dt);
         if (in_slots > 0) {                                     // statistics of the first GroupNorm fused into conv_in
@@ -659,6 +660,7 @@ struct Fwd {
         ++u->launches;
         pool->release(ss);
         drop(hcur);
+        scope.commit();
     }
 };
 
