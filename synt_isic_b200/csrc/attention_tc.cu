@@ -66,6 +66,9 @@ constexpr int ATC_OFF_BAR = ATC_OFF_P + ATC_NS * ATC_P_BYTES;   // P tiles rotat
 constexpr int ATC_SMEM = ATC_OFF_BAR + 256;            // the dynamic window starts 1 KB aligned (checked in the kernel)
 constexpr uint32_t ATC_TMEM_COLS = 256;                // S buffers [0,192), O_h [192+16h, +16)
 constexpr uint32_t ATC_O_COL = 192;
+#ifndef ATC_POLY_HALF
+#define ATC_POLY_HALF 1                                // 1: one more polynomial pair in every second 8-key group (POLY + 1/2 per four pairs)
+#endif
 constexpr int ATC_POLY_DEFAULT = 1;                    // exponentials per 4 pairs on the FMA pipe (SYNT_ATT_POLY overrides)
 constexpr float ATC_LAZY = 8.0f;                       // rescale only when the max grows by more than 2^8
 static_assert(2 * (ATC_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit in shared memory");
@@ -110,7 +113,9 @@ __device__ __forceinline__ float ex2_poly(float x) {
     p = fmaf(p, f, 0.9999276995658875f);
     return __int_as_float(__float_as_int(t) * 8388608 + __float_as_int(p));
 }
-// Measured (B200, round 2, persistent kernel, B=64 N=1024): POLY 0 / 1 / 2 / 3 -> 672 / 653 / 727 / 942 us per launch: the
+// Measured (B200, round 2, final kernel with P in tensor memory): polynomial pairs per 8 pairs 0 / 2 / 3 / 4 -> 620 / 522 / 512 / 555 us
+// per N=1024 launch, hence three in eight (POLY = 1 plus ATC_POLY_HALF).  Earlier (persistent kernel, scalar arithmetic):
+// POLY 0 / 1 / 2 / 3 -> 672 / 653 / 727 / 942 us per launch: the
 // softmax warps are balanced between the MUFU pipe and their issue slots, so one pair in four is the optimum.  A zero-reference
 // fast path (P = 2^S without the subtraction while the row maximum stays within 2^+-40) measured SLOWER (714 us): the second
 // copy of the unrolled loop costs more in registers / spills than the 64 FADDs per unit it removes.
@@ -199,7 +204,7 @@ __device__ __forceinline__ AtcItem atc_item(int it, int nqt) {
 }
 
 // POLY: of every four bf16 pairs of P, POLY are computed with ex2_poly on the FMA pipe instead of MUFU.EX2
-template <int POLY>
+template <int POLY, int HALF = 0>
 __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, int N,
                                                                       int C, int n_items, const bf16* __restrict__ qkv,
                                                                       bf16* __restrict__ out, int* __restrict__ work_ctr,
@@ -539,7 +544,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const __gr
 #if ATC_PACKED
                                     const float2 xx = add2(make_float2(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])), make_float2(-mrow, -mrow));
                                     const float x0 = xx.x, x1 = xx.y;
-                                    if (!(ATC_KNOCK & 1) && POLY > 0 && i >= 4 - POLY) { const float2 y = ex2_poly2(xx); w[i] = pack_bf16x2(y.x, y.y); continue; }
+                                    if (!(ATC_KNOCK & 1) && i >= 4 - POLY - (HALF && q == 1 ? 1 : 0)) { const float2 y = ex2_poly2(xx); w[i] = pack_bf16x2(y.x, y.y); continue; }
 #else
                                     const float x0 = __uint_as_float(cur[e]) - mrow, x1 = __uint_as_float(cur[e + 1]) - mrow;
 #endif
@@ -652,7 +657,9 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
         encode_bf16_sw128(&maps.k, qkv, 2, dims, strides, boxk, "attention k");
     }
     static const int poly = [] { const char* e = getenv("SYNT_ATT_POLY"); const int v = e ? atoi(e) : ATC_POLY_DEFAULT; return v < 0 ? 0 : (v > 3 ? 3 : v); }();
-    auto kern = poly == 0 ? attention_tc_kernel<0> : poly == 1 ? attention_tc_kernel<1> : poly == 2 ? attention_tc_kernel<2> : attention_tc_kernel<3>;
+    static const int half = [] { const char* e = getenv("SYNT_ATT_POLY_HALF"); return e ? (atoi(e) != 0) : (ATC_POLY_HALF != 0); }();
+    auto kern = poly == 0 ? attention_tc_kernel<0> : poly == 1 ? (half ? attention_tc_kernel<1, 1> : attention_tc_kernel<1>)
+              : poly == 2 ? attention_tc_kernel<2> : attention_tc_kernel<3>;
     ensure_dynamic_smem((const void*)(kern), ATC_SMEM);
     static const int num_sms = [] { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
     const int n_items = (N / 128) * (C / 32) * B;            // 128 queries x 4 heads of one image each
