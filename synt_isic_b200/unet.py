@@ -118,7 +118,11 @@ class UNet2DModel(nn.Module):
         return torch.float32
 
     def _version_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # the Parameter objects are stable (``.to()`` swaps their ``.data``); walking the module tree on every call cost ~0.2 ms
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = self.__dict__["_plist"] = list(self.parameters())
+        return tuple((p.data_ptr(), p._version) for p in plist)
 
     def refresh_weights(self):
         """Rebuilds the native weights on the next call.  In-place edits through ``param.data`` (``.data.mul_()``,

@@ -103,8 +103,9 @@ def compute_time_shap(classifier, trajectory, timesteps, target_class, group=Non
     else:
         frames = frames.to(dev).reshape(-1, 3, 128, 128)
         p = _probs(classifier, frames, group)[:, target_class]
-    prob_scores = p.double().cpu().numpy()                      # get_confidence(...).item()
-    confidence_scores = torch.log(p + 1e-8).double().cpu().numpy()   # get_per_class_score(...).item()
+    both = torch.stack([p, torch.log(p + 1e-8)]).double().cpu().numpy()   # ONE device-to-host copy (and one sync) for both score rows
+    prob_scores = both[0]                                       # get_confidence(...).item()
+    confidence_scores = both[1]                                 # get_per_class_score(...).item()
     if len(confidence_scores) > 1 and (confidence_scores.max() - confidence_scores.min()) > 1e-6:
         imp = (confidence_scores - confidence_scores.min()) / (confidence_scores.max() - confidence_scores.min())
     else:
