@@ -77,6 +77,8 @@ CASES = [
     (3, 56, 56, 64, 64, 3, 1, 1, (0, 0), 1, True, True, False),            # ResNet18 layer1 (ragged 56)
     (3, 56, 56, 64, 128, 3, 2, 1, (0, 0), 1, False, True, False),          # ResNet18 layer2.0.conv1
     (3, 28, 28, 128, 128, 3, 1, 1, (64, 0), 2, False, True, False),        # layer2.0.conv2 + 1x1 s2 downsample
+    (3, 56, 56, 64, 128, 1, 2, 0, (0, 0), 1, False, False, False),         # layer2.0 downsample as its own 1x1 / stride-2 conv
+    (3, 28, 28, 128, 128, 3, 1, 1, (0, 0), 1, True, True, False),          # layer2.0.conv2 with the downsample output as residual
     (3, 14, 14, 256, 256, 3, 1, 1, (0, 0), 1, True, True, False),          # 14x14
     (3, 7, 7, 512, 512, 3, 1, 1, (0, 0), 1, True, True, False),            # 7x7, two images per tile, odd B
     (16, 32, 32, 256, 256, 3, 1, 1, (0, 0), 1, True, False, True),         # 128 pixel tiles x 2 -> N tile 128
