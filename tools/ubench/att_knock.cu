@@ -5,7 +5,7 @@
 #include <cstdlib>
 namespace synt { int pdl_mode() { return 0; } }
 int main(int argc, char** argv) {
-    const int B = 64, N = argc > 1 ? atoi(argv[1]) : 1024, C = 256;
+    const int N = argc > 1 ? atoi(argv[1]) : 1024, B = argc > 2 ? atoi(argv[2]) : 64, C = 256;
     const size_t n = (size_t)B * N * 3 * C;
     std::vector<__nv_bfloat16> h(n);
     uint32_t st = 12345u;
