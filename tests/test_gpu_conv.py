@@ -188,6 +188,49 @@ def test_conv_tcgen05_fused_groupnorm_input(cuda_dev, case):
     assert torch.allclose(st[..., 1], want_q, rtol=2e-3, atol=2e-2)
 
 
+K1_CASES = [
+    # B, H, W, Cin, Cout, gn_mode      (no residual, no statistics: the no-halo four-slot variant of conv_tc2)
+    (2, 32, 32, 256, 768, 1),          # qkv projection with the attention block's GroupNorm affine fused
+    (3, 16, 16, 256, 768, 1),          # 16x16 site: two images per super-tile, odd batch
+    (2, 32, 32, 256, 768, 0),          # raw input (TMA only)
+    (70, 32, 32, 256, 768, 1),         # more work items than SMs x ring depth
+]
+
+
+@pytest.mark.parametrize("case", K1_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_tcgen05_1x1_four_slot_variant(cuda_dev, case):
+    """The qkv 1x1 projection path of the sampling step (diffusers Attention.to_q/k/v behind group_norm, reached from
+    core/generator/image_generator.py:400): 1x1 conv with the GroupNorm affine applied to the input inside the kernel."""
+    B, H, W, Cin, Cout, mode = case
+    dev = cuda_dev
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g) * 1.5 + 0.3
+    sc = 0.5 + torch.rand(B, Cin, generator=g)
+    sh = torch.randn(B, Cin, generator=g) * 0.5
+    w = torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5
+    b = torch.randn(Cout, generator=g)
+    q = lambda t: t.to(torch.bfloat16).float()
+    y = q(x).to(dev)
+    if mode:
+        y = q(y * sc.to(dev)[:, :, None, None] + sh.to(dev)[:, :, None, None])
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = F.conv2d(y, q(w).to(dev), b.to(dev))
+    x0 = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(dev)
+    wp = _pack(w, None).to(torch.bfloat16).to(dev)
+    ss = torch.stack([sc, sh], dim=2).contiguous().to(dev)
+    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    slots = C.c_int()
+    b_d = b.to(dev)
+    _lib.check(_lib.lib().synt_debug_conv_gn(x0.data_ptr(), Cin, None, 0, ss.data_ptr() if mode else None, mode, B, H, W, 1, None, 0,
+                                             wp.data_ptr(), b_d.data_ptr(), None, out.data_ptr(), Cout, None, C.byref(slots),
+                                             _lib.current_stream_ptr()), "debug_conv_gn")
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2)
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 4e-3, rel
+
+
 UP_CASES = [
     # B, H, W (low-res), Cin, Cout
     (3, 16, 16, 256, 256),      # up_blocks.0 upsampler: 2 images per super-tile, odd B
