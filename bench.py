@@ -597,6 +597,19 @@ def run_ours(args):
                                                "(tests/test_gpu_benchmarked_config.py); the 1e-3 contract of north_star is "
                                                "held by precision='fp32' (fp32_mode below)"}
         with torch.cuda.stream(stream):
+            # the classifier evaluations alone (no softmax / score post-processing / device-to-host copy of the scores)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.no_grad():
+                clf(traj)
+                g0.record(stream)
+                for _ in range(3):
+                    clf(traj)
+                g1.record(stream)
+            stream.synchronize()
+            sec_fwd = g0.elapsed_time(g1) / 3e3
+            line["time_shap"]["forward_only"] = {"sec_per_image": sec_fwd, "resnet18_img_per_s": T_STEPS / sec_fwd,
+                                                 "tflops": T_STEPS * 3.627e9 / sec_fwd / 1e12,
+                                                 "frac_of_sustained_bf16": T_STEPS * 3.627e9 / sec_fwd / 1e12 / peaks["bf16_sustained"]}
             pf = clf.profile_forward(traj[:512])
             fe_bytes = 512 * (3 * 128 * 128 * 4 + 56 * 56 * 64 * 2)
             line["roofline_hbm"].append({
