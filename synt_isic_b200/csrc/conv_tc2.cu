@@ -64,7 +64,7 @@ struct V2Smem {
     static constexpr int NPASS = BN / EC;
     static constexpr int NBUF = BN == 256 ? 1 : 2;         // TMEM accumulator buffers (each V2_MT x BN columns)
     static constexpr int STAGING = 128 * EC * 2;           // one pass of one M tile of bf16 output (one per epilogue warpgroup)
-    static constexpr int NB = RES ? 12 : (BN == 256 ? 3 : (BN == 128 ? 4 : 8));
+    static constexpr int NB = RES ? 12 : (BN == 256 ? 3 : (BN == 128 ? 4 : 12));   // BN = 64 streamed: 12 x 8 KB fit next to the A slots (b_full waits 9% with 8)
     static constexpr int OFF_B = A_STAGES * A_SLOT;
     static constexpr int OFF_STAGING = OFF_B + NB * B_TILE;
     static constexpr int OFF_BIAS = OFF_STAGING + V2_MT * STAGING;
