@@ -528,7 +528,7 @@ def run_ours(args):
                      "peak": mufu_peak / 1e12, "unit": "T exponentials/s",
                      "frac": att_exps / (att_ms * 1e-3) / mufu_peak if att_ms > 0 else 0.0,
                      "peak_source": "16 results/clk/SM measured (tools/ubench/mufu.cu) x 148 SMs x SM clock under load",
-                     "note": "one pair in four of the exponentials is evaluated on the FMA pipe (packed f32x2 Cody-Waite polynomial), "
+                     "note": "three pairs in eight of the exponentials are evaluated on the FMA pipe (packed f32x2 Cody-Waite polynomial), "
                              "so frac counts every exponential against the MUFU-only peak"}
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
