@@ -21,7 +21,7 @@
 // is scaled in place by the softmax warps (tcgen05.ld/st) while no MMA on O_h is in flight.  The
 // result is mathematically the exact softmax.  d = 8 makes the kernel MUFU bound (N^2 ex2 per head,
 // 16 ex2/clk/SM; the MMAs are <10% of its time): the design goal is to keep the MUFU pipe busy, hence
-// two co-resident CTAs (256 TMEM columns, 112 KB smem, 80 registers/thread each) = 4 softmax warps per SM
+// two co-resident CTAs (256 TMEM columns, 64 KB smem, 80 registers/thread at launch, re-split 48 / 96 by setmaxnreg) = 4 softmax warps per SM
 // sub-partition whose load/max/exp phases interleave, and three rotating P tiles (unit u -> tile u % 3, like the
 // S buffers) so that a softmax warpgroup does not wait for the P.V MMA of its previous unit.
 //
@@ -81,8 +81,8 @@ static_assert(2 * (ATC_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit in 
 // nanosleep per retry in the waits of the roles that have ring slack (ns): A = TMA producer / V^T builder waiting for a free
 // K/V stage (3 chunks = 12 units of slack), B = P.V issuer waiting for a P tile, C = S issuer waiting for a free S buffer
 #ifndef ATC_REGS_ROLE
-#define ATC_REGS_ROLE 56
-#define ATC_REGS_SOFTMAX 88
+#define ATC_REGS_ROLE 48
+#define ATC_REGS_SOFTMAX 96
 #endif
 #ifndef ATC_SLEEP_A
 #define ATC_SLEEP_A 0
