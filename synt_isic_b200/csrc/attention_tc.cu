@@ -32,6 +32,7 @@
 #include "ptx.cuh"
 #include "tmap.cuh"
 #include <cstdio>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -661,19 +662,27 @@ void attention_tc(const void* qkv, int B, int N, int C, void* vt_scratch, void* 
     auto kern = poly == 0 ? attention_tc_kernel<0> : poly == 1 ? (half ? attention_tc_kernel<1, 1> : attention_tc_kernel<1>)
               : poly == 2 ? attention_tc_kernel<2> : attention_tc_kernel<3>;
     ensure_dynamic_smem((const void*)(kern), ATC_SMEM);
-    static const int num_sms = [] { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    static const int num_sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
     const int n_items = (N / 128) * (C / 32) * B;            // 128 queries x 4 heads of one image each
     const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;     // persistent: two resident CTAs per SM
     // work-queue counters {next item, CTAs done}: a pool of pairs handed out round-robin, zero at rest (the kernel's last CTA
     // re-arms its pair), so that launches captured into different graphs / running on different streams do not share one
-    constexpr int kCtrPairs = 1024;
-    static int* ctr_pool = nullptr;
-    static int ctr_next = 0;
-    if (!ctr_pool) {
-        SYNT_CUDA(cudaMalloc(&ctr_pool, kCtrPairs * 2 * sizeof(int)));
-        SYNT_CUDA(cudaMemset(ctr_pool, 0, kCtrPairs * 2 * sizeof(int)));
+    constexpr int kCtrPairs = 1024, kMaxDev = 64;
+    static int* ctr_pools[kMaxDev] = {nullptr};                      // one pool per device (a process may drive several GPUs)
+    static int ctr_next[kMaxDev] = {0};
+    static std::mutex ctr_mu;
+    int dev = 0;
+    SYNT_CUDA(cudaGetDevice(&dev));
+    SYNT_CHECK(dev >= 0 && dev < kMaxDev, "attention_tc: device index");
+    int* work_ctr;
+    {
+        std::lock_guard<std::mutex> lk(ctr_mu);
+        if (!ctr_pools[dev]) {
+            SYNT_CUDA(cudaMalloc(&ctr_pools[dev], kCtrPairs * 2 * sizeof(int)));
+            SYNT_CUDA(cudaMemset(ctr_pools[dev], 0, kCtrPairs * 2 * sizeof(int)));
+        }
+        work_ctr = ctr_pools[dev] + 2 * (ctr_next[dev]++ % kCtrPairs);
     }
-    int* work_ctr = ctr_pool + 2 * (ctr_next++ % kCtrPairs);
     long long* tl = nullptr;
 #ifdef SYNT_ATT_TIMELINE_BUILD
     static const char* tl_path = getenv("SYNT_ATT_TIMELINE");
