@@ -553,3 +553,22 @@ def test_image_generator_reference_constructor_and_result_contract(tmp_path):
     assert gen.generate_images([("MEL", 1)], str(tmp_path / "out2")) == {"error": "kaboom"}
     keys = ImageGenerator.noise_keys([11, None, 11])
     assert keys[0] == keys[2] == 11 and 0 <= keys[1] < 2 ** 63
+
+
+def test_multiply_high_division_of_the_work_item_decode():
+    """csrc/conv_tc2.cu v2_div: q = umulhi(n, 2^32 // d + 1) equals n // d whenever n * d < 2^32 (the host checks that bound
+    for every launch); d = 1 is special-cased on the device."""
+    import random
+    rng = random.Random(0)
+    for d in list(range(2, 300)) + [511, 512, 513, 1023, 1024, 4095, 4096]:
+        magic = ((1 << 32) // d + 1) & 0xFFFFFFFF
+        hi = ((1 << 32) - 1) // d
+        ns = [0, 1, d - 1, d, d + 1, hi - 1, hi] + [rng.randrange(0, hi + 1) for _ in range(200)]
+        for n in ns:
+            if n < 0 or n * d >= (1 << 32):
+                continue
+            assert (n * magic) >> 32 == n // d, (n, d)
+    # just beyond the bound the identity may fail: the check in conv_tc2() is what makes it safe
+    bad = [(n, d) for d in (3, 7, 100) for n in range((1 << 32) // d, (1 << 32) // d + 50)
+           if ((n * (((1 << 32) // d + 1) & 0xFFFFFFFF)) >> 32) != n // d]
+    assert isinstance(bad, list)
