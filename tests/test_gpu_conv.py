@@ -134,6 +134,8 @@ GN_CASES = [
     (2, 32, 32, 256, 0, 256, 3, 2, 128, False),     # conv2 + raw (untransformed) 1x1 shortcut segment
     (2, 32, 32, 256, 0, 1280, 1, 1, 0, False),      # attention qkv projection: GroupNorm without SiLU
     (1, 128, 128, 64, 0, 64, 3, 2, 0, True),        # 128x128: padding rows/cols must stay zero after the transform
+    (2, 32, 32, 64, 0, 64, 3, 2, 128, False),       # up_blocks.3 conv2 + 1x1 shortcut over 128 channels (Cout = 64, K = 704)
+    (3, 64, 64, 64, 0, 64, 3, 2, 192, False),       # ... over 192 channels (K = 768), more work items than slots
 ]
 
 
